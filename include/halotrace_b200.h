@@ -1,0 +1,368 @@
+/*
+ * halotrace_b200.h — C ABI of the B200 (sm_100a) ice-halo trace engine.
+ *
+ * This is the drop-in boundary. Every entry point mirrors one virtual of the
+ * reference's trace-backend seam `lumice::TraceBackend`
+ * (reference: src/core/backend/trace_backend.hpp:367-641) or one host-side
+ * table builder the reference's GPU backends call before uploading
+ * (reference: src/core/backend/cuda_trace_backend.cu:2436-2542).
+ * A thin C++ subclass of `lumice::TraceBackend` (see adapter/ and
+ * INTEGRATION.md) forwards each virtual to the function named next to it.
+ *
+ * Conventions
+ *   - plain C, POD structs, pointers + sizes; no C++/torch types cross this ABI
+ *   - every function returns HB_OK (0) or a negative HbStatus; the message of
+ *     the last failure on a handle is available from hb_last_error()
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     HB_ERR_NO_DEVICE / HB_ERR_CUDA when no sm_100 device is usable
+ *   - angles are radians unless the field name ends in _deg
+ *   - rays crossing this ABI are world-space except where a field says
+ *     "crystal-local" (parity-only injection/export helpers)
+ */
+#ifndef HALOTRACE_B200_H_
+#define HALOTRACE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1u
+
+/* Limits (reference: src/core/def.hpp:23-31, crystal.hpp:67,76, pcg_shared.h:71). */
+#define HB_MAX_FACES 20u      /* kCrystalGeomMaxFaces */
+#define HB_MAX_FACE_VTX 12u   /* kCrystalGeomMaxVtxPerFace */
+#define HB_MAX_SUBTRIS 64u    /* kMaxTriPerKernel */
+#define HB_MAX_HITS 64u       /* kMaxHits */
+#define HB_MAX_LAYERS 8u      /* C API scatter-layer cap, lumice.h:286-293 */
+#define HB_MAX_CRYSTALS 16u   /* kMaxCrystalNum (per layer) */
+#define HB_LUT_NODES 257u     /* LatLut::kNodes, lat_lut.hpp:31-35 */
+#define HB_MAX_WL 256u        /* wavelength pool cap (kWlPoolSizeMax=255) */
+#define HB_INVALID_FACE 0xFFFFu /* kInvalidId */
+#define HB_MAX_FILTER_PATH 32u  /* C API raypath len cap, lumice.h:286-293 */
+#define HB_MAX_FILTER_TERMS 8u
+
+typedef enum HbStatus {
+  HB_OK = 0,
+  HB_ERR_INVALID_ARG = -1,
+  HB_ERR_NO_DEVICE = -2,   /* maps to lumice::BackendUnavailableError */
+  HB_ERR_CUDA = -3,        /* maps to lumice::BackendUnavailableError */
+  HB_ERR_STATE = -4,       /* call outside the BeginSession/EndSession bracket */
+  HB_ERR_CAPACITY = -5,
+  HB_ERR_UNSUPPORTED = -6,
+  HB_ERR_COMM = -7
+} HbStatus;
+
+/* Distribution types (reference: src/core/math.hpp DistributionType). */
+enum { HB_DIST_NO_RANDOM = 0, HB_DIST_UNIFORM = 1, HB_DIST_GAUSSIAN = 2, HB_DIST_ZIGZAG = 3,
+       HB_DIST_LAPLACIAN = 4, HB_DIST_GAUSSIAN_LEGACY = 5 };
+/* Latitude sampling paths (reference: pcg_shared.h:56-59, lat_path_selection.hpp:39-46). */
+enum { HB_LAT_FULL_SPHERE = 0, HB_LAT_NO_RANDOM = 1, HB_LAT_GAUSS_LEGACY = 3, HB_LAT_LUT = 6 };
+/* Lens types (reference: config/render_config.hpp LensParam::LensType). */
+enum { HB_LENS_LINEAR = 0, HB_LENS_FISHEYE_EQUAL_AREA = 1, HB_LENS_FISHEYE_EQUIDISTANT = 2,
+       HB_LENS_FISHEYE_STEREOGRAPHIC = 3, HB_LENS_DUAL_FISHEYE_EQUAL_AREA = 4,
+       HB_LENS_DUAL_FISHEYE_EQUIDISTANT = 5, HB_LENS_DUAL_FISHEYE_STEREOGRAPHIC = 6,
+       HB_LENS_RECTANGULAR = 7, HB_LENS_FISHEYE_ORTHOGRAPHIC = 8, HB_LENS_DUAL_FISHEYE_ORTHOGRAPHIC = 9,
+       HB_LENS_GLOBE = 10 };
+enum { HB_VISIBLE_UPPER = 0, HB_VISIBLE_LOWER = 1, HB_VISIBLE_FULL = 2 };
+
+/* ---------------------------------------------------------------------------
+ * Tables (what the reference's GPU backends upload per scene)
+ * ------------------------------------------------------------------------- */
+
+/* One convex crystal shape: polygon-face planes + the entry-sampling fan table.
+ * Replaces Crystal::GetPolygonFaceNormal/Dist/GetFn (crystal.hpp:227,281-288) and
+ * detail::BuildEntrySubTris (simulator.cpp:90-129).
+ * plane[f] = (nx,ny,nz,d0), unit outward normal, inside <=> n.x + d0 <= 0. */
+typedef struct HbCrystalTables {
+  uint32_t face_cnt;                      /* compact present faces, <= HB_MAX_FACES */
+  uint32_t subtri_cnt;                    /* <= HB_MAX_SUBTRIS; 0 => degenerate crystal */
+  float plane[HB_MAX_FACES][4];
+  float tri_v[HB_MAX_SUBTRIS][9];         /* 3 corners x xyz (fan 0,k,k+1) */
+  float tri_n[HB_MAX_SUBTRIS][3];         /* raw-winding unit normal */
+  float tri_area[HB_MAX_SUBTRIS];
+  uint8_t tri_face[HB_MAX_SUBTRIS];       /* compact face id of each sub-triangle */
+  uint8_t face_fn[HB_MAX_FACES];          /* GetFn: compact face id -> face number 1..8/13..18/23..28 */
+  uint8_t reserved_[12];
+} HbCrystalTables;
+
+/* Orientation sampler of one crystal population.
+ * Replaces the orientation fields of lm_pcg::GenRootKernelParams (pcg_shared.h:150-189)
+ * + the three LatLut arrays (lat_lut.hpp:31-35). */
+typedef struct HbAxisSampler {
+  uint32_t lat_path;                      /* HB_LAT_* */
+  float lat_mean, lat_std;                /* radians */
+  uint32_t az_type;                       /* HB_DIST_* */
+  float az_mean, az_std;
+  uint32_t roll_type;
+  float roll_mean, roll_std;
+  uint32_t lut_n;                         /* HB_LUT_NODES when lat_path == HB_LAT_LUT else 0 */
+  float lut_theta[HB_LUT_NODES];
+  float lut_cdf[HB_LUT_NODES];
+  float lut_flip[HB_LUT_NODES];
+} HbAxisSampler;
+
+/* Raypath filter, flattened. Replaces DeviceFilterDesc (device_filter_desc.hpp:91-123).
+ * kind: 0 none, 1 raypath, 2 entry-exit, 3 direction, 4 crystal, 5 complex (OR of AND-terms
+ * of simple filters, held in `terms`). action: 0 filter_in, 1 filter_out. */
+typedef struct HbSimpleFilter {
+  uint32_t kind;
+  uint32_t path_len;
+  uint8_t path[HB_MAX_FILTER_PATH];       /* raypath: canonical (symmetry-reduced) face numbers */
+  int32_t entry_fn, exit_fn;              /* entry-exit: -1 = wildcard */
+  uint32_t min_len, max_len;              /* entry-exit: max_len 0 = unbounded */
+  float dir[3]; float cos_radii;          /* direction: unit vector + cos(radius) */
+  uint32_t crystal_id;                    /* crystal filter */
+} HbSimpleFilter;
+
+typedef struct HbFilterDesc {
+  uint32_t kind;                          /* as HbSimpleFilter.kind; 5 = complex */
+  uint32_t action;                        /* 0 in, 1 out */
+  uint32_t symmetry;                      /* bit0 P, bit1 B, bit2 D */
+  int32_t fn_period;                      /* Crystal::FnPeriod (6 for hex crystals, -1 none) */
+  int32_t sigma_a;                        /* D-mirror parameter 0..5 */
+  uint32_t d_applicable;
+  HbSimpleFilter simple;                  /* kind 1..4 */
+  uint32_t term_cnt;                      /* kind 5: number of OR terms */
+  uint32_t term_len[HB_MAX_FILTER_TERMS]; /* number of AND factors in each term */
+  HbSimpleFilter terms[HB_MAX_FILTER_TERMS][4];
+} HbFilterDesc;
+
+/* One crystal population of a scattering layer (reference: ScatteringSetting, proj_config.hpp). */
+typedef struct HbCrystalPopulation {
+  float proportion;                       /* crystal_proportion_ */
+  uint32_t crystal_id;                    /* CrystalConfig::id_ (carried into exit records) */
+  uint32_t shape_cnt;                     /* geometry pool size (1 = deterministic shape) */
+  const HbCrystalTables* shapes;          /* [shape_cnt] */
+  HbAxisSampler axis;
+  HbFilterDesc filter;
+} HbCrystalPopulation;
+
+typedef struct HbLayer {
+  float prob;                             /* MsInfo::prob_ : continue-to-next-layer probability */
+  uint32_t population_cnt;
+  const HbCrystalPopulation* populations;
+} HbLayer;
+
+/* Whole scene (reference: SceneConfig, proj_config.hpp:27-38). */
+typedef struct HbScene {
+  uint32_t max_hits;                      /* surface interactions incl. entry (CPU semantics) */
+  uint32_t layer_cnt;
+  const HbLayer* layers;
+  float sun_lon;                          /* (azimuth + 180 deg) in rad, simulator.cpp:194-196 */
+  float sun_lat;                          /* (-altitude) in rad */
+  float sun_half_angle;                   /* diameter / 2 in rad */
+} HbScene;
+
+/* Wavelength pool entry (reference: WlEntry, backend/wl_pool.hpp:29-36). */
+typedef struct HbWlEntry {
+  float n_idx, spd_weight, cmf_x, cmf_y, cmf_z;
+} HbWlEntry;
+
+/* Projection parameters; field-for-field lm_proj::ProjParams (projection_shared.h:106-118). */
+typedef struct HbProjParams {
+  int32_t proj_type, img_w, img_h, visible_range, lens_shift_x, lens_shift_y;
+  float scale, az0, r_scale, max_abs_dz;
+  float rot[9];
+} HbProjParams;
+
+/* Exit ray record; byte-for-byte lumice::ExitRayRecord (exit_seam.hpp:40-53), 96 B. */
+typedef struct HbExitRecord {
+  float dir[3];
+  float weight;
+  uint8_t path_len;
+  uint8_t path[64];                       /* face numbers (GetFn), entry first */
+  uint8_t pad0_;
+  uint16_t crystal_id;
+  uint8_t ms_layer_idx;
+  uint8_t wl_idx;
+  uint8_t pad1_[2];
+  uint64_t component_mask;
+} HbExitRecord;
+
+typedef struct HbSessionSpec {            /* reference: SessionSpec, trace_backend.hpp:197-215 */
+  uint32_t seed;                          /* never 0 on the reference's call path */
+  uint32_t wl_cnt;                        /* 1 = discrete wavelength session; >1 = per-ray pool draw */
+  const HbWlEntry* wl;                    /* [wl_cnt] */
+  uint64_t ray_num;                       /* hint (pool sizing) */
+  uint32_t record_exits;                  /* 1 => materialise exit records for hb_drain_exits (parity) */
+  uint32_t accumulate;                    /* 1 => fused projection + XYZ accumulate (production) */
+} HbSessionSpec;
+
+typedef struct HbLayerStats {             /* reference: LayerStats + LayerHandle::ContinuationCount */
+  uint64_t root_count;
+  uint64_t continuation_count;
+  uint64_t exit_count;
+  double exit_w_sum;
+} HbLayerStats;
+
+typedef struct HbCounters {               /* measurement helpers (bench.py) */
+  uint64_t kernel_launches;               /* kernels of this library launched since hb_create */
+  uint64_t rays_traced;                   /* root rays over all layers */
+  double last_layer_ms;                   /* CUDA-event time of the last hb_trace_layer */
+  double intersect_ms, optics_ms, gen_ms; /* accumulated per-kernel-family CUDA-event time (profiling mode) */
+  uint64_t intersect_launches, optics_launches, gen_launches;
+  uint64_t intersect_rays, optics_rays;   /* ray-bounces processed by each family */
+} HbCounters;
+
+typedef struct HbEngine HbEngine;         /* opaque; one per TraceBackend instance / GPU */
+
+/* ---------------------------------------------------------------------------
+ * Lifetime + the TraceBackend virtuals
+ * ------------------------------------------------------------------------- */
+uint32_t hb_abi_version(void);
+const char* hb_last_error(const HbEngine* h);         /* h may be NULL: last create failure */
+
+/* CudaTraceBackend ctor/probe (cuda_trace_backend.cu:147-193): fails without an sm_100 device. */
+int hb_create(int device_ordinal, HbEngine** out);
+void hb_destroy(HbEngine* h);
+
+/* Scene + render tables; the engine deep-copies everything (BeginSession's captured
+ * spec.scene/spec.render, trace_backend.hpp:118-122). May be called between sessions. */
+int hb_set_scene(HbEngine* h, const HbScene* scene);
+int hb_set_render(HbEngine* h, const HbProjParams* proj);
+
+/* TraceBackend::BeginSession (trace_backend.hpp:374). */
+int hb_begin_session(HbEngine* h, const HbSessionSpec* spec);
+/* TraceBackend::TraceLayer (trace_backend.hpp:384). First call of a session: n_roots > 0 =
+ * RootRaySource::FromHost{count} with null d/p/w/tf (engine generates roots); later calls:
+ * n_roots == 0 = RootRaySource::FromDevice (continuations of the preceding hb_recombine). */
+int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats);
+/* TraceBackend::Recombine (trace_backend.hpp:389). */
+int hb_recombine(HbEngine* h, int shuffle, uint64_t* continuation_count);
+/* TraceBackend::EndSession (trace_backend.hpp:507). */
+int hb_end_session(HbEngine* h);
+/* TraceBackend::ReadbackXyzAccum (trace_backend.hpp:466): copies W*H*3 floats, ADDS the landed
+ * weight to *landed_weight, then zeroes the device accumulators. Legal between sessions. */
+int hb_readback_xyz(HbEngine* h, float* xyz_wh3, float* landed_weight);
+/* TraceBackend::DrainExits (trace_backend.hpp:443): destructive, grow-not-clamp. Call with
+ * out == NULL to query the count. root_ids (optional) receives the layer-root index of each
+ * exit, for per-ray parity association. */
+int hb_drain_exits(HbEngine* h, HbExitRecord* out, uint32_t* root_ids, uint64_t cap, uint64_t* count);
+
+/* Parity helpers (HostRayBatch injection, trace_backend.hpp:230-239; cpu_trace_backend.cpp:121-144).
+ * hb_inject_rays: trace caller-supplied CRYSTAL-LOCAL rays (population 0, shape 0 of layer 0)
+ * instead of generating roots; rot9 (row-major, optional, identity if NULL) is the per-ray
+ * crystal->world rotation. Must be called after hb_begin_session and replaces the next
+ * hb_trace_layer's generation step. */
+int hb_inject_rays(HbEngine* h, uint64_t n, const float* d3, const float* p3, const float* w,
+                   const uint16_t* to_face, const float* rot9);
+/* hb_export_roots: after a root hb_trace_layer with spec.record_exits, copy out the roots the
+ * engine generated (crystal-local d/p, weight, entry face, rot9, shape index, wl index). */
+int hb_export_roots(HbEngine* h, uint64_t cap, float* d3, float* p3, float* w, uint16_t* to_face,
+                    float* rot9, uint32_t* shape_idx, uint32_t* wl_idx, uint64_t* count);
+
+/* Tuning + measurement. */
+int hb_set_option(HbEngine* h, const char* key, int64_t value);
+int hb_get_counters(HbEngine* h, HbCounters* out);
+int hb_synchronize(HbEngine* h);
+/* Device pointer of the W*H*4 float accumulator (x,y,z,landed) for collectives driven from
+ * outside (torch.distributed); valid until hb_set_render / hb_destroy. */
+int hb_image_device_ptr(HbEngine* h, void** ptr, uint64_t* float_count);
+void* hb_stream(HbEngine* h);             /* cudaStream_t the engine launches on */
+
+/* Multi-GPU frame end: in-place NCCL sum all-reduce of the accumulator. */
+int hb_comm_init(HbEngine* h, const void* nccl_unique_id_128B, int rank, int nranks);
+int hb_comm_unique_id(void* out_128B);
+int hb_allreduce_image(HbEngine* h);
+
+/* ---------------------------------------------------------------------------
+ * Host-side table builders (no GPU needed). The reference adapter uses the
+ * reference's own builders instead; these exist so the library is usable
+ * stand-alone and are parity-tested against the reference's tables.
+ * ------------------------------------------------------------------------- */
+/* Crystal::CreatePrism (crystal.cpp:349-356, geo3d_closedform.cpp ComputeClosedFormPrism). */
+int hb_make_prism(float h, const float dist6[6], HbCrystalTables* out);
+/* Crystal::CreatePyramid wedge-angle form (crystal.cpp:380-384). */
+int hb_make_pyramid(float upper_alpha_deg, float lower_alpha_deg, float h1, float h2, float h3,
+                    const float dist6[6], HbCrystalTables* out);
+/* BuildGenGpParams + GetSharedLatLut (cuda_trace_backend.cu:336-400, lat_lut.cpp:74-180).
+ * type/center/spread triples are in DEGREES as in the JSON config (zenith = 90 - latitude is
+ * resolved by the caller: pass LATITUDE center). */
+int hb_make_axis_sampler(uint32_t lat_type, float lat_center_deg, float lat_spread_deg,
+                         uint32_t az_type, float az_center_deg, float az_spread_deg,
+                         uint32_t roll_type, float roll_center_deg, float roll_spread_deg,
+                         HbAxisSampler* out);
+/* IceRefractiveIndex::Get (optics.cpp:180-198). */
+double hb_ice_refractive_index(double wavelength_nm);
+/* MakeCameraRotation + BuildProjParams (scatter_accum.hpp:18-26, lens_proj_build.hpp:24-140). */
+int hb_make_proj_params(int lens_type, float fov_deg, int img_w, int img_h, float view_az_deg,
+                        float view_el_deg, float view_ro_deg, int visible_range, int lens_shift_x,
+                        int lens_shift_y, float overlap, HbProjParams* out);
+/* PartitionCrystalRayNum (simulator.cpp:519-582). carry is in/out [cnt]. */
+int hb_partition_rays(const float* proportions, uint32_t cnt, uint64_t ray_num, double* carry,
+                      uint64_t* out_counts);
+
+/* ---------------------------------------------------------------------------
+ * Config-level scene description (mirrors SceneConfig / RenderConfig,
+ * reference: src/config/proj_config.hpp:14-38, crystal_config.hpp, filter_config.hpp,
+ * render_config.hpp:71-94) and the host builder that turns it into tables:
+ * MakeCrystal per population (simulator.cpp:405-450, stochastic shapes drawn from a host
+ * mt19937 into a geometry pool), BuildEntrySubTris, GetSharedLatLut, BuildDeviceFilterDesc.
+ * ------------------------------------------------------------------------- */
+typedef struct HbDist { uint32_t type; float center, spread; } HbDist;  /* Distribution, math.hpp */
+
+typedef struct HbCrystalDesc {
+  uint32_t kind;                 /* 0 prism, 1 pyramid */
+  uint32_t id;                   /* CrystalConfig::id_ */
+  HbDist height[3];              /* prism: [0] = h; pyramid: [0] upper h1, [1] prism h2, [2] lower h3 */
+  HbDist face_dist[6];
+  float wedge_upper_deg, wedge_lower_deg;
+  HbDist latitude, azimuth, roll; /* AxisDistribution (latitude center = 90 - zenith), degrees */
+} HbCrystalDesc;
+
+typedef struct HbFilterSpecDesc {
+  uint32_t kind;                 /* 0 none, 1 raypath, 2 entry_exit, 3 direction, 4 crystal */
+  uint32_t action;               /* 0 filter_in, 1 filter_out */
+  uint32_t symmetry;             /* bit0 P, bit1 B, bit2 D */
+  uint32_t path_len;
+  uint8_t path[HB_MAX_FILTER_PATH]; /* raypath: face numbers as written in the config */
+  int32_t entry_fn, exit_fn;     /* -1 wildcard */
+  uint32_t min_len, max_len;     /* max_len 0 = unbounded */
+  float lon_deg, lat_deg, radii_deg;
+  uint32_t crystal_id;
+} HbFilterSpecDesc;
+
+typedef struct HbPopulationDesc {
+  HbCrystalDesc crystal;
+  HbFilterSpecDesc filter;
+  float proportion;
+} HbPopulationDesc;
+
+typedef struct HbLayerDesc {
+  float prob;
+  uint32_t population_cnt;
+  HbPopulationDesc populations[HB_MAX_CRYSTALS];
+} HbLayerDesc;
+
+typedef struct HbSceneDesc {
+  uint32_t max_hits;
+  uint32_t layer_cnt;
+  float sun_altitude_deg, sun_azimuth_deg, sun_diameter_deg;
+  uint32_t geom_pool_size;       /* shapes drawn per stochastic population (K-shape pool); 0 => 1 */
+  HbLayerDesc layers[HB_MAX_LAYERS];
+} HbSceneDesc;
+
+typedef struct HbRenderDesc {
+  int32_t lens_type; float fov_deg;
+  int32_t img_w, img_h;
+  float view_az_deg, view_el_deg, view_ro_deg;
+  int32_t visible_range, lens_shift_x, lens_shift_y;
+  float overlap;
+} HbRenderDesc;
+
+typedef struct HbSceneTables HbSceneTables;  /* owns an HbScene and all its storage */
+int hb_build_scene(const HbSceneDesc* desc, uint32_t geometry_seed, HbSceneTables** out);
+const HbScene* hb_scene_tables_get(const HbSceneTables* t);
+void hb_free_scene(HbSceneTables* t);
+int hb_build_render(const HbRenderDesc* desc, HbProjParams* out);
+/* ComputeWlPool (backend/wl_pool.hpp:67-95) for a discrete wavelength: n from Sellmeier, CMF from
+ * the CIE 1931 2-degree 1-nm table looked up at int(wl + 0.5). */
+int hb_make_wl_entry(float wavelength_nm, float weight, HbWlEntry* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALOTRACE_B200_H_ */
