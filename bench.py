@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the trace hot path on B200 (BASELINE.json metric), contract in the task brief.
+
+One "step" = one full pass of the workload per GPU: config 2 of BASELINE.json
+(examples/config_example.json as shipped: prism h=1.3, zenith gauss(90, 0.3), max_hits 7, sun alt 20,
+9 wavelengths x 50 M root rays, render id 4 = fisheye_equal_area 1920x1080) = 450 M root rays.
+Rays are generated on the device by the engine's counter-based RNG (data: synthetic); weak scaling:
+every rank traces its own 450 M rays (disjoint global ray-index ranges) and the per-GPU XYZ images are
+all-reduced (NCCL) at frame end.
+
+  value : root rays / s with the scene tables resident on the device (kernels only + frame-end all-reduce)
+  e2e   : same, through the TraceBackend-shaped public API with HOST buffers: per step the scene /
+          wavelength tables are uploaded (hb_set_scene, hb_begin_session) and the XYZ image is read back
+          into host memory (hb_readback_xyz) inside the timed region
+  --impl reference : the reference's own multi-threaded legacy CPU path (oracle/_ref perf build when
+          present, else the oracle port) on a bounded sample of the same workload
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WAVELENGTHS = [450.0, 490.0, 530.0, 570.0, 610.0, 650.0, 690.0, 730.0, 770.0]
+RAYS_PER_WL = 50_000_000
+MAX_HITS = 7
+SESSION_RAYS = 1 << 24          # rays per BeginSession/EndSession bracket (the driver's SimBatch size)
+# algorithmic HBM bytes per ray-bounce of each kernel (DESIGN.md "kernels"): state is three float4 per ray
+BYTES_OPTICS = 64               # read P,D,Q (48) + write D (16); + 16 per emitted exit (one v4 reduction)
+BYTES_OPTICS_LAST = 48          # final interaction writes no state
+BYTES_EXIT = 16
+BYTES_INTERSECT = 48            # read P,D (32) + write P (16)
+BYTES_GEN = 48
+EXITS_PER_ROOT = 4.7            # measured on this scene (reference CPU: 4.69-4.71)
+
+
+def workload_desc():
+    import parity
+    return parity.CASES["column_config2"]["scene"](), parity.CASES["column_config2"]["render"]()
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.sm_max = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.sm_max = float(f[1])
+                for nme, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(steps_budget_s=15.0, threads=None):
+    """Reference legacy CPU path on a bounded sample of the workload; returns the cpu_baseline object."""
+    import harness as H
+    A = H.A
+    desc, rdesc = workload_desc()
+    perf_so = os.path.join(ROOT, "oracle", "_ref", "libhalo_ref_perf.so")
+    cores = os.cpu_count() or 1
+    if os.path.exists(perf_so):
+        lib = C.CDLL(perf_so)
+        vp = C.c_void_p
+        lib.ref_legacy_bench.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
+        lib.ref_physical_cores.restype = C.c_uint32
+        phys = int(lib.ref_physical_cores()) or cores
+        nthreads = threads or phys
+        import numpy as np
+        wl = np.array(WAVELENGTHS, np.float32)
+        ww = np.ones(len(wl), np.float32)
+        rate, sec, exits = C.c_double(), C.c_double(), C.c_uint64()
+        # calibrate on a small sample, then size the run for ~steps_budget_s
+        per_wl = 2000 * nthreads
+        lib.ref_legacy_bench(C.byref(desc), C.byref(rdesc), wl.ctypes.data, ww.ctypes.data, len(wl), per_wl, nthreads,
+                             128, C.byref(rate), C.byref(sec), C.byref(exits))
+        per_wl = max(per_wl, int(rate.value * steps_budget_s / len(wl)))
+        lib.ref_legacy_bench(C.byref(desc), C.byref(rdesc), wl.ctypes.data, ww.ctypes.data, len(wl), per_wl, nthreads,
+                             128, C.byref(rate), C.byref(sec), C.byref(exits))
+        return {"value": rate.value / 1e6, "unit": "Mrays/s", "cores": nthreads, "kind": "reference",
+                "sample": f"{len(wl)} wavelengths x {per_wl} root rays, legacy Simulator::Run x{nthreads} threads + "
+                          f"host ScatterOutgoingToXyz consumer, 128-ray dispatch, {sec.value:.1f} s",
+                "physical_cores": phys, "logical_cpus": cores}
+    # oracle port, single thread
+    import numpy as np
+    import parity
+    from ice_halo_sim_b200 import backend as B
+    tables = B.SceneTables(desc, 7)
+    sc = tables.scene()
+    wl = [B.make_wl_entry(WAVELENGTHS[0], 1.0)]
+    wl_arr = (A.HbWlEntry * 1)(*[A.HbWlEntry(*e) for e in wl])
+    orc = H.oracle()
+    n = 200000
+    t0 = time.time()
+    done = 0
+    while time.time() - t0 < steps_budget_s:
+        r = dict(d=np.zeros((n, 3), np.float32), p=np.zeros((n, 3), np.float32), w=np.zeros(n, np.float32),
+                 face=np.zeros(n, np.uint16), rot=np.zeros((n, 9), np.float32), shape=np.zeros(n, np.uint32),
+                 wl=np.zeros(n, np.uint32))
+        orc.orc_gen_roots(tables.scene_ptr, 0, 0, 0, C.addressof(wl_arr), 1, 42, done, n, H.ptr(r["d"]), H.ptr(r["p"]),
+                          H.ptr(r["w"]), H.ptr(r["face"]), None, H.ptr(r["rot"]), H.ptr(r["shape"]), H.ptr(r["wl"]))
+        lp, keep = parity.layer_params(sc, 0, wl_arr, 42, done)
+        ex, er, _ = parity.oracle_trace(lp, r, n * 9)
+        parity.oracle_image(B.make_proj_params(rdesc), wl_arr, ex)
+        done += n
+    sec = time.time() - t0
+    return {"value": done / sec / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+            "sample": f"1 wavelength x {done} root rays, oracle gen+trace+accumulate, single thread, {sec:.1f} s"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    t0 = time.time()
+    vals = []
+    cb = None
+    budget = max(5.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(budget)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = sum(vals) / len(vals)
+    cb["value"] = v
+    line = {"impl": "reference", "metric": "Mrays/sec (9λ×50M single-scatter)", "value": v, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": (time.time() - t0) * 1e3 / max(1, args.steps + args.warmup), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config_example.json scene (9 wavelengths, prism h=1.3 zenith gauss(90,0.3), "
+                                   "max_hits 7), fisheye_equal_area 1920x1080; bounded CPU sample per step"},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays-per-wl", type=int, default=RAYS_PER_WL)
+    ap.add_argument("--tile-rays", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ice_halo_sim_b200 import _abi as A
+    from ice_halo_sim_b200 import backend as B
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    desc, rdesc = workload_desc()
+    tables = B.SceneTables(desc, 7)
+    wl_entries = [B.make_wl_entry(x, 1.0) for x in WAVELENGTHS]
+    be = B.B200TraceBackend(local_rank)
+    if args.tile_rays:
+        be.SetOption("tile_rays", args.tile_rays)
+    be.SetScene(tables)
+    be.SetRender(rdesc)
+    stream = torch.cuda.ExternalStream(be._lib.hb_stream(be._h), device=torch.device("cuda", local_rank))
+    if world > 1:
+        ids = [B.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        be.CommInit(ids[0], rank, world)
+
+    rays_per_wl = args.rays_per_wl
+    rays_per_step = rays_per_wl * len(WAVELENGTHS)
+    h, w = rdesc.img_h, rdesc.img_w
+    host_img = np.empty((h, w, 3), np.float32)
+    scene_bytes = C.sizeof(A.HbCrystalTables) + C.sizeof(A.HbAxisSampler) + C.sizeof(A.HbFilterDesc) + \
+        C.sizeof(A.HbProjParams)
+
+    def trace_step(step_idx, e2e):
+        """One full pass: 9 wavelengths x rays_per_wl roots in SESSION_RAYS-sized sessions."""
+        if e2e:  # host tables travel every step
+            be.SetScene(tables)
+            be.SetRender(rdesc)
+        for wi, wl in enumerate(wl_entries):
+            done = 0
+            while done < rays_per_wl:
+                n = min(SESSION_RAYS, rays_per_wl - done)
+                base = ((step_idx * world + rank) * len(WAVELENGTHS) + wi) * rays_per_wl + done
+                be.BeginSession(B.SessionSpec(seed=42, wl=[wl], ray_num=n, accumulate=True, ray_base=base))
+                be.TraceLayer(B.RootRaySource.FromHost(n), want_stats=False)
+                be.EndSession()
+                done += n
+        if world > 1:
+            be.AllReduceImage()
+        if e2e:
+            be.ReadbackXyzAccum(host_img)
+
+    def barrier():
+        be.Synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, first_idx):
+        barrier()
+        c0 = be.Counters().kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        for s in range(steps):
+            fn(first_idx + s)
+        e1.record(stream)
+        barrier()
+        wall_ms = (time.time() - t0) * 1e3
+        dev_ms = e0.elapsed_time(e1)
+        ms = max(dev_ms, 0.0) if dev_ms > 0 else wall_ms
+        t = torch.tensor([ms, wall_ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), be.Counters().kernel_launches - c0
+
+    step_ctr = 0
+    for _ in range(args.warmup):
+        trace_step(step_ctr, False)
+        step_ctr += 1
+    be.ReadbackXyzAccum(host_img)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    dev_ms, wall_ms, launches = timed(lambda i: trace_step(i, False), args.steps, step_ctr)
+    step_ctr += args.steps
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    img, landed = be.ReadbackXyzAccum(host_img)
+    img_sum = float(img.astype(np.float64).sum())
+
+    # e2e through the public API with host buffers (tables up, image down, every step)
+    trace_step(step_ctr, True)
+    step_ctr += 1
+    e2e_ms, e2e_wall_ms, _ = timed(lambda i: trace_step(i, True), args.steps, step_ctr)
+    step_ctr += args.steps
+    e2e_ms = max(e2e_ms, e2e_wall_ms)  # the D2H read blocks the host: wall clock bounds the step
+
+    # per-kernel live timing for the roofline (CUDA events around every launch, short pass)
+    be.SetOption("profile", 1)
+    c0 = be.Counters()
+    p_rays = min(rays_per_wl, 1 << 24)
+    be.BeginSession(B.SessionSpec(seed=42, wl=[wl_entries[0]], ray_num=p_rays, accumulate=True, ray_base=1 << 40))
+    be.TraceLayer(B.RootRaySource.FromHost(p_rays), want_stats=False)
+    be.EndSession()
+    be.Synchronize()
+    c1 = be.Counters()
+    be.SetOption("profile", 0)
+    be.ReadbackXyzAccum(host_img)
+
+    if rank == 0:
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak_src = "fallback (B200_PROFILING.md)"
+        hbm_peak = 6650.0
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+            hbm_peak = float(peaks.get("hbm_gbs", hbm_peak))
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        o_l = c1.optics_launches - c0.optics_launches
+        i_l = c1.intersect_launches - c0.intersect_launches
+        o_ms = (c1.optics_ms - c0.optics_ms) / max(1, o_l)
+        i_ms = (c1.intersect_ms - c0.intersect_ms) / max(1, i_l)
+        g_ms = (c1.gen_ms - c0.gen_ms) / max(1, c1.gen_launches - c0.gen_launches)
+        tile = (c1.optics_rays - c0.optics_rays) / max(1, o_l)
+        opt_bytes = tile * ((BYTES_OPTICS * (MAX_HITS - 1) + BYTES_OPTICS_LAST) / MAX_HITS +
+                            BYTES_EXIT * EXITS_PER_ROOT / MAX_HITS)
+        int_bytes = tile * BYTES_INTERSECT
+        opt_total = (c1.optics_ms - c0.optics_ms)
+        int_total = (c1.intersect_ms - c0.intersect_ms)
+        dom = "optics" if opt_total >= int_total else "intersect"
+        ach_o = opt_bytes / (o_ms * 1e-3) / 1e9 if o_ms > 0 else 0.0
+        ach_i = int_bytes / (i_ms * 1e-3) / 1e9 if i_ms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": ach_o if dom == "optics" else ach_i,
+                "peak": hbm_peak, "unit": "GB/s", "frac": (ach_o if dom == "optics" else ach_i) / hbm_peak,
+                "traffic": None, "peak_source": peak_src,
+                "per_kernel": {"optics": {"avg_ms": o_ms, "launches": o_l, "achieved_gbs": ach_o,
+                                          "frac": ach_o / hbm_peak, "rays_per_launch": tile},
+                               "intersect": {"avg_ms": i_ms, "launches": i_l, "achieved_gbs": ach_i,
+                                             "frac": ach_i / hbm_peak, "rays_per_launch": tile},
+                               "gen": {"avg_ms": g_ms}},
+                "share_of_step": {"optics": opt_total / max(1e-9, opt_total + int_total + (c1.gen_ms - c0.gen_ms)),
+                                  "intersect": int_total / max(1e-9, opt_total + int_total + (c1.gen_ms - c0.gen_ms))}}
+        total_rays = rays_per_step * world * args.steps
+        value = total_rays / (dev_ms * 1e-3) / 1e6
+        e2e_val = total_rays / (e2e_ms * 1e-3) / 1e6
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb = cpu_baseline(15.0)
+            except Exception as ex:  # the checker is optional at bench time
+                cb = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        line = {
+            "metric": "Mrays/sec (9λ×50M single-scatter)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: config_example.json as shipped, 9 wavelengths x "
+                                   f"{rays_per_wl} root rays per GPU per step, prism h=1.3 zenith gauss(90,0.3) "
+                                   "max_hits 7, fisheye_equal_area 1920x1080",
+                       "rays_per_step_per_gpu": rays_per_step, "session_rays": SESSION_RAYS,
+                       "l2": "ray state per step (21.6 GB) >> 126 MB L2; no reuse across steps",
+                       "parallelism": f"ray-index sharding x{world}, NCCL image all-reduce at frame end"},
+            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": scene_bytes +
+                    len(WAVELENGTHS) * ((rays_per_wl + SESSION_RAYS - 1) // SESSION_RAYS) * C.sizeof(A.HbWlEntry),
+                    "d2h_bytes_per_step": h * w * 3 * 4 + 8, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb,
+            "clocks": sampler.result() if sampler else None,
+            "check": {"image_sum": img_sum, "landed_weight": landed, "wall_ms_per_step": wall_ms / args.steps},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    be.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -96,7 +96,8 @@ class HbExitRecord(C.Structure):
 
 class HbSessionSpec(C.Structure):
     _fields_ = [("seed", u32), ("wl_cnt", u32), ("wl", C.POINTER(HbWlEntry)), ("ray_num", u64),
-                ("record_exits", u32), ("accumulate", u32)]
+                ("record_exits", u32), ("accumulate", u32), ("ray_base", u64), ("use_ray_base", u32),
+                ("reserved_", u32)]
 
 
 class HbLayerStats(C.Structure):

@@ -1,0 +1,293 @@
+"""B200TraceBackend — host-side mirror of the reference's TraceBackend seam over the C ABI.
+
+Method names, argument meaning, call order and error behaviour follow
+`lumice::TraceBackend` (reference: src/core/backend/trace_backend.hpp:367-641):
+
+    BeginSession -> (TraceLayer -> DrainExits -> Recombine)* -> TraceLayer -> DrainExits -> EndSession
+
+and `simulate()` follows the reference driver `Simulator::SimulateOneWavelengthWithBackend`
+(src/core/simulator.cpp:1479-1694). All compute happens in libhalotrace_b200.so on the GPU; this
+module only marshals POD structs. The C++ adapter a Lumice maintainer would compile in is in adapter/.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _abi as A
+from .lib import BackendUnavailableError, HaloTraceError, check, load  # noqa: F401
+
+EXIT_DTYPE = np.dtype([("dir", np.float32, 3), ("weight", np.float32), ("path_len", np.uint8),
+                       ("path", np.uint8, 64), ("pad0", np.uint8), ("crystal_id", np.uint16),
+                       ("ms_layer_idx", np.uint8), ("wl_idx", np.uint8), ("pad1", np.uint8, 2),
+                       ("component_mask", np.uint64)])
+assert EXIT_DTYPE.itemsize == 96  # lumice::ExitRayRecord, exit_seam.hpp:40-53
+
+
+@dataclass
+class SessionSpec:
+    """trace_backend.hpp:197-215. `wl` is the wavelength pool: [(n_idx, spd_weight, cmf_x, cmf_y, cmf_z)]
+    (one entry for a discrete-wavelength session)."""
+    seed: int
+    wl: List[tuple]
+    ray_num: int = 0
+    record_exits: bool = False      # materialise ExitRayRecords (parity path); production = fused accumulate
+    accumulate: bool = True
+    ray_base: Optional[int] = None  # multi-GPU sharding: global index of this session's first root
+
+
+@dataclass
+class LayerHandle:
+    """trace_backend.hpp:309-332 + LayerStats (:297-300)."""
+    root_count: int = 0
+    continuation_count: int = 0
+    exit_count: int = 0
+    exit_w_sum: float = 0.0
+
+    def ContinuationCount(self):
+        return self.continuation_count
+
+    def GetLayerStats(self):
+        return self.exit_count, self.exit_w_sum
+
+
+@dataclass
+class RootRaySource:
+    """trace_backend.hpp:259-276: FromHost{count} (engine generates roots) or FromDevice (continuations)."""
+    is_device: bool = False
+    count: int = 0
+    # HostRayBatch ray injection (parity only; crystal-local rays, cpu_trace_backend.cpp:121-144)
+    d: Optional[np.ndarray] = None
+    p: Optional[np.ndarray] = None
+    w: Optional[np.ndarray] = None
+    tf: Optional[np.ndarray] = None
+    rot: Optional[np.ndarray] = None
+
+    @staticmethod
+    def FromHost(count, d=None, p=None, w=None, tf=None, rot=None):
+        return RootRaySource(False, int(count), d, p, w, tf, rot)
+
+    @staticmethod
+    def FromDevice(count):
+        return RootRaySource(True, int(count))
+
+
+class SceneTables:
+    """Owns an HbSceneTables* built by hb_build_scene (host-side MakeCrystal / LatLut / filter tables)."""
+
+    def __init__(self, desc: A.HbSceneDesc, geometry_seed=1):
+        self._lib = load()
+        self._h = C.c_void_p()
+        check(self._lib.hb_build_scene(C.byref(desc), int(geometry_seed), C.byref(self._h)))
+        self.desc = desc
+
+    @property
+    def scene_ptr(self):
+        return self._lib.hb_scene_tables_get(self._h)
+
+    def scene(self) -> A.HbScene:
+        return C.cast(self.scene_ptr, C.POINTER(A.HbScene)).contents
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.hb_free_scene(self._h)
+            self._h = C.c_void_p()
+
+
+def make_wl_entry(wavelength_nm, weight=1.0):
+    e = A.HbWlEntry()
+    check(load().hb_make_wl_entry(float(wavelength_nm), float(weight), C.byref(e)))
+    return (e.n_idx, e.spd_weight, e.cmf_x, e.cmf_y, e.cmf_z)
+
+
+def make_proj_params(render: A.HbRenderDesc) -> A.HbProjParams:
+    p = A.HbProjParams()
+    check(load().hb_build_render(C.byref(render), C.byref(p)))
+    return p
+
+
+class B200TraceBackend:
+    """One engine instance on one GPU (the reference creates one backend per Simulator::Run thread)."""
+
+    def __init__(self, device_ordinal=0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        check(self._lib.hb_create(int(device_ordinal), C.byref(self._h)))
+        self._keep = []
+        self._in_session = False
+        self._pending: Optional[LayerHandle] = None
+        self._proj: Optional[A.HbProjParams] = None
+
+    # ---- lifetime ----
+    def close(self):
+        if self._h and self._h.value:
+            self._lib.hb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
+
+    def _check(self, status):
+        check(status, self._h)
+
+    # ---- scene / render (captured by BeginSession in the reference; set explicitly here) ----
+    def SetScene(self, scene):
+        """scene: SceneTables, or a ctypes pointer/address of an HbScene built by the caller."""
+        ptr = scene.scene_ptr if isinstance(scene, SceneTables) else scene
+        self._keep = [scene]
+        self._check(self._lib.hb_set_scene(self._h, ptr))
+
+    def SetRender(self, render):
+        """render: HbRenderDesc (built with the library's BuildProjParams twin) or HbProjParams."""
+        proj = make_proj_params(render) if isinstance(render, A.HbRenderDesc) else render
+        self._proj = proj
+        self._check(self._lib.hb_set_render(self._h, C.byref(proj)))
+
+    def IsCompatible(self, render) -> bool:  # trace_backend.hpp:511-514: all 11 lens types supported
+        return 0 <= int(render.lens_type if isinstance(render, A.HbRenderDesc) else render.proj_type) <= 10
+
+    # ---- the seam ----
+    def SupportsDeviceXyzAccum(self) -> bool:
+        return True
+
+    def SupportsThirdClockDrain(self) -> bool:
+        return True
+
+    def WlPoolSize(self) -> int:
+        return 64  # kWlPoolSizeDefault, backend/wl_pool.hpp:38
+
+    def BeginSession(self, spec: SessionSpec):
+        wl = (A.HbWlEntry * len(spec.wl))(*[A.HbWlEntry(*e) for e in spec.wl])
+        s = A.HbSessionSpec()
+        s.seed = int(spec.seed) & 0xFFFFFFFF
+        s.wl_cnt = len(spec.wl)
+        s.wl = wl
+        s.ray_num = int(spec.ray_num)
+        s.record_exits = 1 if spec.record_exits else 0
+        s.accumulate = 1 if spec.accumulate else 0
+        if spec.ray_base is not None:
+            s.ray_base = int(spec.ray_base)
+            s.use_ray_base = 1
+        self._check(self._lib.hb_begin_session(self._h, C.byref(s)))
+        self._in_session = True
+        self._spec = spec
+
+    def TraceLayer(self, roots: RootRaySource, want_stats=True) -> LayerHandle:
+        n = 0 if roots.is_device else roots.count
+        if not roots.is_device and roots.d is not None:
+            d = np.ascontiguousarray(roots.d, np.float32)
+            p = np.ascontiguousarray(roots.p, np.float32)
+            w = np.ascontiguousarray(roots.w, np.float32)
+            tf = np.ascontiguousarray(roots.tf, np.uint16)
+            rot = None if roots.rot is None else np.ascontiguousarray(roots.rot, np.float32)
+            self._check(self._lib.hb_inject_rays(self._h, len(w), d.ctypes.data, p.ctypes.data, w.ctypes.data,
+                                                 tf.ctypes.data, None if rot is None else rot.ctypes.data))
+            n = len(w)
+        st = A.HbLayerStats()
+        self._check(self._lib.hb_trace_layer(self._h, int(n), C.byref(st) if want_stats else None))
+        h = LayerHandle(st.root_count, st.continuation_count, st.exit_count, st.exit_w_sum)
+        self._pending = h
+        return h
+
+    def Recombine(self, handle: LayerHandle, shuffle=True) -> RootRaySource:
+        cnt = C.c_uint64()
+        self._check(self._lib.hb_recombine(self._h, 1 if shuffle else 0, C.byref(cnt)))
+        self._pending = None
+        return RootRaySource.FromDevice(cnt.value)
+
+    def DrainExits(self, with_roots=False):
+        cnt = C.c_uint64()
+        self._check(self._lib.hb_drain_exits(self._h, None, None, 0, C.byref(cnt)))
+        n = cnt.value
+        out = np.zeros(n, EXIT_DTYPE)
+        roots = np.zeros(n, np.uint32)
+        if n:
+            self._check(self._lib.hb_drain_exits(self._h, out.ctypes.data, roots.ctypes.data, n, C.byref(cnt)))
+        return (out, roots) if with_roots else out
+
+    def ExportRoots(self):
+        """Parity helper: the crystal-local roots the engine generated for the last traced layer."""
+        cnt = C.c_uint64()
+        self._check(self._lib.hb_export_roots(self._h, 0, None, None, None, None, None, None, None, C.byref(cnt)))
+        n = cnt.value
+        r = dict(d=np.zeros((n, 3), np.float32), p=np.zeros((n, 3), np.float32), w=np.zeros(n, np.float32),
+                 face=np.zeros(n, np.uint16), rot=np.zeros((n, 9), np.float32), shape=np.zeros(n, np.uint32),
+                 wl=np.zeros(n, np.uint32))
+        if n:
+            self._check(self._lib.hb_export_roots(self._h, n, r["d"].ctypes.data, r["p"].ctypes.data,
+                                                  r["w"].ctypes.data, r["face"].ctypes.data, r["rot"].ctypes.data,
+                                                  r["shape"].ctypes.data, r["wl"].ctypes.data, C.byref(cnt)))
+        return r
+
+    def EndSession(self):
+        self._check(self._lib.hb_end_session(self._h))
+        self._in_session = False
+
+    def ReadbackXyzAccum(self, xyz: Optional[np.ndarray] = None):
+        """Returns (xyz[H, W, 3] float32, landed_weight). Drains + zeroes the device accumulators."""
+        if self._proj is None:
+            raise HaloTraceError(-4, "ReadbackXyzAccum before SetRender")
+        h, w = self._proj.img_h, self._proj.img_w
+        if xyz is None:
+            xyz = np.empty((h, w, 3), np.float32)
+        landed = C.c_float(0.0)
+        self._check(self._lib.hb_readback_xyz(self._h, xyz.ctypes.data, C.byref(landed)))
+        return xyz, landed.value
+
+    # ---- tuning / measurement ----
+    def SetOption(self, key, value):
+        self._check(self._lib.hb_set_option(self._h, key.encode(), int(value)))
+
+    def Synchronize(self):
+        self._check(self._lib.hb_synchronize(self._h))
+
+    def Counters(self) -> A.HbCounters:
+        c = A.HbCounters()
+        self._check(self._lib.hb_get_counters(self._h, C.byref(c)))
+        return c
+
+    def ImageDevicePtr(self):
+        ptr = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self._lib.hb_image_device_ptr(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def AllReduceImage(self):
+        self._check(self._lib.hb_allreduce_image(self._h))
+
+    def CommInit(self, unique_id: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self._lib.hb_comm_init(self._h, buf, rank, nranks))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(load().hb_comm_unique_id(buf))
+    return buf.raw
+
+
+def simulate(backend: B200TraceBackend, layer_cnt: int, spec: SessionSpec, ray_num: int, want_stats=False,
+             drain_exits=False):
+    """One session over all scattering layers — the reference driver loop
+    (SimulateOneWavelengthWithBackend, simulator.cpp:1498-1560)."""
+    backend.BeginSession(spec)
+    exits = []
+    handles = []
+    try:
+        roots = RootRaySource.FromHost(ray_num)
+        for mi in range(layer_cnt):
+            last = mi + 1 == layer_cnt
+            handle = backend.TraceLayer(roots, want_stats=want_stats or not last)
+            handles.append(handle)
+            if drain_exits:
+                exits.append(backend.DrainExits(with_roots=True))
+            if last:
+                break
+            roots = backend.Recombine(handle, shuffle=True)
+    finally:
+        backend.EndSession()
+    return handles, exits

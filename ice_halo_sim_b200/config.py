@@ -1,0 +1,200 @@
+"""Lumice JSON config -> scene / render descriptions (HbSceneDesc, HbRenderDesc).
+
+Mirrors the reference's config front door for the fields the trace path consumes
+(reference: src/config/crystal_config.cpp from_json, src/core/math.cpp:590-725 axis parsing,
+src/config/filter_config.cpp, src/config/render_config.cpp, src/config/config_manager.cpp).
+Complex ("composition") filters and raypath-colour classes are not supported here.
+"""
+import json
+import math
+
+from . import _abi as A
+
+_SYM = {"P": 1, "B": 2, "D": 4}
+
+
+def _dist(obj, default=None):
+    """JSON number or {type, mean, std} -> HbDist (math.cpp from_json(Distribution))."""
+    if obj is None:
+        return default
+    if isinstance(obj, (int, float)):
+        return A.HbDist(A.DIST["none"], float(obj), 0.0)
+    t = obj.get("type")
+    if t not in A.DIST:
+        raise ValueError(f"distribution needs a valid 'type' (got {t!r})")
+    return A.HbDist(A.DIST[t], float(obj.get("mean", 0.0)), float(obj.get("std", 0.0)))
+
+
+def _miller_to_alpha(i1, i4):
+    if i1 == 0:
+        return 28.0
+    return math.degrees(math.atan(0.866025403784 * i4 / i1 / 1.629))
+
+
+def crystal_desc(c):
+    d = A.HbCrystalDesc()
+    d.id = int(c["id"])
+    shape = c.get("shape", {})
+    ones = A.HbDist(0, 1.0, 0.0)
+    for i in range(6):
+        d.face_dist[i] = ones
+    fd = shape.get("face_distance")
+    if fd is not None:
+        for i, e in enumerate(fd[:6]):
+            d.face_dist[i] = _dist(e)
+    if c["type"] == "prism":
+        d.kind = 0
+        d.height[0] = _dist(shape.get("height"), A.HbDist(0, 1.0, 0.0))
+    elif c["type"] == "pyramid":
+        d.kind = 1
+        d.height[0] = _dist(shape.get("upper_h"), A.HbDist(0, 0.0, 0.0))
+        d.height[1] = _dist(shape["prism_h"])
+        d.height[2] = _dist(shape.get("lower_h"), A.HbDist(0, 0.0, 0.0))
+        for upper in (True, False):
+            key = "upper" if upper else "lower"
+            alpha = 28.0
+            if f"{key}_wedge_angle" in shape:
+                alpha = float(shape[f"{key}_wedge_angle"])
+            elif f"{key}_indices" in shape and len(shape[f"{key}_indices"]) == 3:
+                idx = shape[f"{key}_indices"]
+                alpha = _miller_to_alpha(int(idx[0]), int(idx[2]))
+            if upper:
+                d.wedge_upper_deg = alpha
+            else:
+                d.wedge_lower_deg = alpha
+    else:
+        raise ValueError(f"unknown crystal type {c['type']!r}")
+    axis = c.get("axis")
+    if axis is None:  # AxisDistribution default: zenith 0 (latitude 90), no randomness (math.cpp:536-538)
+        d.latitude = A.HbDist(0, 90.0, 0.0)
+        d.azimuth = A.HbDist(0, 0.0, 0.0)
+        d.roll = A.HbDist(0, 0.0, 0.0)
+    else:
+        z = _dist(axis["zenith"])
+        d.latitude = A.HbDist(z.type, 90.0 - z.center, z.spread)  # zenith -> latitude
+        d.azimuth = _dist(axis.get("azimuth"), A.HbDist(1, 0.0, 360.0))
+        d.roll = _dist(axis.get("roll"), A.HbDist(1, 0.0, 360.0))
+    return d
+
+
+def filter_desc(f):
+    d = A.HbFilterSpecDesc()
+    d.entry_fn = -1
+    d.exit_fn = -1
+    if f is None or f.get("type", "none") == "none":
+        return d
+    t = f["type"]
+    d.action = 1 if f.get("action", "filter_in") == "filter_out" else 0
+    d.symmetry = sum(_SYM[ch] for ch in f.get("symmetry", "") if ch in _SYM)
+    if t == "raypath":
+        rp = f["raypath"]
+        if len(rp) > A.HB_MAX_FILTER_PATH:
+            raise ValueError("raypath filter longer than 32 faces")
+        d.kind = 1
+        d.path_len = len(rp)
+        for i, x in enumerate(rp):
+            d.path[i] = int(x)
+    elif t == "entry_exit":
+        d.kind = 2
+        d.entry_fn = int(f["entry"]) if "entry" in f else -1
+        d.exit_fn = int(f["exit"]) if "exit" in f else -1
+        d.min_len = int(f.get("min_len", 1))
+        d.max_len = int(f.get("max_len", 0))
+    elif t == "direction":
+        d.kind = 3
+        d.lon_deg, d.lat_deg, d.radii_deg = float(f["az"]), float(f["el"]), float(f["radii"])
+    elif t == "crystal":
+        d.kind = 4
+        d.crystal_id = int(f["crystal_id"])
+    else:
+        raise ValueError(f"filter type {t!r} is not supported by this backend")
+    return d
+
+
+def render_desc(r):
+    lens = r.get("lens", {})
+    lens_type = A.LENS[lens.get("type", "linear")]
+    if "fov" in lens:
+        fov = float(lens["fov"])
+    elif "f" in lens:  # 35 mm focal length -> fov, half short edge d = 12 mm (render_config.cpp:60-110)
+        f, d = float(lens["f"]), 12.0
+        name = lens.get("type", "linear")
+        if name == "linear":
+            fov = 2.0 * math.degrees(math.atan2(d, f))
+        elif name.endswith("equal_area"):
+            fov = 4.0 * math.degrees(math.asin(d / (2 * f)))
+        elif name.endswith("equidistant"):
+            fov = math.degrees(d / f)
+        elif name.endswith("stereographic"):
+            fov = 4.0 * math.degrees(math.atan(d / (2 * f)))
+        elif name.endswith("orthographic"):
+            fov = 2.0 * math.degrees(math.asin(d / f))
+        else:
+            fov = 0.0
+    else:
+        fov = 90.0
+    res = r.get("resolution", [1920, 1080])
+    view = r.get("view", {})
+    shift = r.get("lens_shift", [0, 0])
+    return A.HbRenderDesc(lens_type, fov, int(res[0]), int(res[1]), float(view.get("azimuth", 0.0)),
+                          float(view.get("elevation", 0.0)), float(view.get("roll", 0.0)),
+                          A.VISIBLE[r.get("visible", "upper")], int(shift[0]), int(shift[1]),
+                          float(r.get("overlap", 0.0)))
+
+
+class SceneConfig:
+    """Parsed config: scene description + renders + spectrum + ray count (per wavelength)."""
+
+    def __init__(self, desc, renders, spectrum, ray_num_total, illuminant=None):
+        self.desc = desc
+        self.renders = renders          # {id: HbRenderDesc}
+        self.spectrum = spectrum        # [(wavelength_nm, weight)]
+        self.ray_num_total = ray_num_total
+        self.illuminant = illuminant
+
+    def rays_per_wavelength(self):
+        """ray_num is the total across wavelengths; per-wavelength = ceil(total / N)
+        (reference: src/server/ray_num_semantics.hpp:12-16)."""
+        n = max(1, len(self.spectrum))
+        return -(-self.ray_num_total // n)
+
+
+def load_config(path_or_dict, geom_pool_size=1):
+    cfg = path_or_dict
+    if not isinstance(cfg, dict):
+        with open(path_or_dict) as f:
+            cfg = json.load(f)
+    crystals = {int(c["id"]): c for c in cfg.get("crystal", [])}
+    filters = {int(f["id"]): f for f in cfg.get("filter", [])}
+    scene = cfg["scene"]
+    ls = scene["light_source"]
+    d = A.HbSceneDesc()
+    d.max_hits = int(scene.get("max_hits", 8))
+    d.sun_altitude_deg = float(ls.get("altitude", 0.0))
+    d.sun_azimuth_deg = float(ls.get("azimuth", 0.0))
+    d.sun_diameter_deg = float(ls.get("diameter", 0.5))
+    d.geom_pool_size = int(geom_pool_size)
+    layers = scene["scattering"]
+    if not 1 <= len(layers) <= A.HB_MAX_LAYERS:
+        raise ValueError("scene needs 1..8 scattering layers")
+    d.layer_cnt = len(layers)
+    for li, layer in enumerate(layers):
+        ld = d.layers[li]
+        ld.prob = float(layer.get("prob", 0.0))
+        entries = layer["entries"]
+        if not 1 <= len(entries) <= A.HB_MAX_CRYSTALS:
+            raise ValueError("a scattering layer needs 1..16 entries")
+        ld.population_cnt = len(entries)
+        for ci, e in enumerate(entries):
+            pop = ld.populations[ci]
+            pop.crystal = crystal_desc(crystals[int(e["crystal"])])
+            pop.filter = filter_desc(filters.get(int(e["filter"])) if "filter" in e else None)
+            pop.proportion = float(e.get("proportion", 1.0))
+    spectrum = ls.get("spectrum", [])
+    illuminant = None
+    if isinstance(spectrum, str):
+        illuminant = spectrum
+        spectrum = []
+    spec = [(float(s["wavelength"]), float(s.get("weight", 1.0))) for s in spectrum]
+    renders = {int(r["id"]): render_desc(r) for r in cfg.get("render", [])}
+    return SceneConfig(d, renders, spec, int(scene.get("ray_num", 0)), illuminant)

@@ -1,0 +1,1465 @@
+// hb_engine.cu — wavefront trace engine for NVIDIA B200 (sm_100a): kernels, session state machine and
+// the compute half of the C ABI declared in include/halotrace_b200.h.
+//
+// Pipeline of one scattering layer over one tile of rays (DESIGN.md "kernels"):
+//   gen_roots / transit_roots      root state  P{p.xyz,bits} D{d.xyz,w} Q{orientation quaternion}  (SoA, float4)
+//   for hit h = 0 .. H-1:
+//     optics   : Fresnel split at the face the ray sits on; the child that leaves the crystal is
+//                rotated to world space, filtered, gated, projected and reduced into the image;
+//                the child that stays inside overwrites D
+//     intersect: slab exit-face search for the inside child; overwrites P (new point + hit face)
+// Reference behaviour restated: simulator.cpp:1308-1336 (hit loop, max_hits counts the entry
+// interaction), optics.cpp:18-177, simulator.cpp:665-762 (emit gate), scatter_accum.hpp:47-110.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "halotrace_b200.h"
+#include "hb_device.cuh"
+
+#ifdef HB_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace hb {
+
+std::string& global_error();  // hb_host.cpp
+
+// ------------------------------------------------------------------------------------------------
+// Kernel parameter blocks
+// ------------------------------------------------------------------------------------------------
+struct LayerTables {            // device pointers, one scattering layer
+  const float4* planes;         // [shape_cnt][HB_MAX_FACES]
+  const uint32_t* shape_meta;   // [shape_cnt] face_cnt | population << 8
+  const uint8_t* face_fn;       // [shape_cnt][HB_MAX_FACES]
+  const HbCrystalTables* shapes;  // [shape_cnt] full tables (entry sampling)
+  const HbFilterDesc* filters;  // [pop_cnt]
+  const uint32_t* pop_crystal_id;  // [pop_cnt]
+  uint32_t shape_cnt;
+  uint32_t pop_cnt;
+  uint32_t any_filter;
+};
+
+enum : uint32_t {
+  kFlagPath = 1u,     // record the face sequence of every ray (filters / exit records)
+  kFlagRecord = 2u,   // materialise HbExitRecord for every outgoing ray
+  kFlagAccum = 4u,    // fused projection + image reduction
+  kFlagGate = 8u,     // layer prob > 0: draw the continue/outgoing gate, append continuations
+  kFlagStats = 16u,   // LayerStats (exit count, weight sum)
+};
+
+struct TraceParams {
+  float4* P;
+  float4* D;
+  float4* Q;
+  uint8_t* path;                // [max_hits][cap] compact face ids (kFlagPath)
+  uint32_t* fork_root;          // [fork_cap] layer-root index of fork rays
+  uint32_t* fork_code;          // [fork_cap] branch code of fork rays
+  uint32_t* fork_count;         // rays appended behind the main slots (near-edge double continuation)
+  uint32_t* fork_snapshot;      // fork_count as of the last intersect kernel
+  uint32_t n_main, cap, fork_cap;
+  uint32_t root_base;           // layer-root index of slot 0 of this tile
+  LayerTables lt;
+  const HbWlEntry* wl;
+  uint32_t wl_cnt;
+  float4* image;                // [H][W] (X, Y, Z, landed weight)
+  HbProjParams proj;
+  uint32_t hit, max_hits, layer_idx, flags;
+  float prob;
+  uint32_t gate_seed;           // session seed ^ gate nonce
+  uint32_t gate_base_lo, gate_base_hi;  // global gate index of layer-root 0
+  float4* cont_dw;              // continuation records: world dir + weight
+  uint32_t* cont_meta;          // wl index | population << 8
+  uint32_t* cont_root;          // layer-root index of the parent (record mode)
+  uint32_t* cont_count;
+  uint32_t cont_cap;
+  HbExitRecord* exits;
+  uint32_t* exit_root;
+  uint32_t* exit_count;
+  uint32_t exit_cap;
+  unsigned long long* stat_exit_count;
+  double* stat_w_sum;
+  uint32_t* error_flag;
+};
+
+struct GenParams {
+  float4* P;
+  float4* D;
+  float4* Q;
+  uint8_t* path;
+  uint32_t slot0;               // first tile slot written by this launch
+  uint32_t count;
+  uint32_t cap;
+  uint32_t idx_lo, idx_hi;      // 64-bit stream index of slot0's ray
+  uint32_t seed;                // session seed ^ stream nonce
+  AxisParams axis;
+  const float* lut;             // [3][HB_LUT_NODES] device
+  const HbCrystalTables* shapes;  // this population's pool (device)
+  uint32_t shape_base, shape_cnt;
+  const HbWlEntry* wl;
+  uint32_t wl_cnt;
+  float sun_lon, sun_lat, sun_half;
+  uint32_t flags;
+  // transit only
+  const float4* cont_dw;
+  const uint32_t* cont_meta;
+  uint32_t cont_n;              // size of the permuted continuation pool
+  uint32_t cont_first;          // pool position of slot0
+  uint32_t shuffle_seed;
+  uint32_t shuffle;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Emission (CollectData branch 1, simulator.cpp:678-730 + ScatterOutgoingToXyz)
+// ------------------------------------------------------------------------------------------------
+struct Tally {
+  unsigned long long exits = 0;
+  double w_sum = 0.0;
+};
+
+template <bool GENERAL>
+HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float lx, float ly, float lz,
+                      float w, uint32_t role, const uint8_t* s_face_fn, Tally& tally) {
+  const Rot r = rot_from_quat(q);
+  float wx, wy, wz;
+  rot_apply(r, lx, ly, lz, wx, wy, wz);
+  const uint32_t wl_i = bits_wl(bits);
+  bool to_next_layer = false;
+  if (GENERAL) {
+    const uint32_t shape = bits_shape(bits);
+    const uint32_t pop = tp.lt.shape_meta[shape] >> 8;
+    uint32_t root, code;
+    if (slot < tp.n_main) {
+      root = tp.root_base + slot;
+      code = 0u;
+    } else {
+      root = tp.fork_root[slot - tp.n_main];
+      code = tp.fork_code[slot - tp.n_main];
+    }
+    uint8_t fn_path[HB_MAX_HITS];
+    const uint32_t len = tp.hit + 1u;
+    if (tp.flags & kFlagPath) {
+      const uint8_t* fn = s_face_fn + shape * HB_MAX_FACES;
+      for (uint32_t k = 0; k < len; k++) fn_path[k] = fn[tp.path[static_cast<size_t>(k) * tp.cap + slot]];
+      if (tp.lt.any_filter) {
+        const HbFilterDesc& f = tp.lt.filters[pop];
+        if (f.kind != 0u) {
+          const float dir[3] = { wx, wy, wz };
+          if (!filter_check(f, fn_path, len, dir, tp.lt.pop_crystal_id[pop])) return;  // filter-fail terminates
+        }
+      }
+    }
+    if (tp.flags & kFlagGate) {
+      // one uniform per filter-passing exit (simulator.cpp:719-723), keyed by (layer root, hit, role):
+      // role 0 = the child on the far side of the face, role 1 = the child that stays on the near side
+      const uint32_t glo = tp.gate_base_lo + root;
+      const uint32_t ghi = tp.gate_base_hi + (glo < tp.gate_base_lo ? 1u : 0u);
+      uint32_t seed = seed_with_high(tp.gate_seed, ghi);
+      if (code != 0u) seed ^= pcg_hash(code);
+      to_next_layer = draw(seed, glo, tp.hit * 2u + role) < tp.prob;
+    }
+    if (tp.flags & kFlagStats) {
+      tally.exits++;
+      tally.w_sum += static_cast<double>(w);
+    }
+    if (to_next_layer) {
+      // warp-aggregated append into the continuation pool (ballot + one atomic per warp)
+      const uint32_t active = __activemask();
+      const uint32_t lane = threadIdx.x & 31u;
+      const uint32_t leader = __ffs(active) - 1u;
+      uint32_t base = 0u;
+      if (lane == leader) base = atomicAdd(tp.cont_count, static_cast<uint32_t>(__popc(active)));
+      base = __shfl_sync(active, base, leader);
+      const uint32_t dst = base + __popc(active & ((1u << lane) - 1u));
+      if (dst < tp.cont_cap) {
+        tp.cont_dw[dst] = make_float4(wx, wy, wz, w);
+        tp.cont_meta[dst] = wl_i | (pop << 8);
+        if (tp.cont_root != nullptr) tp.cont_root[dst] = root;
+      } else {
+        *tp.error_flag = 1u;
+      }
+      return;
+    }
+    if (tp.flags & kFlagRecord) {
+      const uint32_t dst = atomicAdd(tp.exit_count, 1u);
+      if (dst < tp.exit_cap) {
+        HbExitRecord& e = tp.exits[dst];
+        e.dir[0] = wx;
+        e.dir[1] = wy;
+        e.dir[2] = wz;
+        e.weight = w;
+        e.path_len = static_cast<uint8_t>(len);
+        for (uint32_t k = 0; k < HB_MAX_HITS; k++) e.path[k] = k < len ? fn_path[k] : 0;
+        e.pad0_ = 0;
+        e.crystal_id = static_cast<uint16_t>(pop);
+        e.ms_layer_idx = static_cast<uint8_t>(tp.layer_idx);
+        e.wl_idx = static_cast<uint8_t>(wl_i);
+        e.pad1_[0] = e.pad1_[1] = 0;
+        e.component_mask = 0ull;
+        tp.exit_root[dst] = root;
+      } else {
+        *tp.error_flag = 2u;
+      }
+    }
+    if (!(tp.flags & kFlagAccum)) return;
+  }
+  const PixelHits h = project_exit(tp.proj, wx, wy, wz);
+  const HbWlEntry we = tp.wl[wl_i];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    if (k < h.count) {
+      const int px = h.px[k], py = h.py[k];
+      if (px >= 0 && px < tp.proj.img_w && py >= 0 && py < tp.proj.img_h) {
+        red_add_f4(tp.image + (static_cast<size_t>(py) * tp.proj.img_w + px), mul(we.cmf_x, w), mul(we.cmf_y, w),
+                   mul(we.cmf_z, w), h.bump[k] ? w : 0.0f);
+      }
+    }
+  }
+}
+
+// Shared-memory staging of the per-layer crystal tables (planes + face counts + face numbers).
+// Layout in dynamic shared memory: float4 planes[n][20] | uint32 meta[n] | uint8 face_fn[n][20].
+constexpr uint32_t kSmemShapes = 96;  // pools larger than this are read through L1/L2 instead
+struct SharedTables {
+  const float4* planes;
+  const uint32_t* meta;
+  const uint8_t* face_fn;
+};
+__host__ __device__ inline size_t shared_tables_bytes(uint32_t shape_cnt) {
+  const uint32_t n = shape_cnt <= kSmemShapes ? shape_cnt : 0u;
+  return static_cast<size_t>(n) * (HB_MAX_FACES * sizeof(float4) + sizeof(uint32_t) + HB_MAX_FACES) + 16;
+}
+HB_DEV SharedTables stage_tables(const LayerTables& lt, unsigned char* smem, bool want_fn) {
+  SharedTables s;
+  if (lt.shape_cnt > kSmemShapes) {
+    s.planes = lt.planes;
+    s.meta = lt.shape_meta;
+    s.face_fn = lt.face_fn;
+    return s;
+  }
+  const uint32_t n = lt.shape_cnt;
+  float4* pl = reinterpret_cast<float4*>(smem);
+  uint32_t* meta = reinterpret_cast<uint32_t*>(pl + n * HB_MAX_FACES);
+  uint8_t* fn = reinterpret_cast<uint8_t*>(meta + n);
+  for (uint32_t i = threadIdx.x; i < n * HB_MAX_FACES; i += blockDim.x) {
+    pl[i] = lt.planes[i];
+    if (want_fn) fn[i] = lt.face_fn[i];
+  }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) meta[i] = lt.shape_meta[i];
+  __syncthreads();
+  s.planes = pl;
+  s.meta = meta;
+  s.face_fn = fn;
+  return s;
+}
+
+template <bool GENERAL>
+HB_DEV void fork_append(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float px, float py, float pz,
+                        float dx, float dy, float dz, float w, uint32_t new_face) {
+  const uint32_t k = atomicAdd(tp.fork_count, 1u);
+  if (k >= tp.fork_cap) {
+    *tp.error_flag = 3u;
+    return;
+  }
+  const uint32_t dst = tp.n_main + k;
+  const uint32_t nb = bits_with_face(bits, new_face) | (1u << 30);
+  tp.P[dst] = make_float4(px, py, pz, __uint_as_float(nb));
+  tp.D[dst] = make_float4(dx, dy, dz, w);
+  tp.Q[dst] = q;
+  if (GENERAL) {
+    uint32_t root, code;
+    if (slot < tp.n_main) {
+      root = tp.root_base + slot;
+      code = 0u;
+    } else {
+      root = tp.fork_root[slot - tp.n_main];
+      code = tp.fork_code[slot - tp.n_main];
+    }
+    tp.fork_root[k] = root;
+    tp.fork_code[k] = code | (1u << (tp.hit & 31u));
+    if (tp.flags & kFlagPath) {
+      for (uint32_t h = 0; h <= tp.hit; h++)
+        tp.path[static_cast<size_t>(h) * tp.cap + dst] = tp.path[static_cast<size_t>(h) * tp.cap + slot];
+      if (tp.hit + 1u < tp.max_hits) tp.path[static_cast<size_t>(tp.hit + 1u) * tp.cap + dst] = static_cast<uint8_t>(new_face);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optics kernel: one surface interaction per live ray
+// ------------------------------------------------------------------------------------------------
+template <bool GENERAL, bool LAST>
+__global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SharedTables st = stage_tables(tp.lt, smem_raw, GENERAL);
+  const uint32_t total = tp.n_main + *tp.fork_snapshot;
+  Tally tally;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const float4 d4 = tp.D[i];
+    if (!(d4.w >= 0.0f)) continue;  // terminated
+    const float4 p4 = tp.P[i];
+    const uint32_t bits = __float_as_uint(p4.w);
+    const uint32_t face = bits_face(bits);
+    if (face == kFaceInvalid) continue;
+    const float4 q = tp.Q[i];
+    const uint32_t shape = bits_shape(bits);
+    const float4* planes = st.planes + shape * HB_MAX_FACES;
+    const uint32_t face_cnt = st.meta[shape] & 255u;
+    const uint8_t* fn_tab = st.face_fn;
+    const float n_idx = tp.wl[bits_wl(bits)].n_idx;
+
+    const Split s = hit_surface(planes[face], n_idx, d4.x, d4.y, d4.z, d4.w);
+    // The child on the far side of the face normally leaves the crystal: classify it here.
+    const uint32_t out_child = s.cos_in > 0.0f ? 1u : 0u;  // internal hit: refracted; entry: reflected
+    const float ox = out_child ? s.tx : s.rx, oy = out_child ? s.ty : s.ry, oz = out_child ? s.tz : s.rz;
+    const float ow = out_child ? s.tw : s.rw;
+    const float ix = out_child ? s.rx : s.tx, iy = out_child ? s.ry : s.ty, iz = out_child ? s.rz : s.tz;
+    const float iw = out_child ? s.rw : s.tw;
+    if (ow >= 0.0f) {
+      float nx, ny, nz;
+      const uint32_t nf = slab_exit(planes, face_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
+      if (nf == kFaceInvalid) {
+        emit_exit<GENERAL>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, fn_tab, tally);
+      } else if (!LAST) {
+        fork_append<GENERAL>(tp, i, bits, q, nx, ny, nz, ox, oy, oz, ow, nf);  // near-edge leak: both children stay
+      }
+    }
+    if (LAST) {
+      // no intersect pass follows the final interaction: classify the inside child here too
+      if (iw >= 0.0f) {
+        float nx, ny, nz;
+        const uint32_t nf = slab_exit(planes, face_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+        if (nf == kFaceInvalid) emit_exit<GENERAL>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, fn_tab, tally);
+      }
+    } else {
+      tp.D[i] = make_float4(ix, iy, iz, iw);  // iw < 0 (TIR sentinel) terminates the ray
+    }
+  }
+  if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
+    atomicAdd(tp.stat_exit_count, tally.exits);
+    atomicAdd(tp.stat_w_sum, tally.w_sum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// intersect kernel: slab exit-face search for the inside child
+// ------------------------------------------------------------------------------------------------
+template <bool GENERAL>
+__global__ void __launch_bounds__(256) intersect_kernel(const TraceParams tp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SharedTables st = stage_tables(tp.lt, smem_raw, GENERAL);
+  const uint32_t forks = *tp.fork_count;
+  const uint32_t total = tp.n_main + min(forks, tp.fork_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *tp.fork_snapshot = min(forks, tp.fork_cap);
+  Tally tally;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const float4 d4 = tp.D[i];
+    if (!(d4.w >= 0.0f)) continue;
+    const float4 p4 = tp.P[i];
+    const uint32_t bits = __float_as_uint(p4.w);
+    const uint32_t face = bits_face(bits);
+    if (face == kFaceInvalid) continue;
+    if (bits_advanced(bits)) {  // fork ray: advanced when it was created
+      tp.P[i] = make_float4(p4.x, p4.y, p4.z, __uint_as_float(bits & ~(1u << 30)));
+      continue;
+    }
+    const uint32_t shape = bits_shape(bits);
+    const float4* planes = st.planes + shape * HB_MAX_FACES;
+    const uint32_t face_cnt = st.meta[shape] & 255u;
+    float nx, ny, nz;
+    const uint32_t nf = slab_exit(planes, face_cnt, face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz);
+    if (nf == kFaceInvalid) {
+      // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
+      emit_exit<GENERAL>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, st.face_fn, tally);
+      tp.D[i] = make_float4(d4.x, d4.y, d4.z, -1.0f);
+      continue;
+    }
+    tp.P[i] = make_float4(nx, ny, nz, __uint_as_float(bits_with_face(bits, nf)));
+    if (GENERAL && (tp.flags & kFlagPath) && tp.hit + 1u < tp.max_hits)
+      tp.path[static_cast<size_t>(tp.hit + 1u) * tp.cap + i] = static_cast<uint8_t>(nf);
+  }
+  if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
+    atomicAdd(tp.stat_exit_count, tally.exits);
+    atomicAdd(tp.stat_w_sum, tally.w_sum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// root generation / layer transit
+// ------------------------------------------------------------------------------------------------
+struct GenShared {
+  float lut[3 * HB_LUT_NODES];
+  HbCrystalTables shape0;  // single-shape populations: entry fan table staged on chip
+};
+
+template <bool TRANSIT>
+__global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenShared* gs = reinterpret_cast<GenShared*>(smem_raw);
+  if (gp.axis.lat_path == HB_LAT_LUT) {
+    for (uint32_t i = threadIdx.x; i < 3 * HB_LUT_NODES; i += blockDim.x) gs->lut[i] = gp.lut[i];
+  }
+  if (gp.shape_cnt == 1u) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gp.shapes);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&gs->shape0);
+    for (uint32_t i = threadIdx.x; i < sizeof(HbCrystalTables) / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gp.count; k += gridDim.x * blockDim.x) {
+    const uint32_t lo = gp.idx_lo + k;
+    const uint32_t hi = gp.idx_hi + (lo < gp.idx_lo ? 1u : 0u);
+    const uint32_t s0 = seed_with_high(gp.seed, hi);
+    uint32_t wl_i = 0u;
+    float wx, wy, wz, weight;
+    if (TRANSIT) {
+      uint32_t src = gp.cont_first + k;
+      if (gp.shuffle) src = feistel(src, gp.cont_n, gp.shuffle_seed);
+      const float4 c = gp.cont_dw[src];
+      wx = c.x;
+      wy = c.y;
+      wz = c.z;
+      weight = c.w;
+      wl_i = gp.cont_meta[src] & 255u;
+    } else if (gp.wl_cnt > 1u) {
+      wl_i = min(static_cast<uint32_t>(draw(s0 ^ kNonceWl, lo, 0u) * static_cast<float>(gp.wl_cnt)), gp.wl_cnt - 1u);
+    }
+    Stream s{ s0, lo, 0u };
+    float lon, lat, roll;
+    sample_lon_lat_roll(s, gp.axis, gs->lut, lon, lat, roll);
+    const float4 q = quat_from_angles(lon, lat, roll);
+    const Rot r = rot_from_quat(q);
+    if (!TRANSIT) {
+      sample_sph_cap(s, gp.sun_lon, gp.sun_lat, gp.sun_half, wx, wy, wz);
+      weight = gp.wl[wl_i].spd_weight;
+    }
+    float dx, dy, dz;
+    rot_apply_t(r.m, wx, wy, wz, dx, dy, dz);
+    uint32_t sh = 0u;
+    if (gp.shape_cnt > 1u) {
+      sh = min(static_cast<uint32_t>(draw(s0 ^ kNonceShape, lo, 0u) * static_cast<float>(gp.shape_cnt)), gp.shape_cnt - 1u);
+    }
+    const HbCrystalTables* tab = gp.shape_cnt == 1u ? &gs->shape0 : gp.shapes + sh;
+    float px = 0.0f, py = 0.0f, pz = 0.0f;
+    uint32_t face = kFaceInvalid;
+    if (tab->subtri_cnt == 0u) {
+      weight = -1.0f;  // degenerate crystal: nothing to trace (zero-weight discard, simulator.cpp:149-159)
+    } else {
+      sample_entry(s, tab, dx, dy, dz, px, py, pz, face);
+    }
+    const uint32_t slot = gp.slot0 + k;
+    gp.P[slot] = make_float4(px, py, pz, __uint_as_float(pack_bits(face, wl_i, gp.shape_base + sh, 0u)));
+    gp.D[slot] = make_float4(dx, dy, dz, weight);
+    gp.Q[slot] = q;
+    if ((gp.flags & kFlagPath) && gp.path != nullptr) gp.path[slot] = static_cast<uint8_t>(face);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// image drain: (X,Y,Z,landed) float4 -> packed XYZ + landed-weight sum, then zero
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) drain_image_kernel(float4* image, float* xyz, double* landed, uint32_t pixels) {
+  double acc = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const float4 v = image[i];
+    xyz[static_cast<size_t>(i) * 3 + 0] = v.x;
+    xyz[static_cast<size_t>(i) * 3 + 1] = v.y;
+    xyz[static_cast<size_t>(i) * 3 + 2] = v.z;
+    acc += static_cast<double>(v.w);
+    image[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double warp_sum[8];
+  if ((threadIdx.x & 31u) == 0u) warp_sum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += warp_sum[w];
+    atomicAdd(landed, t);
+  }
+}
+
+// Export helper: quaternion -> rot9 with the device's own arithmetic (parity harness).
+__global__ void quat_to_rot_kernel(const float4* Q, float* rot9, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Rot r = rot_from_quat(Q[i]);
+  for (int k = 0; k < 9; k++) rot9[static_cast<size_t>(i) * 9 + k] = r.m[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct PopHost {
+  float proportion;
+  uint32_t crystal_id;
+  uint32_t shape_base, shape_cnt;
+  AxisParams axis;
+  bool has_filter;
+};
+
+struct LayerDev {
+  float prob = 0.0f;
+  std::vector<PopHost> pops;
+  std::vector<double> carry;  // PartitionCrystalRayNum carry (simulator.cpp:519-582)
+  uint32_t shape_cnt = 0;
+  bool any_filter = false;
+  DevBuf<float4> planes;
+  DevBuf<uint32_t> shape_meta;
+  DevBuf<uint8_t> face_fn;
+  DevBuf<HbCrystalTables> shapes;
+  DevBuf<HbFilterDesc> filters;
+  DevBuf<uint32_t> pop_crystal_id;
+  DevBuf<float> luts;  // [pop][3][257]
+};
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int family;       // 0 gen, 1 optics, 2 intersect
+  uint64_t rays;
+};
+
+uint32_t pcg_hash_host(uint32_t x);
+uint32_t bits_face_host(const float4& p);
+
+}  // namespace hb
+
+using namespace hb;  // NOLINT
+
+struct HbEngine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::string error;
+
+  // scene / render
+  uint32_t max_hits = 0;
+  float sun_lon = 0, sun_lat = 0, sun_half = 0;
+  std::vector<std::unique_ptr<LayerDev>> layers;
+  bool have_scene = false, have_render = false;
+  HbProjParams proj{};
+  DevBuf<float4> image;
+  DevBuf<float> xyz_stage;
+  DevBuf<double> landed_dev;
+
+  // session
+  bool in_session = false;
+  HbSessionSpec spec{};
+  struct WlSlot {
+    std::vector<HbWlEntry> host;
+    DevBuf<HbWlEntry> dev;
+  };
+  std::vector<WlSlot> wl_cache;
+  size_t wl_cache_next = 0;
+  const HbWlEntry* wl_cur = nullptr;
+  uint32_t wl_cnt = 0;
+  uint32_t layer_idx = 0;       // next layer to trace
+  bool layer_traced = false;    // a TraceLayer result is pending Recombine
+  uint64_t cont_n = 0;          // continuation pool size after Recombine
+  bool cont_shuffle = false;
+  uint32_t shuffle_round = 0;
+
+  // monotone stream counters (never reset per session; cuda_trace_backend.cu:3717-3754)
+  uint64_t gen_base = 0, gate_base = 0, transit_base = 0;
+
+  // tile buffers
+  uint64_t tile_rays = 1u << 22;
+  DevBuf<float4> P, D, Q;
+  DevBuf<uint8_t> path;
+  DevBuf<uint32_t> fork_root, fork_code;
+  DevBuf<uint32_t> counters;    // [0] fork_count [1] fork_snapshot [2] cont_count [3] exit_count [4] error
+  DevBuf<unsigned long long> stat_cnt;
+  DevBuf<double> stat_sum;
+  DevBuf<float4> cont_dw[2];
+  DevBuf<uint32_t> cont_meta[2];
+  DevBuf<uint32_t> cont_root[2];
+  int cont_cur = 0;             // pool being appended by the current layer
+  DevBuf<HbExitRecord> exits_dev;
+  DevBuf<uint32_t> exit_root_dev;
+  std::vector<HbExitRecord> exits_host;
+  std::vector<uint32_t> exit_roots_host;
+
+  // parity: injected / exported roots
+  bool injected = false;
+  std::vector<float4> inj_P, inj_D, inj_Q;
+  std::vector<float> exp_d, exp_p, exp_w, exp_rot;
+  std::vector<uint16_t> exp_face;
+  std::vector<uint32_t> exp_shape, exp_wl;
+
+  // measurement
+  HbCounters ctr{};
+  bool profile = false;
+  std::vector<EventPair> ev_pool;
+  size_t ev_used = 0;
+  int blocks_per_sm = 8;
+#ifdef HB_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  int nranks = 1, rank = 0;
+};
+
+namespace {
+
+std::string g_create_error;
+
+#define HB_CUDA(h, expr)                                                                            \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      (h)->error = std::string(#expr) + ": " + cudaGetErrorString(e_);                              \
+      return HB_ERR_CUDA;                                                                           \
+    }                                                                                               \
+  } while (0)
+
+int fail(HbEngine* h, int code, const std::string& msg) {
+  h->error = msg;
+  return code;
+}
+
+void flush_events(HbEngine* h) {
+  for (size_t i = 0; i < h->ev_used; i++) {
+    float ms = 0.0f;
+    EventPair& e = h->ev_pool[i];
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+      if (e.family == 0) {
+        h->ctr.gen_ms += ms;
+      } else if (e.family == 1) {
+        h->ctr.optics_ms += ms;
+      } else {
+        h->ctr.intersect_ms += ms;
+      }
+    }
+  }
+  h->ev_used = 0;
+}
+
+EventPair* begin_event(HbEngine* h, int family, uint64_t rays) {
+  if (!h->profile) return nullptr;
+  if (h->ev_used == h->ev_pool.size()) {
+    if (h->ev_pool.size() >= 8192) {
+      cudaStreamSynchronize(h->stream);
+      flush_events(h);
+    } else {
+      EventPair e{};
+      cudaEventCreate(&e.a);
+      cudaEventCreate(&e.b);
+      h->ev_pool.push_back(e);
+    }
+  }
+  EventPair* e = &h->ev_pool[h->ev_used++];
+  e->family = family;
+  e->rays = rays;
+  cudaEventRecord(e->a, h->stream);
+  return e;
+}
+void end_event(HbEngine* h, EventPair* e) {
+  if (e) cudaEventRecord(e->b, h->stream);
+}
+
+uint32_t grid_for(const HbEngine* h, uint64_t n) {
+  uint64_t blocks = (n + 255) / 256;
+  uint64_t cap = static_cast<uint64_t>(h->sm_count) * h->blocks_per_sm;
+  return static_cast<uint32_t>(std::max<uint64_t>(1, std::min(blocks, cap)));
+}
+
+size_t trace_smem(const LayerDev& L) { return shared_tables_bytes(L.shape_cnt); }
+
+int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
+  L->prob = src.prob;
+  L->pops.clear();
+  std::vector<float4> planes;
+  std::vector<uint32_t> meta;
+  std::vector<uint8_t> fn;
+  std::vector<HbCrystalTables> shapes;
+  std::vector<HbFilterDesc> filters;
+  std::vector<uint32_t> cid;
+  std::vector<float> luts;
+  L->any_filter = false;
+  for (uint32_t ci = 0; ci < src.population_cnt; ci++) {
+    const HbCrystalPopulation& p = src.populations[ci];
+    if (p.shape_cnt == 0 || p.shapes == nullptr) return fail(h, HB_ERR_INVALID_ARG, "population without shapes");
+    PopHost ph{};
+    ph.proportion = p.proportion;
+    ph.crystal_id = p.crystal_id;
+    ph.shape_base = static_cast<uint32_t>(shapes.size());
+    ph.shape_cnt = p.shape_cnt;
+    ph.axis = AxisParams{ p.axis.lat_path, p.axis.lat_mean, p.axis.lat_std, p.axis.az_type, p.axis.az_mean, p.axis.az_std,
+                          p.axis.roll_type, p.axis.roll_mean, p.axis.roll_std, p.axis.lut_n };
+    ph.has_filter = p.filter.kind != 0;
+    L->any_filter = L->any_filter || ph.has_filter;
+    for (uint32_t s = 0; s < p.shape_cnt; s++) {
+      const HbCrystalTables& t = p.shapes[s];
+      if (t.face_cnt > HB_MAX_FACES || t.subtri_cnt > HB_MAX_SUBTRIS) return fail(h, HB_ERR_INVALID_ARG, "crystal table too large");
+      shapes.push_back(t);
+      meta.push_back(t.face_cnt | (ci << 8));
+      for (uint32_t f = 0; f < HB_MAX_FACES; f++) {
+        planes.push_back(make_float4(t.plane[f][0], t.plane[f][1], t.plane[f][2], t.plane[f][3]));
+        fn.push_back(t.face_fn[f]);
+      }
+    }
+    filters.push_back(p.filter);
+    cid.push_back(p.crystal_id);
+    luts.insert(luts.end(), p.axis.lut_theta, p.axis.lut_theta + HB_LUT_NODES);
+    luts.insert(luts.end(), p.axis.lut_cdf, p.axis.lut_cdf + HB_LUT_NODES);
+    luts.insert(luts.end(), p.axis.lut_flip, p.axis.lut_flip + HB_LUT_NODES);
+    L->pops.push_back(ph);
+  }
+  if (shapes.size() > 65535) return fail(h, HB_ERR_CAPACITY, "more than 65535 crystal shapes in one layer");
+  L->shape_cnt = static_cast<uint32_t>(shapes.size());
+  L->carry.assign(L->pops.size(), 0.0);
+  HB_CUDA(h, L->planes.ensure(planes.size()));
+  HB_CUDA(h, L->shape_meta.ensure(meta.size()));
+  HB_CUDA(h, L->face_fn.ensure(fn.size()));
+  HB_CUDA(h, L->shapes.ensure(shapes.size()));
+  HB_CUDA(h, L->filters.ensure(filters.size()));
+  HB_CUDA(h, L->pop_crystal_id.ensure(cid.size()));
+  HB_CUDA(h, L->luts.ensure(luts.size()));
+  HB_CUDA(h, cudaMemcpy(L->planes.p, planes.data(), planes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(L->shape_meta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(L->face_fn.p, fn.data(), fn.size(), cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(L->shapes.p, shapes.data(), shapes.size() * sizeof(HbCrystalTables), cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(L->filters.p, filters.data(), filters.size() * sizeof(HbFilterDesc), cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(L->pop_crystal_id.p, cid.data(), cid.size() * 4, cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(L->luts.p, luts.data(), luts.size() * 4, cudaMemcpyHostToDevice));
+  return HB_OK;
+}
+
+uint32_t session_flags(const HbEngine* h, const LayerDev& L, bool last_layer) {
+  uint32_t f = 0;
+  if (h->spec.accumulate) f |= kFlagAccum;
+  if (h->spec.record_exits) f |= kFlagRecord | kFlagPath | kFlagStats;
+  if (L.any_filter) f |= kFlagPath;
+  if (L.prob > 0.0f) f |= kFlagGate;
+  (void)last_layer;
+  return f;
+}
+
+int ensure_tile(HbEngine* h, uint64_t cap, uint64_t fork_cap, uint32_t flags) {
+  HB_CUDA(h, h->P.ensure(cap));
+  HB_CUDA(h, h->D.ensure(cap));
+  HB_CUDA(h, h->Q.ensure(cap));
+  HB_CUDA(h, h->counters.ensure(8));
+  HB_CUDA(h, h->stat_cnt.ensure(1));
+  HB_CUDA(h, h->stat_sum.ensure(1));
+  HB_CUDA(h, h->fork_root.ensure(fork_cap));
+  HB_CUDA(h, h->fork_code.ensure(fork_cap));
+  if (flags & kFlagPath) HB_CUDA(h, h->path.ensure(cap * h->max_hits));
+  return HB_OK;
+}
+
+// Trace one tile [root0, root0 + n) of layer `li`; roots come from gen (li == 0, not injected),
+// the injected host batch, or the continuation pool (li > 0).
+int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::vector<uint64_t>& pop_begin,
+               uint32_t flags, uint64_t layer_total) {
+  LayerDev& L = *h->layers[li];
+  const uint32_t fork_cap = std::max<uint32_t>(4096u, n / 64u);
+  const uint32_t cap = n + fork_cap;
+  int rc = ensure_tile(h, cap, fork_cap, flags);
+  if (rc != HB_OK) return rc;
+  const bool general = (flags & (kFlagPath | kFlagRecord | kFlagGate | kFlagStats)) != 0 || !(flags & kFlagAccum);
+  HB_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 2 * sizeof(uint32_t), h->stream));  // fork_count, fork_snapshot
+  if (flags & kFlagRecord) {
+    const uint64_t ecap = static_cast<uint64_t>(n) * (h->max_hits + 1) + fork_cap;
+    HB_CUDA(h, h->exits_dev.ensure(ecap));
+    HB_CUDA(h, h->exit_root_dev.ensure(ecap));
+    HB_CUDA(h, cudaMemsetAsync(h->counters.p + 3, 0, sizeof(uint32_t), h->stream));
+  }
+
+  // ---- roots ----
+  if (li == 0 && h->injected) {
+    HB_CUDA(h, cudaMemcpyAsync(h->P.p, h->inj_P.data() + root0, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(h->D.p, h->inj_D.data() + root0, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(h->Q.p, h->inj_Q.data() + root0, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    if (flags & kFlagPath) {
+      std::vector<uint8_t> p0(n);
+      for (uint32_t i = 0; i < n; i++) p0[i] = static_cast<uint8_t>(bits_face_host(h->inj_P[root0 + i]));
+      HB_CUDA(h, cudaMemcpyAsync(h->path.p, p0.data(), n, cudaMemcpyHostToDevice, h->stream));
+      HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+  } else {
+    for (size_t ci = 0; ci < L.pops.size(); ci++) {
+      const uint64_t b = std::max<uint64_t>(pop_begin[ci], root0), e = std::min<uint64_t>(pop_begin[ci + 1], root0 + n);
+      if (b >= e) continue;
+      const PopHost& ph = L.pops[ci];
+      GenParams gp{};
+      gp.P = h->P.p;
+      gp.D = h->D.p;
+      gp.Q = h->Q.p;
+      gp.path = h->path.p;
+      gp.slot0 = static_cast<uint32_t>(b - root0);
+      gp.count = static_cast<uint32_t>(e - b);
+      gp.cap = cap;
+      const uint64_t base = (li == 0 ? h->gen_base : h->transit_base) + b;
+      gp.idx_lo = static_cast<uint32_t>(base);
+      gp.idx_hi = static_cast<uint32_t>(base >> 32);
+      gp.seed = h->spec.seed ^ (li == 0 ? kNonceGen : kNonceTransit);
+      gp.axis = ph.axis;
+      gp.lut = L.luts.p + ci * 3 * HB_LUT_NODES;
+      gp.shapes = L.shapes.p + ph.shape_base;
+      gp.shape_base = ph.shape_base;
+      gp.shape_cnt = ph.shape_cnt;
+      gp.wl = h->wl_cur;
+      gp.wl_cnt = h->wl_cnt;
+      gp.sun_lon = h->sun_lon;
+      gp.sun_lat = h->sun_lat;
+      gp.sun_half = h->sun_half;
+      gp.flags = flags;
+      EventPair* ev = begin_event(h, 0, gp.count);
+      if (li == 0) {
+        gen_kernel<false><<<grid_for(h, gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
+      } else {
+        const int src = h->cont_cur ^ 1;
+        gp.cont_dw = h->cont_dw[src].p;
+        gp.cont_meta = h->cont_meta[src].p;
+        gp.cont_n = static_cast<uint32_t>(layer_total);
+        gp.cont_first = static_cast<uint32_t>(b);
+        gp.shuffle = h->cont_shuffle ? 1u : 0u;
+        gp.shuffle_seed = pcg_hash_host(h->spec.seed ^ kNonceShuffle ^ h->shuffle_round);
+        gen_kernel<true><<<grid_for(h, gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
+      }
+      end_event(h, ev);
+      h->ctr.kernel_launches++;
+      h->ctr.gen_launches++;
+    }
+  }
+  HB_CUDA(h, cudaGetLastError());
+
+  // ---- parity export of the roots this tile starts from ----
+  if (h->spec.record_exits && !(li == 0 && h->injected)) {
+    std::vector<float4> hp(n), hd(n), hq(n);
+    DevBuf<float> rot;
+    HB_CUDA(h, rot.ensure(static_cast<size_t>(n) * 9));
+    quat_to_rot_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->Q.p, rot.p, n);
+    std::vector<float> hr(static_cast<size_t>(n) * 9);
+    HB_CUDA(h, cudaMemcpyAsync(hp.data(), h->P.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(hd.data(), h->D.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(hr.data(), rot.p, hr.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    rot.release();
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t bits;
+      std::memcpy(&bits, &hp[i].w, 4);
+      h->exp_p.insert(h->exp_p.end(), { hp[i].x, hp[i].y, hp[i].z });
+      h->exp_d.insert(h->exp_d.end(), { hd[i].x, hd[i].y, hd[i].z });
+      h->exp_w.push_back(hd[i].w);
+      const uint32_t f = bits & 63u;
+      h->exp_face.push_back(f == kFaceInvalid ? static_cast<uint16_t>(HB_INVALID_FACE) : static_cast<uint16_t>(f));
+      h->exp_shape.push_back((bits >> 14) & 65535u);
+      h->exp_wl.push_back((bits >> 6) & 255u);
+    }
+    h->exp_rot.insert(h->exp_rot.end(), hr.begin(), hr.end());
+  }
+
+  // ---- hit loop ----
+  TraceParams tp{};
+  tp.P = h->P.p;
+  tp.D = h->D.p;
+  tp.Q = h->Q.p;
+  tp.path = h->path.p;
+  tp.fork_root = h->fork_root.p;
+  tp.fork_code = h->fork_code.p;
+  tp.fork_count = h->counters.p + 0;
+  tp.fork_snapshot = h->counters.p + 1;
+  tp.n_main = n;
+  tp.cap = cap;
+  tp.fork_cap = fork_cap;
+  tp.root_base = static_cast<uint32_t>(root0);
+  tp.lt = LayerTables{ L.planes.p, L.shape_meta.p, L.face_fn.p, L.shapes.p, L.filters.p, L.pop_crystal_id.p,
+                       L.shape_cnt, static_cast<uint32_t>(L.pops.size()), L.any_filter ? 1u : 0u };
+  tp.wl = h->wl_cur;
+  tp.wl_cnt = h->wl_cnt;
+  tp.image = h->image.p;
+  tp.proj = h->proj;
+  tp.max_hits = h->max_hits;
+  tp.layer_idx = li;
+  tp.flags = flags;
+  tp.prob = L.prob;
+  tp.gate_seed = h->spec.seed ^ kNonceGate;
+  tp.gate_base_lo = static_cast<uint32_t>(h->gate_base);
+  tp.gate_base_hi = static_cast<uint32_t>(h->gate_base >> 32);
+  tp.cont_dw = h->cont_dw[h->cont_cur].p;
+  tp.cont_meta = h->cont_meta[h->cont_cur].p;
+  tp.cont_root = h->spec.record_exits ? h->cont_root[h->cont_cur].p : nullptr;
+  tp.cont_count = h->counters.p + 2;
+  tp.cont_cap = static_cast<uint32_t>(h->cont_dw[h->cont_cur].n);
+  tp.exits = h->exits_dev.p;
+  tp.exit_root = h->exit_root_dev.p;
+  tp.exit_count = h->counters.p + 3;
+  tp.exit_cap = static_cast<uint32_t>(std::min<size_t>(h->exits_dev.n, 0xFFFFFFFFu));
+  tp.stat_exit_count = h->stat_cnt.p;
+  tp.stat_w_sum = h->stat_sum.p;
+  tp.error_flag = h->counters.p + 4;
+
+  const uint32_t grid = grid_for(h, cap);
+  const size_t smem = trace_smem(L);
+  for (uint32_t hit = 0; hit < h->max_hits; hit++) {
+    tp.hit = hit;
+    const bool last = hit + 1 == h->max_hits;
+    EventPair* ev = begin_event(h, 1, n);
+    if (general) {
+      if (last) optics_kernel<true, true><<<grid, 256, smem, h->stream>>>(tp);
+      else optics_kernel<true, false><<<grid, 256, smem, h->stream>>>(tp);
+    } else {
+      if (last) optics_kernel<false, true><<<grid, 256, smem, h->stream>>>(tp);
+      else optics_kernel<false, false><<<grid, 256, smem, h->stream>>>(tp);
+    }
+    end_event(h, ev);
+    h->ctr.kernel_launches++;
+    h->ctr.optics_launches++;
+    h->ctr.optics_rays += n;
+    if (!last) {
+      ev = begin_event(h, 2, n);
+      if (general) intersect_kernel<true><<<grid, 256, smem, h->stream>>>(tp);
+      else intersect_kernel<false><<<grid, 256, smem, h->stream>>>(tp);
+      end_event(h, ev);
+      h->ctr.kernel_launches++;
+      h->ctr.intersect_launches++;
+      h->ctr.intersect_rays += n;
+    }
+  }
+  HB_CUDA(h, cudaGetLastError());
+
+  if (flags & kFlagRecord) {  // move this tile's exit records to the host (DrainExits is grow-not-clamp)
+    uint32_t cnt = 0;
+    HB_CUDA(h, cudaMemcpyAsync(&cnt, h->counters.p + 3, 4, cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (cnt > h->exits_dev.n) return fail(h, HB_ERR_CAPACITY, "exit record buffer overflow");
+    const size_t old = h->exits_host.size();
+    h->exits_host.resize(old + cnt);
+    h->exit_roots_host.resize(old + cnt);
+    if (cnt) {
+      HB_CUDA(h, cudaMemcpy(h->exits_host.data() + old, h->exits_dev.p, cnt * sizeof(HbExitRecord), cudaMemcpyDeviceToHost));
+      HB_CUDA(h, cudaMemcpy(h->exit_roots_host.data() + old, h->exit_root_dev.p, cnt * 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  h->ctr.rays_traced += n;
+  return HB_OK;
+}
+
+}  // namespace
+
+// host twins of two tiny device helpers (kept out of the header: host code never traces rays)
+namespace hb {
+uint32_t pcg_hash_host(uint32_t x) {
+  x = x * 747796405u + 2891336453u;
+  x = ((x >> ((x >> 28u) + 4u)) ^ x) * 277803737u;
+  return (x >> 22u) ^ x;
+}
+uint32_t bits_face_host(const float4& p) {
+  uint32_t b;
+  std::memcpy(&b, &p.w, 4);
+  return b & 63u;
+}
+}  // namespace hb
+
+extern "C" {
+
+const char* hb_last_error(const HbEngine* h) {
+  if (h == nullptr) return g_create_error.empty() ? hb::global_error().c_str() : g_create_error.c_str();
+  return h->error.c_str();
+}
+
+int hb_create(int device, HbEngine** out) {
+  if (out == nullptr) return HB_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this engine has no CPU path)";
+    return HB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device ordinal out of range";
+    return HB_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+    g_create_error = "device is not sm_100 or newer (this library carries sm_100a code only)";
+    return HB_ERR_NO_DEVICE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    g_create_error = "cudaSetDevice failed";
+    return HB_ERR_CUDA;
+  }
+  auto h = std::make_unique<HbEngine>();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "cudaStreamCreate failed";
+    return HB_ERR_CUDA;
+  }
+  *out = h.release();
+  return HB_OK;
+}
+
+void hb_destroy(HbEngine* h) {
+  if (h == nullptr) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& e : h->ev_pool) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  for (auto& L : h->layers) {
+    L->planes.release();
+    L->shape_meta.release();
+    L->face_fn.release();
+    L->shapes.release();
+    L->filters.release();
+    L->pop_crystal_id.release();
+    L->luts.release();
+  }
+  h->image.release();
+  h->xyz_stage.release();
+  h->landed_dev.release();
+  for (auto& s : h->wl_cache) s.dev.release();
+  h->P.release();
+  h->D.release();
+  h->Q.release();
+  h->path.release();
+  h->fork_root.release();
+  h->fork_code.release();
+  h->counters.release();
+  h->stat_cnt.release();
+  h->stat_sum.release();
+  for (int i = 0; i < 2; i++) {
+    h->cont_dw[i].release();
+    h->cont_meta[i].release();
+    h->cont_root[i].release();
+  }
+  h->exits_dev.release();
+  h->exit_root_dev.release();
+#ifdef HB_WITH_NCCL
+  if (h->comm) ncclCommDestroy(h->comm);
+#endif
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int hb_set_scene(HbEngine* h, const HbScene* s) {
+  if (h == nullptr || s == nullptr) return HB_ERR_INVALID_ARG;
+  if (h->in_session) return fail(h, HB_ERR_STATE, "hb_set_scene inside a session");
+  if (s->layer_cnt == 0 || s->layer_cnt > HB_MAX_LAYERS || s->max_hits == 0 || s->max_hits > HB_MAX_HITS)
+    return fail(h, HB_ERR_INVALID_ARG, "scene: layer_cnt must be 1..8 and max_hits 1..64");
+  cudaSetDevice(h->device);
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->layers.clear();
+  for (uint32_t li = 0; li < s->layer_cnt; li++) {
+    auto L = std::make_unique<LayerDev>();
+    int rc = upload_layer(h, s->layers[li], L.get());
+    if (rc != HB_OK) return rc;
+    h->layers.push_back(std::move(L));
+  }
+  h->max_hits = s->max_hits;
+  h->sun_lon = s->sun_lon;
+  h->sun_lat = s->sun_lat;
+  h->sun_half = s->sun_half_angle;
+  h->have_scene = true;
+  return HB_OK;
+}
+
+int hb_set_render(HbEngine* h, const HbProjParams* p) {
+  if (h == nullptr || p == nullptr) return HB_ERR_INVALID_ARG;
+  if (h->in_session) return fail(h, HB_ERR_STATE, "hb_set_render inside a session");
+  if (p->img_w <= 0 || p->img_h <= 0) return fail(h, HB_ERR_INVALID_ARG, "render: empty image");
+  cudaSetDevice(h->device);
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const size_t pix = static_cast<size_t>(p->img_w) * p->img_h;
+  const bool realloc = !h->have_render || p->img_w != h->proj.img_w || p->img_h != h->proj.img_h;
+  h->proj = *p;
+  if (realloc) {  // resolution change => realloc + zero (cuda_trace_backend.cu:3799-3835)
+    HB_CUDA(h, h->image.ensure(pix));
+    HB_CUDA(h, h->xyz_stage.ensure(pix * 3));
+    HB_CUDA(h, h->landed_dev.ensure(1));
+    HB_CUDA(h, cudaMemset(h->image.p, 0, pix * sizeof(float4)));
+    HB_CUDA(h, cudaMemset(h->landed_dev.p, 0, sizeof(double)));
+  }
+  h->have_render = true;
+  return HB_OK;
+}
+
+int hb_begin_session(HbEngine* h, const HbSessionSpec* spec) {
+  if (h == nullptr || spec == nullptr) return HB_ERR_INVALID_ARG;
+  if (h->in_session) return fail(h, HB_ERR_STATE, "BeginSession on an already-open session");
+  if (!h->have_scene) return fail(h, HB_ERR_STATE, "BeginSession before hb_set_scene");
+  if (spec->accumulate && !h->have_render) return fail(h, HB_ERR_STATE, "accumulate session before hb_set_render");
+  if (spec->wl == nullptr || spec->wl_cnt == 0 || spec->wl_cnt > HB_MAX_WL)
+    return fail(h, HB_ERR_INVALID_ARG, "session: wavelength pool must hold 1..256 entries");
+  cudaSetDevice(h->device);
+  h->spec = *spec;
+  h->wl_cnt = spec->wl_cnt;
+  h->spec.wl = nullptr;  // borrowed only for the call
+  // Wavelength pools are tiny and recur (one per discrete wavelength): keep the last few on the device so a
+  // steady-state BeginSession issues no copy and no synchronisation.
+  {
+    const size_t bytes = spec->wl_cnt * sizeof(HbWlEntry);
+    int hit = -1;
+    for (size_t i = 0; i < h->wl_cache.size(); i++) {
+      if (h->wl_cache[i].host.size() == spec->wl_cnt && std::memcmp(h->wl_cache[i].host.data(), spec->wl, bytes) == 0) {
+        hit = static_cast<int>(i);
+        break;
+      }
+    }
+    if (hit < 0) {
+      if (h->wl_cache.size() < 32) {
+        h->wl_cache.emplace_back();
+        hit = static_cast<int>(h->wl_cache.size()) - 1;
+      } else {
+        hit = static_cast<int>(h->wl_cache_next++ % 32);
+        HB_CUDA(h, cudaStreamSynchronize(h->stream));  // the evicted table may still be in use
+      }
+      HbEngine::WlSlot& s = h->wl_cache[hit];
+      s.host.assign(spec->wl, spec->wl + spec->wl_cnt);
+      HB_CUDA(h, s.dev.ensure(spec->wl_cnt));
+      HB_CUDA(h, cudaMemcpy(s.dev.p, s.host.data(), bytes, cudaMemcpyHostToDevice));
+    }
+    h->wl_cur = h->wl_cache[hit].dev.p;
+  }
+  if (spec->use_ray_base) h->gen_base = spec->ray_base;
+  h->layer_idx = 0;
+  h->layer_traced = false;
+  h->cont_n = 0;
+  h->injected = false;
+  h->exits_host.clear();
+  h->exit_roots_host.clear();
+  h->exp_d.clear();
+  h->exp_p.clear();
+  h->exp_w.clear();
+  h->exp_rot.clear();
+  h->exp_face.clear();
+  h->exp_shape.clear();
+  h->exp_wl.clear();
+  h->in_session = true;
+  return HB_OK;
+}
+
+int hb_inject_rays(HbEngine* h, uint64_t n, const float* d3, const float* p3, const float* w, const uint16_t* to_face,
+                   const float* rot9) {
+  if (h == nullptr || d3 == nullptr || p3 == nullptr || w == nullptr || to_face == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->in_session || h->layer_idx != 0 || h->layer_traced) return fail(h, HB_ERR_STATE, "inject_rays: only before the first TraceLayer");
+  h->inj_P.resize(n);
+  h->inj_D.resize(n);
+  h->inj_Q.resize(n);
+  for (uint64_t i = 0; i < n; i++) {
+    const uint32_t f = to_face[i] == HB_INVALID_FACE ? kFaceInvalid : (to_face[i] & 63u);
+    const uint32_t bits = (f & 63u);
+    float fb;
+    std::memcpy(&fb, &bits, 4);
+    h->inj_P[i] = make_float4(p3[i * 3], p3[i * 3 + 1], p3[i * 3 + 2], fb);
+    h->inj_D[i] = make_float4(d3[i * 3], d3[i * 3 + 1], d3[i * 3 + 2], w[i]);
+    float4 q = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+    if (rot9 != nullptr) {  // rotation matrix -> unit quaternion (approximate inverse of rot_from_quat)
+      const float* m = rot9 + i * 9;
+      const float tr = m[0] + m[4] + m[8];
+      if (tr > 0.0f) {
+        float s = std::sqrt(tr + 1.0f) * 2.0f;
+        q = make_float4(0.25f * s, (m[7] - m[5]) / s, (m[2] - m[6]) / s, (m[3] - m[1]) / s);
+      } else if (m[0] > m[4] && m[0] > m[8]) {
+        float s = std::sqrt(1.0f + m[0] - m[4] - m[8]) * 2.0f;
+        q = make_float4((m[7] - m[5]) / s, 0.25f * s, (m[1] + m[3]) / s, (m[2] + m[6]) / s);
+      } else if (m[4] > m[8]) {
+        float s = std::sqrt(1.0f + m[4] - m[0] - m[8]) * 2.0f;
+        q = make_float4((m[2] - m[6]) / s, (m[1] + m[3]) / s, 0.25f * s, (m[5] + m[7]) / s);
+      } else {
+        float s = std::sqrt(1.0f + m[8] - m[0] - m[4]) * 2.0f;
+        q = make_float4((m[3] - m[1]) / s, (m[2] + m[6]) / s, (m[5] + m[7]) / s, 0.25f * s);
+      }
+    }
+    h->inj_Q[i] = q;
+  }
+  h->injected = true;
+  return HB_OK;
+}
+
+int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats) {
+  if (h == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->in_session) return fail(h, HB_ERR_STATE, "TraceLayer outside BeginSession/EndSession");
+  if (h->layer_traced) return fail(h, HB_ERR_STATE, "TraceLayer called twice without Recombine");
+  if (h->layer_idx >= h->layers.size()) return fail(h, HB_ERR_STATE, "TraceLayer beyond the configured layers");
+  cudaSetDevice(h->device);
+  const uint32_t li = h->layer_idx;
+  LayerDev& L = *h->layers[li];
+  uint64_t n = 0;
+  if (li == 0) {
+    n = h->injected ? h->inj_P.size() : n_roots;
+  } else {
+    if (n_roots != 0) return fail(h, HB_ERR_INVALID_ARG, "continuation layers take n_roots == 0 (RootRaySource::FromDevice)");
+    n = h->cont_n;
+  }
+  if (n >= (1ull << 31)) return fail(h, HB_ERR_CAPACITY, "one TraceLayer call is limited to 2^31 - 1 rays; split the batch");
+  const bool last_layer = li + 1 == h->layers.size();
+  const uint32_t flags = session_flags(h, L, last_layer);
+
+  // PartitionCrystalRayNum: contiguous index range per population
+  std::vector<uint64_t> counts(L.pops.size(), 0), pop_begin(L.pops.size() + 1, 0);
+  if (li == 0 && h->injected) {
+    counts[0] = n;
+  } else if (n > 0) {
+    std::vector<float> prop;
+    for (auto& p : L.pops) prop.push_back(p.proportion);
+    hb_partition_rays(prop.data(), static_cast<uint32_t>(prop.size()), n, L.carry.data(), counts.data());
+  }
+  for (size_t i = 0; i < counts.size(); i++) pop_begin[i + 1] = pop_begin[i] + counts[i];
+
+  // continuation pool of this layer (only when its exits can continue)
+  HB_CUDA(h, h->counters.ensure(8));
+  HB_CUDA(h, h->stat_cnt.ensure(1));
+  HB_CUDA(h, h->stat_sum.ensure(1));
+  HB_CUDA(h, cudaMemsetAsync(h->counters.p + 2, 0, 3 * sizeof(uint32_t), h->stream));  // cont_count, exit_count, error
+  HB_CUDA(h, cudaMemsetAsync(h->stat_cnt.p, 0, sizeof(unsigned long long), h->stream));
+  HB_CUDA(h, cudaMemsetAsync(h->stat_sum.p, 0, sizeof(double), h->stream));
+  if (flags & kFlagGate) {
+    const uint64_t ccap = std::min<uint64_t>(n * (h->max_hits + 1) + 4096, 0xFFFFFFF0ull);
+    HB_CUDA(h, h->cont_dw[h->cont_cur].ensure(ccap));
+    HB_CUDA(h, h->cont_meta[h->cont_cur].ensure(ccap));
+    if (h->spec.record_exits) HB_CUDA(h, h->cont_root[h->cont_cur].ensure(ccap));
+  }
+
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (stats != nullptr) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->stream);
+  }
+  uint64_t tile = h->tile_rays;
+  if (flags & kFlagRecord) tile = std::min<uint64_t>(tile, 1u << 18);
+  for (uint64_t r0 = 0; r0 < n; r0 += tile) {
+    const uint32_t cnt = static_cast<uint32_t>(std::min<uint64_t>(tile, n - r0));
+    int rc = trace_tile(h, li, r0, cnt, pop_begin, flags, n);
+    if (rc != HB_OK) return rc;
+  }
+  if (li == 0 && !h->injected) h->gen_base += n;
+  if (li > 0) h->transit_base += n;
+  h->gate_base += n;
+  h->layer_traced = true;
+
+  if (stats != nullptr || (flags & kFlagGate)) {
+    uint32_t c[3] = { 0, 0, 0 };
+    unsigned long long ec = 0;
+    double ws = 0.0;
+    if (stats != nullptr) cudaEventRecord(e1, h->stream);
+    HB_CUDA(h, cudaMemcpyAsync(c, h->counters.p + 2, 12, cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(&ec, h->stat_cnt.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(&ws, h->stat_sum.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->profile) flush_events(h);
+    if (c[2] != 0) return fail(h, HB_ERR_CAPACITY, "device buffer overflow (code " + std::to_string(c[2]) + ")");
+    h->cont_n = c[0];
+    if (stats != nullptr) {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      h->ctr.last_layer_ms = ms;
+      stats->root_count = n;
+      stats->continuation_count = c[0];
+      stats->exit_count = ec;
+      stats->exit_w_sum = ws;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+  } else {
+    h->cont_n = 0;
+  }
+  return HB_OK;
+}
+
+int hb_recombine(HbEngine* h, int shuffle, uint64_t* continuation_count) {
+  if (h == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->in_session || !h->layer_traced) return fail(h, HB_ERR_STATE, "Recombine must follow a TraceLayer");
+  h->layer_traced = false;
+  h->layer_idx++;
+  h->cont_shuffle = shuffle != 0 && h->cont_n > 1;
+  h->shuffle_round++;
+  h->cont_cur ^= 1;  // the pool just filled becomes the source of the next layer
+  h->injected = false;
+  if (continuation_count) *continuation_count = h->cont_n;
+  return HB_OK;
+}
+
+int hb_end_session(HbEngine* h) {
+  if (h == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->in_session) return fail(h, HB_ERR_STATE, "EndSession without BeginSession");
+  h->in_session = false;
+  h->layer_traced = false;
+  h->layer_idx = 0;
+  h->injected = false;
+  return HB_OK;
+}
+
+int hb_readback_xyz(HbEngine* h, float* xyz, float* landed) {
+  if (h == nullptr || xyz == nullptr || landed == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->have_render) return fail(h, HB_ERR_STATE, "readback before hb_set_render");
+  cudaSetDevice(h->device);
+  const uint32_t pix = static_cast<uint32_t>(h->proj.img_w) * h->proj.img_h;
+  drain_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->xyz_stage.p, h->landed_dev.p, pix);
+  h->ctr.kernel_launches++;
+  double l = 0.0;
+  HB_CUDA(h, cudaMemcpyAsync(xyz, h->xyz_stage.p, static_cast<size_t>(pix) * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  HB_CUDA(h, cudaMemcpyAsync(&l, h->landed_dev.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  HB_CUDA(h, cudaMemsetAsync(h->landed_dev.p, 0, sizeof(double), h->stream));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->profile) flush_events(h);
+  *landed += static_cast<float>(l);
+  return HB_OK;
+}
+
+int hb_drain_exits(HbEngine* h, HbExitRecord* out, uint32_t* root_ids, uint64_t cap, uint64_t* count) {
+  if (h == nullptr || count == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->in_session) return fail(h, HB_ERR_STATE, "DrainExits outside a session");
+  *count = h->exits_host.size();
+  if (out == nullptr) return HB_OK;
+  if (cap < h->exits_host.size()) return fail(h, HB_ERR_CAPACITY, "DrainExits: caller buffer too small (grow, not clamp)");
+  if (!h->exits_host.empty()) {
+    std::memcpy(out, h->exits_host.data(), h->exits_host.size() * sizeof(HbExitRecord));
+    if (root_ids) std::memcpy(root_ids, h->exit_roots_host.data(), h->exit_roots_host.size() * 4);
+  }
+  h->exits_host.clear();
+  h->exit_roots_host.clear();
+  return HB_OK;
+}
+
+int hb_export_roots(HbEngine* h, uint64_t cap, float* d3, float* p3, float* w, uint16_t* to_face, float* rot9,
+                    uint32_t* shape_idx, uint32_t* wl_idx, uint64_t* count) {
+  if (h == nullptr || count == nullptr) return HB_ERR_INVALID_ARG;
+  const uint64_t n = h->exp_w.size();
+  *count = n;
+  if (d3 == nullptr) return HB_OK;
+  if (cap < n) return fail(h, HB_ERR_CAPACITY, "export_roots: caller buffer too small");
+  std::memcpy(d3, h->exp_d.data(), n * 12);
+  std::memcpy(p3, h->exp_p.data(), n * 12);
+  std::memcpy(w, h->exp_w.data(), n * 4);
+  std::memcpy(to_face, h->exp_face.data(), n * 2);
+  if (rot9) std::memcpy(rot9, h->exp_rot.data(), n * 36);
+  if (shape_idx) std::memcpy(shape_idx, h->exp_shape.data(), n * 4);
+  if (wl_idx) std::memcpy(wl_idx, h->exp_wl.data(), n * 4);
+  h->exp_d.clear();
+  h->exp_p.clear();
+  h->exp_w.clear();
+  h->exp_rot.clear();
+  h->exp_face.clear();
+  h->exp_shape.clear();
+  h->exp_wl.clear();
+  return HB_OK;
+}
+
+int hb_set_option(HbEngine* h, const char* key, int64_t value) {
+  if (h == nullptr || key == nullptr) return HB_ERR_INVALID_ARG;
+  const std::string k(key);
+  if (k == "tile_rays") {
+    if (value < 1024 || value > (1ll << 30)) return fail(h, HB_ERR_INVALID_ARG, "tile_rays out of range");
+    h->tile_rays = static_cast<uint64_t>(value);
+  } else if (k == "profile") {
+    h->profile = value != 0;
+  } else if (k == "blocks_per_sm") {
+    if (value < 1 || value > 32) return fail(h, HB_ERR_INVALID_ARG, "blocks_per_sm out of range");
+    h->blocks_per_sm = static_cast<int>(value);
+  } else if (k == "gen_base") {
+    h->gen_base = static_cast<uint64_t>(value);
+  } else if (k == "stream_base") {  // restart all monotone stream counters (tests: reproducible replays)
+    h->gen_base = h->gate_base = h->transit_base = static_cast<uint64_t>(value);
+    h->shuffle_round = 0;
+    for (auto& L : h->layers) std::fill(L->carry.begin(), L->carry.end(), 0.0);
+  } else {
+    return fail(h, HB_ERR_INVALID_ARG, "unknown option " + k);
+  }
+  return HB_OK;
+}
+
+int hb_get_counters(HbEngine* h, HbCounters* out) {
+  if (h == nullptr || out == nullptr) return HB_ERR_INVALID_ARG;
+  *out = h->ctr;
+  return HB_OK;
+}
+
+int hb_synchronize(HbEngine* h) {
+  if (h == nullptr) return HB_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->profile) flush_events(h);
+  uint32_t err = 0;
+  if (h->counters.p) {
+    HB_CUDA(h, cudaMemcpy(&err, h->counters.p + 4, 4, cudaMemcpyDeviceToHost));
+    if (err != 0) return fail(h, HB_ERR_CAPACITY, "device buffer overflow (code " + std::to_string(err) + ")");
+  }
+  return HB_OK;
+}
+
+int hb_image_device_ptr(HbEngine* h, void** ptr, uint64_t* float_count) {
+  if (h == nullptr || ptr == nullptr || float_count == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->have_render) return fail(h, HB_ERR_STATE, "no render set");
+  *ptr = h->image.p;
+  *float_count = static_cast<uint64_t>(h->proj.img_w) * h->proj.img_h * 4;
+  return HB_OK;
+}
+
+void* hb_stream(HbEngine* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+
+int hb_comm_unique_id(void* out) {
+#ifdef HB_WITH_NCCL
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return HB_ERR_COMM;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  std::memcpy(out, &id, 128);
+  return HB_OK;
+#else
+  (void)out;
+  return HB_ERR_UNSUPPORTED;
+#endif
+}
+
+int hb_comm_init(HbEngine* h, const void* id128, int rank, int nranks) {
+  if (h == nullptr || id128 == nullptr) return HB_ERR_INVALID_ARG;
+#ifdef HB_WITH_NCCL
+  cudaSetDevice(h->device);
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  if (ncclCommInitRank(&h->comm, nranks, id, rank) != ncclSuccess) return fail(h, HB_ERR_COMM, "ncclCommInitRank failed");
+  h->rank = rank;
+  h->nranks = nranks;
+  return HB_OK;
+#else
+  (void)rank;
+  (void)nranks;
+  return fail(h, HB_ERR_UNSUPPORTED, "library built without NCCL");
+#endif
+}
+
+int hb_allreduce_image(HbEngine* h) {
+  if (h == nullptr) return HB_ERR_INVALID_ARG;
+#ifdef HB_WITH_NCCL
+  if (h->comm == nullptr) return fail(h, HB_ERR_STATE, "hb_comm_init not called");
+  cudaSetDevice(h->device);
+  const size_t cnt = static_cast<size_t>(h->proj.img_w) * h->proj.img_h * 4;
+  if (ncclAllReduce(h->image.p, h->image.p, cnt, ncclFloat, ncclSum, h->comm, h->stream) != ncclSuccess)
+    return fail(h, HB_ERR_COMM, "ncclAllReduce failed");
+  return HB_OK;
+#else
+  return fail(h, HB_ERR_UNSUPPORTED, "library built without NCCL");
+#endif
+}
+
+}  // extern "C"

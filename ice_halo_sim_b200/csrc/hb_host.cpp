@@ -1,0 +1,819 @@
+// hb_host.cpp — host-side table builders of the B200 trace engine (no CUDA in this file).
+//
+// These turn a config-level scene description into the POD tables the kernels consume. When the
+// engine runs behind the reference's TraceBackend seam the adapter fills the same tables with the
+// reference's own host code (MakeCrystal, BuildEntrySubTris, GetSharedLatLut, BuildProjParams,
+// ComputeWlPool); the builders here make the library usable stand-alone and are parity-tested
+// against the reference's tables (tests/test_host_tables.py, tests/golden/).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "halotrace_b200.h"
+#include "hb_filter.h"
+
+namespace hb {
+
+std::string& global_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+namespace {
+
+constexpr double kPiD = 3.14159265358979323846;
+constexpr float kPiF = 3.14159265359f;           // reference math::kPi (src/core/math.hpp:20)
+constexpr float kDeg2RadF = kPiF / 180.0f;       // math::kDegreeToRad
+constexpr float kSqrt3F = 1.73205080757f;        // math::kSqrt3
+constexpr float kFloatEps = 1e-5f;               // math::kFloatEps
+constexpr double kSqrt3Half = 0.86602540378443864676;
+// Hexagon face-normal directions (theta_i = i*60 deg) and corner directions (i*60 - 30 deg),
+// reference: geo3d_closedform.hpp:12-19.
+const double kFaceCos[6] = { 1.0, 0.5, -0.5, -1.0, -0.5, 0.5 };
+const double kFaceSin[6] = { 0.0, kSqrt3Half, kSqrt3Half, 0.0, -kSqrt3Half, -kSqrt3Half };
+const double kVtxCos[6] = { kSqrt3Half, kSqrt3Half, 0.0, -kSqrt3Half, -kSqrt3Half, 0.0 };
+const double kVtxSin[6] = { -0.5, 0.5, 1.0, 0.5, -0.5, -1.0 };
+
+struct V3 {
+  double x, y, z;
+};
+V3 operator+(V3 a, V3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+V3 operator-(V3 a, V3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+V3 operator*(V3 a, double s) { return { a.x * s, a.y * s, a.z * s }; }
+double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+V3 cross(V3 a, V3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+
+// A convex crystal given as up to 20 half-spaces coef.(x,y,z,1) <= 0 in the reference's slot order
+// (0,1 basal; 2-7 prism; 8-13 upper pyramid; 14-19 lower pyramid; crystal.cpp:326-346).
+struct PlaneSet {
+  int slot_cnt = 0;
+  float coef[HB_MAX_FACES][4]{};
+  float unit_n[HB_MAX_FACES][3]{};
+  int face_number[HB_MAX_FACES]{};
+  bool candidate[HB_MAX_FACES]{};
+};
+
+// Clip a convex polygon (3-D points on a plane) by the half-space c.(p,1) <= 0 (Sutherland-Hodgman).
+void ClipPolygon(std::vector<V3>& poly, const double c[4], double tol) {
+  if (poly.empty()) return;
+  std::vector<V3> out;
+  size_t n = poly.size();
+  for (size_t i = 0; i < n; i++) {
+    V3 a = poly[i], b = poly[(i + 1) % n];
+    double fa = c[0] * a.x + c[1] * a.y + c[2] * a.z + c[3];
+    double fb = c[0] * b.x + c[1] * b.y + c[2] * b.z + c[3];
+    bool ina = fa <= tol, inb = fb <= tol;
+    if (ina) out.push_back(a);
+    if (ina != inb) {
+      double t = fa / (fa - fb);
+      out.push_back(a + (b - a) * t);
+    }
+  }
+  poly.swap(out);
+}
+
+void DedupRing(std::vector<V3>& poly, double tol) {
+  std::vector<V3> out;
+  for (const V3& p : poly) {
+    if (!out.empty()) {
+      V3 d = p - out.back();
+      if (std::sqrt(dot(d, d)) < tol) continue;
+    }
+    out.push_back(p);
+  }
+  while (out.size() > 1) {
+    V3 d = out.front() - out.back();
+    if (std::sqrt(dot(d, d)) < tol) out.pop_back(); else break;
+  }
+  poly.swap(out);
+}
+
+// Face polygons of the intersection of the candidate half-spaces, each CCW seen from outside.
+// Produces the compact present-face tables + the entry fan table (BuildEntrySubTris convention:
+// fan (0,k,k+1), raw-winding normal, area = |cross|/2; simulator.cpp:90-129).
+int BuildTablesFromPlanes(const PlaneSet& ps, HbCrystalTables* out) {
+  std::memset(out, 0, sizeof(*out));
+  uint32_t face = 0, tri = 0;
+  for (int s = 0; s < ps.slot_cnt; s++) {
+    if (!ps.candidate[s]) continue;
+    V3 n{ ps.coef[s][0], ps.coef[s][1], ps.coef[s][2] };
+    double mag = std::sqrt(dot(n, n));
+    if (!(mag > 0)) continue;
+    V3 nu = n * (1.0 / mag);
+    double d0 = ps.coef[s][3] / mag;
+    V3 origin = nu * (-d0);
+    V3 helper = std::fabs(nu.z) < 0.9 ? V3{ 0, 0, 1 } : V3{ 1, 0, 0 };
+    V3 t1 = cross(helper, nu);
+    t1 = t1 * (1.0 / std::sqrt(dot(t1, t1)));
+    V3 t2 = cross(nu, t1);  // t1 x t2 = nu  => (t1,t2)-CCW is CCW seen from outside
+    const double big = 1.0e3;
+    std::vector<V3> poly = { origin + t1 * (-big) + t2 * (-big), origin + t1 * big + t2 * (-big),
+                             origin + t1 * big + t2 * big, origin + t1 * (-big) + t2 * big };
+    for (int j = 0; j < ps.slot_cnt && !poly.empty(); j++) {
+      if (j == s || !ps.candidate[j]) continue;
+      double c[4] = { ps.coef[j][0], ps.coef[j][1], ps.coef[j][2], ps.coef[j][3] };
+      double cm = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+      if (!(cm > 0)) continue;
+      for (double& v : c) v /= cm;
+      ClipPolygon(poly, c, 1e-12);
+    }
+    DedupRing(poly, 1e-7);
+    if (poly.size() < 3) continue;
+    double area2 = 0;
+    for (size_t k = 1; k + 1 < poly.size(); k++) {
+      V3 cr = cross(poly[k] - poly[0], poly[k + 1] - poly[0]);
+      area2 += dot(cr, nu);
+    }
+    if (!(area2 > 1e-10)) continue;
+    if (poly.size() > HB_MAX_FACE_VTX) {
+      global_error() = "crystal face has more than 12 corners";
+      return HB_ERR_CAPACITY;
+    }
+    // --- present face: plane entry (PopulateFromCfGeom, crystal.cpp:304-347) ---
+    out->plane[face][0] = ps.unit_n[s][0];
+    out->plane[face][1] = ps.unit_n[s][1];
+    out->plane[face][2] = ps.unit_n[s][2];
+    const float* cf = ps.coef[s];
+    float nrm = std::sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]);
+    out->plane[face][3] = nrm > kFloatEps ? cf[3] / nrm : 0.0f;
+    out->face_fn[face] = static_cast<uint8_t>(ps.face_number[s]);
+    // --- fan sub-triangles ---
+    std::vector<float> v(poly.size() * 3);
+    for (size_t k = 0; k < poly.size(); k++) {
+      v[k * 3 + 0] = static_cast<float>(poly[k].x);
+      v[k * 3 + 1] = static_cast<float>(poly[k].y);
+      v[k * 3 + 2] = static_cast<float>(poly[k].z);
+    }
+    for (size_t k = 1; k + 1 < poly.size(); k++) {
+      if (tri >= HB_MAX_SUBTRIS) {
+        global_error() = "crystal needs more than 64 entry sub-triangles";
+        return HB_ERR_CAPACITY;
+      }
+      float* tv = out->tri_v[tri];
+      std::memcpy(tv + 0, &v[0], 12);
+      std::memcpy(tv + 3, &v[k * 3], 12);
+      std::memcpy(tv + 6, &v[(k + 1) * 3], 12);
+      float e1[3] = { tv[3] - tv[0], tv[4] - tv[1], tv[5] - tv[2] };
+      float e2[3] = { tv[6] - tv[0], tv[7] - tv[1], tv[8] - tv[2] };
+      float cr[3] = { -e2[1] * e1[2] + e1[1] * e2[2], e2[0] * e1[2] - e1[0] * e2[2], -e2[0] * e1[1] + e1[0] * e2[1] };
+      float len = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+      out->tri_area[tri] = len / 2.0f;
+      for (int q = 0; q < 3; q++) out->tri_n[tri][q] = len > 0.0f ? cr[q] / len : 0.0f;
+      out->tri_face[tri] = static_cast<uint8_t>(face);
+      tri++;
+    }
+    face++;
+  }
+  out->face_cnt = face;
+  out->subtri_cnt = tri;
+  if (face < 4) {  // not a solid: the reference returns an empty Crystal (crystal.cpp:80-100)
+    std::memset(out, 0, sizeof(*out));
+  }
+  return HB_OK;
+}
+
+// Largest inset m (in face-distance units) for which the hexagonal cross-section
+// { n_i . x <= (sqrt3/4)(dist_i - m) } is non-empty: a 3-variable LP solved by vertex enumeration.
+// This is the apex height parameter of a pyramidal segment (geo3d_closedform.cpp MaxFeasibleInsetLP).
+double ApexInset(const float dist[6]) {
+  const double k = 0.25 * 1.7320508075688772935;
+  double best = -std::numeric_limits<double>::infinity();
+  bool found = false;
+  for (int a = 0; a < 6; a++)
+    for (int b = a + 1; b < 6; b++)
+      for (int c = b + 1; c < 6; c++) {
+        int id[3] = { a, b, c };
+        double M[3][4];
+        for (int r = 0; r < 3; r++) {
+          M[r][0] = kFaceCos[id[r]];
+          M[r][1] = kFaceSin[id[r]];
+          M[r][2] = k;
+          M[r][3] = k * dist[id[r]];
+        }
+        double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                     M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+        if (std::fabs(det) < 1e-12) continue;
+        auto det3 = [&](int col) {
+          double T[3][3];
+          for (int r = 0; r < 3; r++)
+            for (int q = 0; q < 3; q++) T[r][q] = q == col ? M[r][3] : M[r][q];
+          return T[0][0] * (T[1][1] * T[2][2] - T[1][2] * T[2][1]) - T[0][1] * (T[1][0] * T[2][2] - T[1][2] * T[2][0]) +
+                 T[0][2] * (T[1][0] * T[2][1] - T[1][1] * T[2][0]);
+        };
+        double u = det3(0) / det, v = det3(1) / det, m = det3(2) / det;
+        bool ok = true;
+        for (int i = 0; i < 6 && ok; i++) ok = kFaceCos[i] * u + kFaceSin[i] * v + k * m <= k * dist[i] + 1e-9;
+        if (ok && (!found || m > best)) {
+          best = m;
+          found = true;
+        }
+      }
+  return found ? std::max(best, 0.0) : 0.0;
+}
+
+void PrismPlanes(float h, const float dist[6], PlaneSet* ps) {
+  // geo3d_closedform.cpp ComputeClosedFormPrism: basal (0,0,+-1,-h/2); side i 0.5(cos,sin,0), d = -dist*sqrt3/8.
+  ps->slot_cnt = 8;
+  float hh = 0.5f * h;
+  float basal[2][4] = { { 0, 0, 1, -hh }, { 0, 0, -1, -hh } };
+  for (int s = 0; s < 2; s++) {
+    std::memcpy(ps->coef[s], basal[s], 16);
+    ps->unit_n[s][0] = 0;
+    ps->unit_n[s][1] = 0;
+    ps->unit_n[s][2] = basal[s][2];
+    ps->face_number[s] = s + 1;
+    ps->candidate[s] = true;
+  }
+  double kd = static_cast<double>(kSqrt3F) / 8.0;
+  for (int i = 0; i < 6; i++) {
+    int s = 2 + i;
+    ps->coef[s][0] = 0.5f * static_cast<float>(kFaceCos[i]);
+    ps->coef[s][1] = 0.5f * static_cast<float>(kFaceSin[i]);
+    ps->coef[s][2] = 0.0f;
+    ps->coef[s][3] = -static_cast<float>(kd * static_cast<double>(dist[i]));
+    ps->unit_n[s][0] = static_cast<float>(kFaceCos[i]);
+    ps->unit_n[s][1] = static_cast<float>(kFaceSin[i]);
+    ps->unit_n[s][2] = 0.0f;
+    ps->face_number[s] = 3 + i;
+    ps->candidate[s] = true;
+  }
+}
+
+}  // namespace
+}  // namespace hb
+
+using namespace hb;  // NOLINT
+
+extern "C" {
+
+uint32_t hb_abi_version(void) { return HB_ABI_VERSION; }
+
+int hb_make_prism(float h, const float dist6[6], HbCrystalTables* out) {
+  if (out == nullptr || dist6 == nullptr) return HB_ERR_INVALID_ARG;
+  std::memset(out, 0, sizeof(*out));
+  if (!(h > kFloatEps)) return HB_OK;  // zero-volume: empty crystal (crystal.cpp:80-82)
+  PlaneSet ps;
+  PrismPlanes(h, dist6, &ps);
+  return BuildTablesFromPlanes(ps, out);
+}
+
+int hb_make_pyramid(float upper_alpha, float lower_alpha, float h1, float h2, float h3, const float dist[6],
+                    HbCrystalTables* out) {
+  if (out == nullptr || dist == nullptr) return HB_ERR_INVALID_ARG;
+  std::memset(out, 0, sizeof(*out));
+  // geo3d_closedform.cpp ComputeClosedFormPyramid + ComputeClosedFormPyramidInner: a = (sqrt3/4)/tan(alpha)
+  // when the segment exists (h > eps and alpha in [0.1, 89.9] deg).
+  double a1 = -1.0, a2 = -1.0;
+  const float sqrt3_4 = kSqrt3F / 4.0f;
+  if (h1 > kFloatEps && upper_alpha >= 0.1f && upper_alpha <= 89.9f)
+    a1 = static_cast<double>(sqrt3_4) / std::tan(static_cast<double>(upper_alpha) * static_cast<double>(kDeg2RadF));
+  if (h3 > kFloatEps && lower_alpha >= 0.1f && lower_alpha <= 89.9f)
+    a2 = static_cast<double>(sqrt3_4) / std::tan(static_cast<double>(lower_alpha) * static_cast<double>(kDeg2RadF));
+  bool has_upper = a1 > 0, has_lower = a2 > 0;
+  const double h2_2 = 0.5 * static_cast<double>(h2);
+  if (!has_upper && !has_lower && h2 < kFloatEps) return HB_OK;
+
+  PlaneSet ps;
+  ps.slot_cnt = 20;
+  ps.face_number[0] = 1;
+  ps.face_number[1] = 2;
+  for (int i = 0; i < 6; i++) {
+    ps.face_number[2 + i] = 3 + i;
+    ps.face_number[8 + i] = 13 + i;
+    ps.face_number[14 + i] = 23 + i;
+    int i2 = (i + 1) % 6;
+    double x1 = 0.5 * kVtxCos[i], x2 = 0.5 * kVtxCos[i2], y1 = 0.5 * kVtxSin[i], y2 = 0.5 * kVtxSin[i2];
+    double det = x1 * y2 - x2 * y1;
+    float* c = ps.coef[2 + i];
+    c[0] = static_cast<float>(y2 - y1);
+    c[1] = static_cast<float>(x1 - x2);
+    c[2] = 0;
+    c[3] = static_cast<float>(-static_cast<double>(dist[i]) * det);
+    ps.candidate[2 + i] = h2 > 0.0f || true;
+    if (has_upper) {
+      float* u = ps.coef[8 + i];
+      u[0] = static_cast<float>(a1 * (y2 - y1));
+      u[1] = static_cast<float>(a1 * (x1 - x2));
+      u[2] = static_cast<float>(det);
+      u[3] = static_cast<float>(-(h2_2 + a1 * static_cast<double>(dist[i])) * det);
+      ps.candidate[8 + i] = true;
+    }
+    if (has_lower) {
+      float* l = ps.coef[14 + i];
+      l[0] = static_cast<float>(a2 * (y2 - y1));
+      l[1] = static_cast<float>(a2 * (x1 - x2));
+      l[2] = static_cast<float>(-det);
+      l[3] = static_cast<float>(-(h2_2 + a2 * static_cast<double>(dist[i])) * det);
+      ps.candidate[14 + i] = true;
+    }
+  }
+  double m_apex = (has_upper || has_lower) ? ApexInset(dist) : 0.0;
+  double m_top = has_upper ? std::min(static_cast<double>(h1) * m_apex, m_apex) : 0.0;
+  double m_bot = has_lower ? std::min(static_cast<double>(h3) * m_apex, m_apex) : 0.0;
+  double z_top = has_upper ? h2_2 + a1 * m_top : h2_2;
+  double z_bot = has_lower ? -h2_2 - a2 * m_bot : -h2_2;
+  float basal[2][4] = { { 0, 0, 1, static_cast<float>(-z_top) }, { 0, 0, -1, static_cast<float>(z_bot) } };
+  for (int s = 0; s < 2; s++) {
+    std::memcpy(ps.coef[s], basal[s], 16);
+    ps.candidate[s] = true;
+  }
+  ps.unit_n[0][2] = 1.0f;
+  ps.unit_n[1][2] = -1.0f;
+  for (int s = 2; s < 20; s++) {
+    double nx = ps.coef[s][0], ny = ps.coef[s][1], nz = ps.coef[s][2];
+    double mag = std::sqrt(nx * nx + ny * ny + nz * nz);
+    if (mag > 0) {
+      ps.unit_n[s][0] = static_cast<float>(nx / mag);
+      ps.unit_n[s][1] = static_cast<float>(ny / mag);
+      ps.unit_n[s][2] = static_cast<float>(nz / mag);
+    }
+  }
+  return BuildTablesFromPlanes(ps, out);
+}
+
+// IceRefractiveIndex::Get, optics.cpp:180-198 (Sellmeier fit, valid 350..900 nm, float coefficients).
+double hb_ice_refractive_index(double wl) {
+  const float coef[4] = { 0.701777f, 1.091144f, 0.884400f, 0.796950f };
+  if (wl < 350.0f || wl > 900.0f) return 1.0f;
+  wl /= 1e3;
+  double n = 1.0;
+  n += coef[0] / (1 - coef[2] * 1e-2f / wl / wl);
+  n += coef[1] / (1 - coef[3] * 1e2f / wl / wl);
+  return std::sqrt(n);
+}
+
+}  // extern "C"
+
+// ---- CIE 1931 2-degree observer, 1 nm, 360..830 nm -------------------------------------------------
+namespace hb {
+namespace {
+const float kCie1931[471][3] = {
+#include "cie1931_2deg_1nm.inc"
+};
+
+// --- latitude inverse-CDF LUT: area-measure mass of the latitude proposal over colatitude,
+// resampled to 257 uniform-theta nodes (reference: lat_lut.cpp:74-180). ---
+void FoldLatitude(float phi, float& phi_out, bool& flip) {  // pcg_shared.h:311-322
+  const float pi = 3.14159265358979323846f, pi2 = 1.5707963267948966f;
+  float theta = pi2 - phi;
+  theta = std::fmod(theta, 2.0f * pi);
+  if (theta < 0.0f) theta += 2.0f * pi;
+  flip = theta > pi;
+  if (flip) theta = 2.0f * pi - theta;
+  phi_out = pi2 - theta;
+}
+
+void DegenerateLut(double colat, HbAxisSampler* out) {
+  float c = static_cast<float>(std::min(std::max(colat, 0.0), kPiD));
+  for (uint32_t i = 0; i < HB_LUT_NODES; i++) {
+    out->lut_theta[i] = c;
+    out->lut_cdf[i] = static_cast<float>(i) / static_cast<float>(HB_LUT_NODES - 1);
+    out->lut_flip[i] = 0.0f;
+  }
+}
+
+void BuildLatLut(uint32_t type, float center_deg, float spread_deg, HbAxisSampler* out) {
+  const int kFine = 4096, kQuad = 1 << 16;
+  const double mean = static_cast<double>(center_deg) * (kPiD / 180.0);
+  const double scale = static_cast<double>(spread_deg) * (kPiD / 180.0);
+  const double dth = kPiD / kFine;
+  std::vector<double> mass(kFine, 0.0), fmass(kFine, 0.0);
+  auto add = [&](double lat, double weight) {
+    float phi = 0;
+    bool flip = false;
+    FoldLatitude(static_cast<float>(lat), phi, flip);
+    double th = kPiD / 2.0 - static_cast<double>(phi);
+    double w = weight * std::sin(th);
+    if (w <= 0.0) return;
+    int bin = std::min(std::max(static_cast<int>(th / dth), 0), kFine - 1);
+    mass[bin] += w;
+    if (flip) fmass[bin] += w;
+  };
+  if (type == HB_DIST_GAUSSIAN) {
+    double lo = mean - 12.0 * scale, hi = mean + 12.0 * scale, dl = (hi - lo) / kQuad;
+    double inv = scale > 0.0 ? 1.0 / (2.0 * scale * scale) : 0.0;
+    for (int i = 0; i < kQuad; i++) {
+      double l = lo + (i + 0.5) * dl, d = l - mean;
+      add(l, std::exp(-d * d * inv) * dl);
+    }
+  } else {
+    double du = 1.0 / kQuad;
+    for (int i = 0; i < kQuad; i++) {
+      double u = (i + 0.5) * du, l = mean;
+      if (type == HB_DIST_UNIFORM) {
+        l = (u - 0.5) * scale + mean;
+      } else if (type == HB_DIST_ZIGZAG) {
+        l = std::fabs(scale * std::sin(u * 2.0 * kPiD) + mean);
+      } else if (type == HB_DIST_LAPLACIAN) {
+        double sg = u < 0.5 ? -1.0 : 1.0;
+        l = mean - scale * sg * std::log(std::max(1.0 - 2.0 * std::fabs(u - 0.5), 1e-30));
+      }
+      add(l, du);
+    }
+  }
+  std::vector<double> cm(kFine + 1, 0.0), cf(kFine + 1, 0.0);
+  for (int i = 0; i < kFine; i++) {
+    cm[i + 1] = cm[i] + mass[i];
+    cf[i + 1] = cf[i] + fmass[i];
+  }
+  auto lerp = [&](const std::vector<double>& c, double th) {
+    double x = th / dth;
+    int i = static_cast<int>(x);
+    if (i < 0) return c.front();
+    if (i >= kFine) return c.back();
+    double f = x - i;
+    return c[i] * (1.0 - f) + c[i + 1] * f;
+  };
+  double total = cm[kFine];
+  if (!(total > 0.0)) {
+    float phi = 0;
+    bool flip = false;
+    FoldLatitude(static_cast<float>(mean), phi, flip);
+    DegenerateLut(kPiD / 2.0 - static_cast<double>(phi), out);
+    return;
+  }
+  double tlo = 0.0, thi = kPiD;
+  for (int i = 0; i <= kFine; i++)
+    if (cm[i] / total >= 1e-7) {
+      tlo = i * dth;
+      break;
+    }
+  for (int i = kFine; i >= 0; i--)
+    if (cm[i] / total <= 1.0 - 1e-7) {
+      thi = i * dth;
+      break;
+    }
+  if (!(thi > tlo)) {
+    DegenerateLut(0.5 * (tlo + thi), out);
+    return;
+  }
+  const uint32_t N = HB_LUT_NODES;
+  for (uint32_t n = 0; n < N; n++) {
+    double t = tlo + (thi - tlo) * n / (N - 1);
+    out->lut_theta[n] = static_cast<float>(t);
+    out->lut_cdf[n] = static_cast<float>(lerp(cm, t) / total);
+  }
+  for (uint32_t n = 1; n < N; n++)
+    if (out->lut_cdf[n] <= out->lut_cdf[n - 1])
+      out->lut_cdf[n] = std::nextafter(out->lut_cdf[n - 1], std::numeric_limits<float>::infinity());
+  for (uint32_t n = 0; n + 1 < N; n++) {
+    double t0 = out->lut_theta[n], t1 = out->lut_theta[n + 1];
+    double m = lerp(cm, t1) - lerp(cm, t0), fm = lerp(cf, t1) - lerp(cf, t0);
+    out->lut_flip[n] = m > 0.0 ? static_cast<float>(std::min(std::max(fm / m, 0.0), 1.0)) : 0.0f;
+  }
+  out->lut_flip[N - 1] = out->lut_flip[N - 2];
+}
+
+bool FloatEq(float a, float b) { return std::fabs(a - b) < kFloatEps; }
+
+// Rotation::FillMat / Chain, geo3d.cpp:35-111 (float arithmetic, left-multiply).
+void AxisAngle(const float* ax, float th, float* m) {
+  float c = std::cos(th), s = std::sin(th), cc = 1 - c;
+  m[0] = ax[0] * ax[0] * cc + c;
+  m[1] = ax[0] * ax[1] * cc - ax[2] * s;
+  m[2] = ax[0] * ax[2] * cc + ax[1] * s;
+  m[3] = ax[0] * ax[1] * cc + ax[2] * s;
+  m[4] = ax[1] * ax[1] * cc + c;
+  m[5] = ax[1] * ax[2] * cc - ax[0] * s;
+  m[6] = ax[0] * ax[2] * cc - ax[1] * s;
+  m[7] = ax[1] * ax[2] * cc + ax[0] * s;
+  m[8] = ax[2] * ax[2] * cc + c;
+}
+void ChainLeft(float* m, const float* r) {
+  float m0[9];
+  std::memcpy(m0, m, 36);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      m[i * 3 + j] = 0;
+      for (int k = 0; k < 3; k++) m[i * 3 + j] += r[i * 3 + k] * m0[k * 3 + j];
+    }
+}
+
+struct SceneStorage {
+  HbScene scene{};
+  std::vector<HbLayer> layers;
+  std::vector<std::vector<HbCrystalPopulation>> pops;
+  std::vector<std::unique_ptr<std::vector<HbCrystalTables>>> shapes;
+};
+
+float DrawDist(std::mt19937& gen, const HbDist& d) {  // RandomNumberGenerator::Get, math.cpp:419-444
+  std::uniform_real_distribution<float> uni(0.0f, 1.0f);
+  std::normal_distribution<float> gau(0.0f, 1.0f);
+  switch (d.type) {
+    case HB_DIST_UNIFORM:
+      return (uni(gen) - 0.5f) * d.spread + d.center;
+    case HB_DIST_GAUSSIAN:
+    case HB_DIST_GAUSSIAN_LEGACY:
+      return gau(gen) * d.spread + d.center;
+    case HB_DIST_ZIGZAG:
+      return std::fabs(d.spread * std::sin(uni(gen) * 2.0f * kPiF) + d.center);
+    case HB_DIST_LAPLACIAN: {
+      float u = uni(gen), sg = u < 0.5f ? -1.0f : 1.0f;
+      float arg = std::max(1.0f - 2.0f * std::fabs(u - 0.5f), std::numeric_limits<float>::min());
+      return d.center - d.spread * sg * std::log(arg);
+    }
+    default:
+      return d.center;
+  }
+}
+
+bool ShapeIsDeterministic(const HbCrystalDesc& c) {  // IsDeterministic, simulator.cpp:453-471
+  int hn = c.kind == 0 ? 1 : 3;
+  for (int i = 0; i < hn; i++)
+    if (c.height[i].type != HB_DIST_NO_RANDOM) return false;
+  for (int i = 0; i < 6; i++)
+    if (c.face_dist[i].type != HB_DIST_NO_RANDOM) return false;
+  return true;
+}
+
+int MakeShape(std::mt19937& gen, const HbCrystalDesc& c, HbCrystalTables* out) {  // MakeCrystal, simulator.cpp:405-450
+  float dist[6];
+  if (c.kind == 0) {
+    float h = std::fabs(DrawDist(gen, c.height[0]));
+    for (int i = 0; i < 6; i++) dist[i] = DrawDist(gen, c.face_dist[i]);
+    return hb_make_prism(h, dist, out);
+  }
+  float h1 = std::fabs(DrawDist(gen, c.height[0]));
+  float h2 = std::fabs(DrawDist(gen, c.height[1]));
+  float h3 = std::fabs(DrawDist(gen, c.height[2]));
+  for (int i = 0; i < 6; i++) dist[i] = DrawDist(gen, c.face_dist[i]);
+  return hb_make_pyramid(c.wedge_upper_deg, c.wedge_lower_deg, h1, h2, h3, dist, out);
+}
+
+// BuildDeviceFilterDesc, device_filter_desc.cpp:130-143 (+ crystal.cpp:710-730 D-symmetry helpers).
+void BuildFilter(const HbPopulationDesc& p, HbFilterDesc* out) {
+  std::memset(out, 0, sizeof(*out));
+  const HbFilterSpecDesc& f = p.filter;
+  out->kind = f.kind;
+  out->action = f.action;
+  out->symmetry = f.symmetry;
+  out->fn_period = 6;
+  const HbDist& az = p.crystal.azimuth;
+  bool az_sym = az.type == HB_DIST_UNIFORM && FloatEq(az.spread, 360.0f);
+  float rem = std::fmod(std::fmod(p.crystal.roll.center, 30.0f) + 30.0f, 30.0f);
+  bool roll30 = FloatEq(rem, 0.0f) || FloatEq(rem, 30.0f);
+  bool d_app = az_sym && roll30;
+  out->d_applicable = d_app ? 1u : 0u;
+  int sigma = 0;
+  if (d_app && !(std::fabs(p.crystal.roll.center) > 1e6f)) {
+    int n = (static_cast<int>(std::round(p.crystal.roll.center / 30.0f)) % 6 + 6) % 6;
+    sigma = (6 - n) % 6;
+  }
+  out->sigma_a = sigma;
+  HbSimpleFilter& s = out->simple;
+  s.kind = f.kind;
+  s.entry_fn = -1;
+  s.exit_fn = -1;
+  if (f.kind == 1) {
+    s.path_len = std::min<uint32_t>(f.path_len, HB_MAX_FILTER_PATH);
+    std::memcpy(s.path, f.path, s.path_len);
+    filter_reduce(s.path, s.path_len, f.symmetry, sigma, d_app);
+  } else if (f.kind == 2) {
+    s.entry_fn = f.entry_fn >= 0 ? 1 : -1;
+    s.exit_fn = f.exit_fn >= 0 ? 1 : -1;
+    s.min_len = f.min_len == 0 ? 1 : f.min_len;
+    s.max_len = f.max_len;
+    uint32_t n = 0;
+    if (f.entry_fn >= 0) s.path[n++] = static_cast<uint8_t>(f.entry_fn);
+    if (f.exit_fn >= 0) s.path[n++] = static_cast<uint8_t>(f.exit_fn);
+    s.path_len = n;
+    if (n > 0) filter_reduce(s.path, n, f.symmetry, sigma, d_app);
+  } else if (f.kind == 3) {
+    float lon = f.lon_deg * kDeg2RadF, lat = f.lat_deg * kDeg2RadF;
+    s.dir[0] = std::cos(lat) * std::cos(lon);
+    s.dir[1] = std::cos(lat) * std::sin(lon);
+    s.dir[2] = std::sin(lat);
+    s.cos_radii = std::cos(f.radii_deg * kDeg2RadF);
+  } else if (f.kind == 4) {
+    s.crystal_id = f.crystal_id;
+  }
+}
+
+}  // namespace
+}  // namespace hb
+
+struct HbSceneTables {
+  hb::SceneStorage st;
+};
+
+extern "C" {
+
+int hb_make_wl_entry(float wl, float weight, HbWlEntry* out) {
+  if (out == nullptr) return HB_ERR_INVALID_ARG;
+  out->n_idx = static_cast<float>(hb_ice_refractive_index(wl));  // Crystal::GetRefractiveIndex, crystal.cpp:703
+  out->spd_weight = weight;
+  int key = static_cast<int>(wl + 0.5f);  // ComputeCmf, wl_pool.hpp:47-58
+  if (key < 360 || key > 830) {
+    out->cmf_x = out->cmf_y = out->cmf_z = 0.0f;
+  } else {
+    out->cmf_x = kCie1931[key - 360][0];
+    out->cmf_y = kCie1931[key - 360][1];
+    out->cmf_z = kCie1931[key - 360][2];
+  }
+  return HB_OK;
+}
+
+int hb_make_axis_sampler(uint32_t lat_type, float lat_c, float lat_s, uint32_t az_type, float az_c, float az_s,
+                         uint32_t roll_type, float roll_c, float roll_s, HbAxisSampler* out) {
+  if (out == nullptr) return HB_ERR_INVALID_ARG;
+  std::memset(out, 0, sizeof(*out));
+  // SelectLatPath, lat_path_selection.hpp:67-81 + AxisDistribution::IsFullSphereUniform, math.cpp:555-559
+  bool full = az_type == HB_DIST_UNIFORM && FloatEq(az_c, 0.0f) && FloatEq(az_s, 360.0f) &&
+              lat_type == HB_DIST_UNIFORM && FloatEq(lat_c, 90.0f) && FloatEq(lat_s, 360.0f);
+  if (full) out->lat_path = HB_LAT_FULL_SPHERE;
+  else if (lat_type == HB_DIST_NO_RANDOM) out->lat_path = HB_LAT_NO_RANDOM;
+  else if (lat_type == HB_DIST_GAUSSIAN_LEGACY) out->lat_path = HB_LAT_GAUSS_LEGACY;
+  else out->lat_path = HB_LAT_LUT;
+  out->lat_mean = lat_c * kDeg2RadF;
+  out->lat_std = lat_s * kDeg2RadF;
+  out->az_type = az_type;
+  out->az_mean = az_c * kDeg2RadF;
+  out->az_std = az_s * kDeg2RadF;
+  out->roll_type = roll_type;
+  out->roll_mean = roll_c * kDeg2RadF;
+  out->roll_std = roll_s * kDeg2RadF;
+  if (out->lat_path == HB_LAT_LUT) {
+    out->lut_n = HB_LUT_NODES;
+    BuildLatLut(lat_type, lat_c, lat_s, out);
+  }
+  return HB_OK;
+}
+
+int hb_make_proj_params(int lens_type, float fov_deg, int img_w, int img_h, float az, float el, float ro,
+                        int visible, int shift_x, int shift_y, float overlap, HbProjParams* out) {
+  if (out == nullptr || img_w <= 0 || img_h <= 0 || lens_type < 0 || lens_type > 10) return HB_ERR_INVALID_ARG;
+  std::memset(out, 0, sizeof(*out));
+  // MakeCameraRotation, scatter_accum.hpp:18-26
+  float m[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, r[9];
+  const float ez[3] = { 0, 0, 1 }, ey[3] = { 0, 1, 0 };
+  AxisAngle(ez, (-90.0f + ro) * kDeg2RadF, r);
+  ChainLeft(m, r);
+  AxisAngle(ey, (90.0f - el) * kDeg2RadF, r);
+  ChainLeft(m, r);
+  AxisAngle(ez, az * kDeg2RadF, r);
+  ChainLeft(m, r);
+  // BuildProjParams + ComputeScaleAz0, lens_proj_build.hpp:24-140
+  out->proj_type = lens_type;
+  out->img_w = img_w;
+  out->img_h = img_h;
+  out->visible_range = visible;
+  out->lens_shift_x = shift_x;
+  out->lens_shift_y = shift_y;
+  out->r_scale = 1.0f;
+  out->max_abs_dz = 0.0f;
+  std::memcpy(out->rot, m, 36);
+  float short_pix = static_cast<float>(std::min(img_w, img_h));
+  float fov = fov_deg * kDeg2RadF;
+  const float pi_2 = kPiF / 2.0f;
+  out->scale = 1.0f;
+  out->az0 = 0.0f;
+  switch (lens_type) {
+    case HB_LENS_LINEAR:
+    case HB_LENS_GLOBE:
+      out->scale = short_pix / 2.0f / std::tan(fov / 2.0f);
+      break;
+    case HB_LENS_FISHEYE_EQUAL_AREA:
+      out->scale = short_pix / 2.0f / std::sqrt(2.0f) / std::sin(fov / 4.0f);
+      break;
+    case HB_LENS_FISHEYE_EQUIDISTANT:
+      out->scale = short_pix * pi_2 / fov;
+      break;
+    case HB_LENS_FISHEYE_STEREOGRAPHIC:
+      out->scale = short_pix / 2.0f / std::tan(fov / 4.0f);
+      break;
+    case HB_LENS_FISHEYE_ORTHOGRAPHIC:
+      out->scale = short_pix / 2.0f / std::sin(fov / 2.0f);
+      break;
+    case HB_LENS_RECTANGULAR: {
+      int short_res = std::min(img_w / 2, img_h);
+      out->scale = static_cast<float>(short_res) / kPiF;
+      float zx = m[2], zy = m[5];  // rot.Apply((0,0,1)) = third column
+      out->az0 = std::atan2(zy, zx);
+      break;
+    }
+    default:
+      break;
+  }
+  if (overlap > 0) {  // projection.cpp:194-204
+    if (lens_type == HB_LENS_DUAL_FISHEYE_EQUAL_AREA) {
+      out->max_abs_dz = overlap;
+      out->r_scale = 1.0f / std::sqrt(1.0f + overlap);
+    } else if (lens_type == HB_LENS_DUAL_FISHEYE_EQUIDISTANT) {
+      out->max_abs_dz = overlap;
+      out->r_scale = pi_2 / (pi_2 + std::asin(overlap));
+    } else if (lens_type == HB_LENS_DUAL_FISHEYE_STEREOGRAPHIC) {
+      out->max_abs_dz = overlap;
+      out->r_scale = 1.0f / std::tan((pi_2 + std::asin(overlap)) / 2.0f);
+    }
+  }
+  return HB_OK;
+}
+
+int hb_build_render(const HbRenderDesc* d, HbProjParams* out) {
+  if (d == nullptr) return HB_ERR_INVALID_ARG;
+  return hb_make_proj_params(d->lens_type, d->fov_deg, d->img_w, d->img_h, d->view_az_deg, d->view_el_deg,
+                             d->view_ro_deg, d->visible_range, d->lens_shift_x, d->lens_shift_y, d->overlap, out);
+}
+
+// PartitionCrystalRayNum, simulator.cpp:519-582: floor of the ideal share + per-population carry, then a
+// largest-remainder correction so the counts sum to ray_num exactly.
+int hb_partition_rays(const float* prop, uint32_t cnt, uint64_t ray_num, double* carry, uint64_t* out) {
+  if (prop == nullptr || carry == nullptr || out == nullptr) return HB_ERR_INVALID_ARG;
+  for (uint32_t i = 0; i < cnt; i++) out[i] = 0;
+  if (cnt == 0 || ray_num == 0) return HB_OK;
+  float total = 0.0f;
+  for (uint32_t i = 0; i < cnt; i++) total += std::max(0.0f, prop[i]);
+  if (total <= 0.0f) return HB_OK;
+  uint64_t assigned = 0;
+  for (uint32_t i = 0; i < cnt; i++) {
+    double ideal = carry[i] + (static_cast<double>(std::max(0.0f, prop[i])) / total) * ray_num;
+    uint64_t a = static_cast<uint64_t>(std::max(0.0, ideal));
+    carry[i] = ideal - static_cast<double>(a);
+    out[i] = a;
+    assigned += a;
+  }
+  std::vector<uint32_t> idx(cnt);
+  for (uint32_t i = 0; i < cnt; i++) idx[i] = i;
+  if (assigned < ray_num) {
+    uint64_t deficit = ray_num - assigned;
+    std::partial_sort(idx.begin(), idx.begin() + std::min<uint64_t>(deficit, cnt), idx.end(),
+                      [&](uint32_t a, uint32_t b) { return carry[a] > carry[b]; });
+    for (uint64_t i = 0; i < deficit && i < cnt; i++) {
+      out[idx[i]]++;
+      carry[idx[i]] -= 1.0;
+    }
+  } else if (assigned > ray_num) {
+    uint64_t surplus = assigned - ray_num;
+    auto end = std::partition(idx.begin(), idx.end(), [&](uint32_t i) { return out[i] > 0; });
+    uint64_t m = std::min<uint64_t>(surplus, static_cast<uint64_t>(end - idx.begin()));
+    std::partial_sort(idx.begin(), idx.begin() + m, end, [&](uint32_t a, uint32_t b) { return carry[a] < carry[b]; });
+    for (uint64_t i = 0; i < m; i++) {
+      out[idx[i]]--;
+      carry[idx[i]] += 1.0;
+    }
+  }
+  return HB_OK;
+}
+
+int hb_build_scene(const HbSceneDesc* d, uint32_t geometry_seed, HbSceneTables** out) {
+  if (d == nullptr || out == nullptr) return HB_ERR_INVALID_ARG;
+  if (d->layer_cnt == 0 || d->layer_cnt > HB_MAX_LAYERS || d->max_hits == 0 || d->max_hits > HB_MAX_HITS) {
+    global_error() = "scene: layer_cnt must be 1..8 and max_hits 1..64";
+    return HB_ERR_INVALID_ARG;
+  }
+  auto t = std::make_unique<HbSceneTables>();
+  hb::SceneStorage& st = t->st;
+  std::mt19937 gen(geometry_seed);
+  st.layers.resize(d->layer_cnt);
+  st.pops.resize(d->layer_cnt);
+  for (uint32_t li = 0; li < d->layer_cnt; li++) {
+    const HbLayerDesc& ld = d->layers[li];
+    if (ld.population_cnt == 0 || ld.population_cnt > HB_MAX_CRYSTALS) {
+      global_error() = "scene: a layer needs 1..16 crystal populations";
+      return HB_ERR_INVALID_ARG;
+    }
+    st.pops[li].resize(ld.population_cnt);
+    for (uint32_t ci = 0; ci < ld.population_cnt; ci++) {
+      const HbPopulationDesc& pd = ld.populations[ci];
+      HbCrystalPopulation& p = st.pops[li][ci];
+      std::memset(&p, 0, sizeof(p));
+      p.proportion = pd.proportion;
+      p.crystal_id = pd.crystal.id;
+      uint32_t pool = ShapeIsDeterministic(pd.crystal) ? 1u : std::max(1u, d->geom_pool_size);
+      auto shapes = std::make_unique<std::vector<HbCrystalTables>>(pool);
+      for (uint32_t s = 0; s < pool; s++) {
+        int rc = MakeShape(gen, pd.crystal, &(*shapes)[s]);
+        if (rc != HB_OK) return rc;
+      }
+      p.shape_cnt = pool;
+      p.shapes = shapes->data();
+      st.shapes.push_back(std::move(shapes));
+      int rc = hb_make_axis_sampler(pd.crystal.latitude.type, pd.crystal.latitude.center, pd.crystal.latitude.spread,
+                                    pd.crystal.azimuth.type, pd.crystal.azimuth.center, pd.crystal.azimuth.spread,
+                                    pd.crystal.roll.type, pd.crystal.roll.center, pd.crystal.roll.spread, &p.axis);
+      if (rc != HB_OK) return rc;
+      BuildFilter(pd, &p.filter);
+    }
+    st.layers[li].prob = ld.prob;
+    st.layers[li].population_cnt = ld.population_cnt;
+    st.layers[li].populations = st.pops[li].data();
+  }
+  st.scene.max_hits = d->max_hits;
+  st.scene.layer_cnt = d->layer_cnt;
+  st.scene.layers = st.layers.data();
+  st.scene.sun_lon = (d->sun_azimuth_deg + 180.0f) * kDeg2RadF;  // cuda_trace_backend.cu:395-397
+  st.scene.sun_lat = -d->sun_altitude_deg * kDeg2RadF;
+  st.scene.sun_half_angle = (d->sun_diameter_deg * 0.5f) * kDeg2RadF;
+  *out = t.release();
+  return HB_OK;
+}
+
+const HbScene* hb_scene_tables_get(const HbSceneTables* t) { return t ? &t->st.scene : nullptr; }
+void hb_free_scene(HbSceneTables* t) { delete t; }
+
+}  // extern "C"

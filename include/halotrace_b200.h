@@ -189,6 +189,12 @@ typedef struct HbSessionSpec {            /* reference: SessionSpec, trace_backe
   uint64_t ray_num;                       /* hint (pool sizing) */
   uint32_t record_exits;                  /* 1 => materialise exit records for hb_drain_exits (parity) */
   uint32_t accumulate;                    /* 1 => fused projection + XYZ accumulate (production) */
+  uint64_t ray_base;                      /* global index of this session's first root ray when
+                                             use_ray_base != 0 (multi-GPU sharding: disjoint index ranges per
+                                             rank); otherwise the engine's own monotone counter
+                                             (cuda_trace_backend.cu:3717-3754) is used */
+  uint32_t use_ray_base;
+  uint32_t reserved_;
 } HbSessionSpec;
 
 typedef struct HbLayerStats {             /* reference: LayerStats + LayerHandle::ContinuationCount */

@@ -1,0 +1,76 @@
+/*
+ * halo_oracle.h — CPU restatement of the reference's per-ray trace path.
+ *
+ * TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg — never by the product library, which has no CPU path at all.
+ *
+ * Pinning: tests/test_oracle_vs_reference.py checks every function here against the UNMODIFIED
+ * reference CPU core (oracle/_ref, built from /root/reference by oracle/Makefile) when that library
+ * is present, and tests/test_oracle_golden.py checks it against the committed fixtures in
+ * tests/golden/ (generated from the same reference library by oracle/make_golden.py), which also
+ * hold the reference's own known-answer values (test_optics.cpp, test_cpu_golden_rays.cpp).
+ */
+#ifndef HALO_ORACLE_H_
+#define HALO_ORACLE_H_
+
+#include <stdint.h>
+
+#include "halotrace_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One scattering layer as the engine sees it: shapes flattened over populations. */
+typedef struct OrcLayerParams {
+  const HbCrystalTables* shapes;        /* [shape_cnt], population 0's pool first */
+  const uint32_t* shape_pop;            /* [shape_cnt] population index of each shape */
+  uint32_t shape_cnt;
+  const HbCrystalPopulation* pops;      /* [pop_cnt] (filter + crystal_id) */
+  uint32_t pop_cnt;
+  const HbWlEntry* wl;                  /* [wl_cnt] */
+  uint32_t wl_cnt;
+  uint32_t max_hits;
+  float prob;
+  uint32_t layer_idx;
+  uint32_t seed;                        /* session seed (gate stream = seed ^ gate nonce) */
+  uint64_t gate_base;                   /* global index of layer-ray 0 in the gate stream */
+} OrcLayerParams;
+
+uint32_t orc_pcg_hash(uint32_t x);
+float orc_draw(uint32_t seed, uint32_t idx, uint32_t slot);
+uint32_t orc_feistel(uint32_t i, uint32_t n, uint32_t seed);
+
+/* Root generation (engine stream spec, DESIGN.md "RNG streams"; samplers restate pcg_shared.h). */
+int orc_gen_roots(const HbScene* scene, uint32_t layer, uint32_t pop, uint32_t shape_base, const HbWlEntry* wl,
+                  uint32_t wl_cnt, uint32_t seed, uint64_t ray_base, uint64_t n, float* d3, float* p3, float* w,
+                  uint16_t* face, float* quat4, float* rot9, uint32_t* shape_idx, uint32_t* wl_idx);
+/* Layer transit (InitRayOtherMs, simulator.cpp:309-339): world dir in -> new crystal-local root. */
+int orc_transit(const HbScene* scene, uint32_t layer, uint32_t pop, uint32_t shape_base, uint32_t seed,
+                uint64_t ray_base, uint64_t n, const float* d_world3, float* d3, float* p3, uint16_t* face,
+                float* quat4, float* rot9, uint32_t* shape_idx);
+
+/* Hit loop + emit gate (simulator.cpp:585-762, optics.cpp:18-177). Rays are crystal-local. */
+int orc_trace_layer(const OrcLayerParams* lp, uint64_t n, const float* d3, const float* p3, const float* w,
+                    const uint16_t* face, const float* rot9, const uint32_t* shape_idx, const uint32_t* wl_idx,
+                    uint64_t cap, HbExitRecord* exits, uint32_t* exit_root, uint64_t* exit_cnt, float* cont_d3,
+                    float* cont_w, uint32_t* cont_wl, uint32_t* cont_root, uint64_t* cont_cnt);
+
+/* Primitives, one call = n independent evaluations. */
+int orc_hit_surface(const HbCrystalTables* t, float n_idx, uint64_t n, const float* d3, const float* w,
+                    const uint16_t* face, float* d_out6, float* w_out2);
+int orc_propagate(const HbCrystalTables* t, uint64_t n, const float* d3, const float* p3, const float* w,
+                  const uint16_t* from_face, float* p_out3, uint16_t* to_face);
+int orc_project(const HbProjParams* p, uint64_t n, const float* dir3, int32_t* px2, int32_t* py2, int32_t* cnt,
+                int32_t* bump2);
+/* ScatterOutgoingToXyz (scatter_accum.hpp:47-110) with per-ray wavelength-pool CMF. */
+int orc_accumulate(const HbProjParams* p, const HbWlEntry* wl, uint32_t wl_cnt, uint64_t n, const float* dir3,
+                   const float* w, const uint8_t* wl_idx, float* xyz_wh3, double* landed);
+int orc_filter_check(const HbFilterDesc* f, const uint8_t* face_fn, uint32_t pop_crystal_id, uint64_t n,
+                     const uint8_t* paths64, const uint8_t* path_len, const float* dir3, uint8_t* pass);
+void orc_quat_to_rot9(const float* q4, float* rot9);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

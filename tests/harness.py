@@ -1,0 +1,133 @@
+"""Shared test plumbing: loads the oracle (oracle/_build), the reference library (oracle/_ref, only
+present where /root/reference was available at build time) and the product library, and wraps their
+C entry points for numpy. TEST INFRASTRUCTURE — the product package never imports this."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from ice_halo_sim_b200 import _abi as A  # noqa: E402
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libhalo_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libhalo_ref.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+_vp = C.c_void_p
+
+
+def ptr(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def build_oracle():
+    src = os.path.join(ROOT, "oracle", "halo_oracle.cpp")
+    if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle"])
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        build_oracle()
+        lib = C.CDLL(ORACLE_SO)
+        lib.orc_pcg_hash.restype = C.c_uint32
+        lib.orc_pcg_hash.argtypes = [C.c_uint32]
+        lib.orc_draw.restype = C.c_float
+        lib.orc_draw.argtypes = [C.c_uint32] * 3
+        lib.orc_feistel.restype = C.c_uint32
+        lib.orc_feistel.argtypes = [C.c_uint32] * 3
+        lib.orc_gen_roots.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32,
+                                      C.c_uint64, C.c_uint64] + [_vp] * 8
+        lib.orc_transit.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64] + \
+            [_vp] * 7
+        lib.orc_trace_layer.argtypes = [_vp, C.c_uint64] + [_vp] * 7 + [C.c_uint64] + [_vp] * 8
+        lib.orc_hit_surface.argtypes = [_vp, C.c_float, C.c_uint64] + [_vp] * 5
+        lib.orc_propagate.argtypes = [_vp, C.c_uint64] + [_vp] * 6
+        lib.orc_project.argtypes = [_vp, C.c_uint64] + [_vp] * 5
+        lib.orc_accumulate.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64] + [_vp] * 5
+        lib.orc_filter_check.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64] + [_vp] * 4
+        lib.orc_quat_to_rot9.argtypes = [_vp, _vp]
+        _oracle = lib
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_SO)
+        lib.ref_refractive_index.restype = C.c_double
+        lib.ref_refractive_index.argtypes = [C.c_double]
+        lib.ref_make_tables.argtypes = [_vp, _vp]
+        lib.ref_make_axis_sampler.argtypes = [_vp] * 4
+        lib.ref_make_proj_params.argtypes = [_vp, _vp]
+        lib.ref_wl_entry.argtypes = [C.c_float, C.c_float, _vp]
+        lib.ref_wl_pool_illuminant.argtypes = [C.c_int, C.c_uint32, _vp]
+        lib.ref_cmf_table.argtypes = [_vp]
+        lib.ref_filter_desc.argtypes = [_vp] * 3
+        lib.ref_hit_surface.argtypes = [_vp, C.c_float, C.c_uint64] + [_vp] * 5
+        lib.ref_propagate.argtypes = [_vp, C.c_uint64] + [_vp] * 6
+        lib.ref_project.argtypes = [_vp, C.c_uint64] + [_vp] * 5
+        lib.ref_scatter_xyz.argtypes = [_vp, C.c_float, C.c_uint64] + [_vp] * 4
+        lib.ref_filter_check.argtypes = [_vp, _vp, C.c_uint64] + [_vp] * 4
+        lib.ref_sample_orientations.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint64, _vp, _vp]
+        lib.ref_partition.argtypes = [_vp, C.c_uint32, C.c_uint64, _vp, _vp]
+        lib.ref_trace_injected.argtypes = [_vp, C.c_float, C.c_uint32, C.c_uint64] + [_vp] * 4 + [C.c_uint64] + \
+            [_vp] * 3
+        lib.ref_cpu_backend_run.argtypes = [_vp, _vp, C.c_float, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64] + \
+            [_vp] * 4
+        lib.ref_legacy_bench.argtypes = [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32] + \
+            [_vp] * 3
+        lib.ref_physical_cores.restype = C.c_uint32
+        _ref = lib
+    return _ref
+
+
+def ref_shape(kind=0, h=(1.0, 0.0, 0.0), dist=(1, 1, 1, 1, 1, 1), alpha=(28.0, 28.0)):
+    return A.RefShape(kind, alpha[0], alpha[1], h[0], h[1], h[2], (A.f32 * 6)(*dist))
+
+
+def exits_to_numpy(buf, n):
+    """(HbExitRecord * cap) -> structured numpy view of the first n records."""
+    dt = np.dtype([("dir", np.float32, 3), ("weight", np.float32), ("path_len", np.uint8), ("path", np.uint8, 64),
+                   ("pad0", np.uint8), ("crystal_id", np.uint16), ("ms_layer_idx", np.uint8), ("wl_idx", np.uint8),
+                   ("pad1", np.uint8, 2), ("component_mask", np.uint64)])
+    assert dt.itemsize == 96
+    return np.frombuffer(buf, dtype=dt, count=n)
+
+
+EXIT_DTYPE = np.dtype([("dir", np.float32, 3), ("weight", np.float32), ("path_len", np.uint8), ("path", np.uint8, 64),
+                       ("pad0", np.uint8), ("crystal_id", np.uint16), ("ms_layer_idx", np.uint8), ("wl_idx", np.uint8),
+                       ("pad1", np.uint8, 2), ("component_mask", np.uint64)])
+
+
+def exit_keys(recs, roots):
+    """Canonical per-exit sort key: (root, path_len, path bytes) — unique per exit on a convex crystal."""
+    keys = []
+    for r, root in zip(recs, roots):
+        keys.append((int(root), int(r["path_len"]), bytes(r["path"][: r["path_len"]])))
+    return keys
+
+
+def sort_exits(recs, roots):
+    order = sorted(range(len(recs)), key=lambda i: (int(roots[i]), int(recs[i]["path_len"]),
+                                                     bytes(recs[i]["path"][: recs[i]["path_len"]]),
+                                                     float(recs[i]["weight"])))
+    idx = np.array(order, dtype=np.int64)
+    return recs[idx], np.asarray(roots)[idx]

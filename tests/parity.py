@@ -1,0 +1,272 @@
+"""GPU-vs-oracle parity protocol, shared by tests/test_gpu_parity.py, smoke() and bench.py.
+
+For every scattering layer: the engine traces on the GPU with exit records on, the roots it generated are
+exported (crystal-local d/p/w/face + the rot9 it uses), the oracle replays exactly those roots on the CPU,
+and the two exit lists are compared per root: face-number sequences, world directions and weights
+bit-for-bit. The GPU image is compared with the oracle's accumulation of the same exit list under a
+stated per-pixel tolerance (float atomics reorder the additions).
+"""
+import ctypes as C
+
+import numpy as np
+
+import harness as H
+from ice_halo_sim_b200 import _abi as A
+from ice_halo_sim_b200 import backend as B
+
+# Per-pixel image tolerance: |gpu - oracle| <= IMG_RTOL * (sum of |contributions| to that pixel) + IMG_ATOL.
+# fp32 atomic accumulation of k terms in arbitrary order differs from the sequential sum by <= ~k * 2^-24
+# relative to the sum of magnitudes; 1e-5 covers k up to ~150 contributions per pixel at these sizes.
+IMG_RTOL = 1e-5
+IMG_ATOL = 1e-7
+
+
+class OrcLayerParams(C.Structure):
+    _fields_ = [("shapes", C.c_void_p), ("shape_pop", C.c_void_p), ("shape_cnt", C.c_uint32),
+                ("pops", C.c_void_p), ("pop_cnt", C.c_uint32), ("wl", C.c_void_p), ("wl_cnt", C.c_uint32),
+                ("max_hits", C.c_uint32), ("prob", C.c_float), ("layer_idx", C.c_uint32), ("seed", C.c_uint32),
+                ("gate_base", C.c_uint64)]
+
+
+def dist(t, c=0.0, s=0.0):
+    return A.HbDist(A.DIST[t] if isinstance(t, str) else t, float(c), float(s))
+
+
+def prism_pop(h=1.0, zenith=("none", 0.0, 0.0), azimuth=("uniform", 0, 360), roll=("uniform", 0, 360),
+              face_dist=None, cid=1, proportion=1.0, filt=None):
+    p = A.HbPopulationDesc()
+    p.proportion = proportion
+    c = p.crystal
+    c.kind, c.id = 0, cid
+    c.height[0] = h if isinstance(h, A.HbDist) else dist("none", h)
+    for i in range(6):
+        fd = 1.0 if face_dist is None else face_dist[i]
+        c.face_dist[i] = fd if isinstance(fd, A.HbDist) else dist("none", fd)
+    z = dist(*zenith)
+    c.latitude = A.HbDist(z.type, 90.0 - z.center, z.spread)
+    c.azimuth, c.roll = dist(*azimuth), dist(*roll)
+    p.filter.entry_fn = p.filter.exit_fn = -1
+    if filt is not None:
+        p.filter = filt
+    return p
+
+
+def pyramid_pop(h=(0.3, 0.5, 0.4), alpha=(28.0, 28.0), zenith=("uniform", 90, 360), azimuth=("uniform", 0, 360),
+                roll=("uniform", 0, 360), face_dist=None, cid=2, proportion=1.0):
+    p = A.HbPopulationDesc()
+    p.proportion = proportion
+    c = p.crystal
+    c.kind, c.id = 1, cid
+    for i in range(3):
+        c.height[i] = dist("none", h[i])
+    for i in range(6):
+        fd = 1.0 if face_dist is None else face_dist[i]
+        c.face_dist[i] = fd if isinstance(fd, A.HbDist) else dist("none", fd)
+    c.wedge_upper_deg, c.wedge_lower_deg = alpha
+    z = dist(*zenith)
+    c.latitude = A.HbDist(z.type, 90.0 - z.center, z.spread)
+    c.azimuth, c.roll = dist(*azimuth), dist(*roll)
+    p.filter.entry_fn = p.filter.exit_fn = -1
+    return p
+
+
+def raypath_filter(path, symmetry="", action=0):
+    f = A.HbFilterSpecDesc()
+    f.kind, f.action = 1, action
+    f.symmetry = sum({"P": 1, "B": 2, "D": 4}[ch] for ch in symmetry)
+    f.path_len = len(path)
+    for i, x in enumerate(path):
+        f.path[i] = x
+    f.entry_fn = f.exit_fn = -1
+    return f
+
+
+def scene(layers, max_hits=7, sun=(20.0, 0.0, 0.5), pool=1):
+    """layers: [(prob, [HbPopulationDesc, ...]), ...]"""
+    d = A.HbSceneDesc()
+    d.max_hits = max_hits
+    d.layer_cnt = len(layers)
+    d.sun_altitude_deg, d.sun_azimuth_deg, d.sun_diameter_deg = sun
+    d.geom_pool_size = pool
+    for li, (prob, pops) in enumerate(layers):
+        d.layers[li].prob = prob
+        d.layers[li].population_cnt = len(pops)
+        for ci, p in enumerate(pops):
+            d.layers[li].populations[ci] = p
+    return d
+
+
+def render(lens="fisheye_equal_area", fov=120.0, res=(1920, 1080), view=(0.0, 30.0, 0.0), visible="upper",
+           shift=(0, 0), overlap=0.0):
+    return A.HbRenderDesc(A.LENS[lens], fov, res[0], res[1], view[0], view[1], view[2], A.VISIBLE[visible],
+                          shift[0], shift[1], overlap)
+
+
+# BASELINE.json configs, at parity-test sizes
+CASES = {
+    # config 1/2: examples/config_example.json crystal 3, render id 4
+    "column_config2": dict(scene=lambda: scene([(0.0, [prism_pop(1.3, zenith=("gauss", 90, 0.3), cid=3)])], 7),
+                           render=lambda: render(), wl=[550.0]),
+    # config 3: plate parhelia + raypath filter [3,5] symmetry P
+    "plate_filter_config3": dict(
+        scene=lambda: scene([(0.0, [prism_pop(0.3, zenith=("gauss", 0, 0.8), cid=6,
+                                              filt=raypath_filter([3, 5], "P"))])], 7),
+        render=lambda: render(), wl=[550.0]),
+    # config 4: two layers, plate (prob 1.0) over random column
+    "two_layer_config4": dict(
+        scene=lambda: scene([(1.0, [prism_pop(0.3, zenith=("gauss", 0, 0.8), cid=6)]),
+                             (0.0, [prism_pop(1.3, zenith=("uniform", 90, 360), cid=3)])], 7),
+        render=lambda: render(), wl=[550.0]),
+    # config 5: stochastic prism geometry, rectangular full-sky render, max_hits 8
+    "stoch_config5": dict(
+        scene=lambda: scene([(0.0, [prism_pop(1.0, zenith=("uniform", 90, 360), cid=1,
+                                              face_dist=[dist("gauss", 1.0, 0.15)] * 6)])], 8, pool=64),
+        render=lambda: render("rectangular", 360.0, (2048, 1024), (0.0, 90.0, 0.0), "full"), wl=[550.0]),
+    "pyramid": dict(scene=lambda: scene([(0.0, [pyramid_pop()])], 8),
+                    render=lambda: render("dual_fisheye_equal_area", 120.0, (1024, 512), visible="full", overlap=0.1),
+                    wl=[610.0]),
+    "two_populations": dict(
+        scene=lambda: scene([(0.0, [prism_pop(1.3, zenith=("gauss", 90, 0.3), cid=3, proportion=10.0),
+                                    pyramid_pop(proportion=3.0)])], 6),
+        render=lambda: render("linear", 40.0, (640, 480), (-50.0, 30.0, 0.0)), wl=[490.0]),
+    "partial_prob": dict(
+        scene=lambda: scene([(0.5, [prism_pop(1.0, zenith=("uniform", 90, 360), cid=1)]),
+                             (0.0, [prism_pop(0.5, zenith=("gauss", 0, 2.0), cid=2)])], 5),
+        render=lambda: render("fisheye_equidistant", 180.0, (512, 512), (0.0, 90.0, 0.0)), wl=[530.0]),
+}
+
+
+def layer_params(sc: A.HbScene, li, wl_arr, seed, gate_base):
+    layer = sc.layers[li]
+    shapes, shape_pop = [], []
+    for ci in range(layer.population_cnt):
+        pop = layer.populations[ci]
+        for s in range(pop.shape_cnt):
+            shapes.append(pop.shapes[s])
+            shape_pop.append(ci)
+    arr = (A.HbCrystalTables * len(shapes))(*shapes)
+    sp = np.array(shape_pop, np.uint32)
+    lp = OrcLayerParams(C.addressof(arr), H.ptr(sp), len(shapes), C.addressof(layer.populations.contents),
+                        layer.population_cnt, C.addressof(wl_arr), len(wl_arr), sc.max_hits, layer.prob, li, seed,
+                        gate_base)
+    return lp, (arr, sp)
+
+
+def oracle_trace(lp, roots, cap):
+    orc = H.oracle()
+    n = len(roots["w"])
+    ex = np.zeros(cap, H.EXIT_DTYPE)
+    er = np.zeros(cap, np.uint32)
+    ec = C.c_uint64()
+    cd = np.zeros((cap, 3), np.float32)
+    cw = np.zeros(cap, np.float32)
+    cwl = np.zeros(cap, np.uint32)
+    cr = np.zeros(cap, np.uint32)
+    cc = C.c_uint64()
+    rc = orc.orc_trace_layer(C.byref(lp), n, H.ptr(roots["d"]), H.ptr(roots["p"]), H.ptr(roots["w"]),
+                             H.ptr(roots["face"]), H.ptr(roots["rot"]), H.ptr(roots["shape"]), H.ptr(roots["wl"]), cap,
+                             H.ptr(ex), H.ptr(er), C.byref(ec), H.ptr(cd), H.ptr(cw), H.ptr(cwl), H.ptr(cr),
+                             C.byref(cc))
+    assert rc == 0, rc
+    return ex[: ec.value], er[: ec.value], (cd[: cc.value], cw[: cc.value], cr[: cc.value])
+
+
+def compare_exit_lists(g_ex, g_roots, o_ex, o_roots):
+    g, gr = H.sort_exits(g_ex, g_roots)
+    o, orr = H.sort_exits(o_ex, o_roots)
+    res = dict(n_gpu=len(g), n_oracle=len(o))
+    same_n = len(g) == len(o)
+    res["paths_equal"] = bool(same_n and np.array_equal(gr, orr) and np.array_equal(g["path_len"], o["path_len"]) and
+                              np.array_equal(g["path"], o["path"]))
+    res["dirs_bit_equal"] = bool(same_n and np.array_equal(g["dir"].view(np.uint32), o["dir"].view(np.uint32)))
+    res["weights_bit_equal"] = bool(same_n and np.array_equal(g["weight"].view(np.uint32), o["weight"].view(np.uint32)))
+    res["meta_equal"] = bool(same_n and np.array_equal(g["crystal_id"], o["crystal_id"]) and
+                             np.array_equal(g["ms_layer_idx"], o["ms_layer_idx"]) and
+                             np.array_equal(g["wl_idx"], o["wl_idx"]))
+    return res
+
+
+def oracle_image(proj, wl_arr, exits):
+    orc = H.oracle()
+    h, w = proj.img_h, proj.img_w
+    img = np.zeros((h, w, 3), np.float32)
+    mag = np.zeros((h, w, 3), np.float32)
+    landed = C.c_double(0.0)
+    d = np.ascontiguousarray(exits["dir"])
+    ww = np.ascontiguousarray(exits["weight"])
+    wi = np.ascontiguousarray(exits["wl_idx"])
+    orc.orc_accumulate(C.byref(proj), C.addressof(wl_arr), len(wl_arr), len(ww), H.ptr(d), H.ptr(ww), H.ptr(wi),
+                       H.ptr(img), C.byref(landed))
+    dummy = C.c_double(0.0)
+    orc.orc_accumulate(C.byref(proj), C.addressof(wl_arr), len(wl_arr), len(ww), H.ptr(d), H.ptr(np.abs(ww)),
+                       H.ptr(wi), H.ptr(mag), C.byref(dummy))
+    return img, mag, landed.value
+
+
+def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=7, tile_rays=None):
+    """Full protocol on one case; returns a dict of comparison results (all layers merged)."""
+    desc = case["scene"]()
+    rdesc = case["render"]()
+    tables = B.SceneTables(desc, geometry_seed)
+    sc = tables.scene()
+    wl = [B.make_wl_entry(x, 1.0) for x in case["wl"]]
+    wl_arr = (A.HbWlEntry * len(wl))(*[A.HbWlEntry(*e) for e in wl])
+    own = backend is None
+    be = backend or B.B200TraceBackend(device)
+    if tile_rays:
+        be.SetOption("tile_rays", tile_rays)
+    be.SetScene(tables)
+    be.SetOption("stream_base", 0)
+    be.SetRender(rdesc)
+    proj = B.make_proj_params(rdesc)
+    be.ReadbackXyzAccum()  # start from a zero image
+    be.BeginSession(B.SessionSpec(seed=seed, wl=wl, ray_num=n_rays, record_exits=True, accumulate=True))
+    out = dict(paths_equal=True, dirs_bit_equal=True, weights_bit_equal=True, meta_equal=True, exits=0, layers=[])
+    all_exits = []
+    roots_src = B.RootRaySource.FromHost(n_rays)
+    gate_base = 0
+    stats_ok = True
+    try:
+        for li in range(desc.layer_cnt):
+            handle = be.TraceLayer(roots_src)
+            g_ex, g_roots = be.DrainExits(with_roots=True)
+            roots = be.ExportRoots()
+            lp, keep = layer_params(sc, li, wl_arr, seed, gate_base)
+            cap = len(roots["w"]) * (desc.max_hits + 2) + 16
+            o_ex, o_roots, o_cont = oracle_trace(lp, roots, cap)
+            r = compare_exit_lists(g_ex, g_roots, o_ex, o_roots)
+            r["continuations_gpu"] = handle.continuation_count
+            r["continuations_oracle"] = len(o_cont[1])
+            r["roots"] = len(roots["w"])
+            # LayerStats: exit_count / exit_w_sum cover outgoing + continuation (trace_backend.hpp:279-300)
+            tot_w = float(o_ex["weight"].astype(np.float64).sum() + o_cont[1].astype(np.float64).sum())
+            r["stats_count_equal"] = handle.exit_count == len(o_ex) + len(o_cont[1])
+            r["stats_w_rel_err"] = abs(handle.exit_w_sum - tot_w) / max(tot_w, 1e-30)
+            stats_ok = stats_ok and r["stats_count_equal"] and r["stats_w_rel_err"] < 1e-6
+            for k in ("paths_equal", "dirs_bit_equal", "weights_bit_equal", "meta_equal"):
+                out[k] = out[k] and r[k]
+            out[k] = out[k] and (r["continuations_gpu"] == r["continuations_oracle"])
+            out["exits"] += len(g_ex)
+            out["layers"].append(r)
+            all_exits.append(g_ex)
+            gate_base += len(roots["w"])
+            if li + 1 == desc.layer_cnt:
+                break
+            roots_src = be.Recombine(handle, shuffle=True)
+    finally:
+        be.EndSession()
+    out["stats_ok"] = stats_ok
+    img, landed = be.ReadbackXyzAccum()
+    ex = np.concatenate(all_exits) if all_exits else np.zeros(0, H.EXIT_DTYPE)
+    o_img, o_mag, o_landed = oracle_image(proj, wl_arr, ex)
+    err = np.abs(img - o_img)
+    tol = IMG_RTOL * o_mag + IMG_ATOL
+    out["image_within_tol"] = bool(np.all(err <= tol))
+    out["image_max_rel_err"] = float((err / np.maximum(o_mag, 1e-20)).max()) if o_mag.max() > 0 else 0.0
+    out["image_sum"] = float(img.astype(np.float64).sum())
+    out["landed_gpu"] = float(landed)
+    out["landed_oracle"] = float(o_landed)
+    out["landed_rel_err"] = abs(landed - o_landed) / max(abs(o_landed), 1e-30)
+    if own:
+        be.close()
+    return out
