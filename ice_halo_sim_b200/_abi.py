@@ -148,11 +148,6 @@ class HbRenderDesc(C.Structure):
                 ("visible_range", i32), ("lens_shift_x", i32), ("lens_shift_y", i32), ("overlap", f32)]
 
 
-class RefShape(C.Structure):  # oracle/ref_driver.h (test infrastructure)
-    _fields_ = [("kind", u32), ("upper_alpha_deg", f32), ("lower_alpha_deg", f32),
-                ("h1", f32), ("h2", f32), ("h3", f32), ("dist", f32 * 6)]
-
-
 ALL_STRUCTS = [HbCrystalTables, HbAxisSampler, HbSimpleFilter, HbFilterDesc, HbCrystalPopulation, HbLayer, HbScene,
                HbWlEntry, HbProjParams, HbExitRecord, HbSessionSpec, HbLayerStats, HbCounters, HbDist, HbCrystalDesc,
                HbFilterSpecDesc, HbPopulationDesc, HbLayerDesc, HbSceneDesc, HbRenderDesc]

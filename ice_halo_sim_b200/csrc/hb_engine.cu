@@ -123,9 +123,9 @@ struct Tally {
   double w_sum = 0.0;
 };
 
-template <bool GENERAL>
+template <bool GENERAL, typename TablesT>
 HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float lx, float ly, float lz,
-                      float w, uint32_t role, const uint8_t* s_face_fn, Tally& tally) {
+                      float w, uint32_t role, const TablesT& tb, Tally& tally) {
   const Rot r = rot_from_quat(q);
   float wx, wy, wz;
   rot_apply(r, lx, ly, lz, wx, wy, wz);
@@ -145,8 +145,8 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
     uint8_t fn_path[HB_MAX_HITS];
     const uint32_t len = tp.hit + 1u;
     if (tp.flags & kFlagPath) {
-      const uint8_t* fn = s_face_fn + shape * HB_MAX_FACES;
-      for (uint32_t k = 0; k < len; k++) fn_path[k] = fn[tp.path[static_cast<size_t>(k) * tp.cap + slot]];
+      for (uint32_t k = 0; k < len; k++)
+        fn_path[k] = static_cast<uint8_t>(tb.face_fn(shape, tp.path[static_cast<size_t>(k) * tp.cap + slot]));
       if (tp.lt.any_filter) {
         const HbFilterDesc& f = tp.lt.filters[pop];
         if (f.kind != 0u) {
@@ -225,24 +225,65 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
 
 // Shared-memory staging of the per-layer crystal tables (planes + face counts + face numbers).
 // Layout in dynamic shared memory: float4 planes[n][20] | uint32 meta[n] | uint8 face_fn[n][20].
-constexpr uint32_t kSmemShapes = 96;  // pools larger than this are read through L1/L2 instead
-struct SharedTables {
-  const float4* planes;
-  const uint32_t* meta;
-  const uint8_t* face_fn;
-};
+// Pools of more than kSmemShapes shapes do not fit and are read through the read-only L1/L2 path.
+constexpr uint32_t kSmemShapes = 96;
 __host__ __device__ inline size_t shared_tables_bytes(uint32_t shape_cnt) {
   const uint32_t n = shape_cnt <= kSmemShapes ? shape_cnt : 0u;
   return static_cast<size_t>(n) * (HB_MAX_FACES * sizeof(float4) + sizeof(uint32_t) + HB_MAX_FACES) + 16;
 }
-HB_DEV SharedTables stage_tables(const LayerTables& lt, unsigned char* smem, bool want_fn) {
-  SharedTables s;
-  if (lt.shape_cnt > kSmemShapes) {
-    s.planes = lt.planes;
-    s.meta = lt.shape_meta;
-    s.face_fn = lt.face_fn;
-    return s;
+
+template <bool SMEM>
+struct PlaneRow;
+template <>
+struct PlaneRow<true> {  // explicit shared-space loads (LDS.128), no generic-address resolution
+  uint32_t addr;
+  HB_DEV float4 operator[](uint32_t i) const {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + i * 16u));
+    return v;
   }
+};
+template <>
+struct PlaneRow<false> {
+  const float4* p;
+  HB_DEV float4 operator[](uint32_t i) const { return __ldg(p + i); }
+};
+
+template <bool SMEM>
+struct Tables;
+template <>
+struct Tables<true> {
+  uint32_t planes_addr, meta_addr, fn_addr;
+  HB_DEV PlaneRow<true> planes(uint32_t shape) const { return PlaneRow<true>{ planes_addr + shape * (HB_MAX_FACES * 16u) }; }
+  HB_DEV uint32_t meta(uint32_t shape) const {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(meta_addr + shape * 4u));
+    return v;
+  }
+  HB_DEV uint32_t face_fn(uint32_t shape, uint32_t face) const {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(fn_addr + shape * HB_MAX_FACES + face));
+    return v;
+  }
+};
+template <>
+struct Tables<false> {
+  const float4* planes_p;
+  const uint32_t* meta_p;
+  const uint8_t* fn_p;
+  HB_DEV PlaneRow<false> planes(uint32_t shape) const { return PlaneRow<false>{ planes_p + shape * HB_MAX_FACES }; }
+  HB_DEV uint32_t meta(uint32_t shape) const { return __ldg(meta_p + shape); }
+  HB_DEV uint32_t face_fn(uint32_t shape, uint32_t face) const { return __ldg(fn_p + shape * HB_MAX_FACES + face); }
+};
+
+template <bool SMEM>
+HB_DEV Tables<SMEM> stage_tables(const LayerTables& lt, unsigned char* smem, bool want_fn);
+template <>
+HB_DEV Tables<false> stage_tables<false>(const LayerTables& lt, unsigned char*, bool) {
+  return Tables<false>{ lt.planes, lt.shape_meta, lt.face_fn };
+}
+template <>
+HB_DEV Tables<true> stage_tables<true>(const LayerTables& lt, unsigned char* smem, bool want_fn) {
   const uint32_t n = lt.shape_cnt;
   float4* pl = reinterpret_cast<float4*>(smem);
   uint32_t* meta = reinterpret_cast<uint32_t*>(pl + n * HB_MAX_FACES);
@@ -253,10 +294,8 @@ HB_DEV SharedTables stage_tables(const LayerTables& lt, unsigned char* smem, boo
   }
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) meta[i] = lt.shape_meta[i];
   __syncthreads();
-  s.planes = pl;
-  s.meta = meta;
-  s.face_fn = fn;
-  return s;
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  return Tables<true>{ base, base + n * HB_MAX_FACES * 16u, base + n * HB_MAX_FACES * 16u + n * 4u };
 }
 
 template <bool GENERAL>
@@ -294,10 +333,10 @@ HB_DEV void fork_append(const TraceParams& tp, uint32_t slot, uint32_t bits, flo
 // ------------------------------------------------------------------------------------------------
 // optics kernel: one surface interaction per live ray
 // ------------------------------------------------------------------------------------------------
-template <bool GENERAL, bool LAST>
+template <bool GENERAL, bool LAST, bool SMEM>
 __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SharedTables st = stage_tables(tp.lt, smem_raw, GENERAL);
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw, GENERAL);
   const uint32_t total = tp.n_main + *tp.fork_snapshot;
   Tally tally;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -309,9 +348,8 @@ __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
     if (face == kFaceInvalid) continue;
     const float4 q = tp.Q[i];
     const uint32_t shape = bits_shape(bits);
-    const float4* planes = st.planes + shape * HB_MAX_FACES;
-    const uint32_t face_cnt = st.meta[shape] & 255u;
-    const uint8_t* fn_tab = st.face_fn;
+    const PlaneRow<SMEM> planes = tb.planes(shape);
+    const uint32_t face_cnt = tb.meta(shape) & 255u;
     const float n_idx = tp.wl[bits_wl(bits)].n_idx;
 
     const Split s = hit_surface(planes[face], n_idx, d4.x, d4.y, d4.z, d4.w);
@@ -325,7 +363,7 @@ __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
       float nx, ny, nz;
       const uint32_t nf = slab_exit(planes, face_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
       if (nf == kFaceInvalid) {
-        emit_exit<GENERAL>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, fn_tab, tally);
+        emit_exit<GENERAL>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, tb, tally);
       } else if (!LAST) {
         fork_append<GENERAL>(tp, i, bits, q, nx, ny, nz, ox, oy, oz, ow, nf);  // near-edge leak: both children stay
       }
@@ -335,7 +373,7 @@ __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
       if (iw >= 0.0f) {
         float nx, ny, nz;
         const uint32_t nf = slab_exit(planes, face_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
-        if (nf == kFaceInvalid) emit_exit<GENERAL>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, fn_tab, tally);
+        if (nf == kFaceInvalid) emit_exit<GENERAL>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, tb, tally);
       }
     } else {
       tp.D[i] = make_float4(ix, iy, iz, iw);  // iw < 0 (TIR sentinel) terminates the ray
@@ -350,10 +388,10 @@ __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
 // ------------------------------------------------------------------------------------------------
 // intersect kernel: slab exit-face search for the inside child
 // ------------------------------------------------------------------------------------------------
-template <bool GENERAL>
+template <bool GENERAL, bool SMEM>
 __global__ void __launch_bounds__(256) intersect_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SharedTables st = stage_tables(tp.lt, smem_raw, GENERAL);
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw, GENERAL);
   const uint32_t forks = *tp.fork_count;
   const uint32_t total = tp.n_main + min(forks, tp.fork_cap);
   if (blockIdx.x == 0 && threadIdx.x == 0) *tp.fork_snapshot = min(forks, tp.fork_cap);
@@ -370,13 +408,13 @@ __global__ void __launch_bounds__(256) intersect_kernel(const TraceParams tp) {
       continue;
     }
     const uint32_t shape = bits_shape(bits);
-    const float4* planes = st.planes + shape * HB_MAX_FACES;
-    const uint32_t face_cnt = st.meta[shape] & 255u;
+    const PlaneRow<SMEM> planes = tb.planes(shape);
+    const uint32_t face_cnt = tb.meta(shape) & 255u;
     float nx, ny, nz;
     const uint32_t nf = slab_exit(planes, face_cnt, face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz);
     if (nf == kFaceInvalid) {
       // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
-      emit_exit<GENERAL>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, st.face_fn, tally);
+      emit_exit<GENERAL>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, tb, tally);
       tp.D[i] = make_float4(d4.x, d4.y, d4.z, -1.0f);
       continue;
     }
@@ -617,6 +655,7 @@ struct HbEngine {
   std::vector<EventPair> ev_pool;
   size_t ev_used = 0;
   int blocks_per_sm = 8;
+  int blocks_per_sm_override = 0;
 #ifdef HB_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
@@ -685,6 +724,48 @@ uint32_t grid_for(const HbEngine* h, uint64_t n) {
   uint64_t blocks = (n + 255) / 256;
   uint64_t cap = static_cast<uint64_t>(h->sm_count) * h->blocks_per_sm;
   return static_cast<uint32_t>(std::max<uint64_t>(1, std::min(blocks, cap)));
+}
+
+// Persistent grid-stride launch: exactly as many CTAs as are co-resident (occupancy x SM count), so there is
+// no partially filled second wave.
+template <typename K>
+uint32_t resident_grid(const HbEngine* h, K kernel, size_t smem, uint64_t n) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
+  if (h->blocks_per_sm_override > 0) per_sm = h->blocks_per_sm_override;
+  const uint64_t blocks = (n + 255) / 256;
+  return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(blocks, static_cast<uint64_t>(h->sm_count) * per_sm)));
+}
+
+template <bool G, bool L, bool S>
+void launch_optics_t(HbEngine* h, size_t smem, const TraceParams& tp) {
+  const uint32_t grid = resident_grid(h, optics_kernel<G, L, S>, smem, tp.cap);
+  optics_kernel<G, L, S><<<grid, 256, smem, h->stream>>>(tp);
+}
+void launch_optics(HbEngine* h, bool general, bool last, bool in_smem, size_t smem, const TraceParams& tp) {
+  const int key = (general ? 4 : 0) | (last ? 2 : 0) | (in_smem ? 1 : 0);
+  switch (key) {
+    case 0: launch_optics_t<false, false, false>(h, smem, tp); break;
+    case 1: launch_optics_t<false, false, true>(h, smem, tp); break;
+    case 2: launch_optics_t<false, true, false>(h, smem, tp); break;
+    case 3: launch_optics_t<false, true, true>(h, smem, tp); break;
+    case 4: launch_optics_t<true, false, false>(h, smem, tp); break;
+    case 5: launch_optics_t<true, false, true>(h, smem, tp); break;
+    case 6: launch_optics_t<true, true, false>(h, smem, tp); break;
+    default: launch_optics_t<true, true, true>(h, smem, tp); break;
+  }
+}
+template <bool G, bool S>
+void launch_intersect_t(HbEngine* h, size_t smem, const TraceParams& tp) {
+  const uint32_t grid = resident_grid(h, intersect_kernel<G, S>, smem, tp.cap);
+  intersect_kernel<G, S><<<grid, 256, smem, h->stream>>>(tp);
+}
+void launch_intersect(HbEngine* h, bool general, bool in_smem, size_t smem, const TraceParams& tp) {
+  if (general) {
+    if (in_smem) launch_intersect_t<true, true>(h, smem, tp); else launch_intersect_t<true, false>(h, smem, tp);
+  } else {
+    if (in_smem) launch_intersect_t<false, true>(h, smem, tp); else launch_intersect_t<false, false>(h, smem, tp);
+  }
 }
 
 size_t trace_smem(const LayerDev& L) { return shared_tables_bytes(L.shape_cnt); }
@@ -915,27 +996,20 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.stat_w_sum = h->stat_sum.p;
   tp.error_flag = h->counters.p + 4;
 
-  const uint32_t grid = grid_for(h, cap);
   const size_t smem = trace_smem(L);
+  const bool in_smem = L.shape_cnt <= kSmemShapes;
   for (uint32_t hit = 0; hit < h->max_hits; hit++) {
     tp.hit = hit;
     const bool last = hit + 1 == h->max_hits;
     EventPair* ev = begin_event(h, 1, n);
-    if (general) {
-      if (last) optics_kernel<true, true><<<grid, 256, smem, h->stream>>>(tp);
-      else optics_kernel<true, false><<<grid, 256, smem, h->stream>>>(tp);
-    } else {
-      if (last) optics_kernel<false, true><<<grid, 256, smem, h->stream>>>(tp);
-      else optics_kernel<false, false><<<grid, 256, smem, h->stream>>>(tp);
-    }
+    launch_optics(h, general, last, in_smem, smem, tp);
     end_event(h, ev);
     h->ctr.kernel_launches++;
     h->ctr.optics_launches++;
     h->ctr.optics_rays += n;
     if (!last) {
       ev = begin_event(h, 2, n);
-      if (general) intersect_kernel<true><<<grid, 256, smem, h->stream>>>(tp);
-      else intersect_kernel<false><<<grid, 256, smem, h->stream>>>(tp);
+      launch_intersect(h, general, in_smem, smem, tp);
       end_event(h, ev);
       h->ctr.kernel_launches++;
       h->ctr.intersect_launches++;
@@ -1377,6 +1451,7 @@ int hb_set_option(HbEngine* h, const char* key, int64_t value) {
   } else if (k == "blocks_per_sm") {
     if (value < 1 || value > 32) return fail(h, HB_ERR_INVALID_ARG, "blocks_per_sm out of range");
     h->blocks_per_sm = static_cast<int>(value);
+    h->blocks_per_sm_override = static_cast<int>(value);
   } else if (k == "gen_base") {
     h->gen_base = static_cast<uint64_t>(value);
   } else if (k == "stream_base") {  // restart all monotone stream counters (tests: reproducible replays)

@@ -99,8 +99,13 @@ def ref():
     return _ref
 
 
+class RefShape(C.Structure):  # oracle/ref_driver.h
+    _fields_ = [("kind", C.c_uint32), ("upper_alpha_deg", C.c_float), ("lower_alpha_deg", C.c_float),
+                ("h1", C.c_float), ("h2", C.c_float), ("h3", C.c_float), ("dist", C.c_float * 6)]
+
+
 def ref_shape(kind=0, h=(1.0, 0.0, 0.0), dist=(1, 1, 1, 1, 1, 1), alpha=(28.0, 28.0)):
-    return A.RefShape(kind, alpha[0], alpha[1], h[0], h[1], h[2], (A.f32 * 6)(*dist))
+    return RefShape(kind, alpha[0], alpha[1], h[0], h[1], h[2], (C.c_float * 6)(*dist))
 
 
 def exits_to_numpy(buf, n):

@@ -18,7 +18,7 @@ def test_case_bit_exact(backend, name):
     assert res["weights_bit_equal"], res
     assert res["meta_equal"], res
     assert res["stats_ok"], res
-    assert res["image_within_tol"], res
+    assert res["image_ok"], res
     assert res["landed_rel_err"] < 1e-5, res
 
 
