@@ -451,13 +451,25 @@ int ref_trace_injected(const RefShape* shape, float n_idx, uint32_t max_hits, ui
     spec.wl = WlParam{ 550.0f, 1.0f };
     spec.seed = 1;
     backend.BeginSession(spec);
+    // The session carries the ray under test plus kPad zero-weight copies. The copies only size the
+    // reference's per-session workspace (workspace[0] holds 2 x session rays, cpu_trace_backend.cpp:118-119) the
+    // way a production 32-ray small batch does, so a near-edge double continuation is not dropped for lack of
+    // room; their exits have weight exactly 0 and are discarded below.
+    constexpr size_t kPad = 7;
+    float bd[(kPad + 1) * 3], bp[(kPad + 1) * 3], bw[kPad + 1];
+    IdType btf[kPad + 1];
+    for (size_t q = 0; q <= kPad; q++) {
+      std::memcpy(bd + q * 3, d3 + i * 3, 12);
+      std::memcpy(bp + q * 3, p3 + i * 3, 12);
+      bw[q] = q == 0 ? w[i] : 0.0f;
+      btf[q] = to_face[i];
+    }
     HostRayBatch hb;
-    hb.count = 1;
-    hb.d = d3 + i * 3;
-    hb.p = p3 + i * 3;
-    hb.w = w + i;
-    IdType tf = to_face[i];
-    hb.tf = &tf;
+    hb.count = kPad + 1;
+    hb.d = bd;
+    hb.p = bp;
+    hb.w = bw;
+    hb.tf = btf;
     hb.crystal = &crystal;
     hb.refractive_index = n_idx;
     hb.crystal_id = 0;
@@ -465,6 +477,9 @@ int ref_trace_injected(const RefShape* shape, float n_idx, uint32_t max_hits, ui
     backend.DrainExits(recs);
     backend.EndSession();
     for (const auto& r : recs) {
+      if (r.weight == 0.0f && w[i] != 0.0f) {
+        continue;  // padding ray
+      }
       if (k < cap) {
         std::memcpy(&out[k], &r, sizeof(r));
         out_ray[k] = static_cast<uint32_t>(i);

@@ -199,7 +199,8 @@ def oracle_image(proj, wl_arr, exits):
     orc.orc_accumulate(C.byref(proj), C.addressof(wl_arr), len(wl_arr), len(ww), H.ptr(d), H.ptr(ww), H.ptr(wi),
                        H.ptr(img), C.byref(landed))
     dummy = C.c_double(0.0)
-    orc.orc_accumulate(C.byref(proj), C.addressof(wl_arr), len(wl_arr), len(ww), H.ptr(d), H.ptr(np.abs(ww)),
+    wabs = np.ascontiguousarray(np.abs(ww))
+    orc.orc_accumulate(C.byref(proj), C.addressof(wl_arr), len(wl_arr), len(ww), H.ptr(d), H.ptr(wabs),
                        H.ptr(wi), H.ptr(mag), C.byref(dummy))
     return img, mag, landed.value
 

@@ -71,5 +71,6 @@ def test_product_does_not_reference_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
-                assert "halo_oracle" not in txt and "libhalo_ref" not in txt and "oracle/" not in txt.replace(
-                    "oracle/make_golden.py", ""), f
+                for needle in ("halo_oracle", "libhalo_ref", "ref_driver", "oracle/_", "import harness",
+                               "from oracle", "import oracle"):
+                    assert needle not in txt, (f, needle)
