@@ -1,0 +1,291 @@
+// b200_trace_backend.hpp — the reference-side binding: a `lumice::TraceBackend` that forwards every
+// virtual to the C ABI of libhalotrace_b200.so (include/halotrace_b200.h).
+//
+// This file is compiled INSIDE the reference tree (it includes the reference's own headers and uses its
+// host geometry code to build the tables, as the reference's CUDA backend does,
+// src/core/backend/cuda_trace_backend.cu:2436-2542,3689-3704). It is what a Lumice maintainer adds next
+// to cuda_trace_backend.{hpp,cu}; INTEGRATION.md lists the five small touch points that register it.
+// `make -C oracle adapter_check` compiles it against /root/reference as a syntax/ABI check.
+#ifndef ADAPTER_B200_TRACE_BACKEND_HPP_
+#define ADAPTER_B200_TRACE_BACKEND_HPP_
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "core/backend/trace_backend.hpp"
+#include "core/backend/wl_pool.hpp"
+#include "core/device_filter_desc.hpp"
+#include "core/lat_lut.hpp"
+#include "core/lens_proj_build.hpp"
+#include "core/scatter_accum.hpp"
+#include "core/shared/lat_path_selection.hpp"
+#include "core/simulator.hpp"
+#include "core/trace_ops.hpp"
+#include "halotrace_b200.h"
+
+namespace lumice {
+
+class B200LayerHandle : public LayerHandle {
+ public:
+  size_t ContinuationCount() const override { return static_cast<size_t>(stats_.continuation_count); }
+  LayerStats GetLayerStats() const override {
+    return LayerStats{ static_cast<size_t>(stats_.exit_count), static_cast<float>(stats_.exit_w_sum) };
+  }
+  HbLayerStats stats_{};
+};
+
+class B200TraceBackend : public TraceBackend {
+ public:
+  explicit B200TraceBackend(int device_ordinal = 0) : rng_(0) {
+    if (hb_create(device_ordinal, &h_) != HB_OK) {
+      throw BackendUnavailableError(std::string("B200TraceBackend: ") + hb_last_error(nullptr));
+    }
+  }
+  ~B200TraceBackend() override { hb_destroy(h_); }
+
+  bool SupportsDeviceXyzAccum() const override { return true; }
+  bool SupportsThirdClockDrain() const override { return true; }
+  uint32_t WlPoolSize() const override { return kWlPoolSizeDefault; }
+  bool IsCompatible(const RenderConfig&) const override { return true; }  // all 11 lens types
+
+  void BeginSession(const SessionSpec& spec) override {
+    try {
+      if (spec.scene != scene_ || SceneHasStochasticShapes(*spec.scene)) {
+        UploadScene(*spec.scene);
+      }
+      if (spec.render != render_ || render_snapshot_dirty_) {
+        UploadRender(*spec.render);
+      }
+      // Wavelength pool: one entry for a discrete wavelength, M midpoint samples for an illuminant
+      // (ComputeWlPool, backend/wl_pool.hpp:67-95).
+      const bool illuminant = std::holds_alternative<IlluminantType>(spec.scene->light_source_.spectrum_);
+      std::vector<WlEntry> pool;
+      Crystal probe = Crystal::CreatePrism(1.0f);
+      ComputeWlPool(probe, illuminant,
+                    illuminant ? std::get<IlluminantType>(spec.scene->light_source_.spectrum_) : IlluminantType::kD65,
+                    spec.wl.wl_, spec.wl.weight_, illuminant ? kWlPoolSizeDefault : 1u, pool);
+      static_assert(sizeof(WlEntry) == sizeof(HbWlEntry), "WlEntry layout");
+      HbSessionSpec s{};
+      s.seed = spec.seed;
+      s.wl_cnt = static_cast<uint32_t>(pool.size());
+      s.wl = reinterpret_cast<const HbWlEntry*>(pool.data());
+      s.ray_num = spec.ray_num;
+      s.record_exits = 0;
+      s.accumulate = 1;
+      Check(hb_begin_session(h_, &s), "BeginSession");
+      layer_cnt_ = spec.scene->ms_.size();
+      layer_idx_ = 0;
+    } catch (...) {
+      hb_end_session(h_);  // leave the instance un-sessioned (trace_backend.hpp:149-153)
+      throw;
+    }
+  }
+
+  LayerHandlePtr TraceLayer(const RootRaySource& roots) override {
+    auto handle = std::make_unique<B200LayerHandle>();
+    const bool last = layer_idx_ + 1 == layer_cnt_;
+    // The final layer needs no host-visible counter: launch and return (no synchronisation).
+    Check(hb_trace_layer(h_, roots.is_device ? 0 : roots.host.count, last ? nullptr : &handle->stats_), "TraceLayer");
+    return handle;
+  }
+
+  RootRaySource Recombine(LayerHandlePtr handle, const RecombineSpec& spec) override {
+    (void)handle;
+    uint64_t n = 0;
+    Check(hb_recombine(h_, spec.shuffle ? 1 : 0, &n), "Recombine");
+    layer_idx_++;
+    DeviceRayBatch dev;
+    dev.backend_ptr = h_;
+    dev.count = static_cast<size_t>(n);
+    return RootRaySource::FromDevice(dev);
+  }
+
+  size_t DrainExits(std::vector<ExitRayRecord>& out) override {
+    out.clear();  // device-fused path: exits are reduced into the image, never materialised
+    return 0;
+  }
+
+  void ReadbackXyzAccum(XyzImageData& xyz, float& landed_weight) override {
+    Check(hb_readback_xyz(h_, xyz.data, &landed_weight), "ReadbackXyzAccum");
+  }
+
+  void EndSession() override { Check(hb_end_session(h_), "EndSession"); }
+
+  size_t GetLastBatchStochasticCrystalSampleCount() const override { return stochastic_shapes_last_upload_; }
+
+ private:
+  void Check(int status, const char* what) {
+    if (status == HB_OK) {
+      return;
+    }
+    std::string msg = std::string("B200TraceBackend::") + what + ": " + hb_last_error(h_);
+    if (status == HB_ERR_NO_DEVICE || status == HB_ERR_CUDA) {
+      throw BackendUnavailableError(msg);
+    }
+    throw std::runtime_error(msg);
+  }
+
+  static bool SceneHasStochasticShapes(const SceneConfig& scene) {
+    for (const auto& ms : scene.ms_) {
+      for (const auto& st : ms.setting_) {
+        if (!IsDeterministic(st.crystal_.param_)) {
+          return true;
+        }
+      }
+    }
+    return false;
+  }
+
+  static void FillTables(const Crystal& c, HbCrystalTables* out) {
+    std::memset(out, 0, sizeof(*out));
+    const size_t fc = c.PolygonFaceCount();
+    out->face_cnt = static_cast<uint32_t>(fc);
+    for (size_t i = 0; i < fc; i++) {
+      std::memcpy(out->plane[i], c.GetPolygonFaceNormal() + i * 3, 3 * sizeof(float));
+      out->plane[i][3] = c.GetPolygonFaceDist()[i];
+      out->face_fn[i] = static_cast<uint8_t>(c.GetFn(static_cast<IdType>(i)) & 0xFF);
+    }
+    const size_t tc = detail::CountEntrySubTris(c.CfGeom());
+    if (tc > HB_MAX_SUBTRIS) {
+      throw BackendUnavailableError("B200TraceBackend: crystal needs more than 64 entry sub-triangles");
+    }
+    std::vector<detail::EntrySubTri> sub(tc);
+    if (tc > 0) {
+      detail::BuildEntrySubTris(c.CfGeom(), sub.data());
+    }
+    out->subtri_cnt = static_cast<uint32_t>(tc);
+    for (size_t t = 0; t < tc; t++) {
+      std::memcpy(out->tri_v[t], sub[t].v, 9 * sizeof(float));
+      std::memcpy(out->tri_n[t], sub[t].n, 3 * sizeof(float));
+      out->tri_area[t] = sub[t].area;
+      out->tri_face[t] = static_cast<uint8_t>(sub[t].face_id);
+    }
+  }
+
+  static void FillAxis(const AxisDistribution& axis, HbAxisSampler* out) {
+    std::memset(out, 0, sizeof(*out));
+    const auto decision = lat_path::SelectLatPath(axis);
+    out->lat_path = lat_path::ToWireValue(decision.kind);
+    out->lat_mean = axis.latitude_dist.center * math::kDegreeToRad;
+    out->lat_std = axis.latitude_dist.spread * math::kDegreeToRad;
+    out->az_type = static_cast<uint32_t>(axis.azimuth_dist.type);
+    out->az_mean = axis.azimuth_dist.center * math::kDegreeToRad;
+    out->az_std = axis.azimuth_dist.spread * math::kDegreeToRad;
+    out->roll_type = static_cast<uint32_t>(axis.roll_dist.type);
+    out->roll_mean = axis.roll_dist.center * math::kDegreeToRad;
+    out->roll_std = axis.roll_dist.spread * math::kDegreeToRad;
+    if (decision.kind == lat_path::LatPathKind::kLutInverseCdf) {
+      const LatLut* lut = GetSharedLatLut(axis.latitude_dist);
+      out->lut_n = LatLut::kNodes;
+      std::memcpy(out->lut_theta, lut->theta.data(), sizeof(out->lut_theta));
+      std::memcpy(out->lut_cdf, lut->cdf.data(), sizeof(out->lut_cdf));
+      std::memcpy(out->lut_flip, lut->flip_prob.data(), sizeof(out->lut_flip));
+    }
+  }
+
+  static void FillFilter(const FilterConfig& cfg, const Crystal& crystal, const AxisDistribution& axis, HbFilterDesc* out) {
+    std::memset(out, 0, sizeof(*out));
+    const DeviceFilterDesc d = detail::BuildDeviceFilterDesc(cfg, crystal, axis);
+    if (d.type == kDeviceFilterTypeComplex) {
+      throw BackendUnavailableError("B200TraceBackend: complex filters are not supported yet");
+    }
+    out->kind = d.type;
+    out->action = d.action;
+    out->symmetry = d.symmetry;
+    out->fn_period = d.fn_period;
+    out->sigma_a = d.sigma_a;
+    out->d_applicable = d.d_applicable;
+    out->simple.kind = d.type;
+    out->simple.path_len = d.canonical_len;
+    std::memcpy(out->simple.path, d.canonical_bytes, std::min<size_t>(d.canonical_len, HB_MAX_FILTER_PATH));
+    out->simple.entry_fn = d.has_entry ? 1 : -1;
+    out->simple.exit_fn = d.has_exit ? 1 : -1;
+    out->simple.min_len = d.min_len;
+    out->simple.max_len = d.max_len;
+    std::memcpy(out->simple.dir, d.dir, sizeof(d.dir));
+    out->simple.cos_radii = d.radii_c;
+    out->simple.crystal_id = d.crystal_id;
+  }
+
+  void UploadScene(const SceneConfig& scene) {
+    // Geometry pool per stochastic population: kPoolShapes shapes drawn with MakeCrystal, per-ray pick on the
+    // device (the reference GPU backends' K-shape pool, cuda_trace_backend.cu:1527-1554).
+    constexpr uint32_t kPoolShapes = 256;
+    std::vector<HbLayer> layers(scene.ms_.size());
+    std::vector<std::vector<HbCrystalPopulation>> pops(scene.ms_.size());
+    std::vector<std::unique_ptr<std::vector<HbCrystalTables>>> shapes;
+    stochastic_shapes_last_upload_ = 0;
+    for (size_t li = 0; li < scene.ms_.size(); li++) {
+      const MsInfo& ms = scene.ms_[li];
+      pops[li].resize(ms.setting_.size());
+      for (size_t ci = 0; ci < ms.setting_.size(); ci++) {
+        const ScatteringSetting& st = ms.setting_[ci];
+        HbCrystalPopulation& p = pops[li][ci];
+        std::memset(&p, 0, sizeof(p));
+        p.proportion = st.crystal_proportion_;
+        p.crystal_id = st.crystal_.id_;
+        const bool deterministic = IsDeterministic(st.crystal_.param_);
+        const uint32_t n = deterministic ? 1u : kPoolShapes;
+        auto pool = std::make_unique<std::vector<HbCrystalTables>>(n);
+        Crystal first;
+        for (uint32_t s = 0; s < n; s++) {
+          Crystal c = MakeCrystal(rng_, st.crystal_.param_);
+          FillTables(c, &(*pool)[s]);
+          if (s == 0) {
+            first = c;
+          }
+        }
+        if (!deterministic) {
+          stochastic_shapes_last_upload_ += n;
+        }
+        p.shape_cnt = n;
+        p.shapes = pool->data();
+        shapes.push_back(std::move(pool));
+        FillAxis(st.crystal_.axis_, &p.axis);
+        FillFilter(st.filter_, first, st.crystal_.axis_, &p.filter);
+      }
+      layers[li].prob = ms.prob_;
+      layers[li].population_cnt = static_cast<uint32_t>(pops[li].size());
+      layers[li].populations = pops[li].data();
+    }
+    HbScene s{};
+    s.max_hits = static_cast<uint32_t>(scene.max_hits_);
+    s.layer_cnt = static_cast<uint32_t>(layers.size());
+    s.layers = layers.data();
+    const SunParam& sun = scene.light_source_.param_;
+    s.sun_lon = (sun.azimuth_ + 180.0f) * math::kDegreeToRad;
+    s.sun_lat = -sun.altitude_ * math::kDegreeToRad;
+    s.sun_half_angle = (sun.diameter_ * 0.5f) * math::kDegreeToRad;
+    Check(hb_set_scene(h_, &s), "UploadScene");
+    scene_ = &scene;
+  }
+
+  void UploadRender(const RenderConfig& render) {
+    const Rotation rot = MakeCameraRotation(render);
+    const auto short_pix = static_cast<float>(std::min(render.resolution_[0], render.resolution_[1]));
+    const lm_proj::ProjParams p = BuildProjParams(render, rot, short_pix);
+    static_assert(sizeof(lm_proj::ProjParams) == sizeof(HbProjParams), "ProjParams layout");
+    HbProjParams hp;
+    std::memcpy(&hp, &p, sizeof(hp));
+    Check(hb_set_render(h_, &hp), "UploadRender");
+    render_ = &render;
+    render_snapshot_dirty_ = false;
+  }
+
+  HbEngine* h_ = nullptr;
+  RandomNumberGenerator rng_;
+  const SceneConfig* scene_ = nullptr;
+  const RenderConfig* render_ = nullptr;
+  bool render_snapshot_dirty_ = false;
+  size_t layer_cnt_ = 0;
+  size_t layer_idx_ = 0;
+  size_t stochastic_shapes_last_upload_ = 0;
+};
+
+}  // namespace lumice
+
+#endif  // ADAPTER_B200_TRACE_BACKEND_HPP_

@@ -36,7 +36,8 @@ std::string& global_error();  // hb_host.cpp
 // ------------------------------------------------------------------------------------------------
 struct LayerTables {            // device pointers, one scattering layer
   const float4* planes;         // [shape_cnt][HB_MAX_FACES]
-  const uint32_t* shape_meta;   // [shape_cnt] face_cnt | population << 8
+  const float4* axes;           // [shape_cnt][HB_MAX_FACES][2] paired-plane axis table (see slab_exit)
+  const uint32_t* shape_meta;   // [shape_cnt] face_cnt | population << 8 | axis_cnt << 16
   const uint8_t* face_fn;       // [shape_cnt][HB_MAX_FACES]
   const HbCrystalTables* shapes;  // [shape_cnt] full tables (entry sampling)
   const HbFilterDesc* filters;  // [pop_cnt]
@@ -133,7 +134,7 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
   bool to_next_layer = false;
   if (GENERAL) {
     const uint32_t shape = bits_shape(bits);
-    const uint32_t pop = tp.lt.shape_meta[shape] >> 8;
+    const uint32_t pop = (tp.lt.shape_meta[shape] >> 8) & 255u;
     uint32_t root, code;
     if (slot < tp.n_main) {
       root = tp.root_base + slot;
@@ -223,38 +224,49 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
   }
 }
 
-// Shared-memory staging of the per-layer crystal tables (planes + face counts + face numbers).
-// Layout in dynamic shared memory: float4 planes[n][20] | uint32 meta[n] | uint8 face_fn[n][20].
+// Shared-memory staging of the per-layer crystal tables.
+// Layout in dynamic shared memory, n = shape count:
+//   float4 planes[n][20] | float4 axes[n][20][2] | uint32 meta[n] | uint8 face_fn[n][20]
 // Pools of more than kSmemShapes shapes do not fit and are read through the read-only L1/L2 path.
-constexpr uint32_t kSmemShapes = 96;
+constexpr uint32_t kSmemShapes = 40;
+constexpr uint32_t kShapeSmemBytes = HB_MAX_FACES * 16u + HB_MAX_FACES * 32u + 4u + HB_MAX_FACES;
 __host__ __device__ inline size_t shared_tables_bytes(uint32_t shape_cnt) {
   const uint32_t n = shape_cnt <= kSmemShapes ? shape_cnt : 0u;
-  return static_cast<size_t>(n) * (HB_MAX_FACES * sizeof(float4) + sizeof(uint32_t) + HB_MAX_FACES) + 16;
+  return static_cast<size_t>(n) * kShapeSmemBytes + 16;
+}
+
+HB_DEV float4 lds128(uint32_t addr) {  // explicit shared-space load (LDS.128), no generic-address resolution
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 
 template <bool SMEM>
-struct PlaneRow;
+struct AxisRow;
 template <>
-struct PlaneRow<true> {  // explicit shared-space loads (LDS.128), no generic-address resolution
+struct AxisRow<true> {
   uint32_t addr;
-  HB_DEV float4 operator[](uint32_t i) const {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + i * 16u));
-    return v;
+  HB_DEV void load(uint32_t i, float4& a, float4& b) const {
+    a = lds128(addr + i * 32u);
+    b = lds128(addr + i * 32u + 16u);
   }
 };
 template <>
-struct PlaneRow<false> {
+struct AxisRow<false> {
   const float4* p;
-  HB_DEV float4 operator[](uint32_t i) const { return __ldg(p + i); }
+  HB_DEV void load(uint32_t i, float4& a, float4& b) const {
+    a = __ldg(p + 2u * i);
+    b = __ldg(p + 2u * i + 1u);
+  }
 };
 
 template <bool SMEM>
 struct Tables;
 template <>
 struct Tables<true> {
-  uint32_t planes_addr, meta_addr, fn_addr;
-  HB_DEV PlaneRow<true> planes(uint32_t shape) const { return PlaneRow<true>{ planes_addr + shape * (HB_MAX_FACES * 16u) }; }
+  uint32_t planes_addr, axes_addr, meta_addr, fn_addr;
+  HB_DEV float4 plane(uint32_t shape, uint32_t face) const { return lds128(planes_addr + (shape * HB_MAX_FACES + face) * 16u); }
+  HB_DEV AxisRow<true> axes(uint32_t shape) const { return AxisRow<true>{ axes_addr + shape * (HB_MAX_FACES * 32u) }; }
   HB_DEV uint32_t meta(uint32_t shape) const {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(meta_addr + shape * 4u));
@@ -269,9 +281,11 @@ struct Tables<true> {
 template <>
 struct Tables<false> {
   const float4* planes_p;
+  const float4* axes_p;
   const uint32_t* meta_p;
   const uint8_t* fn_p;
-  HB_DEV PlaneRow<false> planes(uint32_t shape) const { return PlaneRow<false>{ planes_p + shape * HB_MAX_FACES }; }
+  HB_DEV float4 plane(uint32_t shape, uint32_t face) const { return __ldg(planes_p + shape * HB_MAX_FACES + face); }
+  HB_DEV AxisRow<false> axes(uint32_t shape) const { return AxisRow<false>{ axes_p + shape * (HB_MAX_FACES * 2u) }; }
   HB_DEV uint32_t meta(uint32_t shape) const { return __ldg(meta_p + shape); }
   HB_DEV uint32_t face_fn(uint32_t shape, uint32_t face) const { return __ldg(fn_p + shape * HB_MAX_FACES + face); }
 };
@@ -280,22 +294,26 @@ template <bool SMEM>
 HB_DEV Tables<SMEM> stage_tables(const LayerTables& lt, unsigned char* smem, bool want_fn);
 template <>
 HB_DEV Tables<false> stage_tables<false>(const LayerTables& lt, unsigned char*, bool) {
-  return Tables<false>{ lt.planes, lt.shape_meta, lt.face_fn };
+  return Tables<false>{ lt.planes, lt.axes, lt.shape_meta, lt.face_fn };
 }
 template <>
 HB_DEV Tables<true> stage_tables<true>(const LayerTables& lt, unsigned char* smem, bool want_fn) {
   const uint32_t n = lt.shape_cnt;
   float4* pl = reinterpret_cast<float4*>(smem);
-  uint32_t* meta = reinterpret_cast<uint32_t*>(pl + n * HB_MAX_FACES);
+  float4* ax = pl + n * HB_MAX_FACES;
+  uint32_t* meta = reinterpret_cast<uint32_t*>(ax + n * HB_MAX_FACES * 2u);
   uint8_t* fn = reinterpret_cast<uint8_t*>(meta + n);
   for (uint32_t i = threadIdx.x; i < n * HB_MAX_FACES; i += blockDim.x) {
     pl[i] = lt.planes[i];
+    ax[2u * i] = lt.axes[2u * i];
+    ax[2u * i + 1u] = lt.axes[2u * i + 1u];
     if (want_fn) fn[i] = lt.face_fn[i];
   }
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) meta[i] = lt.shape_meta[i];
   __syncthreads();
   const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-  return Tables<true>{ base, base + n * HB_MAX_FACES * 16u, base + n * HB_MAX_FACES * 16u + n * 4u };
+  const uint32_t ax_off = n * HB_MAX_FACES * 16u, meta_off = ax_off + n * HB_MAX_FACES * 32u;
+  return Tables<true>{ base, base + ax_off, base + meta_off, base + meta_off + n * 4u };
 }
 
 template <bool GENERAL>
@@ -338,46 +356,64 @@ __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw, GENERAL);
   const uint32_t total = tp.n_main + *tp.fork_snapshot;
+  const uint32_t stride = gridDim.x * blockDim.x;
   Tally tally;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const float4 d4 = tp.D[i];
-    if (!(d4.w >= 0.0f)) continue;  // terminated
-    const float4 p4 = tp.P[i];
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  // software pipeline: the next ray's state is in flight while this one is being computed
+  float4 d4 = make_float4(0.f, 0.f, 0.f, -1.f), p4 = d4, q = d4;
+  if (i < total) {
+    d4 = tp.D[i];
+    p4 = tp.P[i];
+    q = tp.Q[i];
+  }
+  while (i < total) {
+    const uint32_t i_next = i + stride;
+    float4 d_n = make_float4(0.f, 0.f, 0.f, -1.f), p_n = d_n, q_n = d_n;
+    if (i_next < total) {
+      d_n = tp.D[i_next];
+      p_n = tp.P[i_next];
+      q_n = tp.Q[i_next];
+    }
     const uint32_t bits = __float_as_uint(p4.w);
     const uint32_t face = bits_face(bits);
-    if (face == kFaceInvalid) continue;
-    const float4 q = tp.Q[i];
-    const uint32_t shape = bits_shape(bits);
-    const PlaneRow<SMEM> planes = tb.planes(shape);
-    const uint32_t face_cnt = tb.meta(shape) & 255u;
-    const float n_idx = tp.wl[bits_wl(bits)].n_idx;
+    if (d4.w >= 0.0f && face != kFaceInvalid) {  // else: terminated ray
+      const uint32_t shape = bits_shape(bits);
+      const uint32_t meta = tb.meta(shape);
+      const AxisRow<SMEM> axes = tb.axes(shape);
+      const uint32_t axis_cnt = (meta >> 16) & 255u;
+      const float n_idx = tp.wl[bits_wl(bits)].n_idx;
 
-    const Split s = hit_surface(planes[face], n_idx, d4.x, d4.y, d4.z, d4.w);
-    // The child on the far side of the face normally leaves the crystal: classify it here.
-    const uint32_t out_child = s.cos_in > 0.0f ? 1u : 0u;  // internal hit: refracted; entry: reflected
-    const float ox = out_child ? s.tx : s.rx, oy = out_child ? s.ty : s.ry, oz = out_child ? s.tz : s.rz;
-    const float ow = out_child ? s.tw : s.rw;
-    const float ix = out_child ? s.rx : s.tx, iy = out_child ? s.ry : s.ty, iz = out_child ? s.rz : s.tz;
-    const float iw = out_child ? s.rw : s.tw;
-    if (ow >= 0.0f) {
-      float nx, ny, nz;
-      const uint32_t nf = slab_exit(planes, face_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
-      if (nf == kFaceInvalid) {
-        emit_exit<GENERAL>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, tb, tally);
-      } else if (!LAST) {
-        fork_append<GENERAL>(tp, i, bits, q, nx, ny, nz, ox, oy, oz, ow, nf);  // near-edge leak: both children stay
-      }
-    }
-    if (LAST) {
-      // no intersect pass follows the final interaction: classify the inside child here too
-      if (iw >= 0.0f) {
+      const Split s = hit_surface(tb.plane(shape, face), n_idx, d4.x, d4.y, d4.z, d4.w);
+      // The child on the far side of the face normally leaves the crystal: classify it here.
+      const uint32_t out_child = s.cos_in > 0.0f ? 1u : 0u;  // internal hit: refracted; entry: reflected
+      const float ox = out_child ? s.tx : s.rx, oy = out_child ? s.ty : s.ry, oz = out_child ? s.tz : s.rz;
+      const float ow = out_child ? s.tw : s.rw;
+      const float ix = out_child ? s.rx : s.tx, iy = out_child ? s.ry : s.ty, iz = out_child ? s.rz : s.tz;
+      const float iw = out_child ? s.rw : s.tw;
+      if (ow >= 0.0f) {
         float nx, ny, nz;
-        const uint32_t nf = slab_exit(planes, face_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
-        if (nf == kFaceInvalid) emit_exit<GENERAL>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, tb, tally);
+        const uint32_t nf = slab_exit(axes, axis_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
+        if (nf == kFaceInvalid) {
+          emit_exit<GENERAL>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, tb, tally);
+        } else if (!LAST) {
+          fork_append<GENERAL>(tp, i, bits, q, nx, ny, nz, ox, oy, oz, ow, nf);  // near-edge leak: both children stay
+        }
       }
-    } else {
-      tp.D[i] = make_float4(ix, iy, iz, iw);  // iw < 0 (TIR sentinel) terminates the ray
+      if (LAST) {
+        // no intersect pass follows the final interaction: classify the inside child here too
+        if (iw >= 0.0f) {
+          float nx, ny, nz;
+          const uint32_t nf = slab_exit(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+          if (nf == kFaceInvalid) emit_exit<GENERAL>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, tb, tally);
+        }
+      } else {
+        tp.D[i] = make_float4(ix, iy, iz, iw);  // iw < 0 (TIR sentinel) terminates the ray
+      }
     }
+    d4 = d_n;
+    p4 = p_n;
+    q = q_n;
+    i = i_next;
   }
   if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
     atomicAdd(tp.stat_exit_count, tally.exits);
@@ -395,32 +431,45 @@ __global__ void __launch_bounds__(256) intersect_kernel(const TraceParams tp) {
   const uint32_t forks = *tp.fork_count;
   const uint32_t total = tp.n_main + min(forks, tp.fork_cap);
   if (blockIdx.x == 0 && threadIdx.x == 0) *tp.fork_snapshot = min(forks, tp.fork_cap);
+  const uint32_t stride = gridDim.x * blockDim.x;
   Tally tally;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const float4 d4 = tp.D[i];
-    if (!(d4.w >= 0.0f)) continue;
-    const float4 p4 = tp.P[i];
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 d4 = make_float4(0.f, 0.f, 0.f, -1.f), p4 = d4;
+  if (i < total) {
+    d4 = tp.D[i];
+    p4 = tp.P[i];
+  }
+  while (i < total) {
+    const uint32_t i_next = i + stride;
+    float4 d_n = make_float4(0.f, 0.f, 0.f, -1.f), p_n = d_n;
+    if (i_next < total) {
+      d_n = tp.D[i_next];
+      p_n = tp.P[i_next];
+    }
     const uint32_t bits = __float_as_uint(p4.w);
     const uint32_t face = bits_face(bits);
-    if (face == kFaceInvalid) continue;
-    if (bits_advanced(bits)) {  // fork ray: advanced when it was created
-      tp.P[i] = make_float4(p4.x, p4.y, p4.z, __uint_as_float(bits & ~(1u << 30)));
-      continue;
+    if (d4.w >= 0.0f && face != kFaceInvalid) {
+      if (bits_advanced(bits)) {  // fork ray: advanced when it was created
+        tp.P[i] = make_float4(p4.x, p4.y, p4.z, __uint_as_float(bits & ~(1u << 30)));
+      } else {
+        const uint32_t shape = bits_shape(bits);
+        const uint32_t meta = tb.meta(shape);
+        float nx, ny, nz;
+        const uint32_t nf = slab_exit(tb.axes(shape), (meta >> 16) & 255u, face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz);
+        if (nf == kFaceInvalid) {
+          // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
+          emit_exit<GENERAL>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, tb, tally);
+          tp.D[i] = make_float4(d4.x, d4.y, d4.z, -1.0f);
+        } else {
+          tp.P[i] = make_float4(nx, ny, nz, __uint_as_float(bits_with_face(bits, nf)));
+          if (GENERAL && (tp.flags & kFlagPath) && tp.hit + 1u < tp.max_hits)
+            tp.path[static_cast<size_t>(tp.hit + 1u) * tp.cap + i] = static_cast<uint8_t>(nf);
+        }
+      }
     }
-    const uint32_t shape = bits_shape(bits);
-    const PlaneRow<SMEM> planes = tb.planes(shape);
-    const uint32_t face_cnt = tb.meta(shape) & 255u;
-    float nx, ny, nz;
-    const uint32_t nf = slab_exit(planes, face_cnt, face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz);
-    if (nf == kFaceInvalid) {
-      // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
-      emit_exit<GENERAL>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, tb, tally);
-      tp.D[i] = make_float4(d4.x, d4.y, d4.z, -1.0f);
-      continue;
-    }
-    tp.P[i] = make_float4(nx, ny, nz, __uint_as_float(bits_with_face(bits, nf)));
-    if (GENERAL && (tp.flags & kFlagPath) && tp.hit + 1u < tp.max_hits)
-      tp.path[static_cast<size_t>(tp.hit + 1u) * tp.cap + i] = static_cast<uint8_t>(nf);
+    d4 = d_n;
+    p4 = p_n;
+    i = i_next;
   }
   if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
     atomicAdd(tp.stat_exit_count, tally.exits);
@@ -568,6 +617,7 @@ struct LayerDev {
   uint32_t shape_cnt = 0;
   bool any_filter = false;
   DevBuf<float4> planes;
+  DevBuf<float4> axes;
   DevBuf<uint32_t> shape_meta;
   DevBuf<uint8_t> face_fn;
   DevBuf<HbCrystalTables> shapes;
@@ -774,6 +824,7 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   L->prob = src.prob;
   L->pops.clear();
   std::vector<float4> planes;
+  std::vector<float4> axes;
   std::vector<uint32_t> meta;
   std::vector<uint8_t> fn;
   std::vector<HbCrystalTables> shapes;
@@ -797,11 +848,34 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
       const HbCrystalTables& t = p.shapes[s];
       if (t.face_cnt > HB_MAX_FACES || t.subtri_cnt > HB_MAX_SUBTRIS) return fail(h, HB_ERR_INVALID_ARG, "crystal table too large");
       shapes.push_back(t);
-      meta.push_back(t.face_cnt | (ci << 8));
       for (uint32_t f = 0; f < HB_MAX_FACES; f++) {
         planes.push_back(make_float4(t.plane[f][0], t.plane[f][1], t.plane[f][2], t.plane[f][3]));
         fn.push_back(t.face_fn[f]);
       }
+      // Axis table: faces whose unit normals are exact negatives share one entry (see slab_exit).
+      uint32_t axis_cnt = 0;
+      bool used[HB_MAX_FACES] = {};
+      const size_t ax0 = axes.size();
+      axes.resize(ax0 + HB_MAX_FACES * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+      for (uint32_t f = 0; f < t.face_cnt; f++) {
+        if (used[f]) continue;
+        used[f] = true;
+        uint32_t partner = kFaceInvalid;
+        for (uint32_t g = f + 1; g < t.face_cnt; g++) {
+          if (!used[g] && t.plane[g][0] == -t.plane[f][0] && t.plane[g][1] == -t.plane[f][1] && t.plane[g][2] == -t.plane[f][2]) {
+            partner = g;
+            used[g] = true;
+            break;
+          }
+        }
+        const uint32_t fbits = f | (partner << 8);
+        float fb;
+        std::memcpy(&fb, &fbits, 4);
+        axes[ax0 + 2 * axis_cnt] = make_float4(t.plane[f][0], t.plane[f][1], t.plane[f][2], t.plane[f][3]);
+        axes[ax0 + 2 * axis_cnt + 1] = make_float4(partner == kFaceInvalid ? 0.0f : t.plane[partner][3], fb, 0.f, 0.f);
+        axis_cnt++;
+      }
+      meta.push_back(t.face_cnt | (ci << 8) | (axis_cnt << 16));
     }
     filters.push_back(p.filter);
     cid.push_back(p.crystal_id);
@@ -814,6 +888,7 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   L->shape_cnt = static_cast<uint32_t>(shapes.size());
   L->carry.assign(L->pops.size(), 0.0);
   HB_CUDA(h, L->planes.ensure(planes.size()));
+  HB_CUDA(h, L->axes.ensure(axes.size()));
   HB_CUDA(h, L->shape_meta.ensure(meta.size()));
   HB_CUDA(h, L->face_fn.ensure(fn.size()));
   HB_CUDA(h, L->shapes.ensure(shapes.size()));
@@ -821,6 +896,7 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   HB_CUDA(h, L->pop_crystal_id.ensure(cid.size()));
   HB_CUDA(h, L->luts.ensure(luts.size()));
   HB_CUDA(h, cudaMemcpy(L->planes.p, planes.data(), planes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(L->axes.p, axes.data(), axes.size() * sizeof(float4), cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->shape_meta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->face_fn.p, fn.data(), fn.size(), cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->shapes.p, shapes.data(), shapes.size() * sizeof(HbCrystalTables), cudaMemcpyHostToDevice));
@@ -970,7 +1046,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.cap = cap;
   tp.fork_cap = fork_cap;
   tp.root_base = static_cast<uint32_t>(root0);
-  tp.lt = LayerTables{ L.planes.p, L.shape_meta.p, L.face_fn.p, L.shapes.p, L.filters.p, L.pop_crystal_id.p,
+  tp.lt = LayerTables{ L.planes.p, L.axes.p, L.shape_meta.p, L.face_fn.p, L.shapes.p, L.filters.p, L.pop_crystal_id.p,
                        L.shape_cnt, static_cast<uint32_t>(L.pops.size()), L.any_filter ? 1u : 0u };
   tp.wl = h->wl_cur;
   tp.wl_cnt = h->wl_cnt;
@@ -1101,6 +1177,7 @@ void hb_destroy(HbEngine* h) {
   }
   for (auto& L : h->layers) {
     L->planes.release();
+    L->axes.release();
     L->shape_meta.release();
     L->face_fn.release();
     L->shapes.release();

@@ -1,0 +1,193 @@
+// adapter_main.cpp — drop-in demonstration + cross-backend parity battery (TEST INFRASTRUCTURE).
+//
+// Links the UNMODIFIED reference CPU core with adapter/b200_trace_backend.hpp and drives both
+// `lumice::CpuTraceBackend` (the reference's oracle backend, mt19937 sampling) and `lumice::B200TraceBackend`
+// (this repo's engine behind the same TraceBackend seam) through the reference driver's call sequence
+// (SimulateOneWavelengthWithBackend, simulator.cpp:1498-1560) on the same SceneConfig/RenderConfig objects.
+// Sampling differs (mt19937 vs counter-based PCG), so the comparison is the reference's own statistical
+// battery (test/parity-cross-backend/backend/test_cuda_exit_seam_parity.py:10-16,50-53):
+//   4x4 block-mean Pearson r >= 0.95 on the Y channel, total-Y ratio within 5 %.
+// Prints one JSON line; exit code 0 iff the battery passes.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../adapter/b200_trace_backend.hpp"
+#include "core/backend/cpu_trace_backend.hpp"
+
+using namespace lumice;  // NOLINT
+
+namespace {
+
+SceneConfig MakeScene(int which, size_t max_hits) {
+  SceneConfig scene;
+  scene.ray_num_ = 0;
+  scene.max_hits_ = max_hits;
+  scene.light_source_.param_ = SunParam{ 20.0f, 0.0f, 0.5f };
+  scene.light_source_.spectrum_ = std::vector<WlParam>{ { 550.0f, 1.0f } };
+  auto prism = [](float h, Distribution zen_lat, IdType id) {
+    ScatteringSetting s;
+    s.crystal_.id_ = id;
+    PrismCrystalParam p;
+    p.h_ = Distribution{ DistributionType::kNoRandom, h, 0.0f };
+    for (auto& d : p.d_) {
+      d = Distribution{ DistributionType::kNoRandom, 1.0f, 0.0f };
+    }
+    s.crystal_.param_ = p;
+    s.crystal_.axis_.latitude_dist = zen_lat;
+    s.crystal_.axis_.azimuth_dist = Distribution{ DistributionType::kUniform, 0.0f, 360.0f };
+    s.crystal_.axis_.roll_dist = Distribution{ DistributionType::kUniform, 0.0f, 360.0f };
+    s.filter_ = FilterConfig{};
+    s.crystal_proportion_ = 1.0f;
+    return s;
+  };
+  if (which == 0) {  // BASELINE config 2 scene: column, zenith gauss(90, 0.3) => latitude gauss(0, 0.3)
+    MsInfo ms;
+    ms.prob_ = 0.0f;
+    ms.setting_.push_back(prism(1.3f, Distribution{ DistributionType::kGaussian, 0.0f, 0.3f }, 3));
+    scene.ms_.push_back(std::move(ms));
+  } else {  // two layers: plate (prob 0.6) over column, as MakeCpuScene(…, 2) does
+    MsInfo a;
+    a.prob_ = 0.6f;
+    a.setting_.push_back(prism(0.3f, Distribution{ DistributionType::kGaussian, 90.0f, 0.8f }, 6));
+    scene.ms_.push_back(std::move(a));
+    MsInfo b;
+    b.prob_ = 0.0f;
+    b.setting_.push_back(prism(1.3f, Distribution{ DistributionType::kUniform, 90.0f, 360.0f }, 3));
+    scene.ms_.push_back(std::move(b));
+  }
+  return scene;
+}
+
+RenderConfig MakeRender(int w, int h) {
+  RenderConfig cfg;
+  cfg.id_ = 4;
+  cfg.lens_.type_ = LensParam::kFisheyeEqualArea;
+  cfg.lens_.fov_ = 120.0f;
+  cfg.resolution_[0] = w;
+  cfg.resolution_[1] = h;
+  cfg.view_.el_ = 30.0f;
+  cfg.visible_ = RenderConfig::kUpper;
+  return cfg;
+}
+
+// The reference driver's seam call sequence for one wavelength batch.
+void RunSessions(TraceBackend& be, const SceneConfig& scene, const RenderConfig& render, size_t total, size_t batch,
+                 uint32_t seed, std::vector<float>* cpu_img, float* cpu_landed) {
+  const Rotation cam = MakeCameraRotation(render);
+  std::vector<ExitRayRecord> recs;
+  for (size_t done = 0; done < total; done += batch) {
+    const size_t n = std::min(batch, total - done);
+    SessionSpec spec{};
+    spec.scene = &scene;
+    spec.render = &render;
+    spec.wl = WlParam{ 550.0f, 1.0f };
+    spec.seed = seed;
+    spec.ray_num = n;
+    be.BeginSession(spec);
+    HostRayBatch hb;
+    hb.count = n;
+    RootRaySource roots = RootRaySource::FromHost(hb);
+    for (size_t mi = 0; mi < scene.ms_.size(); mi++) {
+      auto handle = be.TraceLayer(roots);
+      be.DrainExits(recs);
+      if (cpu_img != nullptr && !recs.empty()) {  // exit-record path (CPU backend): host projection
+        std::vector<float> d(recs.size() * 3), w(recs.size());
+        for (size_t i = 0; i < recs.size(); i++) {
+          std::memcpy(&d[i * 3], recs[i].dir, 12);
+          w[i] = recs[i].weight;
+        }
+        ScatterOutgoingToXyz(d.data(), w.data(), w.size(), render, cam, 550.0f, cpu_img->data(), cpu_landed);
+      }
+      if (mi + 1 == scene.ms_.size()) {
+        break;
+      }
+      roots = be.Recombine(std::move(handle), RecombineSpec{ true });
+    }
+    be.EndSession();
+  }
+}
+
+double Pearson(const std::vector<double>& a, const std::vector<double>& b) {
+  double ma = 0, mb = 0;
+  for (size_t i = 0; i < a.size(); i++) {
+    ma += a[i];
+    mb += b[i];
+  }
+  ma /= a.size();
+  mb /= b.size();
+  double sab = 0, saa = 0, sbb = 0;
+  for (size_t i = 0; i < a.size(); i++) {
+    sab += (a[i] - ma) * (b[i] - mb);
+    saa += (a[i] - ma) * (a[i] - ma);
+    sbb += (b[i] - mb) * (b[i] - mb);
+  }
+  return sab / std::sqrt(saa * sbb + 1e-300);
+}
+
+std::vector<double> BlockMeansY(const std::vector<float>& img, int w, int h, int blk) {
+  std::vector<double> out;
+  for (int by = 0; by + blk <= h; by += blk) {
+    for (int bx = 0; bx + blk <= w; bx += blk) {
+      double s = 0;
+      for (int y = 0; y < blk; y++) {
+        for (int x = 0; x < blk; x++) {
+          s += img[(static_cast<size_t>(by + y) * w + bx + x) * 3 + 1];
+        }
+      }
+      out.push_back(s / (blk * blk));
+    }
+  }
+  return out;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  const int which = argc > 1 ? std::atoi(argv[1]) : 0;
+  const size_t total = argc > 2 ? static_cast<size_t>(std::atoll(argv[2])) : 2000000;
+  const int w = 480, h = 270;
+  SceneConfig scene = MakeScene(which, 7);
+  RenderConfig render = MakeRender(w, h);
+  const size_t pix = static_cast<size_t>(w) * h;
+
+  std::vector<float> cpu_img(pix * 3, 0.0f);
+  float cpu_landed = 0.0f;
+  {
+    CpuTraceBackend cpu;
+    RunSessions(cpu, scene, render, total, 4096, 42, &cpu_img, &cpu_landed);
+  }
+
+  std::vector<float> gpu_img(pix * 3, 0.0f);
+  float gpu_landed = 0.0f;
+  try {
+    B200TraceBackend gpu(0);
+    if (!gpu.SupportsDeviceXyzAccum() || !gpu.IsCompatible(render)) {
+      std::printf("{\"error\": \"backend refused the render config\"}\n");
+      return 2;
+    }
+    RunSessions(gpu, scene, render, total, 1 << 20, 42, nullptr, nullptr);
+    XyzImageData xyz{ gpu_img.data(), w, h };
+    gpu.ReadbackXyzAccum(xyz, gpu_landed);
+  } catch (const BackendUnavailableError& e) {
+    std::printf("{\"unavailable\": \"%s\"}\n", e.what());
+    return 3;
+  }
+
+  double ty_c = 0, ty_g = 0;
+  for (size_t i = 0; i < pix; i++) {
+    ty_c += cpu_img[i * 3 + 1];
+    ty_g += gpu_img[i * 3 + 1];
+  }
+  const double r = Pearson(BlockMeansY(cpu_img, w, h, 4), BlockMeansY(gpu_img, w, h, 4));
+  const double ratio = ty_g / (ty_c + 1e-300);
+  const double landed_ratio = gpu_landed / (cpu_landed + 1e-30);
+  const bool ok = r >= 0.95 && std::fabs(ratio - 1.0) <= 0.05 && std::fabs(landed_ratio - 1.0) <= 0.05;
+  std::printf("{\"scene\": %d, \"rays\": %zu, \"pearson_4x4\": %.5f, \"total_y_ratio\": %.5f, \"landed_ratio\": %.5f, "
+              "\"cpu_landed\": %.3f, \"gpu_landed\": %.3f, \"pass\": %s}\n",
+              which, total, r, ratio, landed_ratio, cpu_landed, gpu_landed, ok ? "true" : "false");
+  return ok ? 0 : 1;
+}
