@@ -106,6 +106,7 @@ struct GenParams {
   const HbWlEntry* wl;
   uint32_t wl_cnt;
   float sun_lon, sun_lat, sun_half;
+  float sun_c_cap, sun_c_lon, sun_s_lon, sun_c_lat, sun_s_lat;  // per-launch constants of sample_sph_cap
   uint32_t flags;
   // transit only
   const float4* cont_dw;
@@ -482,8 +483,58 @@ __global__ void __launch_bounds__(256) intersect_kernel(const TraceParams tp) {
 // ------------------------------------------------------------------------------------------------
 struct GenShared {
   float lut[3 * HB_LUT_NODES];
-  HbCrystalTables shape0;  // single-shape populations: entry fan table staged on chip
+  HbCrystalTables shape0;        // single-shape populations: entry fan table staged on chip
+  float4 tri_na[HB_MAX_SUBTRIS];  // (normal, area) per fan triangle: one LDS.128 per categorical term
 };
+
+constexpr uint32_t kFastTris = 24;  // prism = 20 fan triangles: weights kept in registers
+
+// Entry sampling, single-shape fast path: identical arithmetic and summation order as sample_entry, but
+// the triangle weights live in registers (one pass over shared memory, branch-free pick).
+HB_DEV void sample_entry_fast(Stream& s, const GenShared* gs, float dx, float dy, float dz, float& px, float& py,
+                              float& pz, uint32_t& face) {
+  const uint32_t n = gs->shape0.subtri_cnt;
+  float w[kFastTris];
+  float total = 0.0f;
+#pragma unroll
+  for (uint32_t i = 0; i < kFastTris; i++) {
+    w[i] = 0.0f;
+    if (i < n) {
+      const float4 na = gs->tri_na[i];
+      const float dt = dx * na.x + dy * na.y + dz * na.z;
+      w[i] = fmaxf(-dt * na.w, 0.0f);
+      total += w[i];
+    }
+  }
+  const float u_cat = s.next();
+  uint32_t tri = 0u;
+  if (total > 0.0f) {
+    const float target = u_cat * total;
+    float cum = 0.0f;
+    bool found = false;
+    tri = n - 1u;
+#pragma unroll
+    for (uint32_t i = 0; i < kFastTris; i++) {
+      if (i < n) {
+        cum += w[i];
+        if (!found && cum > target) {
+          tri = i;
+          found = true;
+        }
+      }
+    }
+  }
+  float u = s.next(), v = s.next();
+  if (u + v > 1.0f) {
+    u = 1.0f - u;
+    v = 1.0f - v;
+  }
+  const float* tv = gs->shape0.tri_v[tri];
+  px = u * (tv[3] - tv[0]) + v * (tv[6] - tv[0]) + tv[0];
+  py = u * (tv[4] - tv[1]) + v * (tv[7] - tv[1]) + tv[1];
+  pz = u * (tv[5] - tv[2]) + v * (tv[8] - tv[2]) + tv[2];
+  face = gs->shape0.tri_face[tri];
+}
 
 template <bool TRANSIT>
 __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
@@ -496,8 +547,11 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(gp.shapes);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&gs->shape0);
     for (uint32_t i = threadIdx.x; i < sizeof(HbCrystalTables) / 4; i += blockDim.x) dst[i] = src[i];
+    for (uint32_t i = threadIdx.x; i < HB_MAX_SUBTRIS; i += blockDim.x)
+      gs->tri_na[i] = make_float4(gp.shapes->tri_n[i][0], gp.shapes->tri_n[i][1], gp.shapes->tri_n[i][2], gp.shapes->tri_area[i]);
   }
   __syncthreads();
+  const bool fast_entry = gp.shape_cnt == 1u && gs->shape0.subtri_cnt <= kFastTris;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gp.count; k += gridDim.x * blockDim.x) {
     const uint32_t lo = gp.idx_lo + k;
     const uint32_t hi = gp.idx_hi + (lo < gp.idx_lo ? 1u : 0u);
@@ -522,7 +576,16 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
     const float4 q = quat_from_angles(lon, lat, roll);
     const Rot r = rot_from_quat(q);
     if (!TRANSIT) {
-      sample_sph_cap(s, gp.sun_lon, gp.sun_lat, gp.sun_half, wx, wy, wz);
+      // sample_sph_cap (pcg_shared.h:514-529) with the per-launch trigonometry hoisted to the host
+      const float u = s.next();
+      const float x = u + (1.0f - u) * gp.sun_c_cap;
+      const float rr = sqrtf(fmaxf(1.0f - x * x, 0.0f));
+      float sp, cp;
+      sincosf(s.next() * 2.0f * kPiF, &sp, &cp);
+      const float y = cp * rr, z = sp * rr;
+      wx = gp.sun_c_lon * gp.sun_c_lat * x - gp.sun_s_lon * y - gp.sun_c_lon * gp.sun_s_lat * z;
+      wy = gp.sun_s_lon * gp.sun_c_lat * x + gp.sun_c_lon * y - gp.sun_s_lon * gp.sun_s_lat * z;
+      wz = gp.sun_s_lat * x + gp.sun_c_lat * z;
       weight = gp.wl[wl_i].spd_weight;
     }
     float dx, dy, dz;
@@ -537,7 +600,8 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
     if (tab->subtri_cnt == 0u) {
       weight = -1.0f;  // degenerate crystal: nothing to trace (zero-weight discard, simulator.cpp:149-159)
     } else {
-      sample_entry(s, tab, dx, dy, dz, px, py, pz, face);
+      if (fast_entry) sample_entry_fast(s, gs, dx, dy, dz, px, py, pz, face);
+      else sample_entry(s, tab, dx, dy, dz, px, py, pz, face);
     }
     const uint32_t slot = gp.slot0 + k;
     gp.P[slot] = make_float4(px, py, pz, __uint_as_float(pack_bits(face, wl_i, gp.shape_base + sh, 0u)));
@@ -548,17 +612,37 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// image drain: (X,Y,Z,landed) float4 -> packed XYZ + landed-weight sum, then zero
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) drain_image_kernel(float4* image, float* xyz, double* landed, uint32_t pixels) {
-  double acc = 0.0;
+// fp32 accumulators absorb small addends once a pixel grows (a 2e5 sun pixel has ulp 0.016): every
+// `fold_rays` root rays the working float4 image is folded into a double-precision master image and
+// zeroed, which bounds the relative loss (measured 2e-6 at 1 Mi rays, 6e-4 at 16 Mi without folding).
+// The reference bounds the same error by draining every 64 batches into a host Neumaier sum
+// (simulator.hpp:136, accum_shared.h:71-75).
+__global__ void __launch_bounds__(256) fold_image_kernel(float4* image, double4* master, uint32_t pixels) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
     const float4 v = image[i];
-    xyz[static_cast<size_t>(i) * 3 + 0] = v.x;
-    xyz[static_cast<size_t>(i) * 3 + 1] = v.y;
-    xyz[static_cast<size_t>(i) * 3 + 2] = v.z;
-    acc += static_cast<double>(v.w);
-    image[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) {
+      double4 m = master[i];
+      m.x += static_cast<double>(v.x);
+      m.y += static_cast<double>(v.y);
+      m.z += static_cast<double>(v.z);
+      m.w += static_cast<double>(v.w);
+      master[i] = m;
+      image[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  }
+}
+
+// image drain: master (X,Y,Z,landed) double4 -> packed fp32 XYZ + landed-weight sum, then zero
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) drain_image_kernel(double4* master, float* xyz, double* landed, uint32_t pixels) {
+  double acc = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const double4 v = master[i];
+    xyz[static_cast<size_t>(i) * 3 + 0] = static_cast<float>(v.x);
+    xyz[static_cast<size_t>(i) * 3 + 1] = static_cast<float>(v.y);
+    xyz[static_cast<size_t>(i) * 3 + 2] = static_cast<float>(v.z);
+    acc += v.w;
+    master[i] = make_double4(0.0, 0.0, 0.0, 0.0);
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   __shared__ double warp_sum[8];
@@ -652,6 +736,9 @@ struct HbEngine {
   bool have_scene = false, have_render = false;
   HbProjParams proj{};
   DevBuf<float4> image;
+  DevBuf<double4> master;
+  uint64_t rays_since_fold = 0;
+  uint64_t fold_rays = 1u << 21;
   DevBuf<float> xyz_stage;
   DevBuf<double> landed_dev;
 
@@ -985,6 +1072,11 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
       gp.sun_lon = h->sun_lon;
       gp.sun_lat = h->sun_lat;
       gp.sun_half = h->sun_half;
+      gp.sun_c_cap = std::cos(h->sun_half);
+      gp.sun_c_lon = std::cos(h->sun_lon);
+      gp.sun_s_lon = std::sin(h->sun_lon);
+      gp.sun_c_lat = std::cos(h->sun_lat);
+      gp.sun_s_lat = std::sin(h->sun_lat);
       gp.flags = flags;
       EventPair* ev = begin_event(h, 0, gp.count);
       if (li == 0) {
@@ -1108,6 +1200,15 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
     }
   }
   h->ctr.rays_traced += n;
+  if (flags & kFlagAccum) {
+    h->rays_since_fold += n;
+    if (h->rays_since_fold >= h->fold_rays) {
+      const uint32_t pix = static_cast<uint32_t>(h->proj.img_w) * h->proj.img_h;
+      fold_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->master.p, pix);
+      h->ctr.kernel_launches++;
+      h->rays_since_fold = 0;
+    }
+  }
   return HB_OK;
 }
 
@@ -1186,6 +1287,7 @@ void hb_destroy(HbEngine* h) {
     L->luts.release();
   }
   h->image.release();
+  h->master.release();
   h->xyz_stage.release();
   h->landed_dev.release();
   for (auto& s : h->wl_cache) s.dev.release();
@@ -1245,6 +1347,9 @@ int hb_set_render(HbEngine* h, const HbProjParams* p) {
   h->proj = *p;
   if (realloc) {  // resolution change => realloc + zero (cuda_trace_backend.cu:3799-3835)
     HB_CUDA(h, h->image.ensure(pix));
+    HB_CUDA(h, h->master.ensure(pix));
+    HB_CUDA(h, cudaMemset(h->master.p, 0, pix * sizeof(double4)));
+    h->rays_since_fold = 0;
     HB_CUDA(h, h->xyz_stage.ensure(pix * 3));
     HB_CUDA(h, h->landed_dev.ensure(1));
     HB_CUDA(h, cudaMemset(h->image.p, 0, pix * sizeof(float4)));
@@ -1466,8 +1571,10 @@ int hb_readback_xyz(HbEngine* h, float* xyz, float* landed) {
   if (!h->have_render) return fail(h, HB_ERR_STATE, "readback before hb_set_render");
   cudaSetDevice(h->device);
   const uint32_t pix = static_cast<uint32_t>(h->proj.img_w) * h->proj.img_h;
-  drain_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->xyz_stage.p, h->landed_dev.p, pix);
-  h->ctr.kernel_launches++;
+  fold_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->master.p, pix);
+  h->rays_since_fold = 0;
+  drain_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->master.p, h->xyz_stage.p, h->landed_dev.p, pix);
+  h->ctr.kernel_launches += 2;
   double l = 0.0;
   HB_CUDA(h, cudaMemcpyAsync(xyz, h->xyz_stage.p, static_cast<size_t>(pix) * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   HB_CUDA(h, cudaMemcpyAsync(&l, h->landed_dev.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1529,6 +1636,9 @@ int hb_set_option(HbEngine* h, const char* key, int64_t value) {
     if (value < 1 || value > 32) return fail(h, HB_ERR_INVALID_ARG, "blocks_per_sm out of range");
     h->blocks_per_sm = static_cast<int>(value);
     h->blocks_per_sm_override = static_cast<int>(value);
+  } else if (k == "fold_rays") {
+    if (value < 1024) return fail(h, HB_ERR_INVALID_ARG, "fold_rays out of range");
+    h->fold_rays = static_cast<uint64_t>(value);
   } else if (k == "gen_base") {
     h->gen_base = static_cast<uint64_t>(value);
   } else if (k == "stream_base") {  // restart all monotone stream counters (tests: reproducible replays)
@@ -1563,8 +1673,13 @@ int hb_synchronize(HbEngine* h) {
 int hb_image_device_ptr(HbEngine* h, void** ptr, uint64_t* float_count) {
   if (h == nullptr || ptr == nullptr || float_count == nullptr) return HB_ERR_INVALID_ARG;
   if (!h->have_render) return fail(h, HB_ERR_STATE, "no render set");
-  *ptr = h->image.p;
-  *float_count = static_cast<uint64_t>(h->proj.img_w) * h->proj.img_h * 4;
+  cudaSetDevice(h->device);
+  const uint32_t pix = static_cast<uint32_t>(h->proj.img_w) * h->proj.img_h;
+  fold_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->master.p, pix);
+  h->rays_since_fold = 0;
+  h->ctr.kernel_launches++;
+  *ptr = h->master.p;
+  *float_count = static_cast<uint64_t>(pix) * 4;
   return HB_OK;
 }
 
@@ -1606,7 +1721,11 @@ int hb_allreduce_image(HbEngine* h) {
   if (h->comm == nullptr) return fail(h, HB_ERR_STATE, "hb_comm_init not called");
   cudaSetDevice(h->device);
   const size_t cnt = static_cast<size_t>(h->proj.img_w) * h->proj.img_h * 4;
-  if (ncclAllReduce(h->image.p, h->image.p, cnt, ncclFloat, ncclSum, h->comm, h->stream) != ncclSuccess)
+  const uint32_t pix = static_cast<uint32_t>(h->proj.img_w) * h->proj.img_h;
+  fold_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->master.p, pix);
+  h->rays_since_fold = 0;
+  h->ctr.kernel_launches++;
+  if (ncclAllReduce(h->master.p, h->master.p, cnt, ncclDouble, ncclSum, h->comm, h->stream) != ncclSuccess)
     return fail(h, HB_ERR_COMM, "ncclAllReduce failed");
   return HB_OK;
 #else

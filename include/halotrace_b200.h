@@ -264,7 +264,8 @@ int hb_export_roots(HbEngine* h, uint64_t cap, float* d3, float* p3, float* w, u
 int hb_set_option(HbEngine* h, const char* key, int64_t value);
 int hb_get_counters(HbEngine* h, HbCounters* out);
 int hb_synchronize(HbEngine* h);
-/* Device pointer of the W*H*4 float accumulator (x,y,z,landed) for collectives driven from
+/* Device pointer of the W*H*4 DOUBLE master accumulator (x,y,z,landed; the fp32 working image is folded
+ * into it first) for collectives driven from
  * outside (torch.distributed); valid until hb_set_render / hb_destroy. */
 int hb_image_device_ptr(HbEngine* h, void** ptr, uint64_t* float_count);
 void* hb_stream(HbEngine* h);             /* cudaStream_t the engine launches on */
