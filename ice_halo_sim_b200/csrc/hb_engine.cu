@@ -763,7 +763,7 @@ struct HbEngine {
   uint64_t gen_base = 0, gate_base = 0, transit_base = 0;
 
   // tile buffers
-  uint64_t tile_rays = 1u << 22;
+  uint64_t tile_rays = 1u << 24;
   DevBuf<float4> P, D, Q;
   DevBuf<uint8_t> path;
   DevBuf<uint32_t> fork_root, fork_code;
