@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--rays-per-wl", type=int, default=RAYS_PER_WL)
     ap.add_argument("--tile-rays", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--set", action="append", default=[], help="engine option key=value (experiments)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -192,6 +193,9 @@ def main():
     be = B.B200TraceBackend(local_rank)
     if args.tile_rays:
         be.SetOption("tile_rays", args.tile_rays)
+    for kv in args.set:
+        k, v = kv.split("=")
+        be.SetOption(k, int(v))
     be.SetScene(tables)
     be.SetRender(rdesc)
     stream = torch.cuda.ExternalStream(be._lib.hb_stream(be._h), device=torch.device("cuda", local_rank))

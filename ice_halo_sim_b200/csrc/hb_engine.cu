@@ -53,6 +53,7 @@ enum : uint32_t {
   kFlagAccum = 4u,    // fused projection + image reduction
   kFlagGate = 8u,     // layer prob > 0: draw the continue/outgoing gate, append continuations
   kFlagStats = 16u,   // LayerStats (exit count, weight sum)
+  kFlagPixelCache = 32u,  // per-CTA shared-memory pixel cache in the optics kernel
 };
 
 struct TraceParams {
@@ -123,7 +124,62 @@ struct GenParams {
 struct Tally {
   unsigned long long exits = 0;
   double w_sum = 0.0;
+  uint32_t* cache_keys = nullptr;  // per-CTA pixel cache (see PixelCache below); nullptr = reduce straight to L2
+  float* cache_vals = nullptr;
 };
+
+// Per-CTA pixel cache. Halo images are extremely peaked (the undeviated light through parallel faces lands
+// on the ~35 pixels of the sun disk: ~40 % of all exits), and same-address reductions serialise in the L2
+// atomic unit while the fp32 accumulator of such a pixel absorbs small addends. Each CTA therefore keeps a
+// direct-mapped table of kCacheSlots pixels in shared memory (first come, first claimed): contributions to a
+// cached pixel are summed in shared memory and reduced into the global image once, when the CTA retires.
+// Everything else goes straight to the L2 with one red.global.add.v4.f32.
+constexpr uint32_t kCacheSlots = 512;
+constexpr uint32_t kCacheEmpty = 0xFFFFFFFFu;
+constexpr size_t kCacheBytes = kCacheSlots * (sizeof(uint32_t) + 4 * sizeof(float));
+
+HB_DEV void accumulate_pixel(const TraceParams& tp, const Tally& tally, uint32_t pix, float x, float y, float z, float lw) {
+  if (tally.cache_keys != nullptr) {
+    const uint32_t slot = (pix * 2654435761u) >> 23;  // top 9 bits
+    uint32_t k = tally.cache_keys[slot];
+    if (k == kCacheEmpty) {
+      k = atomicCAS(&tally.cache_keys[slot], kCacheEmpty, pix);
+      if (k == kCacheEmpty) k = pix;
+    }
+    if (k == pix) {
+      float* v = tally.cache_vals + slot * 4u;
+      atomicAdd(v + 0, x);
+      atomicAdd(v + 1, y);
+      atomicAdd(v + 2, z);
+      if (lw != 0.0f) atomicAdd(v + 3, lw);
+      return;
+    }
+  }
+  red_add_f4(tp.image + pix, x, y, z, lw);
+}
+
+HB_DEV void cache_init(Tally& tally, unsigned char* smem) {
+  tally.cache_keys = reinterpret_cast<uint32_t*>(smem);
+  tally.cache_vals = reinterpret_cast<float*>(smem + kCacheSlots * sizeof(uint32_t));
+  for (uint32_t i = threadIdx.x; i < kCacheSlots; i += blockDim.x) {
+    tally.cache_keys[i] = kCacheEmpty;
+    tally.cache_vals[4u * i + 0] = 0.0f;
+    tally.cache_vals[4u * i + 1] = 0.0f;
+    tally.cache_vals[4u * i + 2] = 0.0f;
+    tally.cache_vals[4u * i + 3] = 0.0f;
+  }
+}
+
+HB_DEV void cache_flush(const TraceParams& tp, const Tally& tally) {
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kCacheSlots; i += blockDim.x) {
+    const uint32_t k = tally.cache_keys[i];
+    if (k != kCacheEmpty) {
+      const float* v = tally.cache_vals + 4u * i;
+      red_add_f4(tp.image + k, v[0], v[1], v[2], v[3]);
+    }
+  }
+}
 
 template <bool GENERAL, typename TablesT>
 HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float lx, float ly, float lz,
@@ -218,8 +274,8 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
     if (k < h.count) {
       const int px = h.px[k], py = h.py[k];
       if (px >= 0 && px < tp.proj.img_w && py >= 0 && py < tp.proj.img_h) {
-        red_add_f4(tp.image + (static_cast<size_t>(py) * tp.proj.img_w + px), mul(we.cmf_x, w), mul(we.cmf_y, w),
-                   mul(we.cmf_z, w), h.bump[k] ? w : 0.0f);
+        accumulate_pixel(tp, tally, static_cast<uint32_t>(py) * static_cast<uint32_t>(tp.proj.img_w) + static_cast<uint32_t>(px),
+                         mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w), h.bump[k] ? w : 0.0f);
       }
     }
   }
@@ -352,13 +408,22 @@ HB_DEV void fork_append(const TraceParams& tp, uint32_t slot, uint32_t bits, flo
 // ------------------------------------------------------------------------------------------------
 // optics kernel: one surface interaction per live ray
 // ------------------------------------------------------------------------------------------------
+#ifndef HB_OPTICS_MINB
+#define HB_OPTICS_MINB 1
+#endif
+#ifndef HB_INTERSECT_MINB
+#define HB_INTERSECT_MINB 1
+#endif
 template <bool GENERAL, bool LAST, bool SMEM>
-__global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
+__global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw, GENERAL);
+  Tally tally;
+  const bool use_cache = (tp.flags & kFlagPixelCache) != 0u;
+  if (use_cache) cache_init(tally, smem_raw);
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + (use_cache ? kCacheBytes : 0), GENERAL);
+  if (!SMEM && use_cache) __syncthreads();
   const uint32_t total = tp.n_main + *tp.fork_snapshot;
   const uint32_t stride = gridDim.x * blockDim.x;
-  Tally tally;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   // software pipeline: the next ray's state is in flight while this one is being computed
   float4 d4 = make_float4(0.f, 0.f, 0.f, -1.f), p4 = d4, q = d4;
@@ -393,7 +458,7 @@ __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
       const float iw = out_child ? s.rw : s.tw;
       if (ow >= 0.0f) {
         float nx, ny, nz;
-        const uint32_t nf = slab_exit(axes, axis_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
+        const uint32_t nf = slab_exit<true>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
         if (nf == kFaceInvalid) {
           emit_exit<GENERAL>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, tb, tally);
         } else if (!LAST) {
@@ -404,7 +469,7 @@ __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
         // no intersect pass follows the final interaction: classify the inside child here too
         if (iw >= 0.0f) {
           float nx, ny, nz;
-          const uint32_t nf = slab_exit(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+          const uint32_t nf = slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
           if (nf == kFaceInvalid) emit_exit<GENERAL>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, tb, tally);
         }
       } else {
@@ -416,6 +481,7 @@ __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
     q = q_n;
     i = i_next;
   }
+  if (use_cache) cache_flush(tp, tally);
   if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
     atomicAdd(tp.stat_exit_count, tally.exits);
     atomicAdd(tp.stat_w_sum, tally.w_sum);
@@ -426,7 +492,7 @@ __global__ void __launch_bounds__(256) optics_kernel(const TraceParams tp) {
 // intersect kernel: slab exit-face search for the inside child
 // ------------------------------------------------------------------------------------------------
 template <bool GENERAL, bool SMEM>
-__global__ void __launch_bounds__(256) intersect_kernel(const TraceParams tp) {
+__global__ void __launch_bounds__(256, HB_INTERSECT_MINB) intersect_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw, GENERAL);
   const uint32_t forks = *tp.fork_count;
@@ -456,7 +522,7 @@ __global__ void __launch_bounds__(256) intersect_kernel(const TraceParams tp) {
         const uint32_t shape = bits_shape(bits);
         const uint32_t meta = tb.meta(shape);
         float nx, ny, nz;
-        const uint32_t nf = slab_exit(tb.axes(shape), (meta >> 16) & 255u, face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz);
+        const uint32_t nf = slab_exit<false>(tb.axes(shape), (meta >> 16) & 255u, face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz);
         if (nf == kFaceInvalid) {
           // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
           emit_exit<GENERAL>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, tb, tally);
@@ -793,6 +859,7 @@ struct HbEngine {
   size_t ev_used = 0;
   int blocks_per_sm = 8;
   int blocks_per_sm_override = 0;
+  bool pixel_cache = true;
 #ifdef HB_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
@@ -876,6 +943,12 @@ uint32_t resident_grid(const HbEngine* h, K kernel, size_t smem, uint64_t n) {
 
 template <bool G, bool L, bool S>
 void launch_optics_t(HbEngine* h, size_t smem, const TraceParams& tp) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(optics_kernel<G, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(shared_tables_bytes(kSmemShapes) + kCacheBytes));
+    attr_set = true;
+  }
   const uint32_t grid = resident_grid(h, optics_kernel<G, L, S>, smem, tp.cap);
   optics_kernel<G, L, S><<<grid, 256, smem, h->stream>>>(tp);
 }
@@ -996,6 +1069,7 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
 uint32_t session_flags(const HbEngine* h, const LayerDev& L, bool last_layer) {
   uint32_t f = 0;
   if (h->spec.accumulate) f |= kFlagAccum;
+  if (h->spec.accumulate && h->pixel_cache) f |= kFlagPixelCache;
   if (h->spec.record_exits) f |= kFlagRecord | kFlagPath | kFlagStats;
   if (L.any_filter) f |= kFlagPath;
   if (L.prob > 0.0f) f |= kFlagGate;
@@ -1170,7 +1244,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
     tp.hit = hit;
     const bool last = hit + 1 == h->max_hits;
     EventPair* ev = begin_event(h, 1, n);
-    launch_optics(h, general, last, in_smem, smem, tp);
+    launch_optics(h, general, last, in_smem, smem + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
     end_event(h, ev);
     h->ctr.kernel_launches++;
     h->ctr.optics_launches++;
@@ -1636,6 +1710,8 @@ int hb_set_option(HbEngine* h, const char* key, int64_t value) {
     if (value < 1 || value > 32) return fail(h, HB_ERR_INVALID_ARG, "blocks_per_sm out of range");
     h->blocks_per_sm = static_cast<int>(value);
     h->blocks_per_sm_override = static_cast<int>(value);
+  } else if (k == "pixel_cache") {
+    h->pixel_cache = value != 0;
   } else if (k == "fold_rays") {
     if (value < 1024) return fail(h, HB_ERR_INVALID_ARG, "fold_rays out of range");
     h->fold_rays = static_cast<uint64_t>(value);

@@ -10,7 +10,7 @@ import os
 from . import _abi as A
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libhalotrace_b200.so")
+SO_PATH = os.environ.get("HALOTRACE_LIB", os.path.join(HERE, "libhalotrace_b200.so"))  # override: A/B builds
 
 _vp = C.c_void_p
 

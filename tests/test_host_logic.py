@@ -152,7 +152,7 @@ WORKER = textwrap.dedent("""
                           H.ptr(r["w"]), H.ptr(r["face"]), None, H.ptr(r["rot"]), H.ptr(r["shape"]), H.ptr(r["wl"]))
         lp, keep = parity.layer_params(tables.scene(), 0, wl_arr, 42, begin)
         ex, er, _ = parity.oracle_trace(lp, r, n * 9 + 16)
-        img, mag, landed = parity.oracle_image(proj, wl_arr, ex)
+        img, mag, landed, _ = parity.oracle_image(proj, wl_arr, ex)
         return img, landed, len(ex)
 
     img = np.zeros((135, 240, 3), np.float32); landed = 0.0; exits = 0
