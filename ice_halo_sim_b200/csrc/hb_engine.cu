@@ -409,10 +409,10 @@ HB_DEV void fork_append(const TraceParams& tp, uint32_t slot, uint32_t bits, flo
 // optics kernel: one surface interaction per live ray
 // ------------------------------------------------------------------------------------------------
 #ifndef HB_OPTICS_MINB
-#define HB_OPTICS_MINB 1
+#define HB_OPTICS_MINB 4
 #endif
 #ifndef HB_INTERSECT_MINB
-#define HB_INTERSECT_MINB 1
+#define HB_INTERSECT_MINB 5
 #endif
 template <bool GENERAL, bool LAST, bool SMEM>
 __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const TraceParams tp) {
