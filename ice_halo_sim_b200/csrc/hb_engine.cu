@@ -449,7 +449,8 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
       const uint32_t axis_cnt = (meta >> 16) & 255u;
       const float n_idx = tp.wl[bits_wl(bits)].n_idx;
 
-      const Split s = hit_surface(tb.plane(shape, face), n_idx, d4.x, d4.y, d4.z, d4.w);
+      const float4 pl = tb.plane(shape, face);
+      const Split s = hit_surface(pl, n_idx, d4.x, d4.y, d4.z, d4.w);
       // The child on the far side of the face normally leaves the crystal: classify it here.
       const uint32_t out_child = s.cos_in > 0.0f ? 1u : 0u;  // internal hit: refracted; entry: reflected
       const float ox = out_child ? s.tx : s.rx, oy = out_child ? s.ty : s.ry, oz = out_child ? s.tz : s.rz;
@@ -457,8 +458,10 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
       const float ix = out_child ? s.rx : s.tx, iy = out_child ? s.ry : s.ty, iz = out_child ? s.rz : s.tz;
       const float iw = out_child ? s.rw : s.tw;
       if (ow >= 0.0f) {
-        float nx, ny, nz;
-        const uint32_t nf = slab_exit<true>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        uint32_t nf = kFaceInvalid;
+        if (!far_child_surely_exits(axes, axis_cnt, face, pl, p4.x, p4.y, p4.z, ox, oy, oz))
+          nf = slab_exit<true>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
         if (nf == kFaceInvalid) {
           emit_exit<GENERAL>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, tb, tally);
         } else if (!LAST) {
