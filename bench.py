@@ -314,9 +314,15 @@ def main():
         dom = "optics" if opt_total >= int_total else "intersect"
         ach_o = opt_bytes / (o_ms * 1e-3) / 1e9 if o_ms > 0 else 0.0
         ach_i = int_bytes / (i_ms * 1e-3) / 1e9 if i_ms > 0 else 0.0
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if os.path.exists(tr_path):  # DRAM bytes per ray-bounce from the committed ncu --set full capture
+            tr = json.load(open(tr_path))["dram_bytes_per_ray_bounce"]
+            traffic = tr[dom] * tile
         roof = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": ach_o if dom == "optics" else ach_i,
                 "peak": hbm_peak, "unit": "GB/s", "frac": (ach_o if dom == "optics" else ach_i) / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "algorithmic_bytes_per_launch": opt_bytes if dom == "optics" else int_bytes,
+                "peak_source": peak_src,
                 "per_kernel": {"optics": {"avg_ms": o_ms, "launches": o_l, "achieved_gbs": ach_o,
                                           "frac": ach_o / hbm_peak, "rays_per_launch": tile},
                                "intersect": {"avg_ms": i_ms, "launches": i_l, "achieved_gbs": ach_i,
