@@ -187,28 +187,51 @@ class B200TraceBackend : public TraceBackend {
     }
   }
 
+  static void FillSimple(const DeviceFilterDesc& d, HbSimpleFilter* s) {
+    std::memset(s, 0, sizeof(*s));
+    s->kind = d.type;
+    s->path_len = d.canonical_len;
+    std::memcpy(s->path, d.canonical_bytes, std::min<size_t>(d.canonical_len, HB_MAX_FILTER_PATH));
+    s->entry_fn = d.has_entry ? 1 : -1;
+    s->exit_fn = d.has_exit ? 1 : -1;
+    s->min_len = d.min_len;
+    s->max_len = d.max_len;
+    std::memcpy(s->dir, d.dir, sizeof(d.dir));
+    s->cos_radii = d.radii_c;
+    s->crystal_id = d.crystal_id;
+  }
+
   static void FillFilter(const FilterConfig& cfg, const Crystal& crystal, const AxisDistribution& axis, HbFilterDesc* out) {
     std::memset(out, 0, sizeof(*out));
     const DeviceFilterDesc d = detail::BuildDeviceFilterDesc(cfg, crystal, axis);
-    if (d.type == kDeviceFilterTypeComplex) {
-      throw BackendUnavailableError("B200TraceBackend: complex filters are not supported yet");
-    }
     out->kind = d.type;
     out->action = d.action;
     out->symmetry = d.symmetry;
     out->fn_period = d.fn_period;
     out->sigma_a = d.sigma_a;
     out->d_applicable = d.d_applicable;
-    out->simple.kind = d.type;
-    out->simple.path_len = d.canonical_len;
-    std::memcpy(out->simple.path, d.canonical_bytes, std::min<size_t>(d.canonical_len, HB_MAX_FILTER_PATH));
-    out->simple.entry_fn = d.has_entry ? 1 : -1;
-    out->simple.exit_fn = d.has_exit ? 1 : -1;
-    out->simple.min_len = d.min_len;
-    out->simple.max_len = d.max_len;
-    std::memcpy(out->simple.dir, d.dir, sizeof(d.dir));
-    out->simple.cos_radii = d.radii_c;
-    out->simple.crystal_id = d.crystal_id;
+    if (d.type == kDeviceFilterTypeComplex) {
+      std::vector<DeviceFilterDesc> subs;
+      std::vector<uint8_t> counts;
+      detail::BuildComplexSubDescs(std::get<ComplexFilterParam>(cfg.param_), crystal, d.symmetry, d.sigma_a,
+                                   d.d_applicable != 0, subs, counts);
+      if (counts.size() > HB_MAX_FILTER_TERMS) {
+        throw BackendUnavailableError("B200TraceBackend: complex filter with more than 8 OR-clauses");
+      }
+      out->term_cnt = static_cast<uint32_t>(counts.size());
+      size_t k = 0;
+      for (size_t o = 0; o < counts.size(); o++) {
+        if (counts[o] > 4) {
+          throw BackendUnavailableError("B200TraceBackend: complex filter clause with more than 4 AND-terms");
+        }
+        out->term_len[o] = counts[o];
+        for (uint8_t a = 0; a < counts[o]; a++, k++) {
+          FillSimple(subs[k], &out->terms[o][a]);
+        }
+      }
+    } else {
+      FillSimple(d, &out->simple);
+    }
   }
 
   void UploadScene(const SceneConfig& scene) {

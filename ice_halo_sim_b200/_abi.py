@@ -121,11 +121,16 @@ class HbCrystalDesc(C.Structure):
                 ("latitude", HbDist), ("azimuth", HbDist), ("roll", HbDist)]
 
 
+class HbSimpleFilterSpec(C.Structure):
+    _fields_ = [("kind", u32), ("path_len", u32), ("path", u8 * HB_MAX_FILTER_PATH), ("entry_fn", i32),
+                ("exit_fn", i32), ("min_len", u32), ("max_len", u32), ("lon_deg", f32), ("lat_deg", f32),
+                ("radii_deg", f32), ("crystal_id", u32)]
+
+
 class HbFilterSpecDesc(C.Structure):
-    _fields_ = [("kind", u32), ("action", u32), ("symmetry", u32), ("path_len", u32),
-                ("path", u8 * HB_MAX_FILTER_PATH), ("entry_fn", i32), ("exit_fn", i32),
-                ("min_len", u32), ("max_len", u32), ("lon_deg", f32), ("lat_deg", f32), ("radii_deg", f32),
-                ("crystal_id", u32)]
+    _fields_ = [("kind", u32), ("action", u32), ("symmetry", u32), ("simple", HbSimpleFilterSpec),
+                ("term_cnt", u32), ("term_len", u32 * HB_MAX_FILTER_TERMS),
+                ("terms", (HbSimpleFilterSpec * 4) * HB_MAX_FILTER_TERMS)]
 
 
 class HbPopulationDesc(C.Structure):
@@ -150,4 +155,4 @@ class HbRenderDesc(C.Structure):
 
 ALL_STRUCTS = [HbCrystalTables, HbAxisSampler, HbSimpleFilter, HbFilterDesc, HbCrystalPopulation, HbLayer, HbScene,
                HbWlEntry, HbProjParams, HbExitRecord, HbSessionSpec, HbLayerStats, HbCounters, HbDist, HbCrystalDesc,
-               HbFilterSpecDesc, HbPopulationDesc, HbLayerDesc, HbSceneDesc, HbRenderDesc]
+               HbSimpleFilterSpec, HbFilterSpecDesc, HbPopulationDesc, HbLayerDesc, HbSceneDesc, HbRenderDesc]

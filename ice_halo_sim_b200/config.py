@@ -3,7 +3,7 @@
 Mirrors the reference's config front door for the fields the trace path consumes
 (reference: src/config/crystal_config.cpp from_json, src/core/math.cpp:590-725 axis parsing,
 src/config/filter_config.cpp, src/config/render_config.cpp, src/config/config_manager.cpp).
-Complex ("composition") filters and raypath-colour classes are not supported here.
+Complex ("composition") filters are supported up to 8 OR-terms of 4 AND-factors; raypath-colour classes are not.
 """
 import json
 import math
@@ -77,37 +77,68 @@ def crystal_desc(c):
     return d
 
 
-def filter_desc(f):
-    d = A.HbFilterSpecDesc()
-    d.entry_fn = -1
-    d.exit_fn = -1
-    if f is None or f.get("type", "none") == "none":
-        return d
-    t = f["type"]
-    d.action = 1 if f.get("action", "filter_in") == "filter_out" else 0
-    d.symmetry = sum(_SYM[ch] for ch in f.get("symmetry", "") if ch in _SYM)
-    if t == "raypath":
+def _simple_filter(f, s):
+    """Fill an HbSimpleFilterSpec from one simple filter entry of the config."""
+    t = f.get("type", "none")
+    s.entry_fn = -1
+    s.exit_fn = -1
+    if t == "none":
+        s.kind = 0
+    elif t == "raypath":
         rp = f["raypath"]
         if len(rp) > A.HB_MAX_FILTER_PATH:
             raise ValueError("raypath filter longer than 32 faces")
-        d.kind = 1
-        d.path_len = len(rp)
+        s.kind = 1
+        s.path_len = len(rp)
         for i, x in enumerate(rp):
-            d.path[i] = int(x)
+            s.path[i] = int(x)
     elif t == "entry_exit":
-        d.kind = 2
-        d.entry_fn = int(f["entry"]) if "entry" in f else -1
-        d.exit_fn = int(f["exit"]) if "exit" in f else -1
-        d.min_len = int(f.get("min_len", 1))
-        d.max_len = int(f.get("max_len", 0))
+        s.kind = 2
+        s.entry_fn = int(f["entry"]) if "entry" in f else -1
+        s.exit_fn = int(f["exit"]) if "exit" in f else -1
+        s.min_len = int(f.get("min_len", 1))
+        s.max_len = int(f.get("max_len", 0))
     elif t == "direction":
-        d.kind = 3
-        d.lon_deg, d.lat_deg, d.radii_deg = float(f["az"]), float(f["el"]), float(f["radii"])
+        s.kind = 3
+        s.lon_deg, s.lat_deg, s.radii_deg = float(f["az"]), float(f["el"]), float(f["radii"])
     elif t == "crystal":
-        d.kind = 4
-        d.crystal_id = int(f["crystal_id"])
+        s.kind = 4
+        s.crystal_id = int(f["crystal_id"])
     else:
-        raise ValueError(f"filter type {t!r} is not supported by this backend")
+        raise ValueError(f"filter type {t!r} cannot be used here")
+
+
+def filter_desc(f, all_filters=None):
+    """FilterConfig (filter_config.cpp from_json). A "complex" filter is an OR over its `composition`
+    entries, each a filter id or a list of ids that are AND-ed; the sub-filters contribute their parameters
+    only (symmetry and action come from the complex filter itself, device_filter_desc.cpp:146-166)."""
+    d = A.HbFilterSpecDesc()
+    d.simple.entry_fn = d.simple.exit_fn = -1
+    if f is None or f.get("type", "none") == "none":
+        return d
+    d.action = 1 if f.get("action", "filter_in") == "filter_out" else 0
+    d.symmetry = sum(_SYM[ch] for ch in f.get("symmetry", "") if ch in _SYM)
+    if f["type"] == "complex":
+        comp = f["composition"]
+        if all_filters is None:
+            raise ValueError("complex filter needs the filter table")
+        if len(comp) > A.HB_MAX_FILTER_TERMS:
+            raise ValueError("complex filter with more than 8 OR-terms is not supported by this backend")
+        d.kind = 5
+        d.term_cnt = len(comp)
+        for o, term in enumerate(comp):
+            ids = term if isinstance(term, list) else [term]
+            if len(ids) > 4:
+                raise ValueError("complex filter term with more than 4 AND-factors is not supported")
+            d.term_len[o] = len(ids)
+            for a, fid in enumerate(ids):
+                sub = all_filters[int(fid)]
+                if sub.get("type") == "complex":
+                    raise ValueError("complex filters cannot nest")
+                _simple_filter(sub, d.terms[o][a])
+        return d
+    _simple_filter(f, d.simple)
+    d.kind = d.simple.kind
     return d
 
 
@@ -188,7 +219,7 @@ def load_config(path_or_dict, geom_pool_size=1):
         for ci, e in enumerate(entries):
             pop = ld.populations[ci]
             pop.crystal = crystal_desc(crystals[int(e["crystal"])])
-            pop.filter = filter_desc(filters.get(int(e["filter"])) if "filter" in e else None)
+            pop.filter = filter_desc(filters.get(int(e["filter"])) if "filter" in e else None, filters)
             pop.proportion = float(e.get("proportion", 1.0))
     spectrum = ls.get("spectrum", [])
     illuminant = None

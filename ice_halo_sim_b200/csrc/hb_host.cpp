@@ -565,32 +565,43 @@ void BuildFilter(const HbPopulationDesc& p, HbFilterDesc* out) {
     sigma = (6 - n) % 6;
   }
   out->sigma_a = sigma;
-  HbSimpleFilter& s = out->simple;
-  s.kind = f.kind;
-  s.entry_fn = -1;
-  s.exit_fn = -1;
-  if (f.kind == 1) {
-    s.path_len = std::min<uint32_t>(f.path_len, HB_MAX_FILTER_PATH);
-    std::memcpy(s.path, f.path, s.path_len);
-    filter_reduce(s.path, s.path_len, f.symmetry, sigma, d_app);
-  } else if (f.kind == 2) {
-    s.entry_fn = f.entry_fn >= 0 ? 1 : -1;
-    s.exit_fn = f.exit_fn >= 0 ? 1 : -1;
-    s.min_len = f.min_len == 0 ? 1 : f.min_len;
-    s.max_len = f.max_len;
-    uint32_t n = 0;
-    if (f.entry_fn >= 0) s.path[n++] = static_cast<uint8_t>(f.entry_fn);
-    if (f.exit_fn >= 0) s.path[n++] = static_cast<uint8_t>(f.exit_fn);
-    s.path_len = n;
-    if (n > 0) filter_reduce(s.path, n, f.symmetry, sigma, d_app);
-  } else if (f.kind == 3) {
-    float lon = f.lon_deg * kDeg2RadF, lat = f.lat_deg * kDeg2RadF;
-    s.dir[0] = std::cos(lat) * std::cos(lon);
-    s.dir[1] = std::cos(lat) * std::sin(lon);
-    s.dir[2] = std::sin(lat);
-    s.cos_radii = std::cos(f.radii_deg * kDeg2RadF);
-  } else if (f.kind == 4) {
-    s.crystal_id = f.crystal_id;
+  auto fill = [&](const HbSimpleFilterSpec& f, HbSimpleFilter& s) {
+    std::memset(&s, 0, sizeof(s));
+    s.kind = f.kind;
+    s.entry_fn = -1;
+    s.exit_fn = -1;
+    if (f.kind == 1) {
+      s.path_len = std::min<uint32_t>(f.path_len, HB_MAX_FILTER_PATH);
+      std::memcpy(s.path, f.path, s.path_len);
+      filter_reduce(s.path, s.path_len, out->symmetry, sigma, d_app);
+    } else if (f.kind == 2) {
+      s.entry_fn = f.entry_fn >= 0 ? 1 : -1;
+      s.exit_fn = f.exit_fn >= 0 ? 1 : -1;
+      s.min_len = f.min_len == 0 ? 1 : f.min_len;
+      s.max_len = f.max_len;
+      uint32_t n = 0;
+      if (f.entry_fn >= 0) s.path[n++] = static_cast<uint8_t>(f.entry_fn);
+      if (f.exit_fn >= 0) s.path[n++] = static_cast<uint8_t>(f.exit_fn);
+      s.path_len = n;
+      if (n > 0) filter_reduce(s.path, n, out->symmetry, sigma, d_app);
+    } else if (f.kind == 3) {
+      float lon = f.lon_deg * kDeg2RadF, lat = f.lat_deg * kDeg2RadF;
+      s.dir[0] = std::cos(lat) * std::cos(lon);
+      s.dir[1] = std::cos(lat) * std::sin(lon);
+      s.dir[2] = std::sin(lat);
+      s.cos_radii = std::cos(f.radii_deg * kDeg2RadF);
+    } else if (f.kind == 4) {
+      s.crystal_id = f.crystal_id;
+    }
+  };
+  if (f.kind == 5) {  // BuildComplexSubDescs, device_filter_desc.cpp:146-166: sub-filters inherit symmetry
+    out->term_cnt = std::min<uint32_t>(f.term_cnt, HB_MAX_FILTER_TERMS);
+    for (uint32_t o = 0; o < out->term_cnt; o++) {
+      out->term_len[o] = std::min<uint32_t>(f.term_len[o], 4u);
+      for (uint32_t a = 0; a < out->term_len[o]; a++) fill(f.terms[o][a], out->terms[o][a]);
+    }
+  } else {
+    fill(f.simple, out->simple);
   }
 }
 

@@ -320,16 +320,24 @@ typedef struct HbCrystalDesc {
   HbDist latitude, azimuth, roll; /* AxisDistribution (latitude center = 90 - zenith), degrees */
 } HbCrystalDesc;
 
-typedef struct HbFilterSpecDesc {
+typedef struct HbSimpleFilterSpec {
   uint32_t kind;                 /* 0 none, 1 raypath, 2 entry_exit, 3 direction, 4 crystal */
-  uint32_t action;               /* 0 filter_in, 1 filter_out */
-  uint32_t symmetry;             /* bit0 P, bit1 B, bit2 D */
   uint32_t path_len;
   uint8_t path[HB_MAX_FILTER_PATH]; /* raypath: face numbers as written in the config */
   int32_t entry_fn, exit_fn;     /* -1 wildcard */
   uint32_t min_len, max_len;     /* max_len 0 = unbounded */
   float lon_deg, lat_deg, radii_deg;
   uint32_t crystal_id;
+} HbSimpleFilterSpec;
+
+typedef struct HbFilterSpecDesc {  /* FilterConfig, filter_config.hpp:70-84 */
+  uint32_t kind;                 /* as HbSimpleFilterSpec.kind; 5 = complex: OR over terms of AND-ed simple filters */
+  uint32_t action;               /* 0 filter_in, 1 filter_out */
+  uint32_t symmetry;             /* bit0 P, bit1 B, bit2 D */
+  HbSimpleFilterSpec simple;     /* kind 1..4 */
+  uint32_t term_cnt;             /* kind 5: <= HB_MAX_FILTER_TERMS OR-terms */
+  uint32_t term_len[HB_MAX_FILTER_TERMS]; /* AND-factors per term, <= 4 */
+  HbSimpleFilterSpec terms[HB_MAX_FILTER_TERMS][4];
 } HbFilterSpecDesc;
 
 typedef struct HbPopulationDesc {

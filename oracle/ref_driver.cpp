@@ -69,19 +69,14 @@ RenderConfig ToRender(const HbRenderDesc& r) {
   return cfg;
 }
 
-FilterConfig ToFilter(const HbFilterSpecDesc& f) {
-  FilterConfig c{};
-  c.id_ = 1;
-  c.symmetry_ = static_cast<uint8_t>(f.symmetry);
-  c.action_ = f.action == 0 ? FilterConfig::kFilterIn : FilterConfig::kFilterOut;
+SimpleFilterParam ToSimple(const HbSimpleFilterSpec& f) {
   switch (f.kind) {
     case 1: {
       RaypathFilterParam p;
       for (uint32_t i = 0; i < f.path_len; i++) {
         p.raypath_.push_back(static_cast<IdType>(f.path[i]));
       }
-      c.param_ = SimpleFilterParam{ p };
-      break;
+      return SimpleFilterParam{ p };
     }
     case 2: {
       EntryExitFilterParam p;
@@ -95,18 +90,34 @@ FilterConfig ToFilter(const HbFilterSpecDesc& f) {
       if (f.max_len != 0) {
         p.max_len_ = f.max_len;
       }
-      c.param_ = SimpleFilterParam{ p };
-      break;
+      return SimpleFilterParam{ p };
     }
     case 3:
-      c.param_ = SimpleFilterParam{ DirectionFilterParam{ f.lon_deg, f.lat_deg, f.radii_deg } };
-      break;
+      return SimpleFilterParam{ DirectionFilterParam{ f.lon_deg, f.lat_deg, f.radii_deg } };
     case 4:
-      c.param_ = SimpleFilterParam{ CrystalFilterParam{ static_cast<IdType>(f.crystal_id) } };
-      break;
+      return SimpleFilterParam{ CrystalFilterParam{ static_cast<IdType>(f.crystal_id) } };
     default:
-      c.param_ = SimpleFilterParam{ NoneFilterParam{} };
-      break;
+      return SimpleFilterParam{ NoneFilterParam{} };
+  }
+}
+
+FilterConfig ToFilter(const HbFilterSpecDesc& f) {
+  FilterConfig c{};
+  c.id_ = 1;
+  c.symmetry_ = static_cast<uint8_t>(f.symmetry);
+  c.action_ = f.action == 0 ? FilterConfig::kFilterIn : FilterConfig::kFilterOut;
+  if (f.kind == 5) {
+    ComplexFilterParam cp;
+    for (uint32_t o = 0; o < f.term_cnt; o++) {
+      std::vector<std::pair<IdType, SimpleFilterParam>> term;
+      for (uint32_t a = 0; a < f.term_len[o]; a++) {
+        term.emplace_back(static_cast<IdType>(o * 4 + a + 1), ToSimple(f.terms[o][a]));
+      }
+      cp.filters_.push_back(std::move(term));
+    }
+    c.param_ = cp;
+  } else {
+    c.param_ = ToSimple(f.simple);
   }
   return c;
 }
@@ -262,6 +273,20 @@ int ref_cmf_table(float* xyz) {
   return n;
 }
 
+static void FillSimpleFromDevice(const DeviceFilterDesc& d, HbSimpleFilter* s) {
+  std::memset(s, 0, sizeof(*s));
+  s->kind = d.type;
+  s->path_len = d.canonical_len;
+  std::memcpy(s->path, d.canonical_bytes, HB_MAX_FILTER_PATH);
+  s->entry_fn = d.has_entry ? 1 : -1;  // presence flags only; canonical bytes carry the values
+  s->exit_fn = d.has_exit ? 1 : -1;
+  s->min_len = d.min_len;
+  s->max_len = d.max_len;
+  std::memcpy(s->dir, d.dir, sizeof(float) * 3);
+  s->cos_radii = d.radii_c;
+  s->crystal_id = d.crystal_id;
+}
+
 int ref_filter_desc(const HbPopulationDesc* pop, const RefShape* shape, HbFilterDesc* out) {
   std::memset(out, 0, sizeof(*out));
   Crystal c = MakeShape(*shape);
@@ -274,16 +299,24 @@ int ref_filter_desc(const HbPopulationDesc* pop, const RefShape* shape, HbFilter
   out->fn_period = d.fn_period;
   out->sigma_a = d.sigma_a;
   out->d_applicable = d.d_applicable;
-  out->simple.kind = d.type;
-  out->simple.path_len = d.canonical_len;
-  std::memcpy(out->simple.path, d.canonical_bytes, HB_MAX_FILTER_PATH);
-  out->simple.entry_fn = d.has_entry ? 1 : -1;  // presence flags only; canonical bytes carry the values
-  out->simple.exit_fn = d.has_exit ? 1 : -1;
-  out->simple.min_len = d.min_len;
-  out->simple.max_len = d.max_len;
-  std::memcpy(out->simple.dir, d.dir, sizeof(float) * 3);
-  out->simple.cos_radii = d.radii_c;
-  out->simple.crystal_id = d.crystal_id;
+  if (d.type == kDeviceFilterTypeComplex) {
+    std::vector<DeviceFilterDesc> subs;
+    std::vector<uint8_t> counts;
+    detail::BuildComplexSubDescs(std::get<ComplexFilterParam>(fc.param_), c, d.symmetry, d.sigma_a, d.d_applicable != 0,
+                                 subs, counts);
+    out->term_cnt = static_cast<uint32_t>(counts.size());
+    size_t k = 0;
+    for (size_t o = 0; o < counts.size() && o < HB_MAX_FILTER_TERMS; o++) {
+      out->term_len[o] = counts[o];
+      for (uint8_t a = 0; a < counts[o]; a++, k++) {
+        if (a < 4) {
+          FillSimpleFromDevice(subs[k], &out->terms[o][a]);
+        }
+      }
+    }
+  } else {
+    FillSimpleFromDevice(d, &out->simple);
+  }
   return 0;
 }
 

@@ -48,7 +48,7 @@ def prism_pop(h=1.0, zenith=("none", 0.0, 0.0), azimuth=("uniform", 0, 360), rol
     z = dist(*zenith)
     c.latitude = A.HbDist(z.type, 90.0 - z.center, z.spread)
     c.azimuth, c.roll = dist(*azimuth), dist(*roll)
-    p.filter.entry_fn = p.filter.exit_fn = -1
+    p.filter.simple.entry_fn = p.filter.simple.exit_fn = -1
     if filt is not None:
         p.filter = filt
     return p
@@ -69,7 +69,7 @@ def pyramid_pop(h=(0.3, 0.5, 0.4), alpha=(28.0, 28.0), zenith=("uniform", 90, 36
     z = dist(*zenith)
     c.latitude = A.HbDist(z.type, 90.0 - z.center, z.spread)
     c.azimuth, c.roll = dist(*azimuth), dist(*roll)
-    p.filter.entry_fn = p.filter.exit_fn = -1
+    p.filter.simple.entry_fn = p.filter.simple.exit_fn = -1
     return p
 
 
@@ -77,10 +77,35 @@ def raypath_filter(path, symmetry="", action=0):
     f = A.HbFilterSpecDesc()
     f.kind, f.action = 1, action
     f.symmetry = sum({"P": 1, "B": 2, "D": 4}[ch] for ch in symmetry)
-    f.path_len = len(path)
+    f.simple.kind = 1
+    f.simple.path_len = len(path)
     for i, x in enumerate(path):
-        f.path[i] = x
-    f.entry_fn = f.exit_fn = -1
+        f.simple.path[i] = x
+    f.simple.entry_fn = f.simple.exit_fn = -1
+    return f
+
+
+def simple_spec(s, kind, path=(), entry=-1, exit=-1, min_len=1, max_len=0, lon=0.0, lat=0.0, radii=0.0, crystal_id=0):
+    s.kind = kind
+    s.path_len = len(path)
+    for i, x in enumerate(path):
+        s.path[i] = x
+    s.entry_fn, s.exit_fn, s.min_len, s.max_len = entry, exit, min_len, max_len
+    s.lon_deg, s.lat_deg, s.radii_deg, s.crystal_id = lon, lat, radii, crystal_id
+    return s
+
+
+def complex_filter(terms, symmetry="", action=0):
+    """terms: [[dict(kind=..., ...), ...], ...] — OR over terms, AND inside a term."""
+    f = A.HbFilterSpecDesc()
+    f.kind, f.action = 5, action
+    f.symmetry = sum({"P": 1, "B": 2, "D": 4}[ch] for ch in symmetry)
+    f.simple.entry_fn = f.simple.exit_fn = -1
+    f.term_cnt = len(terms)
+    for o, term in enumerate(terms):
+        f.term_len[o] = len(term)
+        for a, kw in enumerate(term):
+            simple_spec(f.terms[o][a], **kw)
     return f
 
 
@@ -125,6 +150,12 @@ CASES = {
         scene=lambda: scene([(0.0, [prism_pop(1.0, zenith=("uniform", 90, 360), cid=1,
                                               face_dist=[dist("gauss", 1.0, 0.15)] * 6)])], 8, pool=64),
         render=lambda: render("rectangular", 360.0, (2048, 1024), (0.0, 90.0, 0.0), "full"), wl=[550.0]),
+    # config_example.json filter 7: complex composition [raypath | (raypath & crystal) | direction-out]
+    "complex_filter": dict(
+        scene=lambda: scene([(0.0, [prism_pop(1.3, zenith=("gauss", 90, 5.0), cid=3, filt=complex_filter(
+            [[dict(kind=1, path=[3, 5])], [dict(kind=1, path=[1, 3, 2]), dict(kind=4, crystal_id=3)],
+             [dict(kind=2, entry=3, exit=6), dict(kind=3, lon=180.0, lat=25.0, radii=40.0)]], "PB"))])], 6),
+        render=lambda: render(res=(960, 540)), wl=[570.0]),
     "pyramid": dict(scene=lambda: scene([(0.0, [pyramid_pop()])], 8),
                     render=lambda: render("dual_fisheye_equal_area", 120.0, (1024, 512), visible="full", overlap=0.1),
                     wl=[610.0]),

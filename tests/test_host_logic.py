@@ -64,8 +64,8 @@ def test_config_parsing():
     assert (plate.crystal.latitude.type, plate.crystal.latitude.center) == (A.DIST["gauss"], 90.0)
     assert abs(plate.crystal.latitude.spread - 0.8) < 1e-6
     assert (plate.crystal.azimuth.type, plate.crystal.azimuth.spread) == (A.DIST["uniform"], 360.0)
-    assert (plate.filter.kind, plate.filter.symmetry, plate.filter.path_len) == (1, 1, 2)
-    assert list(plate.filter.path[:2]) == [3, 5]
+    assert (plate.filter.kind, plate.filter.symmetry, plate.filter.simple.path_len) == (1, 1, 2)
+    assert list(plate.filter.simple.path[:2]) == [3, 5]
     pyr = l0.populations[1]
     assert pyr.crystal.kind == 1 and abs(pyr.crystal.height[1].center - 1.2) < 1e-6
     assert abs(pyr.crystal.wedge_upper_deg - np.degrees(np.arctan(0.866025403784 * 3 / 2 / 1.629))) < 1e-4
@@ -84,8 +84,17 @@ def test_config_parsing():
         json.dump(EXAMPLE, f)
     assert CFG.load_config(f.name).desc.layer_cnt == 2
     os.unlink(f.name)
+    # complex filter (config_example.json filter 7): OR over [2, (3 AND 6), 5]
+    ex2 = json.loads(json.dumps(EXAMPLE))
+    ex2["filter"].append({"id": 7, "type": "complex", "composition": [2, [3, 6], 5], "symmetry": "P"})
+    ex2["scene"]["scattering"][0]["entries"][0]["filter"] = 7
+    f7 = CFG.load_config(ex2).desc.layers[0].populations[0].filter
+    assert f7.kind == 5 and f7.term_cnt == 3 and list(f7.term_len)[:3] == [1, 2, 1] and f7.symmetry == 1
+    assert f7.terms[0][0].kind == 1 and f7.terms[0][0].path_len == 5
+    assert f7.terms[1][0].kind == 1 and f7.terms[1][1].kind == 4 and f7.terms[1][1].crystal_id == 3
+    assert f7.terms[2][0].kind == 3 and abs(f7.terms[2][0].radii_deg - 0.5) < 1e-7
     with pytest.raises(ValueError):
-        CFG.load_config({**EXAMPLE, "filter": [{"id": 3, "type": "complex", "composition": [1]}]})
+        CFG.load_config({**EXAMPLE, "filter": [{"id": 3, "type": "complex", "composition": list(range(9))}]})
 
 
 def test_scene_tables_from_config():

@@ -112,6 +112,11 @@ FILTERS = [
     dict(kind=3, lon=180.0, lat=25.0, radii=30.0, action=1),  # filter 5 (wider cone so both outcomes occur)
     dict(kind=4, crystal_id=3),
     dict(kind=4, crystal_id=9),
+    # complex: OR of AND-terms (examples/config_example.json filter 7 shape: [1, [2, 6], 5])
+    dict(kind=5, sym="P", terms=[[dict(kind=1, path=[3, 5])], [dict(kind=1, path=[1, 3, 2]), dict(kind=4, crystal_id=3)],
+                                 [dict(kind=3, lon=180.0, lat=25.0, radii=30.0)]]),
+    dict(kind=5, sym="PBD", action=1, terms=[[dict(kind=2, entry=3, exit=5), dict(kind=1, path=[3, 1, 5])],
+                                             [dict(kind=4, crystal_id=9)]]),
 ]
 
 
@@ -124,15 +129,14 @@ def test_filter_check_matches_filter_spec(spec, roll):
     import parity
     pop = parity.prism_pop(1.2, zenith=("gauss", 90, 1.0), roll=("uniform", 0, 360), cid=3)
     pop.crystal.roll = A.HbDist(*roll)
-    f = A.HbFilterSpecDesc()
-    f.kind, f.action, f.symmetry = spec["kind"], spec.get("action", 0), spec.get("symmetry", 0)
-    f.entry_fn, f.exit_fn = spec.get("entry", -1), spec.get("exit", -1)
-    f.min_len, f.max_len = spec.get("min_len", 1), spec.get("max_len", 0)
-    for i, x in enumerate(spec.get("path", [])):
-        f.path[i] = x
-    f.path_len = len(spec.get("path", []))
-    f.lon_deg, f.lat_deg, f.radii_deg = spec.get("lon", 0.0), spec.get("lat", 0.0), spec.get("radii", 0.0)
-    f.crystal_id = spec.get("crystal_id", 0)
+    if spec["kind"] == 5:
+        f = parity.complex_filter(spec["terms"], spec.get("sym", ""), spec.get("action", 0))
+    else:
+        f = A.HbFilterSpecDesc()
+        f.kind, f.action, f.symmetry = spec["kind"], spec.get("action", 0), spec.get("symmetry", 0)
+        parity.simple_spec(f.simple, spec["kind"], spec.get("path", []), spec.get("entry", -1), spec.get("exit", -1),
+                           spec.get("min_len", 1), spec.get("max_len", 0), spec.get("lon", 0.0), spec.get("lat", 0.0),
+                           spec.get("radii", 0.0), spec.get("crystal_id", 0))
     pop.filter = f
     sh = H.ref_shape(0, (1.2, 0, 0))
     t = A.HbCrystalTables()
@@ -146,10 +150,19 @@ def test_filter_check_matches_filter_spec(spec, roll):
     mine = tables.scene().layers[0].populations[0].filter
     for fld in ("kind", "action", "symmetry", "fn_period", "sigma_a", "d_applicable"):
         assert getattr(mine, fld) == getattr(rdesc, fld), fld
-    assert mine.simple.path_len == rdesc.simple.path_len
-    assert bytes(mine.simple.path)[: mine.simple.path_len] == bytes(rdesc.simple.path)[: rdesc.simple.path_len]
-    assert np.allclose(list(mine.simple.dir), list(rdesc.simple.dir), atol=1e-7)
-    assert abs(mine.simple.cos_radii - rdesc.simple.cos_radii) < 1e-7
+    def same_simple(a, b):
+        assert a.kind == b.kind and a.path_len == b.path_len
+        assert bytes(a.path)[: a.path_len] == bytes(b.path)[: b.path_len]
+        assert (a.entry_fn >= 0) == (b.entry_fn >= 0) and (a.exit_fn >= 0) == (b.exit_fn >= 0)
+        assert np.allclose(list(a.dir), list(b.dir), atol=1e-7) and abs(a.cos_radii - b.cos_radii) < 1e-7
+        assert a.crystal_id == b.crystal_id
+    if spec["kind"] == 5:
+        assert mine.term_cnt == rdesc.term_cnt and list(mine.term_len) == list(rdesc.term_len)
+        for o in range(mine.term_cnt):
+            for a in range(mine.term_len[o]):
+                same_simple(mine.terms[o][a], rdesc.terms[o][a])
+    else:
+        same_simple(mine.simple, rdesc.simple)
     # random paths (compact ids 0..7 == face numbers 1..8 on a prism) incl. the filter's own path and its images
     rng = np.random.default_rng(99)
     n = 4000
@@ -157,8 +170,10 @@ def test_filter_check_matches_filter_spec(spec, roll):
     paths = np.zeros((n, 64), np.uint8)
     for i in range(n):
         paths[i, : plen[i]] = rng.integers(0, 8, plen[i])
-    if spec["kind"] == 1:
-        base = np.array(spec["path"]) - 1
+    seed_paths = [spec["path"]] if spec["kind"] == 1 else \
+        [t["path"] for term in spec.get("terms", []) for t in term if t["kind"] == 1]
+    for base_fn in seed_paths:
+        base = np.array(base_fn) - 1
         for i in range(0, 600):
             k = int(rng.integers(0, 6))
             img = np.where(base >= 2, (base - 2 + k) % 6 + 2, base)
