@@ -101,6 +101,21 @@ def make_wl_entry(wavelength_nm, weight=1.0):
     return (e.n_idx, e.spd_weight, e.cmf_x, e.cmf_y, e.cmf_z)
 
 
+ILLUMINANTS = {"D50": 0, "D55": 1, "D65": 2, "D75": 3, "A": 4, "E": 5}  # util/illuminant_data.hpp:12-28
+
+
+def make_wl_pool(illuminant, m=64):
+    """Illuminant-mode wavelength pool (ComputeWlPool, backend/wl_pool.hpp:73-84): `m` mid-point samples of
+    [380, 780] nm weighted by the illuminant's SPD; m defaults to the reference's kWlPoolSizeDefault."""
+    if isinstance(illuminant, str):
+        if illuminant not in ILLUMINANTS:
+            raise ValueError(f"unknown illuminant {illuminant!r}")
+        illuminant = ILLUMINANTS[illuminant]
+    pool = (A.HbWlEntry * int(m))()
+    check(load().hb_make_wl_pool_illuminant(int(illuminant), int(m), pool))
+    return [(e.n_idx, e.spd_weight, e.cmf_x, e.cmf_y, e.cmf_z) for e in pool]
+
+
 def make_proj_params(render: A.HbRenderDesc) -> A.HbProjParams:
     p = A.HbProjParams()
     check(load().hb_build_render(C.byref(render), C.byref(p)))

@@ -355,6 +355,10 @@ namespace {
 const float kCie1931[471][3] = {
 #include "cie1931_2deg_1nm.inc"
 };
+// CIE daylight basis S0/S1/S2, 5 nm, 300..830 nm
+const float kDaylightBasis[107][3] = {
+#include "cie_daylight_basis_5nm.inc"
+};
 
 // --- latitude inverse-CDF LUT: area-measure mass of the latitude proposal over colatitude,
 // resampled to 257 uniform-theta nodes (reference: lat_lut.cpp:74-180). ---
@@ -625,6 +629,51 @@ int hb_make_wl_entry(float wl, float weight, HbWlEntry* out) {
     out->cmf_x = kCie1931[key - 360][0];
     out->cmf_y = kCie1931[key - 360][1];
     out->cmf_z = kCie1931[key - 360][2];
+  }
+  return HB_OK;
+}
+
+float hb_illuminant_spd(int illuminant, float wl) {
+  if (illuminant < 0 || illuminant > HB_ILLUMINANT_E) return 0.0f;
+  if (wl < 300.0f || wl > 830.0f) return 0.0f;  // illuminant.cpp:62-64,122-131
+  if (illuminant == HB_ILLUMINANT_E) return 1.0f;
+  if (illuminant == HB_ILLUMINANT_A) {  // Planck 2856 K relative to 560 nm, illuminant.cpp:95-104
+    const float ref_wl = 560.0f, temp = 2856.0f, c2 = 1.4388e7f;
+    float ratio = ref_wl / wl;
+    float ratio5 = ratio * ratio * ratio * ratio * ratio;
+    float exp_ref = std::exp(c2 / (temp * ref_wl));
+    float exp_lam = std::exp(c2 / (temp * wl));
+    return 100.0f * ratio5 * (exp_ref - 1.0f) / (exp_lam - 1.0f);
+  }
+  // D-series: chromaticity from the correlated colour temperature, then S0 + M1*S1 + M2*S2
+  // (CIE 015; illuminant.cpp:14-42,62-90).
+  const float cct_of[4] = { 5003.0f, 5503.0f, 6504.0f, 7504.0f };
+  float cct = cct_of[illuminant];
+  float ti = 1.0f / cct, ti2 = ti * ti, ti3 = ti2 * ti;
+  float xd = cct <= 7000.0f ? 0.244063f + 0.09911e3f * ti + 2.9678e6f * ti2 - 4.6070e9f * ti3
+                            : 0.237040f + 0.24748e3f * ti + 1.9018e6f * ti2 - 2.0064e9f * ti3;
+  float yd = -3.000f * xd * xd + 2.870f * xd - 0.275f;
+  float denom = 0.0241f + 0.2562f * xd - 0.7341f * yd;
+  float m1 = (-1.3515f - 1.7703f * xd + 5.9114f * yd) / denom;
+  float m2 = (0.0300f - 31.4424f * xd + 30.0717f * yd) / denom;
+  float fi = (wl - 300.0f) / 5.0f;
+  int i0 = static_cast<int>(fi);
+  float frac = fi - static_cast<float>(i0);
+  if (i0 >= 106) {
+    i0 = 106;
+    frac = 0.0f;
+  }
+  int i1 = i0 + (i0 < 106 ? 1 : 0);
+  float basis[3];
+  for (int k = 0; k < 3; k++) basis[k] = kDaylightBasis[i0][k] + frac * (kDaylightBasis[i1][k] - kDaylightBasis[i0][k]);
+  return basis[0] + m1 * basis[1] + m2 * basis[2];
+}
+
+int hb_make_wl_pool_illuminant(int illuminant, uint32_t m, HbWlEntry* out) {
+  if (out == nullptr || m == 0 || m > 255 || illuminant < 0 || illuminant > HB_ILLUMINANT_E) return HB_ERR_INVALID_ARG;
+  for (uint32_t i = 0; i < m; i++) {
+    float wl = 380.0f + (static_cast<float>(i) + 0.5f) * 400.0f / static_cast<float>(m);
+    hb_make_wl_entry(wl, hb_illuminant_spd(illuminant, wl), &out[i]);
   }
   return HB_OK;
 }

@@ -50,6 +50,8 @@ PROTOTYPES = {
     "hb_free_scene": (None, [_vp]),
     "hb_build_render": (C.c_int, [_vp, _vp]),
     "hb_make_wl_entry": (C.c_int, [C.c_float, C.c_float, _vp]),
+    "hb_make_wl_pool_illuminant": (C.c_int, [C.c_int, C.c_uint32, _vp]),
+    "hb_illuminant_spd": (C.c_float, [C.c_int, C.c_float]),
 }
 
 _lib = None

@@ -376,6 +376,19 @@ int hb_build_render(const HbRenderDesc* desc, HbProjParams* out);
 /* ComputeWlPool (backend/wl_pool.hpp:67-95) for a discrete wavelength: n from Sellmeier, CMF from
  * the CIE 1931 2-degree 1-nm table looked up at int(wl + 0.5). */
 int hb_make_wl_entry(float wavelength_nm, float weight, HbWlEntry* out);
+/* ComputeWlPool in illuminant mode (backend/wl_pool.hpp:73-84): M mid-point wavelengths across
+ * [380, 780] nm, spd_weight = GetIlluminantSpd (util/illuminant.cpp:113-135; D-series rebuilt from the CIE
+ * S0/S1/S2 daylight basis, A = Planck 2856 K normalised at 560 nm, E = 1). One session traced with this pool
+ * draws a per-ray wavelength index (pcg_shared.h wl stream), as the reference's device backends do.
+ * `illuminant`: HB_ILLUMINANT_*; 1 <= m <= 255. */
+#define HB_ILLUMINANT_D50 0
+#define HB_ILLUMINANT_D55 1
+#define HB_ILLUMINANT_D65 2
+#define HB_ILLUMINANT_D75 3
+#define HB_ILLUMINANT_A 4
+#define HB_ILLUMINANT_E 5
+int hb_make_wl_pool_illuminant(int illuminant, uint32_t m, HbWlEntry* out);
+float hb_illuminant_spd(int illuminant, float wavelength_nm);
 
 #ifdef __cplusplus
 }

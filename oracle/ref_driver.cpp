@@ -263,6 +263,15 @@ double ref_refractive_index(double wl) {
   return IceRefractiveIndex::Get(wl);
 }
 
+int ref_daylight_basis(float* s012) {
+  for (int i = 0; i < kDaylightNumPoints; i++) {
+    s012[i * 3 + 0] = kDaylightS0[i];
+    s012[i * 3 + 1] = kDaylightS1[i];
+    s012[i * 3 + 2] = kDaylightS2[i];
+  }
+  return kDaylightNumPoints;
+}
+
 int ref_cmf_table(float* xyz) {
   int n = kCmfMaxWavelength - kCmfMinWavelength + 1;
   for (int i = 0; i < n; i++) {

@@ -80,6 +80,7 @@ def ref():
         lib.ref_wl_entry.argtypes = [C.c_float, C.c_float, _vp]
         lib.ref_wl_pool_illuminant.argtypes = [C.c_int, C.c_uint32, _vp]
         lib.ref_cmf_table.argtypes = [_vp]
+        lib.ref_daylight_basis.argtypes = [_vp]
         lib.ref_filter_desc.argtypes = [_vp] * 3
         lib.ref_hit_surface.argtypes = [_vp, C.c_float, C.c_uint64] + [_vp] * 5
         lib.ref_propagate.argtypes = [_vp, C.c_uint64] + [_vp] * 6

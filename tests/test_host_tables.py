@@ -113,6 +113,22 @@ def test_wl_entries_and_sellmeier_bit_exact():
         assert np.array_equal(bits(np.array([m.n_idx, m.spd_weight, m.cmf_x, m.cmf_y, m.cmf_z], np.float32)), bits(e))
 
 
+def test_illuminant_wl_pools_bit_exact():
+    """hb_make_wl_pool_illuminant == ComputeWlPool(illuminant_mode) for D50/D55/D65/D75/A/E (wl_pool.hpp:73-84)."""
+    lib = L.load()
+    g = np.load(os.path.join(G, "wl_pools.npz"))
+    for key in g.files:
+        ill, m = int(key[3]), int(key.split("_m")[1])
+        pool = (A.HbWlEntry * m)()
+        assert lib.hb_make_wl_pool_illuminant(ill, m, pool) == 0
+        mine = np.frombuffer(pool, np.float32).reshape(m, 5)
+        assert np.array_equal(bits(mine), bits(g[key])), key
+    assert lib.hb_make_wl_pool_illuminant(9, 64, pool) != 0 and lib.hb_make_wl_pool_illuminant(2, 0, pool) != 0
+    assert lib.hb_illuminant_spd(2, 299.0) == 0.0 and lib.hb_illuminant_spd(5, 500.0) == 1.0
+    from ice_halo_sim_b200 import make_wl_pool
+    assert len(make_wl_pool("D65")) == 64
+
+
 def partition(prop, n, carry):
     lib = L.load()
     p = np.array(prop, np.float32)
