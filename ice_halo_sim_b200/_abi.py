@@ -16,6 +16,7 @@ HB_MAX_WL = 256
 HB_INVALID_FACE = 0xFFFF
 HB_MAX_FILTER_PATH = 32
 HB_MAX_FILTER_TERMS = 8
+HB_MAX_RENDERS = 8
 
 HB_OK = 0
 STATUS_NAMES = {0: "HB_OK", -1: "HB_ERR_INVALID_ARG", -2: "HB_ERR_NO_DEVICE", -3: "HB_ERR_CUDA",
@@ -153,6 +154,10 @@ class HbRenderDesc(C.Structure):
                 ("visible_range", i32), ("lens_shift_x", i32), ("lens_shift_y", i32), ("overlap", f32)]
 
 
+class HbSnapshotDesc(C.Structure):
+    _fields_ = [("intensity_factor", f32), ("ray_color", f32 * 3), ("background", f32 * 3)]
+
+
 ALL_STRUCTS = [HbCrystalTables, HbAxisSampler, HbSimpleFilter, HbFilterDesc, HbCrystalPopulation, HbLayer, HbScene,
                HbWlEntry, HbProjParams, HbExitRecord, HbSessionSpec, HbLayerStats, HbCounters, HbDist, HbCrystalDesc,
-               HbSimpleFilterSpec, HbFilterSpecDesc, HbPopulationDesc, HbLayerDesc, HbSceneDesc, HbRenderDesc]
+               HbSimpleFilterSpec, HbFilterSpecDesc, HbPopulationDesc, HbLayerDesc, HbSceneDesc, HbRenderDesc, HbSnapshotDesc]

@@ -158,9 +158,15 @@ class B200TraceBackend:
 
     def SetRender(self, render):
         """render: HbRenderDesc (built with the library's BuildProjParams twin) or HbProjParams."""
-        proj = make_proj_params(render) if isinstance(render, A.HbRenderDesc) else render
-        self._proj = proj
-        self._check(self._lib.hb_set_render(self._h, C.byref(proj)))
+        self.SetRenders([render])
+
+    def SetRenders(self, renders):
+        """N projections of one trace (hb_set_renders): every exit lands in each render's own accumulator."""
+        projs = [make_proj_params(r) if isinstance(r, A.HbRenderDesc) else r for r in renders]
+        arr = (A.HbProjParams * len(projs))(*projs)
+        self._check(self._lib.hb_set_renders(self._h, len(projs), arr))
+        self._projs = projs
+        self._proj = projs[0]
 
     def IsCompatible(self, render) -> bool:  # trace_backend.hpp:511-514: all 11 lens types supported
         return 0 <= int(render.lens_type if isinstance(render, A.HbRenderDesc) else render.proj_type) <= 10
@@ -242,16 +248,35 @@ class B200TraceBackend:
         self._check(self._lib.hb_end_session(self._h))
         self._in_session = False
 
-    def ReadbackXyzAccum(self, xyz: Optional[np.ndarray] = None):
-        """Returns (xyz[H, W, 3] float32, landed_weight). Drains + zeroes the device accumulators."""
+    def ReadbackXyzAccum(self, xyz: Optional[np.ndarray] = None, render=0):
+        """Returns (xyz[H, W, 3] float32, landed_weight). Drains + zeroes that render's device accumulators."""
         if self._proj is None:
             raise HaloTraceError(-4, "ReadbackXyzAccum before SetRender")
-        h, w = self._proj.img_h, self._proj.img_w
+        if not 0 <= render < len(self._projs):
+            raise HaloTraceError(-1, "ReadbackXyzAccum: no such render")
+        h, w = self._projs[render].img_h, self._projs[render].img_w
         if xyz is None:
             xyz = np.empty((h, w, 3), np.float32)
         landed = C.c_float(0.0)
-        self._check(self._lib.hb_readback_xyz(self._h, xyz.ctypes.data, C.byref(landed)))
+        self._check(self._lib.hb_readback_xyz_render(self._h, render, xyz.ctypes.data, C.byref(landed)))
         return xyz, landed.value
+
+    def Snapshot(self, render=0, intensity_factor=1.0, ray_color=(-1.0, -1.0, -1.0), background=(0.0, 0.0, 0.0),
+                 want_xyz=False):
+        """Device display sink (RenderConsumer::PrepareSnapshot + PostSnapshot, server/render.cpp:463-577):
+        returns (rgb8[H, W, 3] uint8, xyz[H, W, 3] float32 or None, snapshot_intensity). Non-destructive."""
+        if self._proj is None:
+            raise HaloTraceError(-4, "Snapshot before SetRender")
+        if not 0 <= render < len(self._projs):
+            raise HaloTraceError(-1, "Snapshot: no such render")
+        h, w = self._projs[render].img_h, self._projs[render].img_w
+        desc = A.HbSnapshotDesc(float(intensity_factor), (C.c_float * 3)(*ray_color), (C.c_float * 3)(*background))
+        rgb = np.empty((h, w, 3), np.uint8)
+        xyz = np.empty((h, w, 3), np.float32) if want_xyz else None
+        inten = C.c_float(0.0)
+        self._check(self._lib.hb_snapshot(self._h, render, C.byref(desc), rgb.ctypes.data,
+                                          xyz.ctypes.data if want_xyz else None, C.byref(inten)))
+        return rgb, xyz, inten.value
 
     # ---- tuning / measurement ----
     def SetOption(self, key, value):

@@ -56,6 +56,13 @@ enum : uint32_t {
   kFlagPixelCache = 32u,  // per-CTA shared-memory pixel cache in the optics kernel
 };
 
+// Additional projections of the same trace (N renderers per trace). Render 0 lives in the
+// kernel parameters; the others are read from this device table on the (rare) emit path.
+struct ExtraRender {
+  HbProjParams proj;
+  uint32_t pixel_offset;        // first pixel of this render in the image arena
+};
+
 struct TraceParams {
   float4* P;
   float4* D;
@@ -70,8 +77,10 @@ struct TraceParams {
   LayerTables lt;
   const HbWlEntry* wl;
   uint32_t wl_cnt;
-  float4* image;                // [H][W] (X, Y, Z, landed weight)
-  HbProjParams proj;
+  float4* image;                // image arena: render r occupies [off_r, off_r + W_r*H_r), (X, Y, Z, landed)
+  HbProjParams proj;            // render 0 (arena offset 0)
+  const ExtraRender* extra;     // renders 1..extra_cnt (device)
+  uint32_t extra_cnt;
   uint32_t hit, max_hits, layer_idx, flags;
   float prob;
   uint32_t gate_seed;           // session seed ^ gate nonce
@@ -181,7 +190,7 @@ HB_DEV void cache_flush(const TraceParams& tp, const Tally& tally) {
   }
 }
 
-template <bool GENERAL, typename TablesT>
+template <bool GENERAL, bool MULTI, typename TablesT>
 HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float lx, float ly, float lz,
                       float w, uint32_t role, const TablesT& tb, Tally& tally) {
   const Rot r = rot_from_quat(q);
@@ -276,6 +285,23 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
       if (px >= 0 && px < tp.proj.img_w && py >= 0 && py < tp.proj.img_h) {
         accumulate_pixel(tp, tally, static_cast<uint32_t>(py) * static_cast<uint32_t>(tp.proj.img_w) + static_cast<uint32_t>(px),
                          mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w), h.bump[k] ? w : 0.0f);
+      }
+    }
+  }
+  if constexpr (MULTI) {  // further projections of the same exit (multi-render traces run the GENERAL+MULTI kernels)
+    for (uint32_t r = 0; r < tp.extra_cnt; r++) {
+      const HbProjParams pr = tp.extra[r].proj;
+      const uint32_t off = tp.extra[r].pixel_offset;
+      const PixelHits hr = project_exit(pr, wx, wy, wz);
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        if (k < hr.count) {
+          const int px = hr.px[k], py = hr.py[k];
+          if (px >= 0 && px < pr.img_w && py >= 0 && py < pr.img_h) {
+            accumulate_pixel(tp, tally, off + static_cast<uint32_t>(py) * static_cast<uint32_t>(pr.img_w) + static_cast<uint32_t>(px),
+                             mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w), hr.bump[k] ? w : 0.0f);
+          }
+        }
       }
     }
   }
@@ -414,7 +440,7 @@ HB_DEV void fork_append(const TraceParams& tp, uint32_t slot, uint32_t bits, flo
 #ifndef HB_INTERSECT_MINB
 #define HB_INTERSECT_MINB 5
 #endif
-template <bool GENERAL, bool LAST, bool SMEM>
+template <bool GENERAL, bool LAST, bool SMEM, bool MULTI>
 __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Tally tally;
@@ -463,7 +489,7 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
         if (!far_child_surely_exits(axes, axis_cnt, face, pl, p4.x, p4.y, p4.z, ox, oy, oz))
           nf = slab_exit<true>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
         if (nf == kFaceInvalid) {
-          emit_exit<GENERAL>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, tb, tally);
+          emit_exit<GENERAL, MULTI>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, tb, tally);
         } else if (!LAST) {
           fork_append<GENERAL>(tp, i, bits, q, nx, ny, nz, ox, oy, oz, ow, nf);  // near-edge leak: both children stay
         }
@@ -473,7 +499,7 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
         if (iw >= 0.0f) {
           float nx, ny, nz;
           const uint32_t nf = slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
-          if (nf == kFaceInvalid) emit_exit<GENERAL>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, tb, tally);
+          if (nf == kFaceInvalid) emit_exit<GENERAL, MULTI>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, tb, tally);
         }
       } else {
         tp.D[i] = make_float4(ix, iy, iz, iw);  // iw < 0 (TIR sentinel) terminates the ray
@@ -494,7 +520,7 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
 // ------------------------------------------------------------------------------------------------
 // intersect kernel: slab exit-face search for the inside child
 // ------------------------------------------------------------------------------------------------
-template <bool GENERAL, bool SMEM>
+template <bool GENERAL, bool SMEM, bool MULTI>
 __global__ void __launch_bounds__(256, HB_INTERSECT_MINB) intersect_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw, GENERAL);
@@ -528,7 +554,7 @@ __global__ void __launch_bounds__(256, HB_INTERSECT_MINB) intersect_kernel(const
         const uint32_t nf = slab_exit<false>(tb.axes(shape), (meta >> 16) & 255u, face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz);
         if (nf == kFaceInvalid) {
           // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
-          emit_exit<GENERAL>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, tb, tally);
+          emit_exit<GENERAL, MULTI>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, tb, tally);
           tp.D[i] = make_float4(d4.x, d4.y, d4.z, -1.0f);
         } else {
           tp.P[i] = make_float4(nx, ny, nz, __uint_as_float(bits_with_face(bits, nf)));
@@ -724,6 +750,87 @@ __global__ void __launch_bounds__(256) drain_image_kernel(double4* master, float
   }
 }
 
+// Non-destructive readout of one render: packed fp32 XYZ + landed-weight sum (the master keeps accumulating).
+__global__ void __launch_bounds__(256) peek_image_kernel(const double4* master, float* xyz, double* landed, uint32_t pixels) {
+  double lsum = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const double4 v = master[i];
+    if (xyz != nullptr) {
+      xyz[3u * i + 0] = static_cast<float>(v.x);
+      xyz[3u * i + 1] = static_cast<float>(v.y);
+      xyz[3u * i + 2] = static_cast<float>(v.z);
+    }
+    lsum += v.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+  if ((threadIdx.x & 31u) == 0u && lsum != 0.0) atomicAdd(landed, lsum);
+}
+
+// Display sink (RenderConsumer::PostSnapshot, server/render.cpp:508-577, with util/color_space.cpp:10-52):
+// XYZ * exposure scale -> gamut clip towards the D65 grey of equal luminance -> linear sRGB -> + background,
+// clamp -> sRGB transfer curve -> 8-bit. With a ray colour the luminance-only branch is taken instead.
+struct SnapshotParams {
+  float scale;
+  float ray_color[3];
+  float background[3];
+  int use_real_color;
+};
+
+HB_DEV float linear_to_srgb(float v) {  // color_space.cpp:47-52
+  if (v < 0.0031308f) return v * 12.92f;
+  return 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+}
+
+__global__ void __launch_bounds__(256) snapshot_srgb_kernel(const double4* master, uint8_t* rgb8, uint32_t pixels, SnapshotParams sp) {
+  const float kWhite[3] = { 0.95047f, 1.00000f, 1.08883f };
+  const float kM[9] = { 3.2404542f, -1.5371385f, -0.4985314f, -0.9692660f, 1.8760108f, 0.0415560f,
+                        0.0556434f, -0.2040259f, 1.0572252f };
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const double4 m = master[i];
+    const float xyz[3] = { mul(static_cast<float>(m.x), sp.scale), mul(static_cast<float>(m.y), sp.scale),
+                           mul(static_cast<float>(m.z), sp.scale) };
+    float gray[3], rgb[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) gray[j] = mul(kWhite[j], xyz[1]);
+    if (sp.use_real_color) {
+      float s = 1.0f, diff[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) diff[j] = sub(xyz[j], gray[j]);
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float a = 0.0f, b = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          a = add(a, mul(-gray[k], kM[j * 3 + k]));
+          b = add(b, mul(diff[k], kM[j * 3 + k]));
+        }
+        if (mul(a, b) > 0.0f && __fdiv_rn(a, b) < s) s = __fdiv_rn(a, b);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) v = add(v, mul(add(mul(diff[k], s), gray[k]), kM[j * 3 + k]));
+        rgb[j] = fminf(fmaxf(v, 0.0f), 1.0f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) v = add(v, mul(gray[k], kM[j * 3 + k]));
+        rgb[j] = mul(v, sp.ray_color[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      float v = add(rgb[j], sp.background[j]);
+      v = fminf(fmaxf(v, 0.0f), 1.0f);
+      rgb8[3u * i + j] = static_cast<uint8_t>(mul(linear_to_srgb(v), 255.0f));
+    }
+  }
+}
+
 // Export helper: quaternion -> rot9 with the device's own arithmetic (parity harness).
 __global__ void quat_to_rot_kernel(const float4* Q, float* rot9, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -803,7 +910,12 @@ struct HbEngine {
   float sun_lon = 0, sun_lat = 0, sun_half = 0;
   std::vector<std::unique_ptr<LayerDev>> layers;
   bool have_scene = false, have_render = false;
-  HbProjParams proj{};
+  HbProjParams proj{};                 // render 0
+  std::vector<HbProjParams> renders;   // all renders of the current trace (1..HB_MAX_RENDERS)
+  std::vector<uint32_t> render_off;    // first pixel of each render in the arena
+  uint32_t arena_pix = 0;              // pixels of all renders together
+  DevBuf<ExtraRender> extra_dev;       // renders 1.. for the emit path
+  DevBuf<uint8_t> rgb_stage;           // 8-bit snapshot staging
   DevBuf<float4> image;
   DevBuf<double4> master;
   uint64_t rays_since_fold = 0;
@@ -933,6 +1045,14 @@ uint32_t grid_for(const HbEngine* h, uint64_t n) {
   return static_cast<uint32_t>(std::max<uint64_t>(1, std::min(blocks, cap)));
 }
 
+// Fold the fp32 working arena (all renders) into the fp64 master.
+void fold_arena(HbEngine* h) {
+  if (h->arena_pix == 0) return;
+  fold_image_kernel<<<grid_for(h, h->arena_pix), 256, 0, h->stream>>>(h->image.p, h->master.p, h->arena_pix);
+  h->ctr.kernel_launches++;
+  h->rays_since_fold = 0;
+}
+
 // Persistent grid-stride launch: exactly as many CTAs as are co-resident (occupancy x SM count), so there is
 // no partially filled second wave.
 template <typename K>
@@ -944,19 +1064,28 @@ uint32_t resident_grid(const HbEngine* h, K kernel, size_t smem, uint64_t n) {
   return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(blocks, static_cast<uint64_t>(h->sm_count) * per_sm)));
 }
 
-template <bool G, bool L, bool S>
+template <bool G, bool L, bool S, bool M = false>
 void launch_optics_t(HbEngine* h, size_t smem, const TraceParams& tp) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(optics_kernel<G, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(optics_kernel<G, L, S, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(shared_tables_bytes(kSmemShapes) + kCacheBytes));
     attr_set = true;
   }
-  const uint32_t grid = resident_grid(h, optics_kernel<G, L, S>, smem, tp.cap);
-  optics_kernel<G, L, S><<<grid, 256, smem, h->stream>>>(tp);
+  const uint32_t grid = resident_grid(h, optics_kernel<G, L, S, M>, smem, tp.cap);
+  optics_kernel<G, L, S, M><<<grid, 256, smem, h->stream>>>(tp);
 }
 void launch_optics(HbEngine* h, bool general, bool last, bool in_smem, size_t smem, const TraceParams& tp) {
   const int key = (general ? 4 : 0) | (last ? 2 : 0) | (in_smem ? 1 : 0);
+  if (tp.extra_cnt != 0u) {  // N projections per trace: GENERAL kernels with the extra-render loop
+    switch (key & 3) {
+      case 0: launch_optics_t<true, false, false, true>(h, smem, tp); break;
+      case 1: launch_optics_t<true, false, true, true>(h, smem, tp); break;
+      case 2: launch_optics_t<true, true, false, true>(h, smem, tp); break;
+      default: launch_optics_t<true, true, true, true>(h, smem, tp); break;
+    }
+    return;
+  }
   switch (key) {
     case 0: launch_optics_t<false, false, false>(h, smem, tp); break;
     case 1: launch_optics_t<false, false, true>(h, smem, tp); break;
@@ -968,13 +1097,15 @@ void launch_optics(HbEngine* h, bool general, bool last, bool in_smem, size_t sm
     default: launch_optics_t<true, true, true>(h, smem, tp); break;
   }
 }
-template <bool G, bool S>
+template <bool G, bool S, bool M = false>
 void launch_intersect_t(HbEngine* h, size_t smem, const TraceParams& tp) {
-  const uint32_t grid = resident_grid(h, intersect_kernel<G, S>, smem, tp.cap);
-  intersect_kernel<G, S><<<grid, 256, smem, h->stream>>>(tp);
+  const uint32_t grid = resident_grid(h, intersect_kernel<G, S, M>, smem, tp.cap);
+  intersect_kernel<G, S, M><<<grid, 256, smem, h->stream>>>(tp);
 }
 void launch_intersect(HbEngine* h, bool general, bool in_smem, size_t smem, const TraceParams& tp) {
-  if (general) {
+  if (tp.extra_cnt != 0u) {
+    if (in_smem) launch_intersect_t<true, true, true>(h, smem, tp); else launch_intersect_t<true, false, true>(h, smem, tp);
+  } else if (general) {
     if (in_smem) launch_intersect_t<true, true>(h, smem, tp); else launch_intersect_t<true, false>(h, smem, tp);
   } else {
     if (in_smem) launch_intersect_t<false, true>(h, smem, tp); else launch_intersect_t<false, false>(h, smem, tp);
@@ -1102,7 +1233,8 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   const uint32_t cap = n + fork_cap;
   int rc = ensure_tile(h, cap, fork_cap, flags);
   if (rc != HB_OK) return rc;
-  const bool general = (flags & (kFlagPath | kFlagRecord | kFlagGate | kFlagStats)) != 0 || !(flags & kFlagAccum);
+  const bool general = (flags & (kFlagPath | kFlagRecord | kFlagGate | kFlagStats)) != 0 || !(flags & kFlagAccum) ||
+                       h->renders.size() > 1;
   HB_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 2 * sizeof(uint32_t), h->stream));  // fork_count, fork_snapshot
   if (flags & kFlagRecord) {
     const uint64_t ecap = static_cast<uint64_t>(n) * (h->max_hits + 1) + fork_cap;
@@ -1221,6 +1353,8 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.wl_cnt = h->wl_cnt;
   tp.image = h->image.p;
   tp.proj = h->proj;
+  tp.extra = h->extra_dev.p;
+  tp.extra_cnt = static_cast<uint32_t>(h->renders.size()) - 1u;
   tp.max_hits = h->max_hits;
   tp.layer_idx = li;
   tp.flags = flags;
@@ -1279,12 +1413,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   h->ctr.rays_traced += n;
   if (flags & kFlagAccum) {
     h->rays_since_fold += n;
-    if (h->rays_since_fold >= h->fold_rays) {
-      const uint32_t pix = static_cast<uint32_t>(h->proj.img_w) * h->proj.img_h;
-      fold_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->master.p, pix);
-      h->ctr.kernel_launches++;
-      h->rays_since_fold = 0;
-    }
+    if (h->rays_since_fold >= h->fold_rays) fold_arena(h);
   }
   return HB_OK;
 }
@@ -1365,6 +1494,8 @@ void hb_destroy(HbEngine* h) {
   }
   h->image.release();
   h->master.release();
+  h->extra_dev.release();
+  h->rgb_stage.release();
   h->xyz_stage.release();
   h->landed_dev.release();
   for (auto& s : h->wl_cache) s.dev.release();
@@ -1413,28 +1544,55 @@ int hb_set_scene(HbEngine* h, const HbScene* s) {
   return HB_OK;
 }
 
-int hb_set_render(HbEngine* h, const HbProjParams* p) {
+int hb_set_renders(HbEngine* h, uint32_t n, const HbProjParams* p) {
   if (h == nullptr || p == nullptr) return HB_ERR_INVALID_ARG;
   if (h->in_session) return fail(h, HB_ERR_STATE, "hb_set_render inside a session");
-  if (p->img_w <= 0 || p->img_h <= 0) return fail(h, HB_ERR_INVALID_ARG, "render: empty image");
+  if (n == 0 || n > HB_MAX_RENDERS) return fail(h, HB_ERR_INVALID_ARG, "render count must be 1..HB_MAX_RENDERS");
+  uint64_t total = 0;
+  for (uint32_t r = 0; r < n; r++) {
+    if (p[r].img_w <= 0 || p[r].img_h <= 0) return fail(h, HB_ERR_INVALID_ARG, "render: empty image");
+    total += static_cast<uint64_t>(p[r].img_w) * p[r].img_h;
+  }
+  if (total >= (1ull << 31)) return fail(h, HB_ERR_CAPACITY, "renders: more than 2^31 pixels");
   cudaSetDevice(h->device);
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
-  const size_t pix = static_cast<size_t>(p->img_w) * p->img_h;
-  const bool realloc = !h->have_render || p->img_w != h->proj.img_w || p->img_h != h->proj.img_h;
-  h->proj = *p;
+  bool realloc = !h->have_render || n != h->renders.size();
+  for (uint32_t r = 0; r < n && !realloc; r++)
+    realloc = p[r].img_w != h->renders[r].img_w || p[r].img_h != h->renders[r].img_h;
+  h->renders.assign(p, p + n);
+  h->proj = p[0];
+  h->render_off.resize(n);
+  std::vector<ExtraRender> extra;
+  uint32_t off = 0;
+  size_t max_pix = 0;
+  for (uint32_t r = 0; r < n; r++) {
+    h->render_off[r] = off;
+    if (r > 0) extra.push_back(ExtraRender{ p[r], off });
+    const size_t pix = static_cast<size_t>(p[r].img_w) * p[r].img_h;
+    max_pix = std::max(max_pix, pix);
+    off += static_cast<uint32_t>(pix);
+  }
+  h->arena_pix = off;
+  if (!extra.empty()) {
+    HB_CUDA(h, h->extra_dev.ensure(extra.size()));
+    HB_CUDA(h, cudaMemcpy(h->extra_dev.p, extra.data(), extra.size() * sizeof(ExtraRender), cudaMemcpyHostToDevice));
+  }
   if (realloc) {  // resolution change => realloc + zero (cuda_trace_backend.cu:3799-3835)
-    HB_CUDA(h, h->image.ensure(pix));
-    HB_CUDA(h, h->master.ensure(pix));
-    HB_CUDA(h, cudaMemset(h->master.p, 0, pix * sizeof(double4)));
+    HB_CUDA(h, h->image.ensure(h->arena_pix));
+    HB_CUDA(h, h->master.ensure(h->arena_pix));
+    HB_CUDA(h, cudaMemset(h->master.p, 0, static_cast<size_t>(h->arena_pix) * sizeof(double4)));
     h->rays_since_fold = 0;
-    HB_CUDA(h, h->xyz_stage.ensure(pix * 3));
+    HB_CUDA(h, h->xyz_stage.ensure(max_pix * 3));
+    HB_CUDA(h, h->rgb_stage.ensure(max_pix * 3));
     HB_CUDA(h, h->landed_dev.ensure(1));
-    HB_CUDA(h, cudaMemset(h->image.p, 0, pix * sizeof(float4)));
+    HB_CUDA(h, cudaMemset(h->image.p, 0, static_cast<size_t>(h->arena_pix) * sizeof(float4)));
     HB_CUDA(h, cudaMemset(h->landed_dev.p, 0, sizeof(double)));
   }
   h->have_render = true;
   return HB_OK;
 }
+
+int hb_set_render(HbEngine* h, const HbProjParams* p) { return hb_set_renders(h, 1, p); }
 
 int hb_begin_session(HbEngine* h, const HbSessionSpec* spec) {
   if (h == nullptr || spec == nullptr) return HB_ERR_INVALID_ARG;
@@ -1643,15 +1801,16 @@ int hb_end_session(HbEngine* h) {
   return HB_OK;
 }
 
-int hb_readback_xyz(HbEngine* h, float* xyz, float* landed) {
+int hb_readback_xyz_render(HbEngine* h, uint32_t render, float* xyz, float* landed) {
   if (h == nullptr || xyz == nullptr || landed == nullptr) return HB_ERR_INVALID_ARG;
   if (!h->have_render) return fail(h, HB_ERR_STATE, "readback before hb_set_render");
+  if (render >= h->renders.size()) return fail(h, HB_ERR_INVALID_ARG, "readback: no such render");
   cudaSetDevice(h->device);
-  const uint32_t pix = static_cast<uint32_t>(h->proj.img_w) * h->proj.img_h;
-  fold_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->master.p, pix);
-  h->rays_since_fold = 0;
-  drain_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->master.p, h->xyz_stage.p, h->landed_dev.p, pix);
-  h->ctr.kernel_launches += 2;
+  const uint32_t pix = static_cast<uint32_t>(h->renders[render].img_w) * h->renders[render].img_h;
+  fold_arena(h);
+  drain_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->master.p + h->render_off[render], h->xyz_stage.p,
+                                                              h->landed_dev.p, pix);
+  h->ctr.kernel_launches++;
   double l = 0.0;
   HB_CUDA(h, cudaMemcpyAsync(xyz, h->xyz_stage.p, static_cast<size_t>(pix) * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   HB_CUDA(h, cudaMemcpyAsync(&l, h->landed_dev.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1659,6 +1818,49 @@ int hb_readback_xyz(HbEngine* h, float* xyz, float* landed) {
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->profile) flush_events(h);
   *landed += static_cast<float>(l);
+  return HB_OK;
+}
+
+int hb_readback_xyz(HbEngine* h, float* xyz, float* landed) { return hb_readback_xyz_render(h, 0, xyz, landed); }
+
+int hb_snapshot(HbEngine* h, uint32_t render, const HbSnapshotDesc* desc, uint8_t* rgb8, float* xyz, float* intensity) {
+  if (h == nullptr || desc == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->have_render) return fail(h, HB_ERR_STATE, "snapshot before hb_set_render");
+  if (render >= h->renders.size()) return fail(h, HB_ERR_INVALID_ARG, "snapshot: no such render");
+  cudaSetDevice(h->device);
+  const uint32_t pix = static_cast<uint32_t>(h->renders[render].img_w) * h->renders[render].img_h;
+  const double4* src = h->master.p + h->render_off[render];
+  fold_arena(h);
+  // PrepareSnapshot (render.cpp:463-495): running sum -> fp32 snapshot + total landed weight
+  HB_CUDA(h, cudaMemsetAsync(h->landed_dev.p, 0, sizeof(double), h->stream));
+  peek_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(src, xyz ? h->xyz_stage.p : nullptr, h->landed_dev.p, pix);
+  h->ctr.kernel_launches++;
+  double l = 0.0;
+  HB_CUDA(h, cudaMemcpyAsync(&l, h->landed_dev.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  HB_CUDA(h, cudaMemsetAsync(h->landed_dev.p, 0, sizeof(double), h->stream));
+  if (xyz)
+    HB_CUDA(h, cudaMemcpyAsync(xyz, h->xyz_stage.p, static_cast<size_t>(pix) * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const float snapshot_intensity = static_cast<float>(l);
+  if (intensity) *intensity = snapshot_intensity;
+  if (rgb8 != nullptr) {
+    if (snapshot_intensity <= 0.0f) {  // PostSnapshot early-out: black frame (render.cpp:514-517)
+      std::memset(rgb8, 0, static_cast<size_t>(pix) * 3);
+      return HB_OK;
+    }
+    SnapshotParams sp{};
+    // ExposureScale (render.cpp:96-102): intensity_factor * kNormScale * total_pix / snapshot_intensity
+    sp.scale = desc->intensity_factor * 0.08f * static_cast<float>(static_cast<int>(pix)) / snapshot_intensity;
+    sp.use_real_color = desc->ray_color[0] < 0.0f ? 1 : 0;
+    for (int j = 0; j < 3; j++) {
+      sp.ray_color[j] = desc->ray_color[j];
+      sp.background[j] = desc->background[j];
+    }
+    snapshot_srgb_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(src, h->rgb_stage.p, pix, sp);
+    h->ctr.kernel_launches++;
+    HB_CUDA(h, cudaMemcpyAsync(rgb8, h->rgb_stage.p, static_cast<size_t>(pix) * 3, cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   return HB_OK;
 }
 
@@ -1753,12 +1955,9 @@ int hb_image_device_ptr(HbEngine* h, void** ptr, uint64_t* float_count) {
   if (h == nullptr || ptr == nullptr || float_count == nullptr) return HB_ERR_INVALID_ARG;
   if (!h->have_render) return fail(h, HB_ERR_STATE, "no render set");
   cudaSetDevice(h->device);
-  const uint32_t pix = static_cast<uint32_t>(h->proj.img_w) * h->proj.img_h;
-  fold_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->master.p, pix);
-  h->rays_since_fold = 0;
-  h->ctr.kernel_launches++;
+  fold_arena(h);
   *ptr = h->master.p;
-  *float_count = static_cast<uint64_t>(pix) * 4;
+  *float_count = static_cast<uint64_t>(h->arena_pix) * 4;
   return HB_OK;
 }
 
@@ -1799,11 +1998,9 @@ int hb_allreduce_image(HbEngine* h) {
 #ifdef HB_WITH_NCCL
   if (h->comm == nullptr) return fail(h, HB_ERR_STATE, "hb_comm_init not called");
   cudaSetDevice(h->device);
-  const size_t cnt = static_cast<size_t>(h->proj.img_w) * h->proj.img_h * 4;
-  const uint32_t pix = static_cast<uint32_t>(h->proj.img_w) * h->proj.img_h;
-  fold_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->image.p, h->master.p, pix);
-  h->rays_since_fold = 0;
-  h->ctr.kernel_launches++;
+  if (!h->have_render) return fail(h, HB_ERR_STATE, "no render set");
+  const size_t cnt = static_cast<size_t>(h->arena_pix) * 4;
+  fold_arena(h);
   if (ncclAllReduce(h->master.p, h->master.p, cnt, ncclDouble, ncclSum, h->comm, h->stream) != ncclSuccess)
     return fail(h, HB_ERR_COMM, "ncclAllReduce failed");
   return HB_OK;

@@ -22,11 +22,14 @@ PROTOTYPES = {
     "hb_destroy": (None, [_vp]),
     "hb_set_scene": (C.c_int, [_vp, _vp]),
     "hb_set_render": (C.c_int, [_vp, _vp]),
+    "hb_set_renders": (C.c_int, [_vp, C.c_uint32, _vp]),
     "hb_begin_session": (C.c_int, [_vp, _vp]),
     "hb_trace_layer": (C.c_int, [_vp, C.c_uint64, _vp]),
     "hb_recombine": (C.c_int, [_vp, C.c_int, _vp]),
     "hb_end_session": (C.c_int, [_vp]),
     "hb_readback_xyz": (C.c_int, [_vp, _vp, _vp]),
+    "hb_readback_xyz_render": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
+    "hb_snapshot": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "hb_drain_exits": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "hb_inject_rays": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "hb_export_roots": (C.c_int, [_vp, C.c_uint64] + [_vp] * 8),

@@ -43,6 +43,7 @@ extern "C" {
 #define HB_INVALID_FACE 0xFFFFu /* kInvalidId */
 #define HB_MAX_FILTER_PATH 32u  /* C API raypath len cap, lumice.h:286-293 */
 #define HB_MAX_FILTER_TERMS 8u
+#define HB_MAX_RENDERS 8u
 
 typedef enum HbStatus {
   HB_OK = 0,
@@ -229,6 +230,10 @@ void hb_destroy(HbEngine* h);
  * spec.scene/spec.render, trace_backend.hpp:118-122). May be called between sessions. */
 int hb_set_scene(HbEngine* h, const HbScene* scene);
 int hb_set_render(HbEngine* h, const HbProjParams* proj);
+/* N projections of ONE trace (examples/config_example.json ships four renderers, which the
+ * reference's device backends refuse, server.cpp:402-437): every emitted exit is projected through each of
+ * the n <= HB_MAX_RENDERS lenses into its own accumulator. Render 0 is the one hb_readback_xyz drains. */
+int hb_set_renders(HbEngine* h, uint32_t n, const HbProjParams* proj);
 
 /* TraceBackend::BeginSession (trace_backend.hpp:374). */
 int hb_begin_session(HbEngine* h, const HbSessionSpec* spec);
@@ -243,6 +248,21 @@ int hb_end_session(HbEngine* h);
 /* TraceBackend::ReadbackXyzAccum (trace_backend.hpp:466): copies W*H*3 floats, ADDS the landed
  * weight to *landed_weight, then zeroes the device accumulators. Legal between sessions. */
 int hb_readback_xyz(HbEngine* h, float* xyz_wh3, float* landed_weight);
+int hb_readback_xyz_render(HbEngine* h, uint32_t render, float* xyz_wh3, float* landed_weight);
+
+/* Display sink on the device = RenderConsumer::PrepareSnapshot + PostSnapshot
+ * (server/render.cpp:463-495,508-577; util/color_space.cpp:10-52): NON-destructive; the accumulator keeps
+ * integrating. Writes (each optional) the 8-bit sRGB frame [H][W][3], the fp32 XYZ snapshot [H][W][3] and the
+ * snapshot intensity (total landed weight). Exposure: intensity_factor * 0.08 * W*H / intensity
+ * (ExposureScale, render.cpp:96-102). ray_color[0] < 0 selects real colour (gamut clip towards D65 grey);
+ * otherwise luminance tinted by ray_color. */
+typedef struct HbSnapshotDesc {
+  float intensity_factor;   /* RenderConfig::intensity_factor_ (2^EV), default 1 */
+  float ray_color[3];       /* RenderConfig::ray_color_, default {-1,-1,-1} = real colour */
+  float background[3];      /* RenderConfig::background_, default 0 */
+} HbSnapshotDesc;
+int hb_snapshot(HbEngine* h, uint32_t render, const HbSnapshotDesc* desc, uint8_t* rgb8_wh3, float* xyz_wh3,
+                float* intensity);
 /* TraceBackend::DrainExits (trace_backend.hpp:443): destructive, grow-not-clamp. Call with
  * out == NULL to query the count. root_ids (optional) receives the layer-root index of each
  * exit, for per-ray parity association. */
@@ -264,9 +284,9 @@ int hb_export_roots(HbEngine* h, uint64_t cap, float* d3, float* p3, float* w, u
 int hb_set_option(HbEngine* h, const char* key, int64_t value);
 int hb_get_counters(HbEngine* h, HbCounters* out);
 int hb_synchronize(HbEngine* h);
-/* Device pointer of the W*H*4 DOUBLE master accumulator (x,y,z,landed; the fp32 working image is folded
- * into it first) for collectives driven from
- * outside (torch.distributed); valid until hb_set_render / hb_destroy. */
+/* Device pointer of the DOUBLE master accumulator (x,y,z,landed per pixel; all renders back to back; the
+ * fp32 working image is folded into it first) for collectives driven from outside (torch.distributed);
+ * valid until hb_set_render(s) / hb_destroy. */
 int hb_image_device_ptr(HbEngine* h, void** ptr, uint64_t* float_count);
 void* hb_stream(HbEngine* h);             /* cudaStream_t the engine launches on */
 

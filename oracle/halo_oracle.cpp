@@ -815,4 +815,60 @@ int orc_trace_layer(const OrcLayerParams* lp, uint64_t n, const float* d3, const
   return (ne > cap || nc > cap) ? HB_ERR_CAPACITY : 0;
 }
 
+// ---- display sink (server/render.cpp:508-577; util/color_space.cpp:10-52; util/color_data.hpp:6-13) ----
+static const float kOrcWhiteD65[3] = { 0.95047f, 1.00000f, 1.08883f };
+static const float kOrcXyzToRgb[9] = { 3.2404542f, -1.5371385f, -0.4985314f, -0.9692660f, 1.8760108f,
+                                       0.0415560f, 0.0556434f,  -0.2040259f, 1.0572252f };
+
+static float orc_linear_to_srgb(float v) {
+  if (v < 0.0031308f) return v * 12.92f;
+  return 1.055f * std::pow(v, 1.0f / 2.4f) - 0.055f;
+}
+
+int orc_post_snapshot(const float* xyz_img, int w, int h, float snapshot_intensity, float intensity_factor,
+                      const float* ray_color, const float* background, uint8_t* out) {
+  const int total_pix = w * h;
+  if (total_pix <= 0 || snapshot_intensity <= 0) {
+    std::memset(out, 0, static_cast<size_t>(std::max(total_pix, 0)) * 3);
+    return 0;
+  }
+  const float scale = intensity_factor * 0.08f * total_pix / snapshot_intensity;
+  const bool real_color = ray_color[0] < 0;
+  for (int i = 0; i < total_pix; i++) {
+    float xyz[3], gray[3], rgb[3];
+    for (int j = 0; j < 3; j++) xyz[j] = xyz_img[i * 3 + j] * scale;
+    for (int j = 0; j < 3; j++) gray[j] = kOrcWhiteD65[j] * xyz[1];
+    if (real_color) {
+      float s = 1.0f, diff[3], clipped[3];
+      for (int j = 0; j < 3; j++) diff[j] = xyz[j] - gray[j];
+      for (int j = 0; j < 3; j++) {
+        float a = 0, b = 0;
+        for (int k = 0; k < 3; k++) {
+          a += -gray[k] * kOrcXyzToRgb[j * 3 + k];
+          b += diff[k] * kOrcXyzToRgb[j * 3 + k];
+        }
+        if (a * b > 0 && a / b < s) s = a / b;
+      }
+      for (int j = 0; j < 3; j++) clipped[j] = diff[j] * s + gray[j];
+      for (int j = 0; j < 3; j++) {
+        float v = 0;
+        for (int k = 0; k < 3; k++) v += clipped[k] * kOrcXyzToRgb[j * 3 + k];
+        rgb[j] = std::min(std::max(v, 0.0f), 1.0f);
+      }
+    } else {
+      for (int j = 0; j < 3; j++) {
+        float v = 0;
+        for (int k = 0; k < 3; k++) v += gray[k] * kOrcXyzToRgb[j * 3 + k];
+        rgb[j] = v * ray_color[j];
+      }
+    }
+    for (int j = 0; j < 3; j++) {
+      float v = rgb[j] + background[j];
+      v = std::min(std::max(v, 0.0f), 1.0f);
+      out[i * 3 + j] = static_cast<uint8_t>(orc_linear_to_srgb(v) * 255);
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -69,6 +69,10 @@ int orc_accumulate(const HbProjParams* p, const HbWlEntry* wl, uint32_t wl_cnt, 
 int orc_filter_check(const HbFilterDesc* f, const uint8_t* face_fn, uint32_t pop_crystal_id, uint64_t n,
                      const uint8_t* paths64, const uint8_t* path_len, const float* dir3, uint8_t* pass);
 void orc_quat_to_rot9(const float* q4, float* rot9);
+/* Display sink: RenderConsumer::PostSnapshot (server/render.cpp:508-577) on a snapshot XYZ image with
+ * ExposureScale (render.cpp:96-102), GamutClipXyz / XyzToLinearRgb / LinearToSrgb (util/color_space.cpp:10-52). */
+int orc_post_snapshot(const float* xyz_wh3, int w, int h, float snapshot_intensity, float intensity_factor,
+                      const float* ray_color3, const float* background3, uint8_t* rgb8_wh3);
 
 #ifdef __cplusplus
 }

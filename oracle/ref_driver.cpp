@@ -25,6 +25,9 @@
 #include "core/shared/projection_shared.h"
 #include "core/simulator.hpp"
 #include "core/trace_ops.hpp"
+#include "core/color_util.hpp"
+#include "util/color_data.hpp"
+#include "util/color_space.hpp"
 #include "util/cpu_info.hpp"
 #include "util/illuminant.hpp"
 #include "util/queue.hpp"
@@ -261,6 +264,50 @@ int ref_wl_pool_illuminant(int illuminant, uint32_t m, HbWlEntry* out) {
 
 double ref_refractive_index(double wl) {
   return IceRefractiveIndex::Get(wl);
+}
+
+// RenderConsumer::PostSnapshot's per-pixel loop (server/render.cpp:537-577) driven with the reference's own
+// colour functions (util/color_space.cpp). render.cpp itself pulls in the server layer and is not built here.
+int ref_post_snapshot(const float* xyz_img, int w, int h, float snapshot_intensity, float intensity_factor,
+                      const float* ray_color, const float* background, uint8_t* out) {
+  int total_pix = w * h;
+  if (total_pix <= 0 || snapshot_intensity <= 0) {
+    std::memset(out, 0, static_cast<size_t>(std::max(total_pix, 0)) * 3);
+    return 0;
+  }
+  float scale = intensity_factor * kNormScale * total_pix / snapshot_intensity;
+  bool use_real_color = ray_color[0] < 0;
+  for (int i = 0; i < total_pix; i++) {
+    float xyz[3];
+    for (int j = 0; j < 3; j++) {
+      xyz[j] = xyz_img[i * 3 + j] * scale;
+    }
+    float rgb[3];
+    if (use_real_color) {
+      float clipped[3];
+      GamutClipXyz(xyz, clipped);
+      XyzToLinearRgb(clipped, rgb);
+    } else {
+      float gray[3];
+      for (int j = 0; j < 3; j++) {
+        gray[j] = kWhitePointD65[j] * xyz[1];
+      }
+      for (int j = 0; j < 3; j++) {
+        float v = 0;
+        for (int k = 0; k < 3; k++) {
+          v += gray[k] * kXyzToRgb[j * 3 + k];
+        }
+        rgb[j] = v * ray_color[j];
+      }
+    }
+    for (int j = 0; j < 3; j++) {
+      rgb[j] += background[j];
+      rgb[j] = std::clamp(rgb[j], 0.0f, 1.0f);
+      rgb[j] = LinearToSrgb(rgb[j]);
+      out[i * 3 + j] = static_cast<uint8_t>(rgb[j] * 255);
+    }
+  }
+  return 0;
 }
 
 int ref_daylight_basis(float* s012) {

@@ -33,6 +33,8 @@ int ref_make_proj_params(const HbRenderDesc* r, HbProjParams* out);        /* Ma
 int ref_wl_entry(float wl, float weight, HbWlEntry* out);                  /* ComputeWlPool, discrete */
 int ref_wl_pool_illuminant(int illuminant, uint32_t m, HbWlEntry* out);    /* ComputeWlPool, illuminant */
 double ref_refractive_index(double wl);                                    /* IceRefractiveIndex::Get */
+int ref_post_snapshot(const float* xyz_wh3, int w, int h, float snapshot_intensity, float intensity_factor,
+                      const float* ray_color3, const float* background3, uint8_t* rgb8_wh3); /* PostSnapshot */
 int ref_daylight_basis(float* s012_107x3);                                /* kDaylightS0/S1/S2, 300..830 nm */
 int ref_cmf_table(float* xyz_471x3);                                       /* kCmfX/Y/Z, 360..830 nm */
 int ref_filter_desc(const HbPopulationDesc* pop, const RefShape* shape, HbFilterDesc* out); /* BuildDeviceFilterDesc */

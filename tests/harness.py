@@ -58,6 +58,7 @@ def oracle():
         lib.orc_propagate.argtypes = [_vp, C.c_uint64] + [_vp] * 6
         lib.orc_project.argtypes = [_vp, C.c_uint64] + [_vp] * 5
         lib.orc_accumulate.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64] + [_vp] * 5
+        lib.orc_post_snapshot.argtypes = [_vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp]
         lib.orc_filter_check.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64] + [_vp] * 4
         lib.orc_quat_to_rot9.argtypes = [_vp, _vp]
         _oracle = lib
@@ -81,6 +82,7 @@ def ref():
         lib.ref_wl_pool_illuminant.argtypes = [C.c_int, C.c_uint32, _vp]
         lib.ref_cmf_table.argtypes = [_vp]
         lib.ref_daylight_basis.argtypes = [_vp]
+        lib.ref_post_snapshot.argtypes = [_vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp]
         lib.ref_filter_desc.argtypes = [_vp] * 3
         lib.ref_hit_surface.argtypes = [_vp, C.c_float, C.c_uint64] + [_vp] * 5
         lib.ref_propagate.argtypes = [_vp, C.c_uint64] + [_vp] * 6

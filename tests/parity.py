@@ -156,6 +156,13 @@ CASES = {
             [[dict(kind=1, path=[3, 5])], [dict(kind=1, path=[1, 3, 2]), dict(kind=4, crystal_id=3)],
              [dict(kind=2, entry=3, exit=6), dict(kind=3, lon=180.0, lat=25.0, radii=40.0)]], "PB"))])], 6),
         render=lambda: render(res=(960, 540)), wl=[570.0]),
+    # examples/config_example.json ships several renderers for one scene: N projections of one trace
+    "multi_render": dict(
+        scene=lambda: scene([(0.0, [prism_pop(1.3, zenith=("gauss", 90, 0.3))])], 7),
+        render=lambda: [render(), render("linear", 60.0, (800, 600), view=(0.0, 20.0, 0.0)),
+                        render("dual_fisheye_equal_area", 180.0, (1024, 512), visible="full"),
+                        render("fisheye_orthographic", 170.0, (640, 640), view=(90.0, 90.0, 0.0))],
+        wl=[450.0, 610.0]),
     "pyramid": dict(scene=lambda: scene([(0.0, [pyramid_pop()])], 8),
                     render=lambda: render("dual_fisheye_equal_area", 120.0, (1024, 512), visible="full", overlap=0.1),
                     wl=[610.0]),
@@ -247,7 +254,9 @@ def oracle_image(proj, wl_arr, exits):
 def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=7, tile_rays=None):
     """Full protocol on one case; returns a dict of comparison results (all layers merged)."""
     desc = case["scene"]()
-    rdesc = case["render"]()
+    rdescs = case["render"]()
+    if not isinstance(rdescs, (list, tuple)):
+        rdescs = [rdescs]
     tables = B.SceneTables(desc, geometry_seed)
     sc = tables.scene()
     wl = [B.make_wl_entry(x, 1.0) for x in case["wl"]]
@@ -258,9 +267,10 @@ def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=
         be.SetOption("tile_rays", tile_rays)
     be.SetScene(tables)
     be.SetOption("stream_base", 0)
-    be.SetRender(rdesc)
-    proj = B.make_proj_params(rdesc)
-    be.ReadbackXyzAccum()  # start from a zero image
+    be.SetRenders(rdescs)
+    projs = [B.make_proj_params(r) for r in rdescs]
+    for r in range(len(rdescs)):
+        be.ReadbackXyzAccum(render=r)  # start from zero images
     be.BeginSession(B.SessionSpec(seed=seed, wl=wl, ray_num=n_rays, record_exits=True, accumulate=True))
     out = dict(paths_equal=True, dirs_bit_equal=True, weights_bit_equal=True, meta_equal=True, exits=0, layers=[])
     all_exits = []
@@ -297,24 +307,30 @@ def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=
     finally:
         be.EndSession()
     out["stats_ok"] = stats_ok
-    img, landed = be.ReadbackXyzAccum()
     ex = np.concatenate(all_exits) if all_exits else np.zeros(0, H.EXIT_DTYPE)
-    o_img, o_mag, o_landed, o_cnt = oracle_image(proj, wl_arr, ex)
-    err = np.abs(img - o_img)
-    tol = (IMG_RTOL + IMG_RTOL_PER_TERM * o_cnt) * o_mag + IMG_ATOL
-    out["image_within_tol"] = bool(np.all(err <= tol))
-    # Lenses whose forward map uses atan2/asin/acos/tan differ between glibc (oracle) and libdevice (GPU) by
-    # an ulp, which moves a ray sitting on a pixel boundary into the neighbouring pixel: for those the
-    # per-pixel check is replaced by "total |difference| <= IMG_FLIP_FRAC of the image" (a few rays in 1e5).
-    total = float(o_mag.astype(np.float64).sum())
-    out["image_l1_frac"] = float(err.astype(np.float64).sum()) / max(total, 1e-30)
-    out["lens_transcendental"] = int(proj.proj_type) in (2, 3, 5, 6, 7)
-    out["image_ok"] = out["image_within_tol"] or (out["lens_transcendental"] and out["image_l1_frac"] <= IMG_FLIP_FRAC)
-    out["image_max_rel_err"] = float((err / np.maximum(o_mag, 1e-20)).max()) if o_mag.max() > 0 else 0.0
-    out["image_sum"] = float(img.astype(np.float64).sum())
-    out["landed_gpu"] = float(landed)
-    out["landed_oracle"] = float(o_landed)
-    out["landed_rel_err"] = abs(landed - o_landed) / max(abs(o_landed), 1e-30)
+    out["renders"] = []
+    for r, proj in enumerate(projs):   # every render of the trace against the oracle's projection of the same exits
+        img, landed = be.ReadbackXyzAccum(render=r)
+        o_img, o_mag, o_landed, o_cnt = oracle_image(proj, wl_arr, ex)
+        err = np.abs(img - o_img)
+        tol = (IMG_RTOL + IMG_RTOL_PER_TERM * o_cnt) * o_mag + IMG_ATOL
+        q = dict(image_within_tol=bool(np.all(err <= tol)))
+        # Lenses whose forward map uses atan2/asin/acos/tan differ between glibc (oracle) and libdevice (GPU) by
+        # an ulp, which moves a ray sitting on a pixel boundary into the neighbouring pixel: for those the
+        # per-pixel check is replaced by "total |difference| <= IMG_FLIP_FRAC of the image" (a few rays in 1e5).
+        total = float(o_mag.astype(np.float64).sum())
+        q["image_l1_frac"] = float(err.astype(np.float64).sum()) / max(total, 1e-30)
+        q["lens_transcendental"] = int(proj.proj_type) in (2, 3, 5, 6, 7)
+        q["image_ok"] = q["image_within_tol"] or (q["lens_transcendental"] and q["image_l1_frac"] <= IMG_FLIP_FRAC)
+        q["image_max_rel_err"] = float((err / np.maximum(o_mag, 1e-20)).max()) if o_mag.max() > 0 else 0.0
+        q["image_sum"] = float(img.astype(np.float64).sum())
+        q["landed_gpu"] = float(landed)
+        q["landed_oracle"] = float(o_landed)
+        q["landed_rel_err"] = abs(landed - o_landed) / max(abs(o_landed), 1e-30)
+        out["renders"].append(q)
+    out.update(out["renders"][0])
+    out["image_ok"] = all(q["image_ok"] for q in out["renders"])
+    out["landed_rel_err"] = max(q["landed_rel_err"] for q in out["renders"])
     if own:
         be.close()
     return out

@@ -162,6 +162,27 @@ def test_projection_all_lens_types():
         assert np.array_equal(bump, g[f"{name}.bump"]), name
 
 
+def test_post_snapshot_golden():
+    """Display sink: orc_post_snapshot == the reference's PostSnapshot loop over its own colour functions
+    (fixture from oracle/make_golden.py gen_snapshot), byte for byte."""
+    import sys
+    sys.path.insert(0, os.path.join(H.ROOT, "oracle"))
+    import make_golden as MG
+    orc = H.oracle()
+    g = np.load(os.path.join(G, "snapshot.npz"))
+    xyz = np.ascontiguousarray(g["xyz"])
+    for i, (fac, rc, bg) in enumerate(MG.SNAPSHOT_VARIANTS):
+        rgb = np.zeros(xyz.shape, np.uint8)
+        rc_a, bg_a = np.array(rc, np.float32), np.array(bg, np.float32)  # keep alive across the call
+        orc.orc_post_snapshot(H.ptr(xyz), xyz.shape[1], xyz.shape[0], float(g["intensity"]), fac, H.ptr(rc_a),
+                              H.ptr(bg_a), H.ptr(rgb))
+        assert np.array_equal(rgb, g[f"rgb{i}"]), i
+        assert rgb.max() >= 254 and (i != 0 or 0 < (rgb == 0).mean() < 0.9)   # clipping and the dark end
+    # zero intensity -> black frame (render.cpp:514-517)
+    orc.orc_post_snapshot(H.ptr(xyz), xyz.shape[1], xyz.shape[0], 0.0, 1.0, H.ptr(rc_a), H.ptr(bg_a), H.ptr(rgb))
+    assert not rgb.any()
+
+
 def test_rng_and_feistel_properties():
     orc = H.oracle()
     # pcg_hash known values computed from the definition (pcg_shared.h:193-197)

@@ -224,3 +224,20 @@ def test_orientation_sampler_statistics_match_cpu_sampler():
             se = np.sqrt(a.var() / n + b.var() / n) + 1e-9
             assert abs(a.mean() - b.mean()) < 4.5 * se, (zen, k, a.mean(), b.mean())
             assert abs(np.mean(a * a) - np.mean(b * b)) < 4.5 * np.sqrt(np.var(a * a) / n + np.var(b * b) / n) + 1e-9
+
+
+def test_post_snapshot_matches_reference_colour_pipeline():
+    """orc_post_snapshot == PostSnapshot's loop over the reference's GamutClipXyz / XyzToLinearRgb / LinearToSrgb
+    on a large random image, byte for byte (same libm on both sides)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(H.ROOT, "oracle"))
+    import make_golden as MG
+    ref, orc = H.ref(), H.oracle()
+    xyz, inten = MG.snapshot_input(seed=99, w=640, h=360)
+    for fac, rc, bg in MG.SNAPSHOT_VARIANTS + [(0.25, (0.2, 1.0, 0.3), (0.5, 0.0, 0.0))]:
+        rc_a, bg_a = np.array(rc, np.float32), np.array(bg, np.float32)
+        a = np.zeros(xyz.shape, np.uint8)
+        b = np.zeros(xyz.shape, np.uint8)
+        ref.ref_post_snapshot(H.ptr(xyz), 640, 360, inten, fac, H.ptr(rc_a), H.ptr(bg_a), H.ptr(a))
+        orc.orc_post_snapshot(H.ptr(xyz), 640, 360, inten, fac, H.ptr(rc_a), H.ptr(bg_a), H.ptr(b))
+        assert np.array_equal(a, b) and a.any()
