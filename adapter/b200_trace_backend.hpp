@@ -287,22 +287,62 @@ class B200TraceBackend : public TraceBackend {
     scene_ = &scene;
   }
 
-  void UploadRender(const RenderConfig& render) {
+  static HbProjParams ToProj(const RenderConfig& render) {
     const Rotation rot = MakeCameraRotation(render);
     const auto short_pix = static_cast<float>(std::min(render.resolution_[0], render.resolution_[1]));
     const lm_proj::ProjParams p = BuildProjParams(render, rot, short_pix);
     static_assert(sizeof(lm_proj::ProjParams) == sizeof(HbProjParams), "ProjParams layout");
     HbProjParams hp;
     std::memcpy(&hp, &p, sizeof(hp));
-    Check(hb_set_render(h_, &hp), "UploadRender");
+    return hp;
+  }
+
+  void UploadRender(const RenderConfig& render) {
+    std::vector<HbProjParams> all{ ToProj(render) };  // render 0 = the session's renderer
+    for (const RenderConfig* extra : extra_renders_) {
+      all.push_back(ToProj(*extra));
+    }
+    Check(hb_set_renders(h_, static_cast<uint32_t>(all.size()), all.data()), "UploadRender");
     render_ = &render;
     render_snapshot_dirty_ = false;
   }
+
+ public:
+  // ---- extensions beyond the seam -------------------------------------------------------
+  // Additional renderers projected from the SAME trace (the reference refuses multi-renderer configs on its
+  // device route, server.cpp:402-437). Pointers must outlive the sessions; call between sessions.
+  void SetExtraRenders(std::vector<const RenderConfig*> extra) {
+    if (extra.size() + 1 > HB_MAX_RENDERS) {
+      throw BackendUnavailableError("B200TraceBackend: more than 8 renderers");
+    }
+    extra_renders_ = std::move(extra);
+    render_snapshot_dirty_ = true;
+  }
+  // ReadbackXyzAccum for renderer `index` (0 = the session's own, 1.. = SetExtraRenders order).
+  void ReadbackXyzAccumOf(uint32_t index, XyzImageData& xyz, float& landed_weight) {
+    Check(hb_readback_xyz_render(h_, index, xyz.data, &landed_weight), "ReadbackXyzAccumOf");
+  }
+  // RenderConsumer::PrepareSnapshot + PostSnapshot on the device: 8-bit sRGB frame of renderer `index`,
+  // without draining the accumulator. Returns the snapshot intensity.
+  float SnapshotSrgb(uint32_t index, const RenderConfig& cfg, uint8_t* rgb8) {
+    HbSnapshotDesc d{};
+    d.intensity_factor = cfg.intensity_factor_;
+    for (int j = 0; j < 3; j++) {
+      d.ray_color[j] = cfg.ray_color_[j];
+      d.background[j] = cfg.background_[j];
+    }
+    float intensity = 0.0f;
+    Check(hb_snapshot(h_, index, &d, rgb8, nullptr, &intensity), "SnapshotSrgb");
+    return intensity;
+  }
+
+ private:
 
   HbEngine* h_ = nullptr;
   RandomNumberGenerator rng_;
   const SceneConfig* scene_ = nullptr;
   const RenderConfig* render_ = nullptr;
+  std::vector<const RenderConfig*> extra_renders_;
   bool render_snapshot_dirty_ = false;
   size_t layer_cnt_ = 0;
   size_t layer_idx_ = 0;

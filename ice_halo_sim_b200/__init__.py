@@ -8,5 +8,6 @@ from . import _abi  # noqa: F401
 from .backend import (B200TraceBackend, BackendUnavailableError, HaloTraceError, LayerHandle, RootRaySource,  # noqa: F401
                       SceneTables, SessionSpec, comm_unique_id, make_proj_params, make_wl_entry, make_wl_pool, simulate)
 from .config import SceneConfig, load_config  # noqa: F401
+from .driver import Frame, render_config, trace_session  # noqa: F401
 
 __version__ = "0.1.0"

@@ -228,3 +228,37 @@ def test_device_snapshot_matches_post_snapshot(backend):
     assert np.array_equal(img, xyz0) and abs(landed - inten) <= 1e-6 * inten
     rgb, _, inten = backend.Snapshot()                # drained accumulator: black frame, zero intensity
     assert inten == 0.0 and not rgb.any()
+
+
+def test_driver_renders_whole_config_and_shards_by_rank(backend):
+    """Host driver (ice_halo_sim_b200.driver): a two-layer, filtered, two-renderer, 9-wavelength Lumice config
+    end to end; tracing it as two ranks' shards (summed) lands the same rays as one rank for the first
+    layer, so the frames agree statistically (layer-2 gate/transit streams differ per session)."""
+    import json
+    from test_host_logic import EXAMPLE
+    from ice_halo_sim_b200 import load_config, render_config
+    ex = json.loads(json.dumps(EXAMPLE))
+    ex["scene"]["ray_num"] = 1_800_000
+    cfg = load_config(ex)
+    one = render_config(cfg, backend, seed=9, session_rays=1 << 17, srgb=True)
+    assert sorted(one) == [1, 4]
+    for rid, fr in one.items():
+        assert fr.xyz.shape == (1080, 1920, 3) and fr.rgb.shape == fr.xyz.shape and fr.rgb.dtype == np.uint8
+        assert fr.landed_weight > 0 and fr.xyz.sum() > 0 and fr.rgb.max() > 100
+    halves = [render_config(cfg, backend, seed=9, session_rays=1 << 17, rank=r, world=2, allreduce=False)
+              for r in range(2)]
+    for rid in one:
+        both = halves[0][rid].xyz.astype(np.float64) + halves[1][rid].xyz
+        tot1, tot2 = one[rid].xyz.astype(np.float64).sum(), both.sum()
+        assert abs(tot1 / tot2 - 1.0) < 0.02, (rid, tot1, tot2)
+        landed = halves[0][rid].landed_weight + halves[1][rid].landed_weight
+        assert abs(landed / one[rid].landed_weight - 1.0) < 0.02
+        # block-mean Pearson, the reference battery's statistic (test_cuda_backend_parity.cpp:217-239)
+        a = one[rid].xyz[..., 1].reshape(27, 40, 48, 40).mean(axis=(1, 3)).ravel()
+        b = both[..., 1].reshape(27, 40, 48, 40).mean(axis=(1, 3)).ravel()
+        assert np.corrcoef(a, b)[0, 1] > 0.95, rid
+    # illuminant spectrum: one pool session, per-ray wavelength index
+    ex["scene"]["light_source"]["spectrum"] = "D65"
+    ex["scene"]["ray_num"] = 400_000
+    fr = render_config(load_config(ex), backend, seed=9)[4]
+    assert fr.landed_weight > 0 and (fr.xyz[..., 0].sum() > 0 and fr.xyz[..., 2].sum() > 0)
