@@ -16,6 +16,9 @@
 #include <string>
 #include <vector>
 
+#include "config/color_class_table.hpp"
+#include "config/color_gate_table.hpp"
+#include "config/raypath_color_config.hpp"
 #include "core/backend/trace_backend.hpp"
 #include "core/backend/wl_pool.hpp"
 #include "core/device_filter_desc.hpp"
@@ -54,7 +57,8 @@ class B200TraceBackend : public TraceBackend {
 
   void BeginSession(const SessionSpec& spec) override {
     try {
-      if (spec.scene != scene_ || SceneHasStochasticShapes(*spec.scene)) {
+      raypath_color_ = spec.raypath_color;
+      if (spec.scene != scene_ || raypath_color_ != color_uploaded_ || SceneHasStochasticShapes(*spec.scene)) {
         UploadScene(*spec.scene);
       }
       if (spec.render != render_ || render_snapshot_dirty_) {
@@ -111,6 +115,20 @@ class B200TraceBackend : public TraceBackend {
 
   void ReadbackXyzAccum(XyzImageData& xyz, float& landed_weight) override {
     Check(hb_readback_xyz(h_, xyz.data, &landed_weight), "ReadbackXyzAccum");
+  }
+
+  void ReadbackClassLanes(std::vector<float>& lane_data, size_t& class_count) override {
+    lane_data.clear();
+    class_count = 0;
+    if (render_ == nullptr || !raypath_color_ || raypath_color_->classes_.empty()) {
+      return;  // base behaviour: no colour config, nothing to drain
+    }
+    const size_t pix = static_cast<size_t>(render_->resolution_[0]) * static_cast<size_t>(render_->resolution_[1]);
+    lane_data.resize(raypath_color_->classes_.size() * pix);
+    uint32_t n = 0;
+    Check(hb_readback_class_lanes(h_, lane_data.data(), lane_data.size(), &n), "ReadbackClassLanes");
+    class_count = n;
+    lane_data.resize(static_cast<size_t>(n) * pix);
   }
 
   void EndSession() override { Check(hb_end_session(h_), "EndSession"); }
@@ -234,6 +252,42 @@ class B200TraceBackend : public TraceBackend {
     }
   }
 
+  // One HbColorGroup per symmetry value of the placement's colour predicates (BuildColorSpecGroups,
+  // filter_spec.cpp:389-425, in device-descriptor form).
+  static void FillColorGroups(const ColorGateTable& gate_table, IdType layer, const ScatteringSetting& st,
+                              const Crystal& crystal, HbCrystalPopulation* out) {
+    const ColorGatePlacement placement = ColorGatePlacementFor(gate_table, layer, st.crystal_.id_);
+    if (placement.predicates_.empty()) {
+      return;
+    }
+    const ColorPlacementGrouping grouping = GroupPlacementBySymmetry(placement);
+    const size_t group_cnt = grouping.group_symmetry_.size();
+    if (group_cnt > HB_MAX_COLOR_GROUPS) {
+      throw BackendUnavailableError("B200TraceBackend: more than 4 colour symmetry groups on one placement");
+    }
+    std::vector<ComplexFilterParam> cfps(group_cnt);
+    std::vector<std::vector<uint8_t>> bits(group_cnt);
+    for (size_t k = 0; k < placement.predicates_.size(); k++) {
+      const size_t gi = grouping.group_of_[k];
+      cfps[gi].filters_.push_back({ { kInvalidId, placement.predicates_[k] } });
+      bits[gi].push_back(placement.bits_[k]);
+    }
+    for (size_t gi = 0; gi < group_cnt; gi++) {
+      if (bits[gi].size() > HB_MAX_FILTER_TERMS) {
+        throw BackendUnavailableError("B200TraceBackend: more than 8 colour predicates in one symmetry group");
+      }
+      FilterConfig fc{};
+      fc.id_ = kInvalidId;
+      fc.symmetry_ = grouping.group_symmetry_[gi];
+      fc.action_ = FilterConfig::kFilterIn;
+      fc.param_ = FilterParam{ cfps[gi] };
+      FillFilter(fc, crystal, st.crystal_.axis_, &out->color_groups[gi].filter);
+      std::memset(out->color_groups[gi].bit, 0xFF, sizeof(out->color_groups[gi].bit));
+      std::copy(bits[gi].begin(), bits[gi].end(), out->color_groups[gi].bit);
+    }
+    out->color_group_cnt = static_cast<uint32_t>(group_cnt);
+  }
+
   void UploadScene(const SceneConfig& scene) {
     // Geometry pool per stochastic population: kPoolShapes shapes drawn with MakeCrystal, per-ray pick on the
     // device (the reference GPU backends' K-shape pool, cuda_trace_backend.cu:1527-1554).
@@ -242,6 +296,11 @@ class B200TraceBackend : public TraceBackend {
     std::vector<std::vector<HbCrystalPopulation>> pops(scene.ms_.size());
     std::vector<std::unique_ptr<std::vector<HbCrystalTables>>> shapes;
     stochastic_shapes_last_upload_ = 0;
+    // Raypath colour (Design 2): the same tables the CPU gate uses (cpu_trace_backend.cpp:264-270,371-384)
+    const RaypathColorConfig empty_color;
+    const RaypathColorConfig& color_cfg = raypath_color_ ? *raypath_color_ : empty_color;
+    const ColorGateTable gate_table = BuildColorGateTable(color_cfg, scene);
+    const ColorClassTable class_table = BuildColorClassTable(color_cfg, scene, gate_table);
     for (size_t li = 0; li < scene.ms_.size(); li++) {
       const MsInfo& ms = scene.ms_[li];
       pops[li].resize(ms.setting_.size());
@@ -270,6 +329,7 @@ class B200TraceBackend : public TraceBackend {
         shapes.push_back(std::move(pool));
         FillAxis(st.crystal_.axis_, &p.axis);
         FillFilter(st.filter_, first, st.crystal_.axis_, &p.filter);
+        FillColorGroups(gate_table, static_cast<IdType>(li), st, first, &p);
       }
       layers[li].prob = ms.prob_;
       layers[li].population_cnt = static_cast<uint32_t>(pops[li].size());
@@ -283,8 +343,19 @@ class B200TraceBackend : public TraceBackend {
     s.sun_lon = (sun.azimuth_ + 180.0f) * math::kDegreeToRad;
     s.sun_lat = -sun.altitude_ * math::kDegreeToRad;
     s.sun_half_angle = (sun.diameter_ * 0.5f) * math::kDegreeToRad;
+    if (class_table.classes_.size() > HB_MAX_COLOR_CLASSES) {
+      throw BackendUnavailableError("B200TraceBackend: more than 16 colour classes");
+    }
+    s.color_classes.class_cnt = static_cast<uint32_t>(class_table.classes_.size());
+    for (size_t c = 0; c < class_table.classes_.size(); c++) {
+      s.color_classes.bits[c] = class_table.classes_[c].member_bits_;
+      if (class_table.classes_[c].combine_ == ColorClassCombine::kAll) {
+        s.color_classes.combine_all_mask |= 1u << c;
+      }
+    }
     Check(hb_set_scene(h_, &s), "UploadScene");
     scene_ = &scene;
+    color_uploaded_ = raypath_color_;
   }
 
   static HbProjParams ToProj(const RenderConfig& render) {
@@ -342,6 +413,8 @@ class B200TraceBackend : public TraceBackend {
   RandomNumberGenerator rng_;
   const SceneConfig* scene_ = nullptr;
   const RenderConfig* render_ = nullptr;
+  std::shared_ptr<const RaypathColorConfig> raypath_color_;   // of the current session
+  std::shared_ptr<const RaypathColorConfig> color_uploaded_;  // the one the device tables were built from
   std::vector<const RenderConfig*> extra_renders_;
   bool render_snapshot_dirty_ = false;
   size_t layer_cnt_ = 0;

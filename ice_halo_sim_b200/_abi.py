@@ -17,6 +17,9 @@ HB_INVALID_FACE = 0xFFFF
 HB_MAX_FILTER_PATH = 32
 HB_MAX_FILTER_TERMS = 8
 HB_MAX_RENDERS = 8
+HB_MAX_COLOR_GROUPS = 4
+HB_MAX_COLOR_CLASSES = 16
+HB_MAX_COLOR_PREDS = 32
 
 HB_OK = 0
 STATUS_NAMES = {0: "HB_OK", -1: "HB_ERR_INVALID_ARG", -2: "HB_ERR_NO_DEVICE", -3: "HB_ERR_CUDA",
@@ -64,10 +67,19 @@ class HbFilterDesc(C.Structure):
                 ("terms", (HbSimpleFilter * 4) * HB_MAX_FILTER_TERMS)]
 
 
+class HbColorGroup(C.Structure):
+    _fields_ = [("filter", HbFilterDesc), ("bit", u8 * HB_MAX_FILTER_TERMS)]
+
+
+class HbColorClasses(C.Structure):
+    _fields_ = [("class_cnt", u32), ("combine_all_mask", u32), ("bits", u64 * HB_MAX_COLOR_CLASSES)]
+
+
 class HbCrystalPopulation(C.Structure):
     _fields_ = [("proportion", f32), ("crystal_id", u32), ("shape_cnt", u32),
                 ("shapes", C.POINTER(HbCrystalTables)),
-                ("axis", HbAxisSampler), ("filter", HbFilterDesc)]
+                ("axis", HbAxisSampler), ("filter", HbFilterDesc),
+                ("color_group_cnt", u32), ("reserved_", u32), ("color_groups", HbColorGroup * HB_MAX_COLOR_GROUPS)]
 
 
 class HbLayer(C.Structure):
@@ -76,7 +88,8 @@ class HbLayer(C.Structure):
 
 class HbScene(C.Structure):
     _fields_ = [("max_hits", u32), ("layer_cnt", u32), ("layers", C.POINTER(HbLayer)),
-                ("sun_lon", f32), ("sun_lat", f32), ("sun_half_angle", f32)]
+                ("sun_lon", f32), ("sun_lat", f32), ("sun_half_angle", f32), ("reserved_", u32),
+                ("color_classes", HbColorClasses)]
 
 
 class HbWlEntry(C.Structure):
@@ -134,8 +147,13 @@ class HbFilterSpecDesc(C.Structure):
                 ("terms", (HbSimpleFilterSpec * 4) * HB_MAX_FILTER_TERMS)]
 
 
+class HbColorPredDesc(C.Structure):
+    _fields_ = [("pred", HbSimpleFilterSpec), ("symmetry", u32), ("bit", u32)]
+
+
 class HbPopulationDesc(C.Structure):
-    _fields_ = [("crystal", HbCrystalDesc), ("filter", HbFilterSpecDesc), ("proportion", f32)]
+    _fields_ = [("crystal", HbCrystalDesc), ("filter", HbFilterSpecDesc), ("proportion", f32),
+                ("color_pred_cnt", u32), ("color_preds", HbColorPredDesc * HB_MAX_COLOR_PREDS)]
 
 
 class HbLayerDesc(C.Structure):
@@ -145,7 +163,7 @@ class HbLayerDesc(C.Structure):
 class HbSceneDesc(C.Structure):
     _fields_ = [("max_hits", u32), ("layer_cnt", u32),
                 ("sun_altitude_deg", f32), ("sun_azimuth_deg", f32), ("sun_diameter_deg", f32),
-                ("geom_pool_size", u32), ("layers", HbLayerDesc * HB_MAX_LAYERS)]
+                ("geom_pool_size", u32), ("layers", HbLayerDesc * HB_MAX_LAYERS), ("color_classes", HbColorClasses)]
 
 
 class HbRenderDesc(C.Structure):
@@ -158,6 +176,7 @@ class HbSnapshotDesc(C.Structure):
     _fields_ = [("intensity_factor", f32), ("ray_color", f32 * 3), ("background", f32 * 3)]
 
 
-ALL_STRUCTS = [HbCrystalTables, HbAxisSampler, HbSimpleFilter, HbFilterDesc, HbCrystalPopulation, HbLayer, HbScene,
+ALL_STRUCTS = [HbCrystalTables, HbAxisSampler, HbSimpleFilter, HbFilterDesc, HbColorGroup, HbColorClasses,
+               HbCrystalPopulation, HbLayer, HbScene,
                HbWlEntry, HbProjParams, HbExitRecord, HbSessionSpec, HbLayerStats, HbCounters, HbDist, HbCrystalDesc,
-               HbSimpleFilterSpec, HbFilterSpecDesc, HbPopulationDesc, HbLayerDesc, HbSceneDesc, HbRenderDesc, HbSnapshotDesc]
+               HbSimpleFilterSpec, HbFilterSpecDesc, HbColorPredDesc, HbPopulationDesc, HbLayerDesc, HbSceneDesc, HbRenderDesc, HbSnapshotDesc]

@@ -244,6 +244,15 @@ class B200TraceBackend:
                                                   r["shape"].ctypes.data, r["wl"].ctypes.data, C.byref(cnt)))
         return r
 
+    def ExportRootMasks(self):
+        """Parity only: component masks the exported roots carried in (raypath colour), or an empty array."""
+        cnt = C.c_uint64(0)
+        self._check(self._lib.hb_export_root_masks(self._h, 0, None, C.byref(cnt)))
+        out = np.zeros(cnt.value, np.uint64)
+        if cnt.value:
+            self._check(self._lib.hb_export_root_masks(self._h, cnt.value, out.ctypes.data, C.byref(cnt)))
+        return out
+
     def EndSession(self):
         self._check(self._lib.hb_end_session(self._h))
         self._in_session = False
@@ -260,6 +269,17 @@ class B200TraceBackend:
         landed = C.c_float(0.0)
         self._check(self._lib.hb_readback_xyz_render(self._h, render, xyz.ctypes.data, C.byref(landed)))
         return xyz, landed.value
+
+    def ReadbackClassLanes(self):
+        """TraceBackend::ReadbackClassLanes (trace_backend.hpp:471-493): [class, H, W] float32 Y lanes of render 0,
+        drained + zeroed; None when the scene has no colour classes."""
+        if self._proj is None:
+            raise HaloTraceError(-4, "ReadbackClassLanes before SetRender")
+        h, w = self._projs[0].img_h, self._projs[0].img_w
+        buf = np.zeros((A.HB_MAX_COLOR_CLASSES, h, w), np.float32)
+        cnt = C.c_uint32(0)
+        self._check(self._lib.hb_readback_class_lanes(self._h, buf.ctypes.data, buf.size, C.byref(cnt)))
+        return buf[: cnt.value].copy() if cnt.value else None
 
     def Snapshot(self, render=0, intensity_factor=1.0, ray_color=(-1.0, -1.0, -1.0), background=(0.0, 0.0, 0.0),
                  want_xyz=False):

@@ -3,7 +3,8 @@
 Mirrors the reference's config front door for the fields the trace path consumes
 (reference: src/config/crystal_config.cpp from_json, src/core/math.cpp:590-725 axis parsing,
 src/config/filter_config.cpp, src/config/render_config.cpp, src/config/config_manager.cpp).
-Complex ("composition") filters are supported up to 8 OR-terms of 4 AND-factors; raypath-colour classes are not.
+Complex ("composition") filters are supported up to 8 OR-terms of 4 AND-factors; `raypath_color` classes up to
+16 classes / 64 component bits (config/raypath_color_config.cpp, color_gate_table.cpp, color_class_table.hpp).
 """
 import json
 import math
@@ -173,15 +174,85 @@ def render_desc(r):
                           float(r.get("overlap", 0.0)))
 
 
+def _pred_key(ref):
+    """Structural identity of a colour predicate (SimpleFilterParam operator==, config_compare.hpp)."""
+    t = ref.get("type", "none")
+    if t == "raypath":
+        return (t, tuple(int(x) for x in ref["raypath"]))
+    if t == "entry_exit":
+        return (t, ref.get("entry"), ref.get("exit"), int(ref.get("min_len", 1)), int(ref.get("max_len", 0)))
+    if t == "direction":
+        return (t, float(ref["az"]), float(ref["el"]), float(ref["radii"]))
+    if t == "crystal":
+        return (t, int(ref["crystal_id"]))
+    return ("none",)
+
+
+def apply_raypath_color(rc, d):
+    """`raypath_color` -> per-population colour predicates with component bits + the class table.
+
+    BuildColorGateTable (color_gate_table.cpp:47-95): walk classes[].match[] in order; a ref must name exactly
+    one population of its layer; (layer, crystal, predicate, symmetry) duplicates share a bit; bits are handed
+    out in first-occurrence order, predicates past bit 63 get none. BuildColorClassTable: a class's bit set is
+    the union of its refs' bits, `combine` is "any" or "all". Returns the class list (colour, combine, visible)."""
+    if rc is None:
+        return []
+    classes = rc.get("classes", []) if isinstance(rc, dict) else rc
+    if len(classes) > A.HB_MAX_COLOR_CLASSES:
+        raise ValueError(f"raypath_color: more than {A.HB_MAX_COLOR_CLASSES} colour classes")
+    seen = {}
+    next_bit = 0
+    out = []
+    allm = 0
+    for ci, cls in enumerate(classes):
+        combine = cls.get("combine", "any")
+        if combine not in ("any", "all"):
+            raise ValueError(f"raypath_color: unknown combine {combine!r}")
+        bits = 0
+        for ref in cls["match"]:
+            layer, cid = int(ref["layer"]), int(ref["crystal"])
+            if not 0 <= layer < d.layer_cnt:
+                raise ValueError(f"raypath_color: layer index out of range (layer={layer}, crystal_id={cid})")
+            ld = d.layers[layer]
+            hits = [k for k in range(ld.population_cnt) if ld.populations[k].crystal.id == cid]
+            if len(hits) != 1:
+                raise ValueError(f"raypath_color: crystal_id {cid} matches {len(hits)} scattering settings on layer {layer}")
+            sym = sum(_SYM[ch] for ch in ref.get("symmetry", "") if ch in _SYM)
+            key = (layer, cid, _pred_key(ref), sym)
+            if key not in seen:
+                bit = next_bit if next_bit < 64 else 255
+                next_bit += 1 if next_bit < 64 else 0
+                seen[key] = bit
+                pop = ld.populations[hits[0]]
+                if pop.color_pred_cnt >= A.HB_MAX_COLOR_PREDS:
+                    raise ValueError("raypath_color: more than 32 predicates on one population")
+                cp = pop.color_preds[pop.color_pred_cnt]
+                _simple_filter(ref, cp.pred)
+                cp.symmetry = sym
+                cp.bit = bit
+                pop.color_pred_cnt += 1
+            if seen[key] < 64:
+                bits |= 1 << seen[key]
+        d.color_classes.bits[ci] = bits
+        if combine == "all":
+            allm |= 1 << ci
+        out.append(dict(color=tuple(float(x) for x in cls["color"]), combine=combine,
+                        visible=bool(cls.get("visible", True)), solo=bool(cls.get("solo", False)), bits=bits))
+    d.color_classes.class_cnt = len(classes)
+    d.color_classes.combine_all_mask = allm
+    return out
+
+
 class SceneConfig:
     """Parsed config: scene description + renders + spectrum + ray count (per wavelength)."""
 
-    def __init__(self, desc, renders, spectrum, ray_num_total, illuminant=None):
+    def __init__(self, desc, renders, spectrum, ray_num_total, illuminant=None, color_classes=None):
         self.desc = desc
         self.renders = renders          # {id: HbRenderDesc}
         self.spectrum = spectrum        # [(wavelength_nm, weight)]
         self.ray_num_total = ray_num_total
         self.illuminant = illuminant
+        self.color_classes = color_classes or []   # [{color, combine, visible, solo, bits}] (raypath_color)
 
     def rays_per_wavelength(self):
         """ray_num is the total across wavelengths; per-wavelength = ceil(total / N)
@@ -228,4 +299,5 @@ def load_config(path_or_dict, geom_pool_size=1):
         spectrum = []
     spec = [(float(s["wavelength"]), float(s.get("weight", 1.0))) for s in spectrum]
     renders = {int(r["id"]): render_desc(r) for r in cfg.get("render", [])}
-    return SceneConfig(d, renders, spec, int(scene.get("ray_num", 0)), illuminant)
+    classes = apply_raypath_color(cfg.get("raypath_color"), d)
+    return SceneConfig(d, renders, spec, int(scene.get("ray_num", 0)), illuminant, classes)

@@ -45,6 +45,8 @@ struct LayerTables {            // device pointers, one scattering layer
   uint32_t shape_cnt;
   uint32_t pop_cnt;
   uint32_t any_filter;
+  const HbColorGroup* color_groups;   // [pop_cnt][HB_MAX_COLOR_GROUPS] (nullptr: no colour predicates in this layer)
+  const uint32_t* color_group_cnt;    // [pop_cnt]
 };
 
 enum : uint32_t {
@@ -81,6 +83,13 @@ struct TraceParams {
   HbProjParams proj;            // render 0 (arena offset 0)
   const ExtraRender* extra;     // renders 1..extra_cnt (device)
   uint32_t extra_cnt;
+  // raypath colour (kernels instantiated with MULTI only)
+  uint32_t color_on;            // scene has colour classes
+  uint64_t* M;                  // [cap + fork_cap] component mask carried in from earlier layers (nullptr on layer 0)
+  uint64_t* cont_mask;          // continuation records: component mask
+  float* lane;                  // [class_cnt][lane_stride] per-class Y lanes of render 0
+  uint32_t lane_stride;
+  HbColorClasses classes;
   uint32_t hit, max_hits, layer_idx, flags;
   float prob;
   uint32_t gate_seed;           // session seed ^ gate nonce
@@ -121,6 +130,8 @@ struct GenParams {
   // transit only
   const float4* cont_dw;
   const uint32_t* cont_meta;
+  const uint64_t* cont_mask;    // component masks of the continuations (raypath colour) or nullptr
+  uint64_t* M;                  // per-slot carried mask of the next layer
   uint32_t cont_n;              // size of the permuted continuation pool
   uint32_t cont_first;          // pool position of slot0
   uint32_t shuffle_seed;
@@ -198,6 +209,7 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
   rot_apply(r, lx, ly, lz, wx, wy, wz);
   const uint32_t wl_i = bits_wl(bits);
   bool to_next_layer = false;
+  uint64_t mask = 0ull;  // component mask (raypath colour)
   if (GENERAL) {
     const uint32_t shape = bits_shape(bits);
     const uint32_t pop = (tp.lt.shape_meta[shape] >> 8) & 255u;
@@ -219,6 +231,25 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
         if (f.kind != 0u) {
           const float dir[3] = { wx, wy, wz };
           if (!filter_check(f, fn_path, len, dir, tp.lt.pop_crystal_id[pop])) return;  // filter-fail terminates
+        }
+      }
+    }
+    if constexpr (MULTI) {
+      // Non-destructive colour pass on a filter-admitted exit (simulator.cpp:688-712): every matching
+      // predicate ORs its component bit into the mask carried from earlier layers.
+      if (tp.color_on) {
+        mask = tp.M != nullptr ? tp.M[slot] : 0ull;
+        if (tp.lt.color_groups != nullptr) {
+          const uint32_t gcnt = tp.lt.color_group_cnt[pop];
+          const float dir[3] = { wx, wy, wz };
+          for (uint32_t g = 0; g < gcnt; g++) {
+            const HbColorGroup& cg = tp.lt.color_groups[pop * HB_MAX_COLOR_GROUPS + g];
+            for (uint32_t k = 0; k < cg.filter.term_cnt; k++) {
+              if (cg.bit[k] < 64u &&
+                  filter_match_simple(cg.filter, cg.filter.terms[k][0], fn_path, len, dir, tp.lt.pop_crystal_id[pop]))
+                mask |= 1ull << cg.bit[k];
+            }
+          }
         }
       }
     }
@@ -248,6 +279,9 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
         tp.cont_dw[dst] = make_float4(wx, wy, wz, w);
         tp.cont_meta[dst] = wl_i | (pop << 8);
         if (tp.cont_root != nullptr) tp.cont_root[dst] = root;
+        if constexpr (MULTI) {
+          if (tp.cont_mask != nullptr) tp.cont_mask[dst] = mask;
+        }
       } else {
         *tp.error_flag = 1u;
       }
@@ -268,7 +302,7 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
         e.ms_layer_idx = static_cast<uint8_t>(tp.layer_idx);
         e.wl_idx = static_cast<uint8_t>(wl_i);
         e.pad1_[0] = e.pad1_[1] = 0;
-        e.component_mask = 0ull;
+        e.component_mask = mask;
         tp.exit_root[dst] = root;
       } else {
         *tp.error_flag = 2u;
@@ -283,8 +317,21 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
     if (k < h.count) {
       const int px = h.px[k], py = h.py[k];
       if (px >= 0 && px < tp.proj.img_w && py >= 0 && py < tp.proj.img_h) {
-        accumulate_pixel(tp, tally, static_cast<uint32_t>(py) * static_cast<uint32_t>(tp.proj.img_w) + static_cast<uint32_t>(px),
-                         mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w), h.bump[k] ? w : 0.0f);
+        const uint32_t pix = static_cast<uint32_t>(py) * static_cast<uint32_t>(tp.proj.img_w) + static_cast<uint32_t>(px);
+        accumulate_pixel(tp, tally, pix, mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w), h.bump[k] ? w : 0.0f);
+        if constexpr (MULTI) {
+          // FanColorClassLanes (cuda_trace_backend.cu:538-556): Y into every satisfied class, overlap-ring hits too
+          if (tp.color_on && mask != 0ull) {
+            const float y = mul(we.cmf_y, w);
+            for (uint32_t c = 0; c < tp.classes.class_cnt; c++) {
+              const uint64_t cb = tp.classes.bits[c];
+              if (cb == 0ull) continue;
+              const uint64_t m = mask & cb;
+              const bool ok = ((tp.classes.combine_all_mask >> c) & 1u) ? (m == cb) : (m != 0ull);
+              if (ok) atomicAdd(tp.lane + static_cast<size_t>(c) * tp.lane_stride + pix, y);
+            }
+          }
+        }
       }
     }
   }
@@ -423,6 +470,7 @@ HB_DEV void fork_append(const TraceParams& tp, uint32_t slot, uint32_t bits, flo
     }
     tp.fork_root[k] = root;
     tp.fork_code[k] = code | (1u << (tp.hit & 31u));
+    if (tp.M != nullptr) tp.M[dst] = tp.M[slot];
     if (tp.flags & kFlagPath) {
       for (uint32_t h = 0; h <= tp.hit; h++)
         tp.path[static_cast<size_t>(h) * tp.cap + dst] = tp.path[static_cast<size_t>(h) * tp.cap + slot];
@@ -662,6 +710,7 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
       wz = c.z;
       weight = c.w;
       wl_i = gp.cont_meta[src] & 255u;
+      if (gp.cont_mask != nullptr) gp.M[gp.slot0 + k] = gp.cont_mask[src];
     } else if (gp.wl_cnt > 1u) {
       wl_i = min(static_cast<uint32_t>(draw(s0 ^ kNonceWl, lo, 0u) * static_cast<float>(gp.wl_cnt)), gp.wl_cnt - 1u);
     }
@@ -884,6 +933,9 @@ struct LayerDev {
   DevBuf<HbFilterDesc> filters;
   DevBuf<uint32_t> pop_crystal_id;
   DevBuf<float> luts;  // [pop][3][257]
+  bool any_color = false;              // some population carries colour predicates
+  DevBuf<HbColorGroup> color_groups;   // [pop][HB_MAX_COLOR_GROUPS]
+  DevBuf<uint32_t> color_group_cnt;    // [pop]
 };
 
 struct EventPair {
@@ -915,6 +967,11 @@ struct HbEngine {
   std::vector<uint32_t> render_off;    // first pixel of each render in the arena
   uint32_t arena_pix = 0;              // pixels of all renders together
   DevBuf<ExtraRender> extra_dev;       // renders 1.. for the emit path
+  HbColorClasses classes{};            // raypath colour classes of the scene (class_cnt 0 = off)
+  DevBuf<float> lanes;                 // [class_cnt][pixels of render 0] per-class Y lanes
+  uint64_t lanes_floats = 0;
+  DevBuf<uint64_t> mask_tile;          // [cap] carried component mask per ray slot (layers >= 1)
+  DevBuf<uint64_t> cont_mask[2];       // component masks of the continuation pools
   DevBuf<uint8_t> rgb_stage;           // 8-bit snapshot staging
   DevBuf<float4> image;
   DevBuf<double4> master;
@@ -966,6 +1023,7 @@ struct HbEngine {
   std::vector<float> exp_d, exp_p, exp_w, exp_rot;
   std::vector<uint16_t> exp_face;
   std::vector<uint32_t> exp_shape, exp_wl;
+  std::vector<uint64_t> exp_mask;
 
   // measurement
   HbCounters ctr{};
@@ -1077,7 +1135,7 @@ void launch_optics_t(HbEngine* h, size_t smem, const TraceParams& tp) {
 }
 void launch_optics(HbEngine* h, bool general, bool last, bool in_smem, size_t smem, const TraceParams& tp) {
   const int key = (general ? 4 : 0) | (last ? 2 : 0) | (in_smem ? 1 : 0);
-  if (tp.extra_cnt != 0u) {  // N projections per trace: GENERAL kernels with the extra-render loop
+  if (tp.extra_cnt != 0u || tp.color_on != 0u) {  // N projections per trace / raypath colour: extended GENERAL kernels
     switch (key & 3) {
       case 0: launch_optics_t<true, false, false, true>(h, smem, tp); break;
       case 1: launch_optics_t<true, false, true, true>(h, smem, tp); break;
@@ -1103,7 +1161,7 @@ void launch_intersect_t(HbEngine* h, size_t smem, const TraceParams& tp) {
   intersect_kernel<G, S, M><<<grid, 256, smem, h->stream>>>(tp);
 }
 void launch_intersect(HbEngine* h, bool general, bool in_smem, size_t smem, const TraceParams& tp) {
-  if (tp.extra_cnt != 0u) {
+  if (tp.extra_cnt != 0u || tp.color_on != 0u) {
     if (in_smem) launch_intersect_t<true, true, true>(h, smem, tp); else launch_intersect_t<true, false, true>(h, smem, tp);
   } else if (general) {
     if (in_smem) launch_intersect_t<true, true>(h, smem, tp); else launch_intersect_t<true, false>(h, smem, tp);
@@ -1125,7 +1183,10 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   std::vector<HbFilterDesc> filters;
   std::vector<uint32_t> cid;
   std::vector<float> luts;
+  std::vector<HbColorGroup> cgroups;
+  std::vector<uint32_t> cgroup_cnt;
   L->any_filter = false;
+  L->any_color = false;
   for (uint32_t ci = 0; ci < src.population_cnt; ci++) {
     const HbCrystalPopulation& p = src.populations[ci];
     if (p.shape_cnt == 0 || p.shapes == nullptr) return fail(h, HB_ERR_INVALID_ARG, "population without shapes");
@@ -1173,6 +1234,10 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
     }
     filters.push_back(p.filter);
     cid.push_back(p.crystal_id);
+    if (p.color_group_cnt > HB_MAX_COLOR_GROUPS) return fail(h, HB_ERR_INVALID_ARG, "population: too many colour groups");
+    cgroup_cnt.push_back(p.color_group_cnt);
+    cgroups.insert(cgroups.end(), p.color_groups, p.color_groups + HB_MAX_COLOR_GROUPS);
+    L->any_color = L->any_color || p.color_group_cnt != 0;
     luts.insert(luts.end(), p.axis.lut_theta, p.axis.lut_theta + HB_LUT_NODES);
     luts.insert(luts.end(), p.axis.lut_cdf, p.axis.lut_cdf + HB_LUT_NODES);
     luts.insert(luts.end(), p.axis.lut_flip, p.axis.lut_flip + HB_LUT_NODES);
@@ -1197,6 +1262,12 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   HB_CUDA(h, cudaMemcpy(L->filters.p, filters.data(), filters.size() * sizeof(HbFilterDesc), cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->pop_crystal_id.p, cid.data(), cid.size() * 4, cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->luts.p, luts.data(), luts.size() * 4, cudaMemcpyHostToDevice));
+  if (L->any_color) {
+    HB_CUDA(h, L->color_groups.ensure(cgroups.size()));
+    HB_CUDA(h, L->color_group_cnt.ensure(cgroup_cnt.size()));
+    HB_CUDA(h, cudaMemcpy(L->color_groups.p, cgroups.data(), cgroups.size() * sizeof(HbColorGroup), cudaMemcpyHostToDevice));
+    HB_CUDA(h, cudaMemcpy(L->color_group_cnt.p, cgroup_cnt.data(), cgroup_cnt.size() * 4, cudaMemcpyHostToDevice));
+  }
   return HB_OK;
 }
 
@@ -1205,7 +1276,7 @@ uint32_t session_flags(const HbEngine* h, const LayerDev& L, bool last_layer) {
   if (h->spec.accumulate) f |= kFlagAccum;
   if (h->spec.accumulate && h->pixel_cache) f |= kFlagPixelCache;
   if (h->spec.record_exits) f |= kFlagRecord | kFlagPath | kFlagStats;
-  if (L.any_filter) f |= kFlagPath;
+  if (L.any_filter || L.any_color) f |= kFlagPath;
   if (L.prob > 0.0f) f |= kFlagGate;
   (void)last_layer;
   return f;
@@ -1221,6 +1292,7 @@ int ensure_tile(HbEngine* h, uint64_t cap, uint64_t fork_cap, uint32_t flags) {
   HB_CUDA(h, h->fork_root.ensure(fork_cap));
   HB_CUDA(h, h->fork_code.ensure(fork_cap));
   if (flags & kFlagPath) HB_CUDA(h, h->path.ensure(cap * h->max_hits));
+  if (h->classes.class_cnt != 0) HB_CUDA(h, h->mask_tile.ensure(cap));
   return HB_OK;
 }
 
@@ -1233,8 +1305,9 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   const uint32_t cap = n + fork_cap;
   int rc = ensure_tile(h, cap, fork_cap, flags);
   if (rc != HB_OK) return rc;
+  const bool color_on = h->classes.class_cnt != 0;
   const bool general = (flags & (kFlagPath | kFlagRecord | kFlagGate | kFlagStats)) != 0 || !(flags & kFlagAccum) ||
-                       h->renders.size() > 1;
+                       h->renders.size() > 1 || color_on;
   HB_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 2 * sizeof(uint32_t), h->stream));  // fork_count, fork_snapshot
   if (flags & kFlagRecord) {
     const uint64_t ecap = static_cast<uint64_t>(n) * (h->max_hits + 1) + fork_cap;
@@ -1294,6 +1367,10 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
         const int src = h->cont_cur ^ 1;
         gp.cont_dw = h->cont_dw[src].p;
         gp.cont_meta = h->cont_meta[src].p;
+        if (color_on) {
+          gp.cont_mask = h->cont_mask[src].p;
+          gp.M = h->mask_tile.p;
+        }
         gp.cont_n = static_cast<uint32_t>(layer_total);
         gp.cont_first = static_cast<uint32_t>(b);
         gp.shuffle = h->cont_shuffle ? 1u : 0u;
@@ -1331,6 +1408,11 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
       h->exp_wl.push_back((bits >> 6) & 255u);
     }
     h->exp_rot.insert(h->exp_rot.end(), hr.begin(), hr.end());
+    if (color_on) {  // component masks the roots carry in from earlier layers
+      const size_t old = h->exp_mask.size();
+      h->exp_mask.resize(old + n, 0ull);
+      if (li > 0) HB_CUDA(h, cudaMemcpy(h->exp_mask.data() + old, h->mask_tile.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
   }
 
   // ---- hit loop ----
@@ -1348,13 +1430,20 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.fork_cap = fork_cap;
   tp.root_base = static_cast<uint32_t>(root0);
   tp.lt = LayerTables{ L.planes.p, L.axes.p, L.shape_meta.p, L.face_fn.p, L.shapes.p, L.filters.p, L.pop_crystal_id.p,
-                       L.shape_cnt, static_cast<uint32_t>(L.pops.size()), L.any_filter ? 1u : 0u };
+                       L.shape_cnt, static_cast<uint32_t>(L.pops.size()), L.any_filter ? 1u : 0u,
+                       L.any_color ? L.color_groups.p : nullptr, L.color_group_cnt.p };
   tp.wl = h->wl_cur;
   tp.wl_cnt = h->wl_cnt;
   tp.image = h->image.p;
   tp.proj = h->proj;
   tp.extra = h->extra_dev.p;
   tp.extra_cnt = static_cast<uint32_t>(h->renders.size()) - 1u;
+  tp.color_on = color_on ? 1u : 0u;
+  tp.M = (color_on && li > 0) ? h->mask_tile.p : nullptr;
+  tp.cont_mask = (color_on && (flags & kFlagGate)) ? h->cont_mask[h->cont_cur].p : nullptr;
+  tp.lane = h->lanes.p;
+  tp.lane_stride = h->renders.empty() ? 0u : static_cast<uint32_t>(h->renders[0].img_w) * h->renders[0].img_h;
+  tp.classes = h->classes;
   tp.max_hits = h->max_hits;
   tp.layer_idx = li;
   tp.flags = flags;
@@ -1495,6 +1584,10 @@ void hb_destroy(HbEngine* h) {
   h->image.release();
   h->master.release();
   h->extra_dev.release();
+  h->lanes.release();
+  h->mask_tile.release();
+  h->cont_mask[0].release();
+  h->cont_mask[1].release();
   h->rgb_stage.release();
   h->xyz_stage.release();
   h->landed_dev.release();
@@ -1540,6 +1633,8 @@ int hb_set_scene(HbEngine* h, const HbScene* s) {
   h->sun_lon = s->sun_lon;
   h->sun_lat = s->sun_lat;
   h->sun_half = s->sun_half_angle;
+  if (s->color_classes.class_cnt > HB_MAX_COLOR_CLASSES) return fail(h, HB_ERR_INVALID_ARG, "scene: more than 16 colour classes");
+  h->classes = s->color_classes;
   h->have_scene = true;
   return HB_OK;
 }
@@ -1602,6 +1697,15 @@ int hb_begin_session(HbEngine* h, const HbSessionSpec* spec) {
   if (spec->wl == nullptr || spec->wl_cnt == 0 || spec->wl_cnt > HB_MAX_WL)
     return fail(h, HB_ERR_INVALID_ARG, "session: wavelength pool must hold 1..256 entries");
   cudaSetDevice(h->device);
+  // per-class Y lanes (render 0) follow the scene's class count and the render's resolution
+  if (spec->accumulate && h->classes.class_cnt != 0) {
+    const uint64_t want = static_cast<uint64_t>(h->classes.class_cnt) * h->renders[0].img_w * h->renders[0].img_h;
+    if (want != h->lanes_floats) {
+      HB_CUDA(h, h->lanes.ensure(want));
+      HB_CUDA(h, cudaMemsetAsync(h->lanes.p, 0, want * sizeof(float), h->stream));
+      h->lanes_floats = want;
+    }
+  }
   h->spec = *spec;
   h->wl_cnt = spec->wl_cnt;
   h->spec.wl = nullptr;  // borrowed only for the call
@@ -1728,6 +1832,7 @@ int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats) {
     const uint64_t ccap = std::min<uint64_t>(n * (h->max_hits + 1) + 4096, 0xFFFFFFF0ull);
     HB_CUDA(h, h->cont_dw[h->cont_cur].ensure(ccap));
     HB_CUDA(h, h->cont_meta[h->cont_cur].ensure(ccap));
+    if (h->classes.class_cnt != 0) HB_CUDA(h, h->cont_mask[h->cont_cur].ensure(ccap));
     if (h->spec.record_exits) HB_CUDA(h, h->cont_root[h->cont_cur].ensure(ccap));
   }
 
@@ -1823,6 +1928,19 @@ int hb_readback_xyz_render(HbEngine* h, uint32_t render, float* xyz, float* land
 
 int hb_readback_xyz(HbEngine* h, float* xyz, float* landed) { return hb_readback_xyz_render(h, 0, xyz, landed); }
 
+int hb_readback_class_lanes(HbEngine* h, float* lanes, uint64_t cap_floats, uint32_t* class_count) {
+  if (h == nullptr || class_count == nullptr) return HB_ERR_INVALID_ARG;
+  *class_count = 0;
+  if (!h->have_scene || h->classes.class_cnt == 0 || h->lanes_floats == 0) return HB_OK;  // base impl: empty
+  if (lanes == nullptr || cap_floats < h->lanes_floats) return fail(h, HB_ERR_CAPACITY, "ReadbackClassLanes: buffer too small");
+  cudaSetDevice(h->device);
+  HB_CUDA(h, cudaMemcpyAsync(lanes, h->lanes.p, h->lanes_floats * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  HB_CUDA(h, cudaMemsetAsync(h->lanes.p, 0, h->lanes_floats * sizeof(float), h->stream));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  *class_count = h->classes.class_cnt;
+  return HB_OK;
+}
+
 int hb_snapshot(HbEngine* h, uint32_t render, const HbSnapshotDesc* desc, uint8_t* rgb8, float* xyz, float* intensity) {
   if (h == nullptr || desc == nullptr) return HB_ERR_INVALID_ARG;
   if (!h->have_render) return fail(h, HB_ERR_STATE, "snapshot before hb_set_render");
@@ -1900,6 +2018,16 @@ int hb_export_roots(HbEngine* h, uint64_t cap, float* d3, float* p3, float* w, u
   h->exp_face.clear();
   h->exp_shape.clear();
   h->exp_wl.clear();
+  return HB_OK;
+}
+
+int hb_export_root_masks(HbEngine* h, uint64_t cap, uint64_t* masks, uint64_t* count) {
+  if (h == nullptr || count == nullptr) return HB_ERR_INVALID_ARG;
+  *count = h->exp_mask.size();
+  if (masks == nullptr) return HB_OK;
+  if (cap < h->exp_mask.size()) return fail(h, HB_ERR_CAPACITY, "export_root_masks: caller buffer too small");
+  if (!h->exp_mask.empty()) std::memcpy(masks, h->exp_mask.data(), h->exp_mask.size() * sizeof(uint64_t));
+  h->exp_mask.clear();
   return HB_OK;
 }
 

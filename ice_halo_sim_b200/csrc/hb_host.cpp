@@ -550,9 +550,8 @@ int MakeShape(std::mt19937& gen, const HbCrystalDesc& c, HbCrystalTables* out) {
 }
 
 // BuildDeviceFilterDesc, device_filter_desc.cpp:130-143 (+ crystal.cpp:710-730 D-symmetry helpers).
-void BuildFilter(const HbPopulationDesc& p, HbFilterDesc* out) {
+void BuildFilter(const HbPopulationDesc& p, const HbFilterSpecDesc& f, HbFilterDesc* out) {
   std::memset(out, 0, sizeof(*out));
-  const HbFilterSpecDesc& f = p.filter;
   out->kind = f.kind;
   out->action = f.action;
   out->symmetry = f.symmetry;
@@ -607,6 +606,41 @@ void BuildFilter(const HbPopulationDesc& p, HbFilterDesc* out) {
   } else {
     fill(f.simple, out->simple);
   }
+}
+
+// BuildColorSpecGroups (filter_spec.cpp:389-425) over GroupPlacementBySymmetry (color_gate_table.hpp): the
+// population's colour predicates grouped by symmetry value in first-occurrence order; each group becomes one
+// complex descriptor with a single-factor OR-term per predicate.
+int BuildColorGroups(const HbPopulationDesc& p, HbCrystalPopulation* out) {
+  out->color_group_cnt = 0;
+  if (p.color_pred_cnt > HB_MAX_COLOR_PREDS) return HB_ERR_INVALID_ARG;
+  std::vector<uint32_t> group_sym;
+  std::vector<HbFilterSpecDesc> specs;
+  for (uint32_t k = 0; k < p.color_pred_cnt; k++) {
+    const HbColorPredDesc& cp = p.color_preds[k];
+    if (cp.pred.kind > 4u) return HB_ERR_INVALID_ARG;
+    size_t gi = 0;
+    while (gi < group_sym.size() && group_sym[gi] != cp.symmetry) gi++;
+    if (gi == group_sym.size()) {
+      if (gi == HB_MAX_COLOR_GROUPS) return HB_ERR_UNSUPPORTED;  // kColorMaxGroupsPerSlot
+      group_sym.push_back(cp.symmetry);
+      HbFilterSpecDesc fs;
+      std::memset(&fs, 0, sizeof(fs));
+      fs.kind = 5;
+      fs.symmetry = cp.symmetry;
+      specs.push_back(fs);
+      std::memset(out->color_groups[gi].bit, 0xFF, sizeof(out->color_groups[gi].bit));
+    }
+    HbFilterSpecDesc& fs = specs[gi];
+    if (fs.term_cnt == HB_MAX_FILTER_TERMS) return HB_ERR_UNSUPPORTED;  // kDeviceFilterMaxOrClauses
+    fs.term_len[fs.term_cnt] = 1;
+    fs.terms[fs.term_cnt][0] = cp.pred;
+    out->color_groups[gi].bit[fs.term_cnt] = static_cast<uint8_t>(std::min<uint32_t>(cp.bit, 255u));
+    fs.term_cnt++;
+  }
+  for (size_t gi = 0; gi < specs.size(); gi++) BuildFilter(p, specs[gi], &out->color_groups[gi].filter);
+  out->color_group_cnt = static_cast<uint32_t>(specs.size());
+  return HB_OK;
 }
 
 }  // namespace
@@ -857,7 +891,12 @@ int hb_build_scene(const HbSceneDesc* d, uint32_t geometry_seed, HbSceneTables**
                                     pd.crystal.azimuth.type, pd.crystal.azimuth.center, pd.crystal.azimuth.spread,
                                     pd.crystal.roll.type, pd.crystal.roll.center, pd.crystal.roll.spread, &p.axis);
       if (rc != HB_OK) return rc;
-      BuildFilter(pd, &p.filter);
+      BuildFilter(pd, pd.filter, &p.filter);
+      rc = BuildColorGroups(pd, &p);
+      if (rc != HB_OK) {
+        global_error() = "scene: more than 4 colour symmetry groups or 8 predicates per group in a population";
+        return rc;
+      }
     }
     st.layers[li].prob = ld.prob;
     st.layers[li].population_cnt = ld.population_cnt;
@@ -869,6 +908,11 @@ int hb_build_scene(const HbSceneDesc* d, uint32_t geometry_seed, HbSceneTables**
   st.scene.sun_lon = (d->sun_azimuth_deg + 180.0f) * kDeg2RadF;  // cuda_trace_backend.cu:395-397
   st.scene.sun_lat = -d->sun_altitude_deg * kDeg2RadF;
   st.scene.sun_half_angle = (d->sun_diameter_deg * 0.5f) * kDeg2RadF;
+  if (d->color_classes.class_cnt > HB_MAX_COLOR_CLASSES) {
+    global_error() = "scene: more than 16 colour classes";
+    return HB_ERR_UNSUPPORTED;
+  }
+  st.scene.color_classes = d->color_classes;
   *out = t.release();
   return HB_OK;
 }

@@ -29,6 +29,8 @@ PROTOTYPES = {
     "hb_end_session": (C.c_int, [_vp]),
     "hb_readback_xyz": (C.c_int, [_vp, _vp, _vp]),
     "hb_readback_xyz_render": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
+    "hb_export_root_masks": (C.c_int, [_vp, C.c_uint64, _vp, _vp]),
+    "hb_readback_class_lanes": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     "hb_snapshot": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "hb_drain_exits": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "hb_inject_rays": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),

@@ -44,6 +44,9 @@ extern "C" {
 #define HB_MAX_FILTER_PATH 32u  /* C API raypath len cap, lumice.h:286-293 */
 #define HB_MAX_FILTER_TERMS 8u
 #define HB_MAX_RENDERS 8u
+#define HB_MAX_COLOR_GROUPS 4u   /* colour-predicate symmetry groups per population (kColorMaxGroupsPerSlot) */
+#define HB_MAX_COLOR_CLASSES 16u /* kMaxColorClassesDevice */
+#define HB_MAX_COLOR_PREDS 32u   /* colour predicates per population in a scene description */
 
 typedef enum HbStatus {
   HB_OK = 0,
@@ -131,6 +134,25 @@ typedef struct HbFilterDesc {
   HbSimpleFilter terms[HB_MAX_FILTER_TERMS][4];
 } HbFilterDesc;
 
+/* Raypath-colour predicates of one population that share a symmetry value (reference: ColorSpecGroup,
+ * filter_spec.cpp:389-425): `filter` is a complex descriptor whose OR-term k is predicate k (one AND factor),
+ * bit[k] the component bit (< 64) a match sets in the exit's component mask; bit >= 64 = no bit
+ * (ColorGateEntry::bit_ overflow, color_gate_table.hpp:25-33). Evaluated after the physical filter admits an
+ * exit; never changes survival, weight or the gate draw (simulator.cpp:684-712). */
+typedef struct HbColorGroup {
+  HbFilterDesc filter;
+  uint8_t bit[HB_MAX_FILTER_TERMS];
+} HbColorGroup;
+
+/* Colour classes (reference: ColorClassTable / ColorGateParams, cuda_trace_backend.cu:311-318): class c is
+ * satisfied by an exit whose mask m has (m & bits[c]) != 0 ("any") or == bits[c] ("all", bit c of
+ * combine_all_mask); each satisfied class receives the exit's Y in its own W*H lane of render 0. */
+typedef struct HbColorClasses {
+  uint32_t class_cnt;                     /* 0 = colour off (no lanes, no mask work) */
+  uint32_t combine_all_mask;
+  uint64_t bits[HB_MAX_COLOR_CLASSES];
+} HbColorClasses;
+
 /* One crystal population of a scattering layer (reference: ScatteringSetting, proj_config.hpp). */
 typedef struct HbCrystalPopulation {
   float proportion;                       /* crystal_proportion_ */
@@ -139,6 +161,9 @@ typedef struct HbCrystalPopulation {
   const HbCrystalTables* shapes;          /* [shape_cnt] */
   HbAxisSampler axis;
   HbFilterDesc filter;
+  uint32_t color_group_cnt;               /* 0..HB_MAX_COLOR_GROUPS */
+  uint32_t reserved_;
+  HbColorGroup color_groups[HB_MAX_COLOR_GROUPS];
 } HbCrystalPopulation;
 
 typedef struct HbLayer {
@@ -155,6 +180,8 @@ typedef struct HbScene {
   float sun_lon;                          /* (azimuth + 180 deg) in rad, simulator.cpp:194-196 */
   float sun_lat;                          /* (-altitude) in rad */
   float sun_half_angle;                   /* diameter / 2 in rad */
+  uint32_t reserved_;
+  HbColorClasses color_classes;
 } HbScene;
 
 /* Wavelength pool entry (reference: WlEntry, backend/wl_pool.hpp:29-36). */
@@ -249,6 +276,10 @@ int hb_end_session(HbEngine* h);
  * weight to *landed_weight, then zeroes the device accumulators. Legal between sessions. */
 int hb_readback_xyz(HbEngine* h, float* xyz_wh3, float* landed_weight);
 int hb_readback_xyz_render(HbEngine* h, uint32_t render, float* xyz_wh3, float* landed_weight);
+/* TraceBackend::ReadbackClassLanes (trace_backend.hpp:471-493): copies the class_cnt * W*H per-class Y lanes of
+ * render 0 (layout lane[c * W*H + py*W + px]) and zeroes them. *class_count receives the class count
+ * (0 when the scene has no colour classes; nothing is written then). */
+int hb_readback_class_lanes(HbEngine* h, float* lanes, uint64_t cap_floats, uint32_t* class_count);
 
 /* Display sink on the device = RenderConsumer::PrepareSnapshot + PostSnapshot
  * (server/render.cpp:463-495,508-577; util/color_space.cpp:10-52): NON-destructive; the accumulator keeps
@@ -279,6 +310,10 @@ int hb_inject_rays(HbEngine* h, uint64_t n, const float* d3, const float* p3, co
  * engine generated (crystal-local d/p, weight, entry face, rot9, shape index, wl index). */
 int hb_export_roots(HbEngine* h, uint64_t cap, float* d3, float* p3, float* w, uint16_t* to_face,
                     float* rot9, uint32_t* shape_idx, uint32_t* wl_idx, uint64_t* count);
+
+/* Raypath colour, parity only: component masks the exported roots carry in from earlier layers (all zero on
+ * layer 0); same order as hb_export_roots. Empty when the scene has no colour classes. */
+int hb_export_root_masks(HbEngine* h, uint64_t cap, uint64_t* masks, uint64_t* count);
 
 /* Tuning + measurement. */
 int hb_set_option(HbEngine* h, const char* key, int64_t value);
@@ -360,10 +395,19 @@ typedef struct HbFilterSpecDesc {  /* FilterConfig, filter_config.hpp:70-84 */
   HbSimpleFilterSpec terms[HB_MAX_FILTER_TERMS][4];
 } HbFilterSpecDesc;
 
+/* One colour predicate of a population (reference: ColorGateEntry, color_gate_table.hpp:25-48). */
+typedef struct HbColorPredDesc {
+  HbSimpleFilterSpec pred;       /* kind 0 = whole crystal */
+  uint32_t symmetry;             /* P=1 | B=2 | D=4 */
+  uint32_t bit;                  /* component bit, >= 64 = none */
+} HbColorPredDesc;
+
 typedef struct HbPopulationDesc {
   HbCrystalDesc crystal;
   HbFilterSpecDesc filter;
   float proportion;
+  uint32_t color_pred_cnt;       /* grouped by symmetry in first-occurrence order (GroupPlacementBySymmetry) */
+  HbColorPredDesc color_preds[HB_MAX_COLOR_PREDS];
 } HbPopulationDesc;
 
 typedef struct HbLayerDesc {
@@ -378,6 +422,7 @@ typedef struct HbSceneDesc {
   float sun_altitude_deg, sun_azimuth_deg, sun_diameter_deg;
   uint32_t geom_pool_size;       /* shapes drawn per stochastic population (K-shape pool); 0 => 1 */
   HbLayerDesc layers[HB_MAX_LAYERS];
+  HbColorClasses color_classes;
 } HbSceneDesc;
 
 typedef struct HbRenderDesc {

@@ -7,6 +7,9 @@
 // Sampling differs (mt19937 vs counter-based PCG), so the comparison is the reference's own statistical
 // battery (test/parity-cross-backend/backend/test_cuda_exit_seam_parity.py:10-16,50-53):
 //   4x4 block-mean Pearson r >= 0.95 on the Y channel, total-Y ratio within 5 %.
+// Scene 2 adds a raypath_color config (three classes over two layers): the per-class Y lanes read back through
+// TraceBackend::ReadbackClassLanes must match lanes built on the host from the CPU backend's
+// ExitRayRecord::component_mask (same battery per class).
 // Prints one JSON line; exit code 0 iff the battery passes.
 #include <algorithm>
 #include <cmath>
@@ -75,8 +78,37 @@ RenderConfig MakeRender(int w, int h) {
 }
 
 // The reference driver's seam call sequence for one wavelength batch.
+std::shared_ptr<const RaypathColorConfig> MakeColors() {
+  auto cfg = std::make_shared<RaypathColorConfig>();
+  auto ref = [](IdType layer, IdType crystal, SimpleFilterParam pred, uint8_t sym) {
+    RaypathColorRef r;
+    r.layer_ = layer;
+    r.crystal_ = crystal;
+    r.predicate_ = std::move(pred);
+    r.symmetry_ = sym;
+    return r;
+  };
+  RaypathFilterParam plate_path;
+  plate_path.raypath_ = { 3, 5 };
+  EntryExitFilterParam ee;
+  ee.entry_ = 1;
+  ee.exit_ = 3;
+  ColorClassConfig c0;  // plate rays entering face 3 and leaving face 5 (any prism-face rotation)
+  c0.match_.push_back(ref(0, 6, SimpleFilterParam{ plate_path }, FilterConfig::kSymP));
+  ColorClassConfig c1;  // everything the second-layer column emits
+  c1.match_.push_back(ref(1, 3, SimpleFilterParam{ NoneFilterParam{} }, FilterConfig::kSymNone));
+  ColorClassConfig c2;  // "all": entered the plate's top face, left a side face, and then crossed the column
+  c2.combine_ = "all";
+  c2.match_.push_back(ref(0, 6, SimpleFilterParam{ ee }, FilterConfig::kSymP | FilterConfig::kSymB | FilterConfig::kSymD));
+  c2.match_.push_back(ref(1, 3, SimpleFilterParam{ NoneFilterParam{} }, FilterConfig::kSymNone));
+  cfg->classes_ = { c0, c1, c2 };
+  return cfg;
+}
+
 void RunSessions(TraceBackend& be, const SceneConfig& scene, const RenderConfig& render, size_t total, size_t batch,
-                 uint32_t seed, std::vector<float>* cpu_img, float* cpu_landed) {
+                 uint32_t seed, std::vector<float>* cpu_img, float* cpu_landed,
+                 std::shared_ptr<const RaypathColorConfig> colors = nullptr, const ColorClassTable* classes = nullptr,
+                 std::vector<std::vector<float>>* cpu_lanes = nullptr) {
   const Rotation cam = MakeCameraRotation(render);
   std::vector<ExitRayRecord> recs;
   for (size_t done = 0; done < total; done += batch) {
@@ -87,6 +119,7 @@ void RunSessions(TraceBackend& be, const SceneConfig& scene, const RenderConfig&
     spec.wl = WlParam{ 550.0f, 1.0f };
     spec.seed = seed;
     spec.ray_num = n;
+    spec.raypath_color = colors;
     be.BeginSession(spec);
     HostRayBatch hb;
     hb.count = n;
@@ -101,6 +134,25 @@ void RunSessions(TraceBackend& be, const SceneConfig& scene, const RenderConfig&
           w[i] = recs[i].weight;
         }
         ScatterOutgoingToXyz(d.data(), w.data(), w.size(), render, cam, 550.0f, cpu_img->data(), cpu_landed);
+        if (classes != nullptr && cpu_lanes != nullptr) {  // host-side lanes from the CPU component masks
+          for (size_t c = 0; c < classes->classes_.size(); c++) {
+            const ColorClass& cls = classes->classes_[c];
+            std::vector<float> dc, wc;
+            for (size_t i = 0; i < recs.size(); i++) {
+              const uint64_t m = recs[i].component_mask & cls.member_bits_;
+              const bool ok = cls.member_bits_ != 0 &&
+                              (cls.combine_ == ColorClassCombine::kAll ? m == cls.member_bits_ : m != 0);
+              if (ok) {
+                dc.insert(dc.end(), recs[i].dir, recs[i].dir + 3);
+                wc.push_back(recs[i].weight);
+              }
+            }
+            float dummy = 0.0f;
+            if (!wc.empty()) {
+              ScatterOutgoingToXyz(dc.data(), wc.data(), wc.size(), render, cam, 550.0f, (*cpu_lanes)[c].data(), &dummy);
+            }
+          }
+        }
       }
       if (mi + 1 == scene.ms_.size()) {
         break;
@@ -147,18 +199,30 @@ std::vector<double> BlockMeansY(const std::vector<float>& img, int w, int h, int
 }  // namespace
 
 int main(int argc, char** argv) {
-  const int which = argc > 1 ? std::atoi(argv[1]) : 0;
+  const int mode = argc > 1 ? std::atoi(argv[1]) : 0;
+  const int which = mode == 2 ? 1 : mode;
   const size_t total = argc > 2 ? static_cast<size_t>(std::atoll(argv[2])) : 2000000;
   const int w = 480, h = 270;
   SceneConfig scene = MakeScene(which, 7);
   RenderConfig render = MakeRender(w, h);
   const size_t pix = static_cast<size_t>(w) * h;
 
+  std::shared_ptr<const RaypathColorConfig> colors = mode == 2 ? MakeColors() : nullptr;
+  ColorClassTable class_table;
+  if (colors) {
+    class_table = BuildColorClassTable(*colors, scene, BuildColorGateTable(*colors, scene));
+  }
+  const size_t ncls = class_table.classes_.size();
+  std::vector<std::vector<float>> cpu_lanes(ncls, std::vector<float>(pix * 3, 0.0f));
+  std::vector<float> gpu_lanes;
+  size_t gpu_ncls = 0;
+
   std::vector<float> cpu_img(pix * 3, 0.0f);
   float cpu_landed = 0.0f;
   {
     CpuTraceBackend cpu;
-    RunSessions(cpu, scene, render, total, 4096, 42, &cpu_img, &cpu_landed);
+    RunSessions(cpu, scene, render, total, 4096, 42, &cpu_img, &cpu_landed, colors, colors ? &class_table : nullptr,
+                &cpu_lanes);
   }
 
   std::vector<float> gpu_img(pix * 3, 0.0f);
@@ -169,9 +233,10 @@ int main(int argc, char** argv) {
       std::printf("{\"error\": \"backend refused the render config\"}\n");
       return 2;
     }
-    RunSessions(gpu, scene, render, total, 1 << 20, 42, nullptr, nullptr);
+    RunSessions(gpu, scene, render, total, 1 << 20, 42, nullptr, nullptr, colors);
     XyzImageData xyz{ gpu_img.data(), w, h };
     gpu.ReadbackXyzAccum(xyz, gpu_landed);
+    gpu.ReadbackClassLanes(gpu_lanes, gpu_ncls);
   } catch (const BackendUnavailableError& e) {
     std::printf("{\"unavailable\": \"%s\"}\n", e.what());
     return 3;
@@ -185,9 +250,26 @@ int main(int argc, char** argv) {
   const double r = Pearson(BlockMeansY(cpu_img, w, h, 4), BlockMeansY(gpu_img, w, h, 4));
   const double ratio = ty_g / (ty_c + 1e-300);
   const double landed_ratio = gpu_landed / (cpu_landed + 1e-30);
-  const bool ok = r >= 0.95 && std::fabs(ratio - 1.0) <= 0.05 && std::fabs(landed_ratio - 1.0) <= 0.05;
+  bool ok = r >= 0.95 && std::fabs(ratio - 1.0) <= 0.05 && std::fabs(landed_ratio - 1.0) <= 0.05;
+  if (colors) {
+    ok = ok && gpu_ncls == ncls && gpu_lanes.size() == ncls * pix;
+    for (size_t c = 0; c < ncls && ok; c++) {
+      std::vector<float> lane3(pix * 3, 0.0f);  // GPU lane as the Y channel of an XYZ image, for BlockMeansY
+      double tg = 0, tc = 0;
+      for (size_t i = 0; i < pix; i++) {
+        lane3[i * 3 + 1] = gpu_lanes[c * pix + i];
+        tg += gpu_lanes[c * pix + i];
+        tc += cpu_lanes[c][i * 3 + 1];
+      }
+      const double rc = Pearson(BlockMeansY(cpu_lanes[c], w, h, 8), BlockMeansY(lane3, w, h, 8));
+      const double lr = tg / (tc + 1e-300);
+      std::printf("{\"class\": %zu, \"lane_y_cpu\": %.3f, \"lane_y_gpu\": %.3f, \"ratio\": %.5f, \"pearson_8x8\": %.5f}\n", c,
+                  tc, tg, lr, rc);
+      ok = ok && tc > 0 && std::fabs(lr - 1.0) <= 0.05 && rc >= 0.95;
+    }
+  }
   std::printf("{\"scene\": %d, \"rays\": %zu, \"pearson_4x4\": %.5f, \"total_y_ratio\": %.5f, \"landed_ratio\": %.5f, "
               "\"cpu_landed\": %.3f, \"gpu_landed\": %.3f, \"pass\": %s}\n",
-              which, total, r, ratio, landed_ratio, cpu_landed, gpu_landed, ok ? "true" : "false");
+              mode, total, r, ratio, landed_ratio, cpu_landed, gpu_landed, ok ? "true" : "false");
   return ok ? 0 : 1;
 }

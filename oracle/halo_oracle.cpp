@@ -701,6 +701,32 @@ int orc_accumulate(const HbProjParams* p, const HbWlEntry* wl, uint32_t wl_cnt, 
   return 0;
 }
 
+int orc_accumulate_lanes(const HbProjParams* p, const HbWlEntry* wl, uint32_t wl_cnt, const HbColorClasses* classes,
+                         uint64_t n, const float* dir3, const float* w, const uint8_t* wl_idx, const uint64_t* mask,
+                         float* lanes) {
+  const size_t stride = static_cast<size_t>(p->img_w) * p->img_h;
+  for (uint64_t i = 0; i < n; i++) {
+    if (mask[i] == 0) continue;
+    Hits h = Project(*p, dir3[i * 3], dir3[i * 3 + 1], dir3[i * 3 + 2]);
+    uint32_t wi = wl_idx ? wl_idx[i] : 0;
+    if (wi >= wl_cnt) wi = 0;
+    const float y = wl[wi].cmf_y * w[i];
+    for (int k = 0; k < h.count; k++) {
+      int px = h.px[k], py = h.py[k];
+      if (px < 0 || px >= p->img_w || py < 0 || py >= p->img_h) continue;
+      size_t pix = static_cast<size_t>(py) * p->img_w + px;
+      for (uint32_t c = 0; c < classes->class_cnt; c++) {
+        uint64_t bits = classes->bits[c];
+        if (bits == 0) continue;
+        uint64_t m = mask[i] & bits;
+        bool ok = ((classes->combine_all_mask >> c) & 1u) ? (m == bits) : (m != 0);
+        if (ok) lanes[c * stride + pix] += y;
+      }
+    }
+  }
+  return 0;
+}
+
 int orc_filter_check(const HbFilterDesc* f, const uint8_t* face_fn, uint32_t crystal_id, uint64_t n,
                      const uint8_t* paths64, const uint8_t* path_len, const float* dir3, uint8_t* pass) {
   for (uint64_t i = 0; i < n; i++) {
@@ -780,6 +806,17 @@ int orc_trace_layer(const OrcLayerParams* lp, uint64_t n, const float* d3, const
           bool pass = true;
           if (pop != nullptr && pop->filter.kind != 0) pass = FilterCheck(pop->filter, fnp, r.len, dw, pop->crystal_id);
           if (!pass) continue;  // filter-fail terminates
+          // Colour pass (simulator.cpp:688-712): non-destructive, after the physical filter, before the gate
+          uint64_t mask = lp->root_mask ? lp->root_mask[i] : 0ull;
+          if (pop != nullptr) {
+            for (uint32_t g = 0; g < pop->color_group_cnt; g++) {
+              const HbColorGroup& cg = pop->color_groups[g];
+              for (uint32_t k = 0; k < cg.filter.term_cnt; k++) {
+                if (cg.bit[k] < 64 && MatchSimple(cg.filter, cg.filter.terms[k][0], fnp, r.len, dw, pop->crystal_id))
+                  mask |= 1ull << cg.bit[k];
+              }
+            }
+          }
           uint32_t es = r.code == 0 ? gseed : gseed ^ PcgHash(r.code);
           float u = Draw(es, glo, hit * 2u + (c == out_child ? 0u : 1u));
           if (u < lp->prob) {
@@ -788,6 +825,7 @@ int orc_trace_layer(const OrcLayerParams* lp, uint64_t n, const float* d3, const
               cont_w[nc] = wc[c];
               cont_wl[nc] = wi;
               cont_root[nc] = static_cast<uint32_t>(i);
+              if (lp->cont_mask != nullptr) lp->cont_mask[nc] = mask;
             }
             nc++;
           } else {
@@ -801,6 +839,7 @@ int orc_trace_layer(const OrcLayerParams* lp, uint64_t n, const float* d3, const
               e.crystal_id = static_cast<uint16_t>(pop_i);
               e.ms_layer_idx = static_cast<uint8_t>(lp->layer_idx);
               e.wl_idx = static_cast<uint8_t>(wi);
+              e.component_mask = mask;
               exit_root[ne] = static_cast<uint32_t>(i);
             }
             ne++;

@@ -35,6 +35,9 @@ typedef struct OrcLayerParams {
   uint32_t layer_idx;
   uint32_t seed;                        /* session seed (gate stream = seed ^ gate nonce) */
   uint64_t gate_base;                   /* global index of layer-ray 0 in the gate stream */
+  /* raypath colour (simulator.cpp:688-712): pops[].color_groups are evaluated on filter-admitted exits */
+  const uint64_t* root_mask;            /* [n] component mask each root carries in (NULL = 0) */
+  uint64_t* cont_mask;                  /* [cap] out: mask of each continuation (NULL = not wanted) */
 } OrcLayerParams;
 
 uint32_t orc_pcg_hash(uint32_t x);
@@ -69,6 +72,11 @@ int orc_accumulate(const HbProjParams* p, const HbWlEntry* wl, uint32_t wl_cnt, 
 int orc_filter_check(const HbFilterDesc* f, const uint8_t* face_fn, uint32_t pop_crystal_id, uint64_t n,
                      const uint8_t* paths64, const uint8_t* path_len, const float* dir3, uint8_t* pass);
 void orc_quat_to_rot9(const float* q4, float* rot9);
+/* FanColorClassLanes (cuda_trace_backend.cu:538-556) over a list of exits: lane[c*W*H + pix] += cmf_y * w for
+ * every class c the exit's mask satisfies; sequential fp32 adds in list order. */
+int orc_accumulate_lanes(const HbProjParams* p, const HbWlEntry* wl, uint32_t wl_cnt, const HbColorClasses* classes,
+                         uint64_t n, const float* dir3, const float* w, const uint8_t* wl_idx, const uint64_t* mask,
+                         float* lanes);
 /* Display sink: RenderConsumer::PostSnapshot (server/render.cpp:508-577) on a snapshot XYZ image with
  * ExposureScale (render.cpp:96-102), GamutClipXyz / XyzToLinearRgb / LinearToSrgb (util/color_space.cpp:10-52). */
 int orc_post_snapshot(const float* xyz_wh3, int w, int h, float snapshot_intensity, float intensity_factor,

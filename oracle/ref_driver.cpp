@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "config/proj_config.hpp"
+#include "config/raypath_color_config.hpp"
 #include "config/render_config.hpp"
 #include "config/sim_data.hpp"
 #include "core/backend/cpu_trace_backend.hpp"
@@ -497,9 +498,9 @@ int ref_partition(const float* proportions, uint32_t cnt, uint64_t ray_num, doub
   return 0;
 }
 
-int ref_trace_injected(const RefShape* shape, float n_idx, uint32_t max_hits, uint64_t n, const float* d3,
-                       const float* p3, const float* w, const uint16_t* to_face, uint64_t cap, HbExitRecord* out,
-                       uint32_t* out_ray, uint64_t* count) {
+static int TraceInjected(const RefShape* shape, float n_idx, uint32_t max_hits, uint64_t n, const float* d3,
+                         const float* p3, const float* w, const uint16_t* to_face, const HbPopulationDesc* color_pop,
+                         uint64_t cap, HbExitRecord* out, uint32_t* out_ray, uint64_t* count) {
   static_assert(sizeof(HbExitRecord) == sizeof(ExitRayRecord), "exit record layout");
   Crystal crystal = MakeShape(*shape);
   crystal.config_id_ = 0;
@@ -519,6 +520,26 @@ int ref_trace_injected(const RefShape* shape, float n_idx, uint32_t max_hits, ui
     d = HbDist{ 0, 1.0f, 0.0f };
   }
   pop.crystal.latitude = HbDist{ 0, 90.0f, 0.0f };
+  // Raypath colour: one class per predicate => BuildColorGateTable assigns bit k to predicate k
+  // (insertion order within the single (layer 0, crystal id) placement, color_gate_table.hpp:25-33).
+  RaypathColorConfig color_cfg;
+  if (color_pop != nullptr) {
+    pop.crystal.id = color_pop->crystal.id;
+    crystal.config_id_ = static_cast<IdType>(color_pop->crystal.id);  // what CrystalSpec::Check compares
+    pop.crystal.azimuth = color_pop->crystal.azimuth;   // decide D-symmetry applicability only (injected rays)
+    pop.crystal.roll = color_pop->crystal.roll;
+    for (uint32_t k = 0; k < color_pop->color_pred_cnt; k++) {
+      const HbColorPredDesc& cp = color_pop->color_preds[k];
+      ColorClassConfig cls;
+      RaypathColorRef ref;
+      ref.layer_ = 0;
+      ref.crystal_ = static_cast<IdType>(color_pop->crystal.id);
+      ref.predicate_ = ToSimple(cp.pred);
+      ref.symmetry_ = static_cast<uint8_t>(cp.symmetry);
+      cls.match_.push_back(ref);
+      color_cfg.classes_.push_back(cls);
+    }
+  }
   std::vector<WlParam> spectrum{ { 550.0f, 1.0f } };
   SceneConfig scene = ToScene(sd, spectrum);
 
@@ -539,6 +560,9 @@ int ref_trace_injected(const RefShape* shape, float n_idx, uint32_t max_hits, ui
     spec.render = &render;
     spec.wl = WlParam{ 550.0f, 1.0f };
     spec.seed = 1;
+    if (color_pop != nullptr) {
+      spec.raypath_color = std::make_shared<const RaypathColorConfig>(color_cfg);
+    }
     backend.BeginSession(spec);
     // The session carries the ray under test plus kPad zero-weight copies. The copies only size the
     // reference's per-session workspace (workspace[0] holds 2 x session rays, cpu_trace_backend.cpp:118-119) the
@@ -561,7 +585,7 @@ int ref_trace_injected(const RefShape* shape, float n_idx, uint32_t max_hits, ui
     hb.tf = btf;
     hb.crystal = &crystal;
     hb.refractive_index = n_idx;
-    hb.crystal_id = 0;
+    hb.crystal_id = color_pop != nullptr ? static_cast<IdType>(color_pop->crystal.id) : 0;
     auto handle = backend.TraceLayer(RootRaySource::FromHost(hb));
     backend.DrainExits(recs);
     backend.EndSession();
@@ -578,6 +602,19 @@ int ref_trace_injected(const RefShape* shape, float n_idx, uint32_t max_hits, ui
   }
   *count = k;
   return k > cap ? -5 : 0;
+}
+
+int ref_trace_injected(const RefShape* shape, float n_idx, uint32_t max_hits, uint64_t n, const float* d3,
+                       const float* p3, const float* w, const uint16_t* to_face, uint64_t cap, HbExitRecord* out,
+                       uint32_t* out_ray, uint64_t* count) {
+  return TraceInjected(shape, n_idx, max_hits, n, d3, p3, w, to_face, nullptr, cap, out, out_ray, count);
+}
+
+int ref_trace_injected_color(const RefShape* shape, float n_idx, uint32_t max_hits, uint64_t n, const float* d3,
+                             const float* p3, const float* w, const uint16_t* to_face,
+                             const HbPopulationDesc* color_pop, uint64_t cap, HbExitRecord* out, uint32_t* out_ray,
+                             uint64_t* count) {
+  return TraceInjected(shape, n_idx, max_hits, n, d3, p3, w, to_face, color_pop, cap, out, out_ray, count);
 }
 
 int ref_cpu_backend_run(const HbSceneDesc* sd, const HbRenderDesc* rd, float wl, float weight, uint32_t seed,

@@ -59,6 +59,12 @@ int ref_partition(const float* proportions, uint32_t cnt, uint64_t ray_num, doub
 int ref_trace_injected(const RefShape* shape, float n_idx, uint32_t max_hits, uint64_t n, const float* d3,
                        const float* p3, const float* w, const uint16_t* to_face, uint64_t cap,
                        HbExitRecord* out, uint32_t* out_ray, uint64_t* count);
+/* Same with raypath-colour predicates (color_pop->color_preds, one colour class per predicate => bit k for
+ * predicate k): exits carry ExitRayRecord::component_mask as CollectData produces it (simulator.cpp:688-712). */
+int ref_trace_injected_color(const RefShape* shape, float n_idx, uint32_t max_hits, uint64_t n, const float* d3,
+                             const float* p3, const float* w, const uint16_t* to_face,
+                             const HbPopulationDesc* color_pop, uint64_t cap, HbExitRecord* out, uint32_t* out_ray,
+                             uint64_t* count);
 
 /* --- CpuTraceBackend, self-generated rays (mt19937), whole scene; image via ReadbackImage --- */
 int ref_cpu_backend_run(const HbSceneDesc* scene, const HbRenderDesc* render, float wl, float weight,

@@ -58,6 +58,7 @@ def oracle():
         lib.orc_propagate.argtypes = [_vp, C.c_uint64] + [_vp] * 6
         lib.orc_project.argtypes = [_vp, C.c_uint64] + [_vp] * 5
         lib.orc_accumulate.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64] + [_vp] * 5
+        lib.orc_accumulate_lanes.argtypes = [_vp, _vp, C.c_uint32, _vp, C.c_uint64] + [_vp] * 5
         lib.orc_post_snapshot.argtypes = [_vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp]
         lib.orc_filter_check.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64] + [_vp] * 4
         lib.orc_quat_to_rot9.argtypes = [_vp, _vp]
@@ -92,6 +93,8 @@ def ref():
         lib.ref_sample_orientations.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint64, _vp, _vp]
         lib.ref_partition.argtypes = [_vp, C.c_uint32, C.c_uint64, _vp, _vp]
         lib.ref_trace_injected.argtypes = [_vp, C.c_float, C.c_uint32, C.c_uint64] + [_vp] * 4 + [C.c_uint64] + \
+            [_vp] * 3
+        lib.ref_trace_injected_color.argtypes = [_vp, C.c_float, C.c_uint32, C.c_uint64] + [_vp] * 5 + [C.c_uint64] + \
             [_vp] * 3
         lib.ref_cpu_backend_run.argtypes = [_vp, _vp, C.c_float, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64] + \
             [_vp] * 4

@@ -28,7 +28,7 @@ class OrcLayerParams(C.Structure):
     _fields_ = [("shapes", C.c_void_p), ("shape_pop", C.c_void_p), ("shape_cnt", C.c_uint32),
                 ("pops", C.c_void_p), ("pop_cnt", C.c_uint32), ("wl", C.c_void_p), ("wl_cnt", C.c_uint32),
                 ("max_hits", C.c_uint32), ("prob", C.c_float), ("layer_idx", C.c_uint32), ("seed", C.c_uint32),
-                ("gate_base", C.c_uint64)]
+                ("gate_base", C.c_uint64), ("root_mask", C.c_void_p), ("cont_mask", C.c_void_p)]
 
 
 def dist(t, c=0.0, s=0.0):
@@ -109,6 +109,28 @@ def complex_filter(terms, symmetry="", action=0):
     return f
 
 
+def color_pred(pop, bit, symmetry="", **spec):
+    """Append one raypath-colour predicate (HbColorPredDesc) to a population description."""
+    cp = pop.color_preds[pop.color_pred_cnt]
+    simple_spec(cp.pred, **spec)
+    cp.symmetry = sum({"P": 1, "B": 2, "D": 4}[ch] for ch in symmetry)
+    cp.bit = bit
+    pop.color_pred_cnt += 1
+    return pop
+
+
+def color_classes(desc, classes):
+    """classes: [(bits, 'any' | 'all')]"""
+    desc.color_classes.class_cnt = len(classes)
+    allm = 0
+    for c, (bits, combine) in enumerate(classes):
+        desc.color_classes.bits[c] = bits
+        if combine == "all":
+            allm |= 1 << c
+    desc.color_classes.combine_all_mask = allm
+    return desc
+
+
 def scene(layers, max_hits=7, sun=(20.0, 0.0, 0.5), pool=1):
     """layers: [(prob, [HbPopulationDesc, ...]), ...]"""
     d = A.HbSceneDesc()
@@ -163,6 +185,19 @@ CASES = {
                         render("dual_fisheye_equal_area", 180.0, (1024, 512), visible="full"),
                         render("fisheye_orthographic", 170.0, (640, 640), view=(90.0, 90.0, 0.0))],
         wl=[450.0, 610.0]),
+    # raypath colour: two layers so masks are carried through the continuation pool; predicates
+    # of every kind, two symmetry groups on the first population; classes with "any" and "all" combines
+    "color_classes": dict(
+        scene=lambda: color_classes(scene([
+            (0.4, [color_pred(color_pred(color_pred(color_pred(
+                prism_pop(1.3, zenith=("gauss", 90, 20.0), cid=3),
+                0, "PBD", kind=1, path=[3, 5]), 1, "PBD", kind=2, entry=1, exit=3), 2, "", kind=0),
+                3, "", kind=3, lon=180.0, lat=-20.0, radii=30.0),
+                   color_pred(prism_pop(0.3, zenith=("gauss", 0, 10.0), cid=6), 4, "P", kind=1, path=[1, 3, 2])]),
+            (0.0, [color_pred(color_pred(prism_pop(1.0, zenith=("uniform", 90, 360), cid=9),
+                                         5, "B", kind=2, entry=3, exit=5), 6, "", kind=4, crystal_id=9)])], 6),
+            [(0b0000011, "any"), (0b0100100, "all"), (0b1000000, "any"), (0b0011000, "any"), (0, "any")]),
+        render=lambda: render(res=(640, 360)), wl=[550.0]),
     "pyramid": dict(scene=lambda: scene([(0.0, [pyramid_pop()])], 8),
                     render=lambda: render("dual_fisheye_equal_area", 120.0, (1024, 512), visible="full", overlap=0.1),
                     wl=[610.0]),
@@ -189,13 +224,16 @@ def layer_params(sc: A.HbScene, li, wl_arr, seed, gate_base):
     sp = np.array(shape_pop, np.uint32)
     lp = OrcLayerParams(C.addressof(arr), H.ptr(sp), len(shapes), C.addressof(layer.populations.contents),
                         layer.population_cnt, C.addressof(wl_arr), len(wl_arr), sc.max_hits, layer.prob, li, seed,
-                        gate_base)
+                        gate_base, None, None)
     return lp, (arr, sp)
 
 
-def oracle_trace(lp, roots, cap):
+def oracle_trace(lp, roots, cap, root_mask=None):
     orc = H.oracle()
     n = len(roots["w"])
+    cm = np.zeros(cap, np.uint64)
+    lp.cont_mask = H.ptr(cm)
+    lp.root_mask = H.ptr(root_mask) if root_mask is not None and len(root_mask) else None
     ex = np.zeros(cap, H.EXIT_DTYPE)
     er = np.zeros(cap, np.uint32)
     ec = C.c_uint64()
@@ -209,7 +247,7 @@ def oracle_trace(lp, roots, cap):
                              H.ptr(ex), H.ptr(er), C.byref(ec), H.ptr(cd), H.ptr(cw), H.ptr(cwl), H.ptr(cr),
                              C.byref(cc))
     assert rc == 0, rc
-    return ex[: ec.value], er[: ec.value], (cd[: cc.value], cw[: cc.value], cr[: cc.value])
+    return ex[: ec.value], er[: ec.value], (cd[: cc.value], cw[: cc.value], cr[: cc.value], cm[: cc.value])
 
 
 def compare_exit_lists(g_ex, g_roots, o_ex, o_roots):
@@ -224,6 +262,7 @@ def compare_exit_lists(g_ex, g_roots, o_ex, o_roots):
     res["meta_equal"] = bool(same_n and np.array_equal(g["crystal_id"], o["crystal_id"]) and
                              np.array_equal(g["ms_layer_idx"], o["ms_layer_idx"]) and
                              np.array_equal(g["wl_idx"], o["wl_idx"]))
+    res["masks_equal"] = bool(same_n and np.array_equal(g["component_mask"], o["component_mask"]))
     return res
 
 
@@ -282,10 +321,16 @@ def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=
             handle = be.TraceLayer(roots_src)
             g_ex, g_roots = be.DrainExits(with_roots=True)
             roots = be.ExportRoots()
+            root_masks = be.ExportRootMasks()
             lp, keep = layer_params(sc, li, wl_arr, seed, gate_base)
             cap = len(roots["w"]) * (desc.max_hits + 2) + 16
-            o_ex, o_roots, o_cont = oracle_trace(lp, roots, cap)
+            o_ex, o_roots, o_cont = oracle_trace(lp, roots, cap, root_masks)
             r = compare_exit_lists(g_ex, g_roots, o_ex, o_roots)
+            out["masks_equal"] = out.get("masks_equal", True) and r["masks_equal"]
+            out["mask_bits_seen"] = out.get("mask_bits_seen", 0) | int(np.bitwise_or.reduce(o_ex["component_mask"])) \
+                if len(o_ex) else out.get("mask_bits_seen", 0)
+            # continuation masks travel with the (shuffled) pool: compare as multisets
+            out["cont_masks_oracle"] = sorted(int(x) for x in o_cont[3])
             r["continuations_gpu"] = handle.continuation_count
             r["continuations_oracle"] = len(o_cont[1])
             r["roots"] = len(roots["w"])
@@ -331,6 +376,27 @@ def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=
     out.update(out["renders"][0])
     out["image_ok"] = all(q["image_ok"] for q in out["renders"])
     out["landed_rel_err"] = max(q["landed_rel_err"] for q in out["renders"])
+    # per-class Y lanes of render 0 (ReadbackClassLanes) against the oracle's fan-out of the same exits
+    ncls = int(sc.color_classes.class_cnt)
+    if ncls:
+        lanes = be.ReadbackClassLanes()
+        proj = projs[0]
+        want = np.zeros((ncls, proj.img_h, proj.img_w), np.float32)
+        mag = np.zeros_like(want)
+        d = np.ascontiguousarray(ex["dir"]); ww = np.ascontiguousarray(ex["weight"])
+        wi = np.ascontiguousarray(ex["wl_idx"]); mk = np.ascontiguousarray(ex["component_mask"])
+        H.oracle().orc_accumulate_lanes(C.byref(proj), C.addressof(wl_arr), len(wl_arr), C.byref(sc.color_classes),
+                                        len(ww), H.ptr(d), H.ptr(ww), H.ptr(wi), H.ptr(mk), H.ptr(want))
+        wabs = np.ascontiguousarray(np.abs(ww))
+        H.oracle().orc_accumulate_lanes(C.byref(proj), C.addressof(wl_arr), len(wl_arr), C.byref(sc.color_classes),
+                                        len(ww), H.ptr(d), H.ptr(wabs), H.ptr(wi), H.ptr(mk), H.ptr(mag))
+        out["lanes_shape_ok"] = lanes is not None and lanes.shape == want.shape
+        if out["lanes_shape_ok"]:
+            err = np.abs(lanes - want)
+            out["lanes_ok"] = bool(np.all(err <= 2e-5 * mag + 1e-7))
+            out["lane_sums"] = [float(x) for x in lanes.reshape(ncls, -1).astype(np.float64).sum(axis=1)]
+        else:
+            out["lanes_ok"] = False
     if own:
         be.close()
     return out

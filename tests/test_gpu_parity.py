@@ -20,6 +20,11 @@ def test_case_bit_exact(backend, name):
     assert res["stats_ok"], res
     assert res["image_ok"], res
     assert res["landed_rel_err"] < 1e-5, res
+    assert res["masks_equal"], res
+    if name == "color_classes":
+        assert res["mask_bits_seen"] == 0b1111111, bin(res["mask_bits_seen"])   # every predicate fired somewhere
+        assert res["lanes_shape_ok"] and res["lanes_ok"], res
+        assert all(x > 0 for x in res["lane_sums"][:4]) and res["lane_sums"][4] == 0.0, res["lane_sums"]
 
 
 def test_seed_and_tile_invariance(backend):
@@ -148,11 +153,15 @@ def test_reference_driver_through_adapter():
     exe = os.path.join(H.ROOT, "oracle", "_ref", "adapter_demo")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/adapter_demo not built (needs /root/reference at build time)")
-    for scene, rays in ((0, 1500000), (1, 600000)):
+    for scene, rays in ((0, 1500000), (1, 600000), (2, 1500000)):
         out = subprocess.run([exe, str(scene), str(rays)], capture_output=True, text=True, timeout=600)
-        res = json.loads(out.stdout.strip().splitlines()[-1])
-        assert out.returncode == 0 and res["pass"], res
+        lines = [json.loads(x) for x in out.stdout.strip().splitlines()]
+        res = lines[-1]
+        assert out.returncode == 0 and res["pass"], lines
         assert res["pearson_4x4"] >= 0.95 and abs(res["total_y_ratio"] - 1) <= 0.05
+        if scene == 2:   # raypath colour: per-class Y lanes vs lanes built from the CPU backend's component masks
+            lanes = [x for x in lines if "class" in x]
+            assert len(lanes) == 3 and all(abs(x["ratio"] - 1) <= 0.05 and x["pearson_8x8"] >= 0.95 for x in lanes), lanes
 
 
 def _fused_run(backend, case, renders, n, seed, wl=None):

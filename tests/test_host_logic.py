@@ -97,6 +97,53 @@ def test_config_parsing():
         CFG.load_config({**EXAMPLE, "filter": [{"id": 3, "type": "complex", "composition": list(range(9))}]})
 
 
+def test_raypath_color_parsing():
+    """raypath_color -> component bits in first-occurrence order with (layer, crystal, predicate, symmetry)
+    dedupe (color_gate_table.cpp:47-95) and class bit sets / combine (color_class_table.hpp)."""
+    ex = json.loads(json.dumps(EXAMPLE))
+    ex["raypath_color"] = [
+        {"color": [1, 0, 0], "match": [{"layer": 0, "crystal": 6, "type": "raypath", "raypath": [3, 5], "symmetry": "P"},
+                                       {"layer": 1, "crystal": 3}]},
+        {"color": [0, 1, 0], "combine": "all",
+         "match": [{"layer": 0, "crystal": 6, "type": "raypath", "raypath": [3, 5], "symmetry": "P"},   # duplicate -> bit 0
+                   {"layer": 0, "crystal": 6, "type": "raypath", "raypath": [3, 5]},                    # other symmetry -> new bit
+                   {"layer": 0, "crystal": 5, "type": "entry_exit", "entry": 1, "exit": 2}]},
+    ]
+    cfg = CFG.load_config(ex)
+    d = cfg.desc
+    assert d.color_classes.class_cnt == 2 and d.color_classes.combine_all_mask == 0b10
+    assert d.color_classes.bits[0] == 0b0011 and d.color_classes.bits[1] == 0b1101
+    plate, pyr, col = d.layers[0].populations[0], d.layers[0].populations[1], d.layers[1].populations[0]
+    assert plate.color_pred_cnt == 2 and [plate.color_preds[k].bit for k in range(2)] == [0, 2]
+    assert [plate.color_preds[k].symmetry for k in range(2)] == [1, 0]
+    assert pyr.color_pred_cnt == 1 and pyr.color_preds[0].bit == 3 and pyr.color_preds[0].pred.kind == 2
+    assert col.color_pred_cnt == 1 and col.color_preds[0].bit == 1 and col.color_preds[0].pred.kind == 0
+    assert cfg.color_classes[1]["combine"] == "all" and cfg.color_classes[0]["color"] == (1.0, 0.0, 0.0)
+    # object form with a composite mode; errors mirror BuildColorGateTable's invalid_argument cases
+    ex["raypath_color"] = {"mode": "additive", "classes": ex["raypath_color"]}
+    assert CFG.load_config(ex).desc.color_classes.class_cnt == 2
+    for bad in ({"layer": 5, "crystal": 6}, {"layer": 0, "crystal": 99}):
+        ex["raypath_color"] = [{"color": [1, 1, 1], "match": [bad]}]
+        with pytest.raises(ValueError):
+            CFG.load_config(ex)
+    ex["raypath_color"] = [{"color": [1, 1, 1], "combine": "xor", "match": []}]
+    with pytest.raises(ValueError):
+        CFG.load_config(ex)
+    # the host builder groups predicates by symmetry value in first-occurrence order
+    from ice_halo_sim_b200 import backend as B
+    ex["raypath_color"] = [{"color": [1, 0, 0], "match": [
+        {"layer": 0, "crystal": 6, "type": "raypath", "raypath": [3, 5], "symmetry": "P"},
+        {"layer": 0, "crystal": 6, "type": "raypath", "raypath": [1, 3, 2]},
+        {"layer": 0, "crystal": 6, "type": "entry_exit", "entry": 3, "exit": 5, "symmetry": "P"}]}]
+    tables = B.SceneTables(CFG.load_config(ex).desc, 1)
+    gp = tables.scene().layers[0].populations[0]
+    assert gp.color_group_cnt == 2
+    g0, g1 = gp.color_groups[0], gp.color_groups[1]
+    assert (g0.filter.kind, g0.filter.symmetry, g0.filter.term_cnt) == (5, 1, 2) and list(g0.bit)[:2] == [0, 2]
+    assert (g1.filter.symmetry, g1.filter.term_cnt) == (0, 1) and g1.bit[0] == 1
+    assert tables.scene().color_classes.class_cnt == 1 and tables.scene().color_classes.bits[0] == 0b111
+
+
 def test_scene_tables_from_config():
     cfg = CFG.load_config(EXAMPLE, geom_pool_size=8)
     t = B.SceneTables(cfg.desc, geometry_seed=3)

@@ -104,13 +104,14 @@ class _Lp(C.Structure):
     _fields_ = [("shapes", C.c_void_p), ("shape_pop", C.c_void_p), ("shape_cnt", C.c_uint32),
                 ("pops", C.c_void_p), ("pop_cnt", C.c_uint32), ("wl", C.c_void_p), ("wl_cnt", C.c_uint32),
                 ("max_hits", C.c_uint32), ("prob", C.c_float), ("layer_idx", C.c_uint32), ("seed", C.c_uint32),
-                ("gate_base", C.c_uint64)]
+                ("gate_base", C.c_uint64), ("root_mask", C.c_void_p), ("cont_mask", C.c_void_p)]
 
 
-def oracle_trace_single(t, n_idx, max_hits, d, p, w, face):
+def oracle_trace_single(t, n_idx, max_hits, d, p, w, face, pop=None):
     orc = H.oracle()
     wl = A.HbWlEntry(float(n_idx), 1.0, 0.0, 0.0, 0.0)
-    lp = _Lp(C.addressof(t), None, 1, None, 0, C.addressof(wl), 1, max_hits, 0.0, 0, 1, 0)
+    lp = _Lp(C.addressof(t), None, 1, C.addressof(pop) if pop is not None else None, 1 if pop is not None else 0,
+             C.addressof(wl), 1, max_hits, 0.0, 0, 1, 0, None, None)
     n = len(w)
     cap = n * (max_hits + 2) + 8
     ex = np.zeros(cap, H.EXIT_DTYPE)
@@ -181,6 +182,28 @@ def test_post_snapshot_golden():
     # zero intensity -> black frame (render.cpp:514-517)
     orc.orc_post_snapshot(H.ptr(xyz), xyz.shape[1], xyz.shape[0], 0.0, 1.0, H.ptr(rc_a), H.ptr(bg_a), H.ptr(rgb))
     assert not rgb.any()
+
+
+def test_colour_component_masks_golden():
+    """Raypath colour: the oracle's colour pass (colour groups built by the product's host builder) reproduces
+    the component masks the reference CpuTraceBackend assigned to the same injected rays (fixture)."""
+    import sys
+    sys.path.insert(0, os.path.join(H.ROOT, "oracle"))
+    import make_golden as MG
+    import parity
+    from ice_halo_sim_b200 import backend as B
+    g = np.load(os.path.join(G, "color_masks.npz"))
+    pop = MG.color_population()
+    tables = B.SceneTables(parity.scene([(0.0, [pop])], 6), 1)
+    gpop = tables.scene().layers[0].populations[0]
+    t = gpop.shapes[0]
+    ex, er = oracle_trace_single(t, np.float32(1.31), 6, g["d"], g["p"], g["w"], g["face"], pop=gpop)
+    a, ar = H.sort_exits(ex, er)
+    assert np.array_equal(ar, g["exit_root"]) and np.array_equal(a["path_len"], g["exit_len"])
+    assert np.array_equal(a["path"][:, :8], g["exit_path"])
+    assert np.array_equal(a["weight"].view(np.uint32), g["exit_w"].view(np.uint32))
+    assert np.array_equal(a["component_mask"], g["exit_mask"])
+    assert bin(int(np.bitwise_or.reduce(a["component_mask"]))).count("1") >= 8
 
 
 def test_rng_and_feistel_properties():

@@ -241,3 +241,44 @@ def test_post_snapshot_matches_reference_colour_pipeline():
         ref.ref_post_snapshot(H.ptr(xyz), 640, 360, inten, fac, H.ptr(rc_a), H.ptr(bg_a), H.ptr(a))
         orc.orc_post_snapshot(H.ptr(xyz), 640, 360, inten, fac, H.ptr(rc_a), H.ptr(bg_a), H.ptr(b))
         assert np.array_equal(a, b) and a.any()
+
+
+@pytest.mark.parametrize("roll", [(1, 0.0, 360.0), (0, 60.0, 0.0)])
+def test_colour_component_masks_match_reference(roll):
+    """Raypath colour (SURVEY 8(f)3): ExitRayRecord::component_mask from the reference CpuTraceBackend with a
+    raypath_color config (one class per predicate => bit k) == the oracle's colour pass over the colour groups
+    the product's host builder derives from the same predicates; rays injected, everything else bit-exact too."""
+    import parity
+    from ice_halo_sim_b200 import backend as B
+    ref = H.ref()
+    rng = np.random.default_rng(77)
+    pop = parity.prism_pop(1.2, zenith=("gauss", 90, 1.0), cid=3)
+    pop.crystal.roll = A.HbDist(*roll)
+    preds = [("PBD", dict(kind=1, path=[3, 5])), ("PBD", dict(kind=2, entry=1, exit=3)), ("", dict(kind=0)),
+             ("", dict(kind=1, path=[1, 3, 2])), ("P", dict(kind=1, path=[3, 1, 5])), ("B", dict(kind=2, entry=3, exit=-1)),
+             ("", dict(kind=3, lon=10.0, lat=20.0, radii=60.0)), ("PBD", dict(kind=1, path=[4, 6])),
+             ("P", dict(kind=2, entry=-1, exit=2, min_len=2, max_len=3)), ("", dict(kind=4, crystal_id=3))]
+    for k, (sym, spec) in enumerate(preds):
+        parity.color_pred(pop, k, sym, **spec)
+    sh = H.ref_shape(0, (1.2, 0, 0))
+    t = A.HbCrystalTables()
+    ref.ref_make_tables(C.byref(sh), C.byref(t))
+    n, mh = 4000, 6
+    d, p, w, f = roots_on_crystal(rng, t, n)
+    cap = n * (mh + 2)
+    ex = np.zeros(cap, H.EXIT_DTYPE)
+    er = np.zeros(cap, np.uint32)
+    ec = C.c_uint64()
+    assert ref.ref_trace_injected_color(C.byref(sh), 1.31, mh, n, H.ptr(d), H.ptr(p), H.ptr(w), H.ptr(f), C.byref(pop),
+                                        cap, H.ptr(ex), H.ptr(er), C.byref(ec)) == 0
+    tables = B.SceneTables(parity.scene([(0.0, [pop])], mh), 1)
+    gpop = tables.scene().layers[0].populations[0]
+    assert gpop.color_group_cnt == 4           # symmetry groups in first-occurrence order: PBD, none, P, B
+    o_ex, o_er = oracle_trace_single(t, np.float32(1.31), mh, d, p, w, f, pop=gpop)
+    a, ar = H.sort_exits(ex[: ec.value], er[: ec.value])
+    b, br = H.sort_exits(o_ex, o_er)
+    assert len(a) == len(b) and np.array_equal(ar, br) and np.array_equal(a["path"], b["path"])
+    assert np.array_equal(bits(a["weight"]), bits(b["weight"]))
+    assert np.array_equal(a["component_mask"], b["component_mask"])
+    seen = int(np.bitwise_or.reduce(a["component_mask"]))
+    assert seen & 0b100 and bin(seen).count("1") >= 8, bin(seen)      # whole-crystal bit + most predicates fire
