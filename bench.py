@@ -41,9 +41,29 @@ BYTES_GEN = 48
 EXITS_PER_ROOT = 4.7            # measured on this scene (reference CPU: 4.69-4.71)
 
 
-def workload_desc():
+# BASELINE.json configs -> parity case, ray budget per wavelength per GPU per step, session size, description.
+# config2 is the default and the only one the driver's bench line is quoted on; the others are measured on
+# request (`--workload`) at reduced ray counts per step (same scene, same per-ray work) for profiles/.
+WORKLOADS = {
+    "config2": dict(case="column_config2", rays_per_wl=RAYS_PER_WL, session=SESSION_RAYS,
+                    what="BASELINE configs[1]: config_example.json as shipped, prism h=1.3 zenith gauss(90,0.3) "
+                         "max_hits 7, fisheye_equal_area 1920x1080"),
+    "config3": dict(case="plate_filter_config3", rays_per_wl=50_000_000, session=SESSION_RAYS,
+                    what="BASELINE configs[2]: plate h=0.3 zenith gauss(0,0.8), raypath filter [3,5] symmetry P, "
+                         "max_hits 7, fisheye_equal_area 1920x1080"),
+    "config4": dict(case="two_layer_config4", rays_per_wl=16_000_000, session=1 << 22,
+                    what="BASELINE configs[3]: two layers, plate (prob 1.0) over full-sphere column, max_hits 7, "
+                         "fisheye_equal_area 1920x1080; every exit of layer 0 re-enters layer 1"),
+    "config5": dict(case="stoch_config5", rays_per_wl=50_000_000, session=SESSION_RAYS,
+                    what="BASELINE configs[4]: bench_config_stoch.json prism h=1 d_i~gauss(1,0.15) full-sphere axis, "
+                         "max_hits 8, rectangular 2048x1024 full sky"),
+}
+
+
+def workload_desc(name="config2"):
     import parity
-    return parity.CASES["column_config2"]["scene"](), parity.CASES["column_config2"]["render"]()
+    case = parity.CASES[WORKLOADS[name]["case"]]
+    return case["scene"](), case["render"]()
 
 
 class ClockSampler(threading.Thread):
@@ -164,7 +184,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays-per-wl", type=int, default=RAYS_PER_WL)
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rays-per-wl", type=int, default=0)
+    ap.add_argument("--geom-pool", type=int, default=0, help="shapes per stochastic population (config5)")
     ap.add_argument("--tile-rays", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--set", action="append", default=[], help="engine option key=value (experiments)")
@@ -182,12 +204,19 @@ def main():
     import torch.distributed as dist
     from ice_halo_sim_b200 import _abi as A
     from ice_halo_sim_b200 import backend as B
+    from ice_halo_sim_b200.driver import trace_session
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    desc, rdesc = workload_desc()
+    wk = WORKLOADS[args.workload]
+    desc, rdesc = workload_desc(args.workload)
+    if args.geom_pool:
+        desc.geom_pool_size = args.geom_pool
+    max_hits = int(desc.max_hits)
+    layer_cnt = int(desc.layer_cnt)
+    session_rays = wk["session"]
     tables = B.SceneTables(desc, 7)
     wl_entries = [B.make_wl_entry(x, 1.0) for x in WAVELENGTHS]
     be = B.B200TraceBackend(local_rank)
@@ -204,7 +233,7 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         be.CommInit(ids[0], rank, world)
 
-    rays_per_wl = args.rays_per_wl
+    rays_per_wl = args.rays_per_wl or wk["rays_per_wl"]
     rays_per_step = rays_per_wl * len(WAVELENGTHS)
     h, w = rdesc.img_h, rdesc.img_w
     host_img = np.empty((h, w, 3), np.float32)
@@ -219,11 +248,10 @@ def main():
         for wi, wl in enumerate(wl_entries):
             done = 0
             while done < rays_per_wl:
-                n = min(SESSION_RAYS, rays_per_wl - done)
+                n = min(session_rays, rays_per_wl - done)
                 base = ((step_idx * world + rank) * len(WAVELENGTHS) + wi) * rays_per_wl + done
-                be.BeginSession(B.SessionSpec(seed=42, wl=[wl], ray_num=n, accumulate=True, ray_base=base))
-                be.TraceLayer(B.RootRaySource.FromHost(n), want_stats=False)
-                be.EndSession()
+                trace_session(be, layer_cnt, B.SessionSpec(seed=42, wl=[wl], ray_num=n, accumulate=True,
+                                                           ray_base=base), n)
                 done += n
         if world > 1:
             be.AllReduceImage()
@@ -282,14 +310,20 @@ def main():
     # per-kernel live timing for the roofline (CUDA events around every launch, short pass)
     be.SetOption("profile", 1)
     c0 = be.Counters()
-    p_rays = min(rays_per_wl, 1 << 24)
-    be.BeginSession(B.SessionSpec(seed=42, wl=[wl_entries[0]], ray_num=p_rays, accumulate=True, ray_base=1 << 40))
-    be.TraceLayer(B.RootRaySource.FromHost(p_rays), want_stats=False)
-    be.EndSession()
+    p_rays = min(rays_per_wl, session_rays)
+    trace_session(be, layer_cnt, B.SessionSpec(seed=42, wl=[wl_entries[0]], ray_num=p_rays, accumulate=True,
+                                               ray_base=1 << 40), p_rays)
     be.Synchronize()
     c1 = be.Counters()
     be.SetOption("profile", 0)
     be.ReadbackXyzAccum(host_img)
+    exits_per_root = EXITS_PER_ROOT
+    if args.workload != "config2":  # exits per layer-0 root of this scene, counted by the engine (LayerStats)
+        be.BeginSession(B.SessionSpec(seed=42, wl=[wl_entries[0]], ray_num=1 << 20, accumulate=True, ray_base=1 << 41))
+        hdl = be.TraceLayer(B.RootRaySource.FromHost(1 << 20), want_stats=True)
+        be.EndSession()
+        exits_per_root = hdl.exit_count / float(1 << 20)  # filter-passing exits (continuing ones included)
+        be.ReadbackXyzAccum(host_img)
 
     if rank == 0:
         peaks = {}
@@ -306,8 +340,8 @@ def main():
         i_ms = (c1.intersect_ms - c0.intersect_ms) / max(1, i_l)
         g_ms = (c1.gen_ms - c0.gen_ms) / max(1, c1.gen_launches - c0.gen_launches)
         tile = (c1.optics_rays - c0.optics_rays) / max(1, o_l)
-        opt_bytes = tile * ((BYTES_OPTICS * (MAX_HITS - 1) + BYTES_OPTICS_LAST) / MAX_HITS +
-                            BYTES_EXIT * EXITS_PER_ROOT / MAX_HITS)
+        opt_bytes = tile * ((BYTES_OPTICS * (max_hits - 1) + BYTES_OPTICS_LAST) / max_hits +
+                            BYTES_EXIT * exits_per_root / max_hits)
         int_bytes = tile * BYTES_INTERSECT
         opt_total = (c1.optics_ms - c0.optics_ms)
         int_total = (c1.intersect_ms - c0.intersect_ms)
@@ -343,14 +377,13 @@ def main():
             "metric": "Mrays/sec (9λ×50M single-scatter)", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: config_example.json as shipped, 9 wavelengths x "
-                                   f"{rays_per_wl} root rays per GPU per step, prism h=1.3 zenith gauss(90,0.3) "
-                                   "max_hits 7, fisheye_equal_area 1920x1080",
-                       "rays_per_step_per_gpu": rays_per_step, "session_rays": SESSION_RAYS,
+            "config": {"workload": f"{wk['what']}; 9 wavelengths x {rays_per_wl} root rays per GPU per step",
+                       "name": args.workload, "exits_per_root": exits_per_root,
+                       "rays_per_step_per_gpu": rays_per_step, "session_rays": session_rays,
                        "l2": "ray state per step (21.6 GB) >> 126 MB L2; no reuse across steps",
                        "parallelism": f"ray-index sharding x{world}, NCCL image all-reduce at frame end"},
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": scene_bytes +
-                    len(WAVELENGTHS) * ((rays_per_wl + SESSION_RAYS - 1) // SESSION_RAYS) * C.sizeof(A.HbWlEntry),
+                    len(WAVELENGTHS) * ((rays_per_wl + session_rays - 1) // session_rays) * C.sizeof(A.HbWlEntry),
                     "d2h_bytes_per_step": h * w * 3 * 4 + 8, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb,
             "clocks": sampler.result() if sampler else None,

@@ -1,0 +1,893 @@
+// hb_kernels.cuh — device kernels of the B200 wavefront trace engine (sm_100a): kernel parameter blocks,
+// emission (filter / gate / projection / image reduction), shared-memory table staging and the
+// gen / optics / intersect / image kernels. Host-side session logic lives in hb_engine.cu.
+//
+// Pipeline of one scattering layer over one tile of rays (DESIGN.md "kernels"):
+//   gen_roots / transit_roots      root state  P{p.xyz,bits} D{d.xyz,w} Q{orientation quaternion}  (SoA, float4)
+//   for hit h = 0 .. H-1:
+//     optics   : Fresnel split at the face the ray sits on; the child that leaves the crystal is
+//                rotated to world space, filtered, gated, projected and reduced into the image;
+//                the child that stays inside overwrites D
+//     intersect: slab exit-face search for the inside child; overwrites P (new point + hit face)
+// Reference behaviour restated: simulator.cpp:1308-1336 (hit loop, max_hits counts the entry
+// interaction), optics.cpp:18-177, simulator.cpp:665-762 (emit gate), scatter_accum.hpp:47-110.
+#ifndef HB_KERNELS_CUH_
+#define HB_KERNELS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "halotrace_b200.h"
+#include "hb_device.cuh"
+
+namespace hb {
+
+// ------------------------------------------------------------------------------------------------
+// Kernel parameter blocks
+// ------------------------------------------------------------------------------------------------
+struct LayerTables {            // device pointers, one scattering layer
+  const float4* planes;         // [shape_cnt][HB_MAX_FACES]
+  const float4* axes;           // [shape_cnt][HB_MAX_FACES][2] paired-plane axis table (see slab_exit)
+  const uint32_t* shape_meta;   // [shape_cnt] face_cnt | population << 8 | axis_cnt << 16
+  const uint8_t* face_fn;       // [shape_cnt][HB_MAX_FACES]
+  const HbCrystalTables* shapes;  // [shape_cnt] full tables (entry sampling)
+  const HbFilterDesc* filters;  // [pop_cnt]
+  const uint32_t* pop_crystal_id;  // [pop_cnt]
+  uint32_t shape_cnt;
+  uint32_t pop_cnt;
+  uint32_t any_filter;
+  const HbColorGroup* color_groups;   // [pop_cnt][HB_MAX_COLOR_GROUPS] (nullptr: no colour predicates in this layer)
+  const uint32_t* color_group_cnt;    // [pop_cnt]
+};
+
+enum : uint32_t {
+  kFlagPath = 1u,     // record the face sequence of every ray (filters / exit records)
+  kFlagRecord = 2u,   // materialise HbExitRecord for every outgoing ray
+  kFlagAccum = 4u,    // fused projection + image reduction
+  kFlagGate = 8u,     // layer prob > 0: draw the continue/outgoing gate, append continuations
+  kFlagStats = 16u,   // LayerStats (exit count, weight sum)
+  kFlagPixelCache = 32u,  // per-CTA shared-memory pixel cache in the optics kernel
+};
+
+// Additional projections of the same trace (N renderers per trace). Render 0 lives in the
+// kernel parameters; the others are read from this device table on the (rare) emit path.
+struct ExtraRender {
+  HbProjParams proj;
+  uint32_t pixel_offset;        // first pixel of this render in the image arena
+};
+
+struct TraceParams {
+  float4* P;
+  float4* D;
+  float4* Q;
+  uint8_t* path;                // [max_hits][cap] compact face ids (kFlagPath)
+  uint32_t* fork_root;          // [fork_cap] layer-root index of fork rays
+  uint32_t* fork_code;          // [fork_cap] branch code of fork rays
+  uint32_t* fork_count;         // rays appended behind the main slots (near-edge double continuation)
+  uint32_t* fork_snapshot;      // fork_count as of the last intersect kernel
+  uint32_t n_main, cap, fork_cap;
+  uint32_t root_base;           // layer-root index of slot 0 of this tile
+  LayerTables lt;
+  const HbWlEntry* wl;
+  uint32_t wl_cnt;
+  float4* image;                // image arena: render r occupies [off_r, off_r + W_r*H_r), (X, Y, Z, landed)
+  HbProjParams proj;            // render 0 (arena offset 0)
+  const ExtraRender* extra;     // renders 1..extra_cnt (device)
+  uint32_t extra_cnt;
+  // raypath colour (kernels instantiated with MULTI only)
+  uint32_t color_on;            // scene has colour classes
+  uint64_t* M;                  // [cap + fork_cap] component mask carried in from earlier layers (nullptr on layer 0)
+  uint64_t* cont_mask;          // continuation records: component mask
+  float* lane;                  // [class_cnt][lane_stride] per-class Y lanes of render 0
+  uint32_t lane_stride;
+  HbColorClasses classes;
+  uint32_t hit, max_hits, layer_idx, flags;
+  float prob;
+  uint32_t gate_seed;           // session seed ^ gate nonce
+  uint32_t gate_base_lo, gate_base_hi;  // global gate index of layer-root 0
+  float4* cont_dw;              // continuation records: world dir + weight
+  uint32_t* cont_meta;          // wl index | population << 8
+  uint32_t* cont_root;          // layer-root index of the parent (record mode)
+  uint32_t* cont_count;
+  uint32_t cont_cap;
+  HbExitRecord* exits;
+  uint32_t* exit_root;
+  uint32_t* exit_count;
+  uint32_t exit_cap;
+  unsigned long long* stat_exit_count;
+  double* stat_w_sum;
+  uint32_t* error_flag;
+};
+
+struct GenParams {
+  float4* P;
+  float4* D;
+  float4* Q;
+  uint8_t* path;
+  uint32_t slot0;               // first tile slot written by this launch
+  uint32_t count;
+  uint32_t cap;
+  uint32_t idx_lo, idx_hi;      // 64-bit stream index of slot0's ray
+  uint32_t seed;                // session seed ^ stream nonce
+  AxisParams axis;
+  const float* lut;             // [3][HB_LUT_NODES] device
+  const HbCrystalTables* shapes;  // this population's pool (device)
+  uint32_t shape_base, shape_cnt;
+  const HbWlEntry* wl;
+  uint32_t wl_cnt;
+  float sun_lon, sun_lat, sun_half;
+  float sun_c_cap, sun_c_lon, sun_s_lon, sun_c_lat, sun_s_lat;  // per-launch constants of sample_sph_cap
+  uint32_t flags;
+  // transit only
+  const float4* cont_dw;
+  const uint32_t* cont_meta;
+  const uint64_t* cont_mask;    // component masks of the continuations (raypath colour) or nullptr
+  uint64_t* M;                  // per-slot carried mask of the next layer
+  uint32_t cont_n;              // size of the permuted continuation pool
+  uint32_t cont_first;          // pool position of slot0
+  uint32_t shuffle_seed;
+  uint32_t shuffle;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Emission (CollectData branch 1, simulator.cpp:678-730 + ScatterOutgoingToXyz)
+// ------------------------------------------------------------------------------------------------
+struct Tally {
+  unsigned long long exits = 0;
+  double w_sum = 0.0;
+  uint32_t* cache_keys = nullptr;  // per-CTA pixel cache (see PixelCache below); nullptr = reduce straight to L2
+  float* cache_vals = nullptr;
+};
+
+// Per-CTA pixel cache. Halo images are extremely peaked (the undeviated light through parallel faces lands
+// on the ~35 pixels of the sun disk: ~40 % of all exits), and same-address reductions serialise in the L2
+// atomic unit while the fp32 accumulator of such a pixel absorbs small addends. Each CTA therefore keeps a
+// direct-mapped table of kCacheSlots pixels in shared memory (first come, first claimed): contributions to a
+// cached pixel are summed in shared memory and reduced into the global image once, when the CTA retires.
+// Everything else goes straight to the L2 with one red.global.add.v4.f32.
+constexpr uint32_t kCacheSlots = 512;
+constexpr uint32_t kCacheEmpty = 0xFFFFFFFFu;
+constexpr size_t kCacheBytes = kCacheSlots * (sizeof(uint32_t) + 4 * sizeof(float));
+
+HB_DEV void accumulate_pixel(const TraceParams& tp, const Tally& tally, uint32_t pix, float x, float y, float z, float lw) {
+  if (tally.cache_keys != nullptr) {
+    const uint32_t slot = (pix * 2654435761u) >> 23;  // top 9 bits
+    uint32_t k = tally.cache_keys[slot];
+    if (k == kCacheEmpty) {
+      k = atomicCAS(&tally.cache_keys[slot], kCacheEmpty, pix);
+      if (k == kCacheEmpty) k = pix;
+    }
+    if (k == pix) {
+      float* v = tally.cache_vals + slot * 4u;
+      atomicAdd(v + 0, x);
+      atomicAdd(v + 1, y);
+      atomicAdd(v + 2, z);
+      if (lw != 0.0f) atomicAdd(v + 3, lw);
+      return;
+    }
+  }
+  red_add_f4(tp.image + pix, x, y, z, lw);
+}
+
+HB_DEV void cache_init(Tally& tally, unsigned char* smem) {
+  tally.cache_keys = reinterpret_cast<uint32_t*>(smem);
+  tally.cache_vals = reinterpret_cast<float*>(smem + kCacheSlots * sizeof(uint32_t));
+  for (uint32_t i = threadIdx.x; i < kCacheSlots; i += blockDim.x) {
+    tally.cache_keys[i] = kCacheEmpty;
+    tally.cache_vals[4u * i + 0] = 0.0f;
+    tally.cache_vals[4u * i + 1] = 0.0f;
+    tally.cache_vals[4u * i + 2] = 0.0f;
+    tally.cache_vals[4u * i + 3] = 0.0f;
+  }
+}
+
+HB_DEV void cache_flush(const TraceParams& tp, const Tally& tally) {
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kCacheSlots; i += blockDim.x) {
+    const uint32_t k = tally.cache_keys[i];
+    if (k != kCacheEmpty) {
+      const float* v = tally.cache_vals + 4u * i;
+      red_add_f4(tp.image + k, v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+template <bool GENERAL, bool MULTI, typename TablesT>
+HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float lx, float ly, float lz,
+                      float w, uint32_t role, const TablesT& tb, Tally& tally) {
+  const Rot r = rot_from_quat(q);
+  float wx, wy, wz;
+  rot_apply(r, lx, ly, lz, wx, wy, wz);
+  const uint32_t wl_i = bits_wl(bits);
+  bool to_next_layer = false;
+  uint64_t mask = 0ull;  // component mask (raypath colour)
+  if (GENERAL) {
+    const uint32_t shape = bits_shape(bits);
+    const uint32_t pop = (tp.lt.shape_meta[shape] >> 8) & 255u;
+    uint32_t root, code;
+    if (slot < tp.n_main) {
+      root = tp.root_base + slot;
+      code = 0u;
+    } else {
+      root = tp.fork_root[slot - tp.n_main];
+      code = tp.fork_code[slot - tp.n_main];
+    }
+    uint8_t fn_path[HB_MAX_HITS];
+    const uint32_t len = tp.hit + 1u;
+    if (tp.flags & kFlagPath) {
+      for (uint32_t k = 0; k < len; k++)
+        fn_path[k] = static_cast<uint8_t>(tb.face_fn(shape, tp.path[static_cast<size_t>(k) * tp.cap + slot]));
+      if (tp.lt.any_filter) {
+        const HbFilterDesc& f = tp.lt.filters[pop];
+        if (f.kind != 0u) {
+          const float dir[3] = { wx, wy, wz };
+          if (!filter_check(f, fn_path, len, dir, tp.lt.pop_crystal_id[pop])) return;  // filter-fail terminates
+        }
+      }
+    }
+    if constexpr (MULTI) {
+      // Non-destructive colour pass on a filter-admitted exit (simulator.cpp:688-712): every matching
+      // predicate ORs its component bit into the mask carried from earlier layers.
+      if (tp.color_on) {
+        mask = tp.M != nullptr ? tp.M[slot] : 0ull;
+        if (tp.lt.color_groups != nullptr) {
+          const uint32_t gcnt = tp.lt.color_group_cnt[pop];
+          const float dir[3] = { wx, wy, wz };
+          for (uint32_t g = 0; g < gcnt; g++) {
+            const HbColorGroup& cg = tp.lt.color_groups[pop * HB_MAX_COLOR_GROUPS + g];
+            for (uint32_t k = 0; k < cg.filter.term_cnt; k++) {
+              if (cg.bit[k] < 64u &&
+                  filter_match_simple(cg.filter, cg.filter.terms[k][0], fn_path, len, dir, tp.lt.pop_crystal_id[pop]))
+                mask |= 1ull << cg.bit[k];
+            }
+          }
+        }
+      }
+    }
+    if (tp.flags & kFlagGate) {
+      // one uniform per filter-passing exit (simulator.cpp:719-723), keyed by (layer root, hit, role):
+      // role 0 = the child on the far side of the face, role 1 = the child that stays on the near side
+      const uint32_t glo = tp.gate_base_lo + root;
+      const uint32_t ghi = tp.gate_base_hi + (glo < tp.gate_base_lo ? 1u : 0u);
+      uint32_t seed = seed_with_high(tp.gate_seed, ghi);
+      if (code != 0u) seed ^= pcg_hash(code);
+      to_next_layer = draw(seed, glo, tp.hit * 2u + role) < tp.prob;
+    }
+    if (tp.flags & kFlagStats) {
+      tally.exits++;
+      tally.w_sum += static_cast<double>(w);
+    }
+    if (to_next_layer) {
+      // warp-aggregated append into the continuation pool (ballot + one atomic per warp)
+      const uint32_t active = __activemask();
+      const uint32_t lane = threadIdx.x & 31u;
+      const uint32_t leader = __ffs(active) - 1u;
+      uint32_t base = 0u;
+      if (lane == leader) base = atomicAdd(tp.cont_count, static_cast<uint32_t>(__popc(active)));
+      base = __shfl_sync(active, base, leader);
+      const uint32_t dst = base + __popc(active & ((1u << lane) - 1u));
+      if (dst < tp.cont_cap) {
+        tp.cont_dw[dst] = make_float4(wx, wy, wz, w);
+        tp.cont_meta[dst] = wl_i | (pop << 8);
+        if (tp.cont_root != nullptr) tp.cont_root[dst] = root;
+        if constexpr (MULTI) {
+          if (tp.cont_mask != nullptr) tp.cont_mask[dst] = mask;
+        }
+      } else {
+        *tp.error_flag = 1u;
+      }
+      return;
+    }
+    if (tp.flags & kFlagRecord) {
+      const uint32_t dst = atomicAdd(tp.exit_count, 1u);
+      if (dst < tp.exit_cap) {
+        HbExitRecord& e = tp.exits[dst];
+        e.dir[0] = wx;
+        e.dir[1] = wy;
+        e.dir[2] = wz;
+        e.weight = w;
+        e.path_len = static_cast<uint8_t>(len);
+        for (uint32_t k = 0; k < HB_MAX_HITS; k++) e.path[k] = k < len ? fn_path[k] : 0;
+        e.pad0_ = 0;
+        e.crystal_id = static_cast<uint16_t>(pop);
+        e.ms_layer_idx = static_cast<uint8_t>(tp.layer_idx);
+        e.wl_idx = static_cast<uint8_t>(wl_i);
+        e.pad1_[0] = e.pad1_[1] = 0;
+        e.component_mask = mask;
+        tp.exit_root[dst] = root;
+      } else {
+        *tp.error_flag = 2u;
+      }
+    }
+    if (!(tp.flags & kFlagAccum)) return;
+  }
+  const PixelHits h = project_exit(tp.proj, wx, wy, wz);
+  const HbWlEntry we = tp.wl[wl_i];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    if (k < h.count) {
+      const int px = h.px[k], py = h.py[k];
+      if (px >= 0 && px < tp.proj.img_w && py >= 0 && py < tp.proj.img_h) {
+        const uint32_t pix = static_cast<uint32_t>(py) * static_cast<uint32_t>(tp.proj.img_w) + static_cast<uint32_t>(px);
+        accumulate_pixel(tp, tally, pix, mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w), h.bump[k] ? w : 0.0f);
+        if constexpr (MULTI) {
+          // FanColorClassLanes (cuda_trace_backend.cu:538-556): Y into every satisfied class, overlap-ring hits too
+          if (tp.color_on && mask != 0ull) {
+            const float y = mul(we.cmf_y, w);
+            for (uint32_t c = 0; c < tp.classes.class_cnt; c++) {
+              const uint64_t cb = tp.classes.bits[c];
+              if (cb == 0ull) continue;
+              const uint64_t m = mask & cb;
+              const bool ok = ((tp.classes.combine_all_mask >> c) & 1u) ? (m == cb) : (m != 0ull);
+              if (ok) atomicAdd(tp.lane + static_cast<size_t>(c) * tp.lane_stride + pix, y);
+            }
+          }
+        }
+      }
+    }
+  }
+  if constexpr (MULTI) {  // further projections of the same exit (multi-render traces run the GENERAL+MULTI kernels)
+    for (uint32_t r = 0; r < tp.extra_cnt; r++) {
+      const HbProjParams pr = tp.extra[r].proj;
+      const uint32_t off = tp.extra[r].pixel_offset;
+      const PixelHits hr = project_exit(pr, wx, wy, wz);
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        if (k < hr.count) {
+          const int px = hr.px[k], py = hr.py[k];
+          if (px >= 0 && px < pr.img_w && py >= 0 && py < pr.img_h) {
+            accumulate_pixel(tp, tally, off + static_cast<uint32_t>(py) * static_cast<uint32_t>(pr.img_w) + static_cast<uint32_t>(px),
+                             mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w), hr.bump[k] ? w : 0.0f);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Shared-memory staging of the per-layer crystal tables.
+// Layout in dynamic shared memory, n = shape count:
+//   float4 planes[n][20] | float4 axes[n][20][2] | uint32 meta[n] | uint8 face_fn[n][20]
+// Pools of more than kSmemShapes shapes do not fit and are read through the read-only L1/L2 path.
+constexpr uint32_t kSmemShapes = 40;
+constexpr uint32_t kShapeSmemBytes = HB_MAX_FACES * 16u + HB_MAX_FACES * 32u + 4u + HB_MAX_FACES;
+__host__ __device__ inline size_t shared_tables_bytes(uint32_t shape_cnt) {
+  const uint32_t n = shape_cnt <= kSmemShapes ? shape_cnt : 0u;
+  return static_cast<size_t>(n) * kShapeSmemBytes + 16;
+}
+
+HB_DEV float4 lds128(uint32_t addr) {  // explicit shared-space load (LDS.128), no generic-address resolution
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+template <bool SMEM>
+struct AxisRow;
+template <>
+struct AxisRow<true> {
+  uint32_t addr;
+  HB_DEV void load(uint32_t i, float4& a, float4& b) const {
+    a = lds128(addr + i * 32u);
+    b = lds128(addr + i * 32u + 16u);
+  }
+};
+template <>
+struct AxisRow<false> {
+  const float4* p;
+  HB_DEV void load(uint32_t i, float4& a, float4& b) const {
+    a = __ldg(p + 2u * i);
+    b = __ldg(p + 2u * i + 1u);
+  }
+};
+
+template <bool SMEM>
+struct Tables;
+template <>
+struct Tables<true> {
+  uint32_t planes_addr, axes_addr, meta_addr, fn_addr;
+  HB_DEV float4 plane(uint32_t shape, uint32_t face) const { return lds128(planes_addr + (shape * HB_MAX_FACES + face) * 16u); }
+  HB_DEV AxisRow<true> axes(uint32_t shape) const { return AxisRow<true>{ axes_addr + shape * (HB_MAX_FACES * 32u) }; }
+  HB_DEV uint32_t meta(uint32_t shape) const {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(meta_addr + shape * 4u));
+    return v;
+  }
+  HB_DEV uint32_t face_fn(uint32_t shape, uint32_t face) const {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(fn_addr + shape * HB_MAX_FACES + face));
+    return v;
+  }
+};
+template <>
+struct Tables<false> {
+  const float4* planes_p;
+  const float4* axes_p;
+  const uint32_t* meta_p;
+  const uint8_t* fn_p;
+  HB_DEV float4 plane(uint32_t shape, uint32_t face) const { return __ldg(planes_p + shape * HB_MAX_FACES + face); }
+  HB_DEV AxisRow<false> axes(uint32_t shape) const { return AxisRow<false>{ axes_p + shape * (HB_MAX_FACES * 2u) }; }
+  HB_DEV uint32_t meta(uint32_t shape) const { return __ldg(meta_p + shape); }
+  HB_DEV uint32_t face_fn(uint32_t shape, uint32_t face) const { return __ldg(fn_p + shape * HB_MAX_FACES + face); }
+};
+
+template <bool SMEM>
+HB_DEV Tables<SMEM> stage_tables(const LayerTables& lt, unsigned char* smem, bool want_fn);
+template <>
+HB_DEV Tables<false> stage_tables<false>(const LayerTables& lt, unsigned char*, bool) {
+  return Tables<false>{ lt.planes, lt.axes, lt.shape_meta, lt.face_fn };
+}
+template <>
+HB_DEV Tables<true> stage_tables<true>(const LayerTables& lt, unsigned char* smem, bool want_fn) {
+  const uint32_t n = lt.shape_cnt;
+  float4* pl = reinterpret_cast<float4*>(smem);
+  float4* ax = pl + n * HB_MAX_FACES;
+  uint32_t* meta = reinterpret_cast<uint32_t*>(ax + n * HB_MAX_FACES * 2u);
+  uint8_t* fn = reinterpret_cast<uint8_t*>(meta + n);
+  for (uint32_t i = threadIdx.x; i < n * HB_MAX_FACES; i += blockDim.x) {
+    pl[i] = lt.planes[i];
+    ax[2u * i] = lt.axes[2u * i];
+    ax[2u * i + 1u] = lt.axes[2u * i + 1u];
+    if (want_fn) fn[i] = lt.face_fn[i];
+  }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) meta[i] = lt.shape_meta[i];
+  __syncthreads();
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const uint32_t ax_off = n * HB_MAX_FACES * 16u, meta_off = ax_off + n * HB_MAX_FACES * 32u;
+  return Tables<true>{ base, base + ax_off, base + meta_off, base + meta_off + n * 4u };
+}
+
+template <bool GENERAL>
+HB_DEV void fork_append(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float px, float py, float pz,
+                        float dx, float dy, float dz, float w, uint32_t new_face) {
+  const uint32_t k = atomicAdd(tp.fork_count, 1u);
+  if (k >= tp.fork_cap) {
+    *tp.error_flag = 3u;
+    return;
+  }
+  const uint32_t dst = tp.n_main + k;
+  const uint32_t nb = bits_with_face(bits, new_face) | (1u << 30);
+  tp.P[dst] = make_float4(px, py, pz, __uint_as_float(nb));
+  tp.D[dst] = make_float4(dx, dy, dz, w);
+  tp.Q[dst] = q;
+  if (GENERAL) {
+    uint32_t root, code;
+    if (slot < tp.n_main) {
+      root = tp.root_base + slot;
+      code = 0u;
+    } else {
+      root = tp.fork_root[slot - tp.n_main];
+      code = tp.fork_code[slot - tp.n_main];
+    }
+    tp.fork_root[k] = root;
+    tp.fork_code[k] = code | (1u << (tp.hit & 31u));
+    if (tp.M != nullptr) tp.M[dst] = tp.M[slot];
+    if (tp.flags & kFlagPath) {
+      for (uint32_t h = 0; h <= tp.hit; h++)
+        tp.path[static_cast<size_t>(h) * tp.cap + dst] = tp.path[static_cast<size_t>(h) * tp.cap + slot];
+      if (tp.hit + 1u < tp.max_hits) tp.path[static_cast<size_t>(tp.hit + 1u) * tp.cap + dst] = static_cast<uint8_t>(new_face);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optics kernel: one surface interaction per live ray
+// ------------------------------------------------------------------------------------------------
+#ifndef HB_OPTICS_MINB
+#define HB_OPTICS_MINB 4
+#endif
+#ifndef HB_INTERSECT_MINB
+#define HB_INTERSECT_MINB 5
+#endif
+template <bool GENERAL, bool LAST, bool SMEM, bool MULTI, bool P4 = false>
+__global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const TraceParams tp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tally tally;
+  const bool use_cache = (tp.flags & kFlagPixelCache) != 0u;
+  if (use_cache) cache_init(tally, smem_raw);
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + (use_cache ? kCacheBytes : 0), GENERAL);
+  if (!SMEM && use_cache) __syncthreads();
+  const uint32_t total = tp.n_main + *tp.fork_snapshot;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  // software pipeline: the next ray's state is in flight while this one is being computed
+  float4 d4 = make_float4(0.f, 0.f, 0.f, -1.f), p4 = d4, q = d4;
+  if (i < total) {
+    d4 = tp.D[i];
+    p4 = tp.P[i];
+    q = tp.Q[i];
+  }
+  while (i < total) {
+    const uint32_t i_next = i + stride;
+    float4 d_n = make_float4(0.f, 0.f, 0.f, -1.f), p_n = d_n, q_n = d_n;
+    if (i_next < total) {
+      d_n = tp.D[i_next];
+      p_n = tp.P[i_next];
+      q_n = tp.Q[i_next];
+    }
+    const uint32_t bits = __float_as_uint(p4.w);
+    const uint32_t face = bits_face(bits);
+    if (d4.w >= 0.0f && face != kFaceInvalid) {  // else: terminated ray
+      const uint32_t shape = bits_shape(bits);
+      const uint32_t meta = tb.meta(shape);
+      const AxisRow<SMEM> axes = tb.axes(shape);
+      const uint32_t axis_cnt = (meta >> 16) & 255u;
+      const float n_idx = tp.wl[bits_wl(bits)].n_idx;
+
+      const float4 pl = tb.plane(shape, face);
+      const Split s = hit_surface(pl, n_idx, d4.x, d4.y, d4.z, d4.w);
+      // The child on the far side of the face normally leaves the crystal: classify it here.
+      const uint32_t out_child = s.cos_in > 0.0f ? 1u : 0u;  // internal hit: refracted; entry: reflected
+      const float ox = out_child ? s.tx : s.rx, oy = out_child ? s.ty : s.ry, oz = out_child ? s.tz : s.rz;
+      const float ow = out_child ? s.tw : s.rw;
+      const float ix = out_child ? s.rx : s.tx, iy = out_child ? s.ry : s.ty, iz = out_child ? s.rz : s.tz;
+      const float iw = out_child ? s.rw : s.tw;
+      if (ow >= 0.0f) {
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        uint32_t nf = kFaceInvalid;
+        if (P4) {
+          if (!far_child_surely_exits_p4(axes, pl, p4.x, p4.y, p4.z, ox, oy, oz))
+            nf = slab_exit_p4<true>(axes, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
+        } else {
+          if (!far_child_surely_exits(axes, axis_cnt, face, pl, p4.x, p4.y, p4.z, ox, oy, oz))
+            nf = slab_exit<true>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
+        }
+        if (nf == kFaceInvalid) {
+          emit_exit<GENERAL, MULTI>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, tb, tally);
+        } else if (!LAST) {
+          fork_append<GENERAL>(tp, i, bits, q, nx, ny, nz, ox, oy, oz, ow, nf);  // near-edge leak: both children stay
+        }
+      }
+      if (LAST) {
+        // no intersect pass follows the final interaction: classify the inside child here too
+        if (iw >= 0.0f) {
+          float nx, ny, nz;
+          const uint32_t nf = P4 ? slab_exit_p4<false>(axes, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz)
+                                 : slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+          if (nf == kFaceInvalid) emit_exit<GENERAL, MULTI>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, tb, tally);
+        }
+      } else {
+        tp.D[i] = make_float4(ix, iy, iz, iw);  // iw < 0 (TIR sentinel) terminates the ray
+      }
+    }
+    d4 = d_n;
+    p4 = p_n;
+    q = q_n;
+    i = i_next;
+  }
+  if (use_cache) cache_flush(tp, tally);
+  if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
+    atomicAdd(tp.stat_exit_count, tally.exits);
+    atomicAdd(tp.stat_w_sum, tally.w_sum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// intersect kernel: slab exit-face search for the inside child
+// ------------------------------------------------------------------------------------------------
+template <bool GENERAL, bool SMEM, bool MULTI, bool P4 = false>
+__global__ void __launch_bounds__(256, HB_INTERSECT_MINB) intersect_kernel(const TraceParams tp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw, GENERAL);
+  const uint32_t forks = *tp.fork_count;
+  const uint32_t total = tp.n_main + min(forks, tp.fork_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *tp.fork_snapshot = min(forks, tp.fork_cap);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  Tally tally;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 d4 = make_float4(0.f, 0.f, 0.f, -1.f), p4 = d4;
+  if (i < total) {
+    d4 = tp.D[i];
+    p4 = tp.P[i];
+  }
+  while (i < total) {
+    const uint32_t i_next = i + stride;
+    float4 d_n = make_float4(0.f, 0.f, 0.f, -1.f), p_n = d_n;
+    if (i_next < total) {
+      d_n = tp.D[i_next];
+      p_n = tp.P[i_next];
+    }
+    const uint32_t bits = __float_as_uint(p4.w);
+    const uint32_t face = bits_face(bits);
+    if (d4.w >= 0.0f && face != kFaceInvalid) {
+      if (bits_advanced(bits)) {  // fork ray: advanced when it was created
+        tp.P[i] = make_float4(p4.x, p4.y, p4.z, __uint_as_float(bits & ~(1u << 30)));
+      } else {
+        const uint32_t shape = bits_shape(bits);
+        const uint32_t meta = tb.meta(shape);
+        float nx, ny, nz;
+        const uint32_t nf = P4 ? slab_exit_p4<false>(tb.axes(shape), face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz)
+                               : slab_exit<false>(tb.axes(shape), (meta >> 16) & 255u, face, p4.x, p4.y, p4.z, d4.x, d4.y,
+                                                  d4.z, nx, ny, nz);
+        if (nf == kFaceInvalid) {
+          // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
+          emit_exit<GENERAL, MULTI>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, tb, tally);
+          tp.D[i] = make_float4(d4.x, d4.y, d4.z, -1.0f);
+        } else {
+          tp.P[i] = make_float4(nx, ny, nz, __uint_as_float(bits_with_face(bits, nf)));
+          if (GENERAL && (tp.flags & kFlagPath) && tp.hit + 1u < tp.max_hits)
+            tp.path[static_cast<size_t>(tp.hit + 1u) * tp.cap + i] = static_cast<uint8_t>(nf);
+        }
+      }
+    }
+    d4 = d_n;
+    p4 = p_n;
+    i = i_next;
+  }
+  if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
+    atomicAdd(tp.stat_exit_count, tally.exits);
+    atomicAdd(tp.stat_w_sum, tally.w_sum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// root generation / layer transit
+// ------------------------------------------------------------------------------------------------
+struct GenShared {
+  float lut[3 * HB_LUT_NODES];
+  HbCrystalTables shape0;        // single-shape populations: entry fan table staged on chip
+  float4 tri_na[HB_MAX_SUBTRIS];  // (normal, area) per fan triangle: one LDS.128 per categorical term
+};
+
+constexpr uint32_t kFastTris = 24;  // prism = 20 fan triangles: weights kept in registers
+
+// Entry sampling, single-shape fast path: identical arithmetic and summation order as sample_entry, but
+// the triangle weights live in registers (one pass over shared memory, branch-free pick).
+HB_DEV void sample_entry_fast(Stream& s, const GenShared* gs, float dx, float dy, float dz, float& px, float& py,
+                              float& pz, uint32_t& face) {
+  const uint32_t n = gs->shape0.subtri_cnt;
+  float w[kFastTris];
+  float total = 0.0f;
+#pragma unroll
+  for (uint32_t i = 0; i < kFastTris; i++) {
+    w[i] = 0.0f;
+    if (i < n) {
+      const float4 na = gs->tri_na[i];
+      const float dt = dx * na.x + dy * na.y + dz * na.z;
+      w[i] = fmaxf(-dt * na.w, 0.0f);
+      total += w[i];
+    }
+  }
+  const float u_cat = s.next();
+  uint32_t tri = 0u;
+  if (total > 0.0f) {
+    const float target = u_cat * total;
+    float cum = 0.0f;
+    bool found = false;
+    tri = n - 1u;
+#pragma unroll
+    for (uint32_t i = 0; i < kFastTris; i++) {
+      if (i < n) {
+        cum += w[i];
+        if (!found && cum > target) {
+          tri = i;
+          found = true;
+        }
+      }
+    }
+  }
+  float u = s.next(), v = s.next();
+  if (u + v > 1.0f) {
+    u = 1.0f - u;
+    v = 1.0f - v;
+  }
+  const float* tv = gs->shape0.tri_v[tri];
+  px = u * (tv[3] - tv[0]) + v * (tv[6] - tv[0]) + tv[0];
+  py = u * (tv[4] - tv[1]) + v * (tv[7] - tv[1]) + tv[1];
+  pz = u * (tv[5] - tv[2]) + v * (tv[8] - tv[2]) + tv[2];
+  face = gs->shape0.tri_face[tri];
+}
+
+template <bool TRANSIT>
+__global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenShared* gs = reinterpret_cast<GenShared*>(smem_raw);
+  if (gp.axis.lat_path == HB_LAT_LUT) {
+    for (uint32_t i = threadIdx.x; i < 3 * HB_LUT_NODES; i += blockDim.x) gs->lut[i] = gp.lut[i];
+  }
+  if (gp.shape_cnt == 1u) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gp.shapes);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&gs->shape0);
+    for (uint32_t i = threadIdx.x; i < sizeof(HbCrystalTables) / 4; i += blockDim.x) dst[i] = src[i];
+    for (uint32_t i = threadIdx.x; i < HB_MAX_SUBTRIS; i += blockDim.x)
+      gs->tri_na[i] = make_float4(gp.shapes->tri_n[i][0], gp.shapes->tri_n[i][1], gp.shapes->tri_n[i][2], gp.shapes->tri_area[i]);
+  }
+  __syncthreads();
+  const bool fast_entry = gp.shape_cnt == 1u && gs->shape0.subtri_cnt <= kFastTris;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gp.count; k += gridDim.x * blockDim.x) {
+    const uint32_t lo = gp.idx_lo + k;
+    const uint32_t hi = gp.idx_hi + (lo < gp.idx_lo ? 1u : 0u);
+    const uint32_t s0 = seed_with_high(gp.seed, hi);
+    uint32_t wl_i = 0u;
+    float wx, wy, wz, weight;
+    if (TRANSIT) {
+      uint32_t src = gp.cont_first + k;
+      if (gp.shuffle) src = feistel(src, gp.cont_n, gp.shuffle_seed);
+      const float4 c = gp.cont_dw[src];
+      wx = c.x;
+      wy = c.y;
+      wz = c.z;
+      weight = c.w;
+      wl_i = gp.cont_meta[src] & 255u;
+      if (gp.cont_mask != nullptr) gp.M[gp.slot0 + k] = gp.cont_mask[src];
+    } else if (gp.wl_cnt > 1u) {
+      wl_i = min(static_cast<uint32_t>(draw(s0 ^ kNonceWl, lo, 0u) * static_cast<float>(gp.wl_cnt)), gp.wl_cnt - 1u);
+    }
+    Stream s{ s0, lo, 0u };
+    float lon, lat, roll;
+    sample_lon_lat_roll(s, gp.axis, gs->lut, lon, lat, roll);
+    const float4 q = quat_from_angles(lon, lat, roll);
+    const Rot r = rot_from_quat(q);
+    if (!TRANSIT) {
+      // sample_sph_cap (pcg_shared.h:514-529) with the per-launch trigonometry hoisted to the host
+      const float u = s.next();
+      const float x = u + (1.0f - u) * gp.sun_c_cap;
+      const float rr = sqrtf(fmaxf(1.0f - x * x, 0.0f));
+      float sp, cp;
+      sincosf(s.next() * 2.0f * kPiF, &sp, &cp);
+      const float y = cp * rr, z = sp * rr;
+      wx = gp.sun_c_lon * gp.sun_c_lat * x - gp.sun_s_lon * y - gp.sun_c_lon * gp.sun_s_lat * z;
+      wy = gp.sun_s_lon * gp.sun_c_lat * x + gp.sun_c_lon * y - gp.sun_s_lon * gp.sun_s_lat * z;
+      wz = gp.sun_s_lat * x + gp.sun_c_lat * z;
+      weight = gp.wl[wl_i].spd_weight;
+    }
+    float dx, dy, dz;
+    rot_apply_t(r.m, wx, wy, wz, dx, dy, dz);
+    uint32_t sh = 0u;
+    if (gp.shape_cnt > 1u) {
+      sh = min(static_cast<uint32_t>(draw(s0 ^ kNonceShape, lo, 0u) * static_cast<float>(gp.shape_cnt)), gp.shape_cnt - 1u);
+    }
+    const HbCrystalTables* tab = gp.shape_cnt == 1u ? &gs->shape0 : gp.shapes + sh;
+    float px = 0.0f, py = 0.0f, pz = 0.0f;
+    uint32_t face = kFaceInvalid;
+    if (tab->subtri_cnt == 0u) {
+      weight = -1.0f;  // degenerate crystal: nothing to trace (zero-weight discard, simulator.cpp:149-159)
+    } else {
+      if (fast_entry) sample_entry_fast(s, gs, dx, dy, dz, px, py, pz, face);
+      else sample_entry(s, tab, dx, dy, dz, px, py, pz, face);
+    }
+    const uint32_t slot = gp.slot0 + k;
+    gp.P[slot] = make_float4(px, py, pz, __uint_as_float(pack_bits(face, wl_i, gp.shape_base + sh, 0u)));
+    gp.D[slot] = make_float4(dx, dy, dz, weight);
+    gp.Q[slot] = q;
+    if ((gp.flags & kFlagPath) && gp.path != nullptr) gp.path[slot] = static_cast<uint8_t>(face);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 accumulators absorb small addends once a pixel grows (a 2e5 sun pixel has ulp 0.016): every
+// `fold_rays` root rays the working float4 image is folded into a double-precision master image and
+// zeroed, which bounds the relative loss (measured 2e-6 at 1 Mi rays, 6e-4 at 16 Mi without folding).
+// The reference bounds the same error by draining every 64 batches into a host Neumaier sum
+// (simulator.hpp:136, accum_shared.h:71-75).
+__global__ void __launch_bounds__(256) fold_image_kernel(float4* image, double4* master, uint32_t pixels) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const float4 v = image[i];
+    if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) {
+      double4 m = master[i];
+      m.x += static_cast<double>(v.x);
+      m.y += static_cast<double>(v.y);
+      m.z += static_cast<double>(v.z);
+      m.w += static_cast<double>(v.w);
+      master[i] = m;
+      image[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  }
+}
+
+// image drain: master (X,Y,Z,landed) double4 -> packed fp32 XYZ + landed-weight sum, then zero
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) drain_image_kernel(double4* master, float* xyz, double* landed, uint32_t pixels) {
+  double acc = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const double4 v = master[i];
+    xyz[static_cast<size_t>(i) * 3 + 0] = static_cast<float>(v.x);
+    xyz[static_cast<size_t>(i) * 3 + 1] = static_cast<float>(v.y);
+    xyz[static_cast<size_t>(i) * 3 + 2] = static_cast<float>(v.z);
+    acc += v.w;
+    master[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double warp_sum[8];
+  if ((threadIdx.x & 31u) == 0u) warp_sum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += warp_sum[w];
+    atomicAdd(landed, t);
+  }
+}
+
+// Non-destructive readout of one render: packed fp32 XYZ + landed-weight sum (the master keeps accumulating).
+__global__ void __launch_bounds__(256) peek_image_kernel(const double4* master, float* xyz, double* landed, uint32_t pixels) {
+  double lsum = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const double4 v = master[i];
+    if (xyz != nullptr) {
+      xyz[3u * i + 0] = static_cast<float>(v.x);
+      xyz[3u * i + 1] = static_cast<float>(v.y);
+      xyz[3u * i + 2] = static_cast<float>(v.z);
+    }
+    lsum += v.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+  if ((threadIdx.x & 31u) == 0u && lsum != 0.0) atomicAdd(landed, lsum);
+}
+
+// Display sink (RenderConsumer::PostSnapshot, server/render.cpp:508-577, with util/color_space.cpp:10-52):
+// XYZ * exposure scale -> gamut clip towards the D65 grey of equal luminance -> linear sRGB -> + background,
+// clamp -> sRGB transfer curve -> 8-bit. With a ray colour the luminance-only branch is taken instead.
+struct SnapshotParams {
+  float scale;
+  float ray_color[3];
+  float background[3];
+  int use_real_color;
+};
+
+HB_DEV float linear_to_srgb(float v) {  // color_space.cpp:47-52
+  if (v < 0.0031308f) return v * 12.92f;
+  return 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+}
+
+__global__ void __launch_bounds__(256) snapshot_srgb_kernel(const double4* master, uint8_t* rgb8, uint32_t pixels, SnapshotParams sp) {
+  const float kWhite[3] = { 0.95047f, 1.00000f, 1.08883f };
+  const float kM[9] = { 3.2404542f, -1.5371385f, -0.4985314f, -0.9692660f, 1.8760108f, 0.0415560f,
+                        0.0556434f, -0.2040259f, 1.0572252f };
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const double4 m = master[i];
+    const float xyz[3] = { mul(static_cast<float>(m.x), sp.scale), mul(static_cast<float>(m.y), sp.scale),
+                           mul(static_cast<float>(m.z), sp.scale) };
+    float gray[3], rgb[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) gray[j] = mul(kWhite[j], xyz[1]);
+    if (sp.use_real_color) {
+      float s = 1.0f, diff[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) diff[j] = sub(xyz[j], gray[j]);
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float a = 0.0f, b = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          a = add(a, mul(-gray[k], kM[j * 3 + k]));
+          b = add(b, mul(diff[k], kM[j * 3 + k]));
+        }
+        if (mul(a, b) > 0.0f && __fdiv_rn(a, b) < s) s = __fdiv_rn(a, b);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) v = add(v, mul(add(mul(diff[k], s), gray[k]), kM[j * 3 + k]));
+        rgb[j] = fminf(fmaxf(v, 0.0f), 1.0f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) v = add(v, mul(gray[k], kM[j * 3 + k]));
+        rgb[j] = mul(v, sp.ray_color[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      float v = add(rgb[j], sp.background[j]);
+      v = fminf(fmaxf(v, 0.0f), 1.0f);
+      rgb8[3u * i + j] = static_cast<uint8_t>(mul(linear_to_srgb(v), 255.0f));
+    }
+  }
+}
+
+// Export helper: quaternion -> rot9 with the device's own arithmetic (parity harness).
+__global__ void quat_to_rot_kernel(const float4* Q, float* rot9, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Rot r = rot_from_quat(Q[i]);
+  for (int k = 0; k < 9; k++) rot9[static_cast<size_t>(i) * 9 + k] = r.m[k];
+}
+
+
+}  // namespace hb
+
+#endif  // HB_KERNELS_CUH_
