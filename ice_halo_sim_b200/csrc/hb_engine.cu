@@ -71,6 +71,7 @@ struct LayerDev {
   DevBuf<uint32_t> shape_meta;
   DevBuf<uint8_t> face_fn;
   DevBuf<HbCrystalTables> shapes;
+  DevBuf<EntryFaces> entry_faces;  // [shape] face groups of the entry fan table
   DevBuf<HbFilterDesc> filters;
   DevBuf<uint32_t> pop_crystal_id;
   DevBuf<float> luts;  // [pop][3][257]
@@ -127,10 +128,14 @@ struct HbEngine {
   struct WlSlot {
     std::vector<HbWlEntry> host;
     DevBuf<HbWlEntry> dev;
+    std::vector<WlDev> host2;  // derived table the trace kernels read (n, 1/n, CMF)
+    DevBuf<WlDev> dev2;
   };
   std::vector<WlSlot> wl_cache;
   size_t wl_cache_next = 0;
   const HbWlEntry* wl_cur = nullptr;
+  const WlDev* wl2_cur = nullptr;
+  WlDev wl0{};
   uint32_t wl_cnt = 0;
   uint32_t layer_idx = 0;       // next layer to trace
   bool layer_traced = false;    // a TraceLayer result is pending Recombine
@@ -333,6 +338,38 @@ void launch_intersect(HbEngine* h, bool general, bool in_smem, bool p4, size_t s
 
 size_t trace_smem(const LayerDev& L) { return shared_tables_bytes(L.shape_cnt); }
 
+// Face groups of one shape's entry fan table (see EntryFaces): runs of consecutive triangles that share
+// the face id and the normal; per triangle the cumulative area fraction inside its run.
+EntryFaces build_entry_faces(const HbCrystalTables& t) {
+  EntryFaces ef;
+  std::memset(&ef, 0, sizeof(ef));
+  uint32_t g = 0;
+  for (uint32_t i = 0; i < t.subtri_cnt;) {
+    uint32_t j = i + 1;
+    while (j < t.subtri_cnt && t.tri_face[j] == t.tri_face[i] && std::fabs(t.tri_n[j][0] - t.tri_n[i][0]) <= 1e-4f &&
+           std::fabs(t.tri_n[j][1] - t.tri_n[i][1]) <= 1e-4f && std::fabs(t.tri_n[j][2] - t.tri_n[i][2]) <= 1e-4f)
+      j++;
+    if (g == HB_MAX_FACES) {  // cannot happen for the reference's crystals; keep the triangle-level sampler
+      ef.group_cnt = 0;
+      return ef;
+    }
+    float area = 0.0f;
+    for (uint32_t k = i; k < j; k++) area += t.tri_area[k];
+    float run = 0.0f;
+    for (uint32_t k = i; k < j; k++) {
+      run += t.tri_area[k];
+      ef.cum[k] = area > 0.0f ? run / area : 1.0f;
+    }
+    ef.na[g] = make_float4(t.tri_n[i][0], t.tri_n[i][1], t.tri_n[i][2], area);
+    ef.first[g] = static_cast<uint8_t>(i);
+    ef.cnt[g] = static_cast<uint8_t>(j - i);
+    g++;
+    i = j;
+  }
+  ef.group_cnt = g;
+  return ef;
+}
+
 int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   L->prob = src.prob;
   L->pops.clear();
@@ -341,6 +378,7 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   std::vector<uint32_t> meta;
   std::vector<uint8_t> fn;
   std::vector<HbCrystalTables> shapes;
+  std::vector<EntryFaces> entry_faces;
   std::vector<HbFilterDesc> filters;
   std::vector<uint32_t> cid;
   std::vector<float> luts;
@@ -365,6 +403,7 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
       const HbCrystalTables& t = p.shapes[s];
       if (t.face_cnt > HB_MAX_FACES || t.subtri_cnt > HB_MAX_SUBTRIS) return fail(h, HB_ERR_INVALID_ARG, "crystal table too large");
       shapes.push_back(t);
+      entry_faces.push_back(build_entry_faces(t));
       for (uint32_t f = 0; f < HB_MAX_FACES; f++) {
         planes.push_back(make_float4(t.plane[f][0], t.plane[f][1], t.plane[f][2], t.plane[f][3]));
         fn.push_back(t.face_fn[f]);
@@ -423,6 +462,8 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   HB_CUDA(h, cudaMemcpy(L->shape_meta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->face_fn.p, fn.data(), fn.size(), cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->shapes.p, shapes.data(), shapes.size() * sizeof(HbCrystalTables), cudaMemcpyHostToDevice));
+  HB_CUDA(h, L->entry_faces.ensure(entry_faces.size()));
+  HB_CUDA(h, cudaMemcpy(L->entry_faces.p, entry_faces.data(), entry_faces.size() * sizeof(EntryFaces), cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->filters.p, filters.data(), filters.size() * sizeof(HbFilterDesc), cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->pop_crystal_id.p, cid.data(), cid.size() * 4, cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->luts.p, luts.data(), luts.size() * 4, cudaMemcpyHostToDevice));
@@ -511,6 +552,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
       gp.axis = ph.axis;
       gp.lut = L.luts.p + ci * 3 * HB_LUT_NODES;
       gp.shapes = L.shapes.p + ph.shape_base;
+      gp.entry_faces = L.entry_faces.p + ph.shape_base;
       gp.shape_base = ph.shape_base;
       gp.shape_cnt = ph.shape_cnt;
       gp.wl = h->wl_cur;
@@ -598,6 +640,8 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
                        L.any_color ? L.color_groups.p : nullptr, L.color_group_cnt.p };
   tp.wl = h->wl_cur;
   tp.wl_cnt = h->wl_cnt;
+  tp.wl0 = h->wl0;
+  tp.wl2 = h->wl2_cur;
   tp.image = h->image.p;
   tp.proj = h->proj;
   tp.extra = h->extra_dev.p;
@@ -738,6 +782,7 @@ void hb_destroy(HbEngine* h) {
   for (auto& L : h->layers) {
     L->planes.release();
     L->axes.release();
+    L->entry_faces.release();
     L->shape_meta.release();
     L->face_fn.release();
     L->shapes.release();
@@ -896,8 +941,18 @@ int hb_begin_session(HbEngine* h, const HbSessionSpec* spec) {
       s.host.assign(spec->wl, spec->wl + spec->wl_cnt);
       HB_CUDA(h, s.dev.ensure(spec->wl_cnt));
       HB_CUDA(h, cudaMemcpy(s.dev.p, s.host.data(), bytes, cudaMemcpyHostToDevice));
+      s.host2.resize(spec->wl_cnt);
+      for (uint32_t i = 0; i < spec->wl_cnt; i++) {
+        const HbWlEntry& e = s.host[i];
+        const volatile float one = 1.0f;  // a correctly rounded single-precision division, whatever the host flags
+        s.host2[i] = WlDev{ e.n_idx, one / e.n_idx, e.spd_weight, 0.0f, e.cmf_x, e.cmf_y, e.cmf_z, 0.0f };
+      }
+      HB_CUDA(h, s.dev2.ensure(spec->wl_cnt));
+      HB_CUDA(h, cudaMemcpy(s.dev2.p, s.host2.data(), spec->wl_cnt * sizeof(WlDev), cudaMemcpyHostToDevice));
     }
     h->wl_cur = h->wl_cache[hit].dev.p;
+    h->wl2_cur = h->wl_cache[hit].dev2.p;
+    h->wl0 = h->wl_cache[hit].host2[0];
   }
   if (spec->use_ray_base) h->gen_base = spec->ray_base;
   h->layer_idx = 0;

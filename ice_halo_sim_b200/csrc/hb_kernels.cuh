@@ -56,6 +56,19 @@ struct ExtraRender {
   uint32_t pixel_offset;        // first pixel of this render in the image arena
 };
 
+// Wavelength-pool entry as the kernels read it: the refractive index with its IEEE reciprocal (the entry-side
+// Fresnel ratio 1/n of HitSurface, optics.cpp:24, computed once on the host instead of once per ray) and the CMF.
+struct WlDev {
+  float n_idx, inv_n, spd_weight, pad0;
+  float cmf_x, cmf_y, cmf_z, pad1;
+};
+HB_DEV WlDev load_wl(const WlDev& wl0, const WlDev* wl2, uint32_t wl_cnt, uint32_t i) {
+  if (wl_cnt == 1u) return wl0;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(wl2 + i));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(wl2 + i) + 1);
+  return WlDev{ a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+}
+
 struct TraceParams {
   float4* P;
   float4* D;
@@ -70,6 +83,8 @@ struct TraceParams {
   LayerTables lt;
   const HbWlEntry* wl;
   uint32_t wl_cnt;
+  WlDev wl0;                    // entry 0 of the derived table: single-wavelength sessions read it from the parameter bank
+  const WlDev* wl2;             // derived table (n, 1/n, CMF), one per pool entry
   float4* image;                // image arena: render r occupies [off_r, off_r + W_r*H_r), (X, Y, Z, landed)
   HbProjParams proj;            // render 0 (arena offset 0)
   const ExtraRender* extra;     // renders 1..extra_cnt (device)
@@ -99,6 +114,7 @@ struct TraceParams {
   uint32_t* error_flag;
 };
 
+struct EntryFaces;
 struct GenParams {
   float4* P;
   float4* D;
@@ -112,6 +128,7 @@ struct GenParams {
   AxisParams axis;
   const float* lut;             // [3][HB_LUT_NODES] device
   const HbCrystalTables* shapes;  // this population's pool (device)
+  const EntryFaces* entry_faces;  // face groups of the same shapes
   uint32_t shape_base, shape_cnt;
   const HbWlEntry* wl;
   uint32_t wl_cnt;
@@ -149,6 +166,39 @@ constexpr uint32_t kCacheSlots = 512;
 constexpr uint32_t kCacheEmpty = 0xFFFFFFFFu;
 constexpr size_t kCacheBytes = kCacheSlots * (sizeof(uint32_t) + 4 * sizeof(float));
 
+// (x, y, z, w) += into one 16-byte shared-memory slot with a single 128-bit compare-and-swap loop
+// (ATOMS.CAS.128). Shared memory has no native fp32 add: four scalar atomicAdd calls are four CAS loops.
+HB_DEV void smem_add_f4(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile(
+      "{\n"
+      ".reg .b128 oldv, newv, got;\n"
+      ".reg .b64 lo, hi, glo, ghi;\n"
+      ".reg .f32 a0, a1, a2, a3;\n"
+      ".reg .pred p, q;\n"
+      "ld.shared.v2.b64 {lo, hi}, [%0];\n"
+      "HB_CAS_RETRY:\n"
+      "mov.b64 {a0, a1}, lo;\n"
+      "mov.b64 {a2, a3}, hi;\n"
+      "mov.b128 oldv, {lo, hi};\n"
+      "add.rn.f32 a0, a0, %1;\n"
+      "add.rn.f32 a1, a1, %2;\n"
+      "add.rn.f32 a2, a2, %3;\n"
+      "add.rn.f32 a3, a3, %4;\n"
+      "mov.b64 glo, {a0, a1};\n"
+      "mov.b64 ghi, {a2, a3};\n"
+      "mov.b128 newv, {glo, ghi};\n"
+      "atom.shared.cas.b128 got, [%0], oldv, newv;\n"
+      "mov.b128 {glo, ghi}, got;\n"
+      "setp.ne.b64 p, glo, lo;\n"
+      "setp.ne.b64 q, ghi, hi;\n"
+      "or.pred p, p, q;\n"
+      "mov.b64 lo, glo;\n"
+      "mov.b64 hi, ghi;\n"
+      "@p bra HB_CAS_RETRY;\n"
+      "}\n" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w)
+      : "memory");
+}
+
 HB_DEV void accumulate_pixel(const TraceParams& tp, const Tally& tally, uint32_t pix, float x, float y, float z, float lw) {
   if (tally.cache_keys != nullptr) {
     const uint32_t slot = (pix * 2654435761u) >> 23;  // top 9 bits
@@ -158,11 +208,7 @@ HB_DEV void accumulate_pixel(const TraceParams& tp, const Tally& tally, uint32_t
       if (k == kCacheEmpty) k = pix;
     }
     if (k == pix) {
-      float* v = tally.cache_vals + slot * 4u;
-      atomicAdd(v + 0, x);
-      atomicAdd(v + 1, y);
-      atomicAdd(v + 2, z);
-      if (lw != 0.0f) atomicAdd(v + 3, lw);
+      smem_add_f4(static_cast<uint32_t>(__cvta_generic_to_shared(tally.cache_vals + slot * 4u)), x, y, z, lw);
       return;
     }
   }
@@ -302,7 +348,7 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
     if (!(tp.flags & kFlagAccum)) return;
   }
   const PixelHits h = project_exit(tp.proj, wx, wy, wz);
-  const HbWlEntry we = tp.wl[wl_i];
+  const WlDev we = load_wl(tp.wl0, tp.wl2, tp.wl_cnt, wl_i);
 #pragma unroll
   for (int k = 0; k < 2; k++) {
     if (k < h.count) {
@@ -512,10 +558,15 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
       const uint32_t meta = tb.meta(shape);
       const AxisRow<SMEM> axes = tb.axes(shape);
       const uint32_t axis_cnt = (meta >> 16) & 255u;
-      const float n_idx = tp.wl[bits_wl(bits)].n_idx;
+      float n_idx = tp.wl0.n_idx, inv_n = tp.wl0.inv_n;
+      if (tp.wl_cnt != 1u) {
+        const float2 nn = __ldg(reinterpret_cast<const float2*>(tp.wl2 + bits_wl(bits)));
+        n_idx = nn.x;
+        inv_n = nn.y;
+      }
 
       const float4 pl = tb.plane(shape, face);
-      const Split s = hit_surface(pl, n_idx, d4.x, d4.y, d4.z, d4.w);
+      const Split s = hit_surface(pl, n_idx, inv_n, d4.x, d4.y, d4.z, d4.w);
       // The child on the far side of the face normally leaves the crystal: classify it here.
       const uint32_t out_child = s.cos_in > 0.0f ? 1u : 0u;  // internal hit: refracted; entry: reflected
       const float ox = out_child ? s.tx : s.rx, oy = out_child ? s.ty : s.ry, oz = out_child ? s.tz : s.rz;
@@ -623,60 +674,113 @@ __global__ void __launch_bounds__(256, HB_INTERSECT_MINB) intersect_kernel(const
 // ------------------------------------------------------------------------------------------------
 // root generation / layer transit
 // ------------------------------------------------------------------------------------------------
-struct GenShared {
-  float lut[3 * HB_LUT_NODES];
-  HbCrystalTables shape0;        // single-shape populations: entry fan table staged on chip
-  float4 tri_na[HB_MAX_SUBTRIS];  // (normal, area) per fan triangle: one LDS.128 per categorical term
+struct EntryFaces;
+struct GenShared;
+
+// Entry sampling by face groups. The reference draws the entry triangle from a categorical over ALL fan
+// triangles with weights max(-d.n_t, 0) * area_t (InitRay_p_fid, simulator.cpp:133-192). The triangles of one
+// face share their normal, so the same distribution is drawn in two levels: a categorical over the faces
+// (weight max(-d.n_f, 0) * A_f, A_f = fan area) and, inside the chosen face, the triangle whose cumulative
+// area fraction brackets the residual of the same uniform. A prism needs 8 dot products instead of 20.
+// Host-built per shape (build_entry_faces, hb_engine.cu); a group is a run of consecutive triangles with the
+// same face id and normal.
+struct EntryFaces {
+  float4 na[HB_MAX_FACES];     // group normal, group area
+  float cum[HB_MAX_SUBTRIS];   // per triangle: cumulative area fraction inside its group
+  uint8_t first[HB_MAX_FACES];
+  uint8_t cnt[HB_MAX_FACES];
+  uint32_t group_cnt;          // 0: more than HB_MAX_FACES groups -> triangle-level sampler (sample_entry)
+  uint32_t pad_[1];
 };
+static_assert(sizeof(EntryFaces) % 16 == 0, "EntryFaces is copied as uint4 words");
 
-constexpr uint32_t kFastTris = 24;  // prism = 20 fan triangles: weights kept in registers
+constexpr uint32_t kFastGroups = 8;  // prism: 8 faces, weights kept in registers
 
-// Entry sampling, single-shape fast path: identical arithmetic and summation order as sample_entry, but
-// the triangle weights live in registers (one pass over shared memory, branch-free pick).
-HB_DEV void sample_entry_fast(Stream& s, const GenShared* gs, float dx, float dy, float dz, float& px, float& py,
-                              float& pz, uint32_t& face) {
-  const uint32_t n = gs->shape0.subtri_cnt;
-  float w[kFastTris];
-  float total = 0.0f;
-#pragma unroll
-  for (uint32_t i = 0; i < kFastTris; i++) {
-    w[i] = 0.0f;
-    if (i < n) {
-      const float4 na = gs->tri_na[i];
-      const float dt = dx * na.x + dy * na.y + dz * na.z;
-      w[i] = fmaxf(-dt * na.w, 0.0f);
-      total += w[i];
-    }
-  }
+// Returns the chosen fan triangle. `ef` may point to shared or global memory (warp-uniform address).
+HB_DEV uint32_t pick_entry_triangle(Stream& s, const EntryFaces* ef, float dx, float dy, float dz) {
+  const uint32_t ng = ef->group_cnt;
   const float u_cat = s.next();
-  uint32_t tri = 0u;
-  if (total > 0.0f) {
+  // not found (rounding pushed the target up to the total): last group, residual 0
+  uint32_t sel = ng - 1u;
+  float resid = 0.0f, w_sel = 0.0f, total = 0.0f;
+  if (ng <= kFastGroups) {
+    float w[kFastGroups];
+#pragma unroll
+    for (uint32_t g = 0; g < kFastGroups; g++) {
+      w[g] = 0.0f;
+      if (g < ng) {
+        const float4 na = ef->na[g];
+        w[g] = fmaxf(-(dx * na.x + dy * na.y + dz * na.z) * na.w, 0.0f);
+        total += w[g];
+      }
+    }
+    if (!(total > 0.0f)) return 0u;
     const float target = u_cat * total;
     float cum = 0.0f;
     bool found = false;
-    tri = n - 1u;
 #pragma unroll
-    for (uint32_t i = 0; i < kFastTris; i++) {
-      if (i < n) {
-        cum += w[i];
-        if (!found && cum > target) {
-          tri = i;
-          found = true;
-        }
+    for (uint32_t g = 0; g < kFastGroups; g++) {
+      if (g < ng) {
+        const float c1 = cum + w[g];
+        const bool hit = !found && c1 > target;
+        sel = hit ? g : sel;
+        resid = hit ? target - cum : resid;
+        w_sel = hit ? w[g] : w_sel;
+        found = found || hit;
+        cum = c1;
       }
     }
+  } else {
+    for (uint32_t g = 0; g < ng; g++) {
+      const float4 na = ef->na[g];
+      total += fmaxf(-(dx * na.x + dy * na.y + dz * na.z) * na.w, 0.0f);
+    }
+    if (!(total > 0.0f)) return 0u;
+    const float target = u_cat * total;
+    float cum = 0.0f;
+    for (uint32_t g = 0; g < ng; g++) {
+      const float4 na = ef->na[g];
+      const float wg = fmaxf(-(dx * na.x + dy * na.y + dz * na.z) * na.w, 0.0f);
+      const float c1 = cum + wg;
+      if (c1 > target) {
+        sel = g;
+        resid = target - cum;
+        w_sel = wg;
+        break;
+      }
+      cum = c1;
+    }
   }
+  const float r = w_sel > 0.0f ? resid / w_sel : 0.0f;
+  const uint32_t t0 = ef->first[sel], c = ef->cnt[sel];
+  uint32_t tri = t0;
+  for (uint32_t j = 0; j + 1u < c; j++) {
+    if (r >= ef->cum[t0 + j]) tri = t0 + j + 1u;
+  }
+  return tri;
+}
+
+// Uniform point in the chosen triangle (SampleTrianglePoint, geo3d.cpp:114-190; sample_triangle, pcg_shared.h:493-509).
+HB_DEV void sample_entry_faces(Stream& s, const EntryFaces* ef, const HbCrystalTables* tab, float dx, float dy, float dz,
+                               float& px, float& py, float& pz, uint32_t& face) {
+  const uint32_t tri = pick_entry_triangle(s, ef, dx, dy, dz);
   float u = s.next(), v = s.next();
   if (u + v > 1.0f) {
     u = 1.0f - u;
     v = 1.0f - v;
   }
-  const float* tv = gs->shape0.tri_v[tri];
+  const float* tv = tab->tri_v[tri];
   px = u * (tv[3] - tv[0]) + v * (tv[6] - tv[0]) + tv[0];
   py = u * (tv[4] - tv[1]) + v * (tv[7] - tv[1]) + tv[1];
   pz = u * (tv[5] - tv[2]) + v * (tv[8] - tv[2]) + tv[2];
-  face = gs->shape0.tri_face[tri];
+  face = tab->tri_face[tri];
 }
+
+struct GenShared {
+  float lut[3 * HB_LUT_NODES];
+  HbCrystalTables shape0;        // single-shape populations: entry fan table staged on chip
+  EntryFaces ef0;                // ... and its face groups
+};
 
 template <bool TRANSIT>
 __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
@@ -689,11 +793,11 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(gp.shapes);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&gs->shape0);
     for (uint32_t i = threadIdx.x; i < sizeof(HbCrystalTables) / 4; i += blockDim.x) dst[i] = src[i];
-    for (uint32_t i = threadIdx.x; i < HB_MAX_SUBTRIS; i += blockDim.x)
-      gs->tri_na[i] = make_float4(gp.shapes->tri_n[i][0], gp.shapes->tri_n[i][1], gp.shapes->tri_n[i][2], gp.shapes->tri_area[i]);
+    const uint4* esrc = reinterpret_cast<const uint4*>(gp.entry_faces);
+    uint4* edst = reinterpret_cast<uint4*>(&gs->ef0);
+    for (uint32_t i = threadIdx.x; i < sizeof(EntryFaces) / 16; i += blockDim.x) edst[i] = esrc[i];
   }
   __syncthreads();
-  const bool fast_entry = gp.shape_cnt == 1u && gs->shape0.subtri_cnt <= kFastTris;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gp.count; k += gridDim.x * blockDim.x) {
     const uint32_t lo = gp.idx_lo + k;
     const uint32_t hi = gp.idx_hi + (lo < gp.idx_lo ? 1u : 0u);
@@ -733,17 +837,21 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
     }
     float dx, dy, dz;
     rot_apply_t(r.m, wx, wy, wz, dx, dy, dz);
+    // Geometry clock: one shape of the pool serves a block of 32 consecutive ray indices, as on the reference's
+    // CPU path (kSmallBatchRayNum, simulator.hpp:144-151). A warp therefore reads ONE shape's tables in every
+    // kernel of the hit loop (uniform addresses: broadcast loads) instead of 32 different ones.
     uint32_t sh = 0u;
     if (gp.shape_cnt > 1u) {
-      sh = min(static_cast<uint32_t>(draw(s0 ^ kNonceShape, lo, 0u) * static_cast<float>(gp.shape_cnt)), gp.shape_cnt - 1u);
+      sh = min(static_cast<uint32_t>(draw(s0 ^ kNonceShape, lo >> 5, 0u) * static_cast<float>(gp.shape_cnt)), gp.shape_cnt - 1u);
     }
     const HbCrystalTables* tab = gp.shape_cnt == 1u ? &gs->shape0 : gp.shapes + sh;
+    const EntryFaces* ef = gp.shape_cnt == 1u ? &gs->ef0 : gp.entry_faces + sh;
     float px = 0.0f, py = 0.0f, pz = 0.0f;
     uint32_t face = kFaceInvalid;
     if (tab->subtri_cnt == 0u) {
       weight = -1.0f;  // degenerate crystal: nothing to trace (zero-weight discard, simulator.cpp:149-159)
     } else {
-      if (fast_entry) sample_entry_fast(s, gs, dx, dy, dz, px, py, pz, face);
+      if (ef->group_cnt != 0u) sample_entry_faces(s, ef, tab, dx, dy, dz, px, py, pz, face);
       else sample_entry(s, tab, dx, dy, dz, px, py, pz, face);
     }
     const uint32_t slot = gp.slot0 + k;

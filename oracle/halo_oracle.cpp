@@ -169,29 +169,107 @@ void SampleSphCap(Stream& s, float lon, float lat, float half, float* d) {
 // Entry point: area x facing categorical pick over the fan table + uniform point in triangle
 // (InitRay_p_fid simulator.cpp:133-192; device twins categorical_sample / sample_triangle
 // pcg_shared.h:496-509,607-624).
-void SampleEntry(Stream& s, const HbCrystalTables& t, const float* d, float* p, uint16_t* face) {
-  float prob[HB_MAX_SUBTRIS];
-  uint32_t n = t.subtri_cnt;
-  float total = 0.0f;
-  for (uint32_t i = 0; i < n; i++) {
-    float dot = d[0] * t.tri_n[i][0] + d[1] * t.tri_n[i][1] + d[2] * t.tri_n[i][2];
-    prob[i] = std::fmax(-dot * t.tri_area[i], 0.0f);
-    total += prob[i];
+// The engine draws the triangle in two levels (face group, then triangle inside the group by cumulative area
+// fraction of the same uniform): the same distribution as the reference's categorical over all fan triangles,
+// because the triangles of one face share their normal. Groups = runs of consecutive triangles with the same
+// face id and normal; more than HB_MAX_FACES groups -> triangle-level categorical.
+struct EntryGroups {
+  float n[HB_MAX_FACES][3], area[HB_MAX_FACES];
+  float cum[HB_MAX_SUBTRIS];
+  uint32_t first[HB_MAX_FACES], cnt[HB_MAX_FACES], group_cnt;
+};
+EntryGroups BuildEntryGroups(const HbCrystalTables& t) {
+  EntryGroups eg;
+  std::memset(&eg, 0, sizeof(eg));
+  uint32_t g = 0;
+  for (uint32_t i = 0; i < t.subtri_cnt;) {
+    uint32_t j = i + 1;
+    while (j < t.subtri_cnt && t.tri_face[j] == t.tri_face[i] && std::fabs(t.tri_n[j][0] - t.tri_n[i][0]) <= 1e-4f &&
+           std::fabs(t.tri_n[j][1] - t.tri_n[i][1]) <= 1e-4f && std::fabs(t.tri_n[j][2] - t.tri_n[i][2]) <= 1e-4f)
+      j++;
+    if (g == HB_MAX_FACES) {
+      eg.group_cnt = 0;
+      return eg;
+    }
+    float area = 0.0f;
+    for (uint32_t k = i; k < j; k++) area += t.tri_area[k];
+    float run = 0.0f;
+    for (uint32_t k = i; k < j; k++) {
+      run += t.tri_area[k];
+      eg.cum[k] = area > 0.0f ? run / area : 1.0f;
+    }
+    for (int q = 0; q < 3; q++) eg.n[g][q] = t.tri_n[i][q];
+    eg.area[g] = area;
+    eg.first[g] = i;
+    eg.cnt[g] = j - i;
+    g++;
+    i = j;
   }
-  float u_cat = s.Next();
-  uint32_t tri = 0;
-  if (total > 0.0f) {
-    float target = u_cat * total;
-    float cum = 0.0f;
-    tri = n - 1;
+  eg.group_cnt = g;
+  return eg;
+}
+
+uint32_t PickEntryTriangle(Stream& s, const HbCrystalTables& t, const float* d, bool* grouped) {
+  const EntryGroups eg = BuildEntryGroups(t);
+  *grouped = eg.group_cnt != 0;
+  if (eg.group_cnt == 0) {  // triangle-level categorical (InitRay_p_fid, simulator.cpp:133-192)
+    float prob[HB_MAX_SUBTRIS];
+    uint32_t n = t.subtri_cnt;
+    float total = 0.0f;
     for (uint32_t i = 0; i < n; i++) {
-      cum += prob[i];
-      if (cum > target) {
-        tri = i;
-        break;
+      float dot = d[0] * t.tri_n[i][0] + d[1] * t.tri_n[i][1] + d[2] * t.tri_n[i][2];
+      prob[i] = std::fmax(-dot * t.tri_area[i], 0.0f);
+      total += prob[i];
+    }
+    float u_cat = s.Next();
+    uint32_t tri = 0;
+    if (total > 0.0f) {
+      float target = u_cat * total;
+      float cum = 0.0f;
+      tri = n - 1;
+      for (uint32_t i = 0; i < n; i++) {
+        cum += prob[i];
+        if (cum > target) {
+          tri = i;
+          break;
+        }
       }
     }
+    return tri;
   }
+  const uint32_t ng = eg.group_cnt;
+  float w[HB_MAX_FACES];
+  float total = 0.0f;
+  for (uint32_t g = 0; g < ng; g++) {
+    float dot = d[0] * eg.n[g][0] + d[1] * eg.n[g][1] + d[2] * eg.n[g][2];
+    w[g] = std::fmax(-dot * eg.area[g], 0.0f);
+    total += w[g];
+  }
+  float u_cat = s.Next();
+  if (!(total > 0.0f)) return 0;
+  float target = u_cat * total;
+  uint32_t sel = ng - 1;
+  float resid = 0.0f, w_sel = 0.0f, cum = 0.0f;
+  for (uint32_t g = 0; g < ng; g++) {
+    float c1 = cum + w[g];
+    if (c1 > target) {
+      sel = g;
+      resid = target - cum;
+      w_sel = w[g];
+      break;
+    }
+    cum = c1;
+  }
+  float r = w_sel > 0.0f ? resid / w_sel : 0.0f;
+  uint32_t t0 = eg.first[sel], c = eg.cnt[sel], tri = t0;
+  for (uint32_t j = 0; j + 1 < c; j++)
+    if (r >= eg.cum[t0 + j]) tri = t0 + j + 1;
+  return tri;
+}
+
+void SampleEntry(Stream& s, const HbCrystalTables& t, const float* d, float* p, uint16_t* face) {
+  bool grouped = false;
+  uint32_t tri = PickEntryTriangle(s, t, d, &grouped);
   float u = s.Next();
   float v = s.Next();
   if (u + v > 1.0f) {
@@ -583,7 +661,7 @@ int orc_gen_roots(const HbScene* scene, uint32_t layer, uint32_t pop_i, uint32_t
     ApplyRotT(m, dw, dl);
     uint32_t sh = 0;
     if (pop.shape_cnt > 1) {
-      sh = static_cast<uint32_t>(Draw(s0 ^ kNonceShape, lo, 0) * static_cast<float>(pop.shape_cnt));
+      sh = static_cast<uint32_t>(Draw(s0 ^ kNonceShape, lo >> 5, 0)  /* geometry clock: 32 rays per shape */ * static_cast<float>(pop.shape_cnt));
       if (sh >= pop.shape_cnt) sh = pop.shape_cnt - 1;
     }
     const HbCrystalTables& t = pop.shapes[sh];
@@ -625,7 +703,7 @@ int orc_transit(const HbScene* scene, uint32_t layer, uint32_t pop_i, uint32_t s
     ApplyRotT(m, d_world3 + i * 3, dl);
     uint32_t sh = 0;
     if (pop.shape_cnt > 1) {
-      sh = static_cast<uint32_t>(Draw(s0 ^ kNonceShape, lo, 0) * static_cast<float>(pop.shape_cnt));
+      sh = static_cast<uint32_t>(Draw(s0 ^ kNonceShape, lo >> 5, 0)  /* geometry clock: 32 rays per shape */ * static_cast<float>(pop.shape_cnt));
       if (sh >= pop.shape_cnt) sh = pop.shape_cnt - 1;
     }
     const HbCrystalTables& t = pop.shapes[sh];

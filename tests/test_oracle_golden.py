@@ -221,3 +221,55 @@ def test_rng_and_feistel_properties():
     for n in (1, 2, 3, 5, 17, 1000, 4097):
         perm = sorted(orc.orc_feistel(i, n, 12345) for i in range(n))
         assert perm == list(range(n))
+
+
+def test_entry_sampling_matches_analytic_distribution():
+    """Entry triangle / point sampling (two-level face-group categorical) against the analytic law the
+    reference samples from (InitRay_p_fid, simulator.cpp:133-192; test/support/incidence_sampling_oracle.hpp):
+    P(face f | d) = max(-d.n_f, 0) A_f / sum_g max(-d.n_g, 0) A_g and a uniform point on the face, i.e.
+    (a) every entry point lies on its face and inside the crystal, (b) face counts agree with the summed
+    per-ray probabilities within 4.5 sigma, (c) the mean entry point of a face is the polygon's centroid."""
+    import ctypes as C
+    import harness as H
+    import parity
+    from ice_halo_sim_b200 import backend as B
+    A = H.A
+    orc = H.oracle()
+    for pop in (parity.prism_pop(1.3, zenith=("gauss", 90, 0.3)), parity.pyramid_pop(),
+                parity.prism_pop(0.4, zenith=("uniform", 90, 360), face_dist=[parity.dist("none", c) for c in (1.0, 0.7, 1.2, 0.9, 1.1, 0.8)])):
+        tables = B.SceneTables(parity.scene([(0.0, [pop])], 3), 1)
+        t = tables.scene().layers[0].populations[0].shapes[0]
+        nf, nt = t.face_cnt, t.subtri_cnt
+        planes = np.ctypeslib.as_array(t.plane)[:nf].astype(np.float64)
+        tri_v = np.ctypeslib.as_array(t.tri_v)[:nt].astype(np.float64).reshape(nt, 3, 3)
+        tri_area = np.ctypeslib.as_array(t.tri_area)[:nt].astype(np.float64)
+        tri_face = np.ctypeslib.as_array(t.tri_face)[:nt]
+        n = 200000
+        wl = A.HbWlEntry(1.31, 1.0, 0, 0, 0)
+        d = np.zeros((n, 3), np.float32); p = np.zeros((n, 3), np.float32); w = np.zeros(n, np.float32)
+        f = np.zeros(n, np.uint16)
+        orc.orc_gen_roots(tables.scene_ptr, 0, 0, 0, C.byref(wl), 1, 99, 0, n, H.ptr(d), H.ptr(p), H.ptr(w), H.ptr(f),
+                          None, None, None, None)
+        assert (f < nf).all()
+        # (a) on the face, inside all other half-spaces
+        s = p.astype(np.float64) @ planes[:, :3].T + planes[:, 3]
+        assert np.abs(s[np.arange(n), f]).max() < 2e-6
+        assert s.max() < 2e-6
+        # (b) face frequencies
+        area_f = np.array([tri_area[tri_face == k].sum() for k in range(nf)])
+        wgt = np.maximum(-(d.astype(np.float64) @ planes[:, :3].T), 0.0) * area_f
+        prob = wgt / wgt.sum(axis=1, keepdims=True)
+        exp = prob.sum(axis=0)
+        sig = np.sqrt((prob * (1 - prob)).sum(axis=0)) + 1e-9
+        cnt = np.bincount(f, minlength=nf)[:nf]
+        assert (np.abs(cnt - exp) < 4.5 * sig + 1).all(), (cnt, exp, sig)
+        # (c) centroid of the entry points of each well-populated face = area-weighted triangle centroid
+        for k in range(nf):
+            sel = f == k
+            if sel.sum() < 3000:
+                continue
+            tris = tri_face == k
+            cen = (tri_v[tris].mean(axis=1) * tri_area[tris, None]).sum(axis=0) / tri_area[tris].sum()
+            got = p[sel].astype(np.float64).mean(axis=0)
+            spread = p[sel].astype(np.float64).std(axis=0).max()
+            assert np.abs(got - cen).max() < 5.0 * spread / np.sqrt(sel.sum()) + 1e-6, (k, got, cen)
