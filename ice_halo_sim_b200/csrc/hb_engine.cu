@@ -274,7 +274,7 @@ void launch_optics_t(HbEngine* h, size_t smem, const TraceParams& tp) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(optics_kernel<G, L, S, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(shared_tables_bytes(kSmemShapes) + kCacheBytes));
+                         static_cast<int>(shared_tables_bytes(kSmemShapes) + kCacheBytes + kStageBytes));
     attr_set = true;
   }
   const uint32_t grid = resident_grid(h, optics_kernel<G, L, S, M, P>, smem, tp.cap);
@@ -678,7 +678,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
     tp.hit = hit;
     const bool last = hit + 1 == h->max_hits;
     EventPair* ev = begin_event(h, 1, n);
-    launch_optics(h, general, last, in_smem, L.p4 && h->p4_enable, smem + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
+    launch_optics(h, general, last, in_smem, L.p4 && h->p4_enable, smem + kStageBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
     end_event(h, ev);
     h->ctr.kernel_launches++;
     h->ctr.optics_launches++;

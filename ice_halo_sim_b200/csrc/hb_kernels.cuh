@@ -519,6 +519,23 @@ HB_DEV void fork_append(const TraceParams& tp, uint32_t slot, uint32_t bits, flo
 // ------------------------------------------------------------------------------------------------
 // optics kernel: one surface interaction per live ray
 // ------------------------------------------------------------------------------------------------
+#ifndef HB_ASYNC_STAGE
+#define HB_ASYNC_STAGE 1
+#endif
+#if HB_ASYNC_STAGE
+constexpr uint32_t kStageBytes = 2u * 3u * 256u * 16u;  // two stages x (D, P, Q) x 256 threads x 16 B
+#else
+constexpr uint32_t kStageBytes = 0u;
+#endif
+HB_DEV void cp_async16(uint32_t saddr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+HB_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+HB_DEV void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 #ifndef HB_OPTICS_MINB
 #define HB_OPTICS_MINB 4
 #endif
@@ -531,11 +548,39 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
   Tally tally;
   const bool use_cache = (tp.flags & kFlagPixelCache) != 0u;
   if (use_cache) cache_init(tally, smem_raw);
-  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + (use_cache ? kCacheBytes : 0), GENERAL);
+  // dynamic shared memory: [pixel cache] [ray staging] [crystal tables]
+  const uint32_t stage_off = use_cache ? static_cast<uint32_t>(kCacheBytes) : 0u;
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + stage_off + kStageBytes, GENERAL);
   if (!SMEM && use_cache) __syncthreads();
   const uint32_t total = tp.n_main + *tp.fork_snapshot;
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+#if HB_ASYNC_STAGE
+  // Software pipeline through shared memory: the next ray's state (D, P, Q) is copied global -> shared with
+  // cp.async (LDGSTS, no registers in flight) while this ray is computed; every thread reads back only the
+  // 48 bytes it requested itself, so cp.async.wait_group is the only synchronisation. The orientation
+  // quaternion stays in shared memory until an exit actually needs it.
+  const uint32_t stage0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw + stage_off)) + threadIdx.x * 16u;
+  uint32_t stage = 0u;
+  if (i < total) {
+    cp_async16(stage0, tp.D + i);
+    cp_async16(stage0 + 4096u, tp.P + i);
+    cp_async16(stage0 + 8192u, tp.Q + i);
+  }
+  cp_async_commit();
+  while (i < total) {
+    const uint32_t i_next = i + stride;
+    const uint32_t cur = stage0 + stage * 12288u, nxt = stage0 + (stage ^ 1u) * 12288u;
+    if (i_next < total) {
+      cp_async16(nxt, tp.D + i_next);
+      cp_async16(nxt + 4096u, tp.P + i_next);
+      cp_async16(nxt + 8192u, tp.Q + i_next);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    const float4 d4 = lds128(cur), p4 = lds128(cur + 4096u);
+#define HB_LOAD_Q() lds128(cur + 8192u)
+#else
   // software pipeline: the next ray's state is in flight while this one is being computed
   float4 d4 = make_float4(0.f, 0.f, 0.f, -1.f), p4 = d4, q = d4;
   if (i < total) {
@@ -551,6 +596,8 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
       p_n = tp.P[i_next];
       q_n = tp.Q[i_next];
     }
+#define HB_LOAD_Q() q
+#endif
     const uint32_t bits = __float_as_uint(p4.w);
     const uint32_t face = bits_face(bits);
     if (d4.w >= 0.0f && face != kFaceInvalid) {  // else: terminated ray
@@ -584,9 +631,9 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
             nf = slab_exit<true>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
         }
         if (nf == kFaceInvalid) {
-          emit_exit<GENERAL, MULTI>(tp, i, bits, q, ox, oy, oz, ow, /*role=*/0u, tb, tally);
+          emit_exit<GENERAL, MULTI>(tp, i, bits, HB_LOAD_Q(), ox, oy, oz, ow, /*role=*/0u, tb, tally);
         } else if (!LAST) {
-          fork_append<GENERAL>(tp, i, bits, q, nx, ny, nz, ox, oy, oz, ow, nf);  // near-edge leak: both children stay
+          fork_append<GENERAL>(tp, i, bits, HB_LOAD_Q(), nx, ny, nz, ox, oy, oz, ow, nf);  // near-edge leak: both children stay
         }
       }
       if (LAST) {
@@ -595,17 +642,22 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
           float nx, ny, nz;
           const uint32_t nf = P4 ? slab_exit_p4<false>(axes, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz)
                                  : slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
-          if (nf == kFaceInvalid) emit_exit<GENERAL, MULTI>(tp, i, bits, q, ix, iy, iz, iw, /*role=*/1u, tb, tally);
+          if (nf == kFaceInvalid) emit_exit<GENERAL, MULTI>(tp, i, bits, HB_LOAD_Q(), ix, iy, iz, iw, /*role=*/1u, tb, tally);
         }
       } else {
         tp.D[i] = make_float4(ix, iy, iz, iw);  // iw < 0 (TIR sentinel) terminates the ray
       }
     }
+#if HB_ASYNC_STAGE
+    stage ^= 1u;
+#else
     d4 = d_n;
     p4 = p_n;
     q = q_n;
+#endif
     i = i_next;
   }
+#undef HB_LOAD_Q
   if (use_cache) cache_flush(tp, tally);
   if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
     atomicAdd(tp.stat_exit_count, tally.exits);
