@@ -1027,7 +1027,8 @@ int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats) {
   }
   if (n >= (1ull << 31)) return fail(h, HB_ERR_CAPACITY, "one TraceLayer call is limited to 2^31 - 1 rays; split the batch");
   const bool last_layer = li + 1 == h->layers.size();
-  const uint32_t flags = session_flags(h, L, last_layer);
+  uint32_t flags = session_flags(h, L, last_layer);
+  if (stats != nullptr) flags |= kFlagStats;  // LayerStats asked for: count exits and their weight (general kernels)
 
   // PartitionCrystalRayNum: contiguous index range per population
   std::vector<uint64_t> counts(L.pops.size(), 0), pop_begin(L.pops.size() + 1, 0);
