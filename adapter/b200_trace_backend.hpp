@@ -58,9 +58,12 @@ class B200TraceBackend : public TraceBackend {
   void BeginSession(const SessionSpec& spec) override {
     try {
       raypath_color_ = spec.raypath_color;
-      if (spec.scene != scene_ || raypath_color_ != color_uploaded_ || SceneHasStochasticShapes(*spec.scene)) {
+      if (spec.scene != scene_ || raypath_color_ != color_uploaded_) {
         UploadScene(*spec.scene);
       }
+      // Stochastic geometry: a fresh pool of kPoolShapes crystals per population and session, drawn and built
+      // on the device (hb_resample_shapes) -- the host no longer calls MakeCrystal per session.
+      ResampleStochasticPools(*spec.scene, spec.seed);
       if (spec.render != render_ || render_snapshot_dirty_) {
         UploadRender(*spec.render);
       }
@@ -156,6 +159,60 @@ class B200TraceBackend : public TraceBackend {
       }
     }
     return false;
+  }
+
+  static HbDist ToHbDist(const Distribution& d) {
+    static_assert(static_cast<int>(DistributionType::kNoRandom) == HB_DIST_NO_RANDOM &&
+                      static_cast<int>(DistributionType::kUniform) == HB_DIST_UNIFORM &&
+                      static_cast<int>(DistributionType::kGaussian) == HB_DIST_GAUSSIAN &&
+                      static_cast<int>(DistributionType::kZigzag) == HB_DIST_ZIGZAG &&
+                      static_cast<int>(DistributionType::kLaplacian) == HB_DIST_LAPLACIAN &&
+                      static_cast<int>(DistributionType::kGaussianLegacy) == HB_DIST_GAUSSIAN_LEGACY,
+                  "DistributionType order");
+    return HbDist{ static_cast<uint32_t>(d.type), d.center, d.spread };
+  }
+
+  // CrystalParam -> the shape part of HbCrystalDesc (distributions of the shape scalars + sync groups,
+  // crystal_config.hpp:62-76); the axis part is not needed for resampling.
+  static HbCrystalDesc ToCrystalDesc(const CrystalConfig& cfg) {
+    HbCrystalDesc d{};
+    d.id = cfg.id_;
+    static_assert(kShapeScalarCount == 10, "HbCrystalDesc::sync_group follows the ShapeScalar order");
+    if (const auto* prism = std::get_if<PrismCrystalParam>(&cfg.param_)) {
+      d.kind = 0;
+      d.height[0] = ToHbDist(prism->h_);
+      for (int i = 0; i < 6; i++) d.face_dist[i] = ToHbDist(prism->d_[i]);
+      for (int i = 0; i < kShapeScalarCount; i++) d.sync_group[i] = prism->sync_group_[i];
+    } else {
+      const auto& pyr = std::get<PyramidCrystalParam>(cfg.param_);
+      d.kind = 1;
+      d.height[0] = ToHbDist(pyr.h_pyr_u_);
+      d.height[1] = ToHbDist(pyr.h_prs_);
+      d.height[2] = ToHbDist(pyr.h_pyr_l_);
+      for (int i = 0; i < 6; i++) d.face_dist[i] = ToHbDist(pyr.d_[i]);
+      for (int i = 0; i < kShapeScalarCount; i++) d.sync_group[i] = pyr.sync_group_[i];
+      d.wedge_upper_deg = pyr.wedge_angle_u_;
+      d.wedge_lower_deg = pyr.wedge_angle_l_;
+    }
+    return d;
+  }
+
+  void ResampleStochasticPools(const SceneConfig& scene, uint32_t seed) {
+    stochastic_shapes_last_upload_ = 0;
+    for (size_t li = 0; li < scene.ms_.size(); li++) {
+      for (size_t ci = 0; ci < scene.ms_[li].setting_.size(); ci++) {
+        const ScatteringSetting& st = scene.ms_[li].setting_[ci];
+        if (IsDeterministic(st.crystal_.param_)) {
+          continue;
+        }
+        const HbCrystalDesc desc = ToCrystalDesc(st.crystal_);
+        uint32_t rejected = 0;
+        Check(hb_resample_shapes(h_, static_cast<uint32_t>(li), static_cast<uint32_t>(ci), &desc, seed, geom_draws_, &rejected),
+              "ResampleShapes");
+        geom_draws_ += kPoolShapes;
+        stochastic_shapes_last_upload_ += kPoolShapes;
+      }
+    }
   }
 
   static void FillTables(const Crystal& c, HbCrystalTables* out) {
@@ -289,9 +346,9 @@ class B200TraceBackend : public TraceBackend {
   }
 
   void UploadScene(const SceneConfig& scene) {
-    // Geometry pool per stochastic population: kPoolShapes shapes drawn with MakeCrystal, per-ray pick on the
-    // device (the reference GPU backends' K-shape pool, cuda_trace_backend.cu:1527-1554).
-    constexpr uint32_t kPoolShapes = 256;
+    // Geometry pool per stochastic population: kPoolShapes slots (filled here once with MakeCrystal so the
+    // filter / colour descriptors have a crystal to probe; redrawn on the device at every BeginSession), one
+    // shape per 32 consecutive rays (the CPU path's geometry clock, simulator.hpp:144-151).
     std::vector<HbLayer> layers(scene.ms_.size());
     std::vector<std::vector<HbCrystalPopulation>> pops(scene.ms_.size());
     std::vector<std::unique_ptr<std::vector<HbCrystalTables>>> shapes;
@@ -420,6 +477,8 @@ class B200TraceBackend : public TraceBackend {
   size_t layer_cnt_ = 0;
   size_t layer_idx_ = 0;
   size_t stochastic_shapes_last_upload_ = 0;
+  static constexpr uint32_t kPoolShapes = 256;
+  uint32_t geom_draws_ = 0;  // monotone shape-stream index: every session draws new crystals
 };
 
 }  // namespace lumice

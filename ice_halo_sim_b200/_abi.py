@@ -132,7 +132,7 @@ class HbDist(C.Structure):
 class HbCrystalDesc(C.Structure):
     _fields_ = [("kind", u32), ("id", u32), ("height", HbDist * 3), ("face_dist", HbDist * 6),
                 ("wedge_upper_deg", f32), ("wedge_lower_deg", f32),
-                ("latitude", HbDist), ("azimuth", HbDist), ("roll", HbDist)]
+                ("latitude", HbDist), ("azimuth", HbDist), ("roll", HbDist), ("sync_group", i32 * 10)]
 
 
 class HbSimpleFilterSpec(C.Structure):

@@ -298,6 +298,27 @@ class B200TraceBackend:
                                           xyz.ctypes.data if want_xyz else None, C.byref(inten)))
         return rgb, xyz, inten.value
 
+    # ---- stochastic geometry pool on the device ----
+    def ResampleShapes(self, layer, population, crystal: A.HbCrystalDesc, seed, draw_base=0):
+        """Redraw every shape of one population's pool on the device (hb_resample_shapes): shape scalars from
+        `crystal`'s height / face-distance distributions, tables built by the code hb_make_prism/pyramid run.
+        Returns the number of shapes the builder rejected (they become empty crystals)."""
+        rejected = C.c_uint32()
+        self._check(self._lib.hb_resample_shapes(self._h, int(layer), int(population), C.byref(crystal), int(seed),
+                                                 int(draw_base), C.byref(rejected)))
+        return rejected.value
+
+    def ExportShapes(self, layer, population):
+        """Parity helper: (HbCrystalTables array, scalars [n, 10] = h1, h2, h3, d0..d5, builder status)."""
+        cnt = C.c_uint32()
+        self._check(self._lib.hb_export_shapes(self._h, int(layer), int(population), 0, None, None, C.byref(cnt)))
+        n = cnt.value
+        tables = (A.HbCrystalTables * n)()
+        scalars = np.zeros((n, 10), np.float32)
+        self._check(self._lib.hb_export_shapes(self._h, int(layer), int(population), n, tables, scalars.ctypes.data,
+                                               C.byref(cnt)))
+        return tables, scalars
+
     # ---- tuning / measurement ----
     def SetOption(self, key, value):
         self._check(self._lib.hb_set_option(self._h, key.encode(), int(value)))

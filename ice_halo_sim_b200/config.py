@@ -32,6 +32,49 @@ def _miller_to_alpha(i1, i4):
     return math.degrees(math.atan(0.866025403784 * i4 / i1 / 1.629))
 
 
+def _sync_groups(d, sg):
+    """Optional "sync_group" sub-map of a crystal shape (ReadSyncGroupJson + PrepareSyncGroups,
+    crystal_config.cpp:47-146,179-205): scalars sharing a non-zero id share one draw per crystal instance.
+    Slots this crystal type lacks and single-member groups are zeroed, survivors renumbered 1..N by first
+    appearance, and every member takes its group leader's distribution."""
+    slots = [0] * 10
+    if sg:
+        keys = {"height": 0} if d.kind == 0 else {"upper_h": 1, "prism_h": 2, "lower_h": 3}
+        for k, slot in keys.items():
+            if k in sg:
+                slots[slot] = int(sg[k])
+        for i, e in enumerate(list(sg.get("face_distance", []))[:6]):
+            slots[4 + i] = int(e)
+    owned = ([0] if d.kind == 0 else [1, 2, 3]) + list(range(4, 10))
+    slots = [g if i in owned else 0 for i, g in enumerate(slots)]
+    slots = [g if g != 0 and slots.count(g) > 1 else 0 for g in slots]
+    remap = {}
+    for i, g in enumerate(slots):
+        if g != 0:
+            slots[i] = remap.setdefault(g, len(remap) + 1)
+
+    def dist_of(slot):
+        return d.face_dist[slot - 4] if slot >= 4 else d.height[0 if slot == 0 else slot - 1]
+
+    def set_dist(slot, v):
+        if slot >= 4:
+            d.face_dist[slot - 4] = v
+        else:
+            d.height[0 if slot == 0 else slot - 1] = v
+
+    leader = {}
+    for i, g in enumerate(slots):
+        if g == 0:
+            continue
+        if g in leader:
+            src = dist_of(leader[g])
+            set_dist(i, A.HbDist(src.type, src.center, src.spread))
+        else:
+            leader[g] = i
+    for i, g in enumerate(slots):
+        d.sync_group[i] = g
+
+
 def crystal_desc(c):
     d = A.HbCrystalDesc()
     d.id = int(c["id"])
@@ -65,6 +108,7 @@ def crystal_desc(c):
                 d.wedge_lower_deg = alpha
     else:
         raise ValueError(f"unknown crystal type {c['type']!r}")
+    _sync_groups(d, shape.get("sync_group"))
     axis = c.get("axis")
     if axis is None:  # AxisDistribution default: zenith 0 (latitude 90), no randomness (math.cpp:536-538)
         d.latitude = A.HbDist(0, 90.0, 0.0)

@@ -57,6 +57,8 @@ struct PopHost {
   uint32_t shape_base, shape_cnt;
   AxisParams axis;
   bool has_filter;
+  bool p4;  // every shape of this population's pool is a full hexagonal prism
+  bool device_pool;  // pool last drawn by hb_resample_shapes (scalars available for export)
 };
 
 struct LayerDev {
@@ -72,6 +74,7 @@ struct LayerDev {
   DevBuf<uint8_t> face_fn;
   DevBuf<HbCrystalTables> shapes;
   DevBuf<EntryFaces> entry_faces;  // [shape] face groups of the entry fan table
+  DevBuf<float> geom_scalars;      // [shape][10] scalars of device-drawn shapes (hb_resample_shapes; parity export)
   DevBuf<HbFilterDesc> filters;
   DevBuf<uint32_t> pop_crystal_id;
   DevBuf<float> luts;  // [pop][3][257]
@@ -178,6 +181,7 @@ struct HbEngine {
   size_t ev_used = 0;
   int blocks_per_sm = 8;
   int blocks_per_sm_override = 0;
+  DevBuf<uint32_t> geom_flags;
   bool p4_enable = true;  // option "prism_fast_path": 0 forces the generic axis-loop kernels (A/B tests)
   bool pixel_cache = true;
 #ifdef HB_WITH_NCCL
@@ -338,38 +342,6 @@ void launch_intersect(HbEngine* h, bool general, bool in_smem, bool p4, size_t s
 
 size_t trace_smem(const LayerDev& L) { return shared_tables_bytes(L.shape_cnt); }
 
-// Face groups of one shape's entry fan table (see EntryFaces): runs of consecutive triangles that share
-// the face id and the normal; per triangle the cumulative area fraction inside its run.
-EntryFaces build_entry_faces(const HbCrystalTables& t) {
-  EntryFaces ef;
-  std::memset(&ef, 0, sizeof(ef));
-  uint32_t g = 0;
-  for (uint32_t i = 0; i < t.subtri_cnt;) {
-    uint32_t j = i + 1;
-    while (j < t.subtri_cnt && t.tri_face[j] == t.tri_face[i] && std::fabs(t.tri_n[j][0] - t.tri_n[i][0]) <= 1e-4f &&
-           std::fabs(t.tri_n[j][1] - t.tri_n[i][1]) <= 1e-4f && std::fabs(t.tri_n[j][2] - t.tri_n[i][2]) <= 1e-4f)
-      j++;
-    if (g == HB_MAX_FACES) {  // cannot happen for the reference's crystals; keep the triangle-level sampler
-      ef.group_cnt = 0;
-      return ef;
-    }
-    float area = 0.0f;
-    for (uint32_t k = i; k < j; k++) area += t.tri_area[k];
-    float run = 0.0f;
-    for (uint32_t k = i; k < j; k++) {
-      run += t.tri_area[k];
-      ef.cum[k] = area > 0.0f ? run / area : 1.0f;
-    }
-    ef.na[g] = make_float4(t.tri_n[i][0], t.tri_n[i][1], t.tri_n[i][2], area);
-    ef.first[g] = static_cast<uint8_t>(i);
-    ef.cnt[g] = static_cast<uint8_t>(j - i);
-    g++;
-    i = j;
-  }
-  ef.group_cnt = g;
-  return ef;
-}
-
 int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   L->prob = src.prob;
   L->pops.clear();
@@ -398,43 +370,22 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
     ph.axis = AxisParams{ p.axis.lat_path, p.axis.lat_mean, p.axis.lat_std, p.axis.az_type, p.axis.az_mean, p.axis.az_std,
                           p.axis.roll_type, p.axis.roll_mean, p.axis.roll_std, p.axis.lut_n };
     ph.has_filter = p.filter.kind != 0;
+    ph.p4 = true;
     L->any_filter = L->any_filter || ph.has_filter;
     for (uint32_t s = 0; s < p.shape_cnt; s++) {
       const HbCrystalTables& t = p.shapes[s];
       if (t.face_cnt > HB_MAX_FACES || t.subtri_cnt > HB_MAX_SUBTRIS) return fail(h, HB_ERR_INVALID_ARG, "crystal table too large");
       shapes.push_back(t);
-      entry_faces.push_back(build_entry_faces(t));
-      for (uint32_t f = 0; f < HB_MAX_FACES; f++) {
-        planes.push_back(make_float4(t.plane[f][0], t.plane[f][1], t.plane[f][2], t.plane[f][3]));
-        fn.push_back(t.face_fn[f]);
-      }
-      // Axis table: faces whose unit normals are exact negatives share one entry (see slab_exit).
-      uint32_t axis_cnt = 0;
-      bool used[HB_MAX_FACES] = {};
-      const size_t ax0 = axes.size();
-      axes.resize(ax0 + HB_MAX_FACES * 2, make_float4(0.f, 0.f, 0.f, 0.f));
-      for (uint32_t f = 0; f < t.face_cnt; f++) {
-        if (used[f]) continue;
-        used[f] = true;
-        uint32_t partner = kFaceInvalid;
-        for (uint32_t g = f + 1; g < t.face_cnt; g++) {
-          if (!used[g] && t.plane[g][0] == -t.plane[f][0] && t.plane[g][1] == -t.plane[f][1] && t.plane[g][2] == -t.plane[f][2]) {
-            partner = g;
-            used[g] = true;
-            break;
-          }
-        }
-        const uint32_t fbits = f | (partner << 8);
-        float fb;
-        std::memcpy(&fb, &fbits, 4);
-        axes[ax0 + 2 * axis_cnt] = make_float4(t.plane[f][0], t.plane[f][1], t.plane[f][2], t.plane[f][3]);
-        axes[ax0 + 2 * axis_cnt + 1] = make_float4(partner == kFaceInvalid ? 0.0f : t.plane[partner][3], fb, 0.f, 0.f);
-        axis_cnt++;
-        if (partner == kFaceInvalid) L->p4 = false;
-      }
-      if (axis_cnt != 4u) L->p4 = false;
-      meta.push_back(t.face_cnt | (ci << 8) | (axis_cnt << 16));
+      planes.resize(planes.size() + HB_MAX_FACES);
+      fn.resize(fn.size() + HB_MAX_FACES);
+      axes.resize(axes.size() + HB_MAX_FACES * 2);
+      meta.push_back(0u);
+      entry_faces.emplace_back();
+      if (!derive_shape_tables(t, ci, &planes[planes.size() - HB_MAX_FACES], &fn[fn.size() - HB_MAX_FACES],
+                               &axes[axes.size() - HB_MAX_FACES * 2], &meta.back(), &entry_faces.back()))
+        ph.p4 = false;
     }
+    L->p4 = L->p4 && ph.p4;
     filters.push_back(p.filter);
     cid.push_back(p.crystal_id);
     if (p.color_group_cnt > HB_MAX_COLOR_GROUPS) return fail(h, HB_ERR_INVALID_ARG, "population: too many colour groups");
@@ -783,6 +734,7 @@ void hb_destroy(HbEngine* h) {
     L->planes.release();
     L->axes.release();
     L->entry_faces.release();
+    L->geom_scalars.release();
     L->shape_meta.release();
     L->face_fn.release();
     L->shapes.release();
@@ -1278,6 +1230,74 @@ int hb_set_option(HbEngine* h, const char* key, int64_t value) {
     for (auto& L : h->layers) std::fill(L->carry.begin(), L->carry.end(), 0.0);
   } else {
     return fail(h, HB_ERR_INVALID_ARG, "unknown option " + k);
+  }
+  return HB_OK;
+}
+
+int hb_resample_shapes(HbEngine* h, uint32_t layer, uint32_t population, const HbCrystalDesc* crystal, uint32_t seed,
+                       uint32_t draw_base, uint32_t* rejected) {
+  if (h == nullptr || crystal == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->have_scene) return fail(h, HB_ERR_STATE, "resample_shapes before hb_set_scene");
+  if (h->in_session) return fail(h, HB_ERR_STATE, "resample_shapes inside a session");
+  if (layer >= h->layers.size() || population >= h->layers[layer]->pops.size())
+    return fail(h, HB_ERR_INVALID_ARG, "resample_shapes: no such layer / population");
+  if (crystal->kind > 1u) return fail(h, HB_ERR_INVALID_ARG, "resample_shapes: crystal kind must be prism (0) or pyramid (1)");
+  cudaSetDevice(h->device);
+  LayerDev& L = *h->layers[layer];
+  PopHost& ph = L.pops[population];
+  HB_CUDA(h, L.geom_scalars.ensure(static_cast<size_t>(L.shape_cnt) * 10));
+  HB_CUDA(h, h->geom_flags.ensure(2));
+  HB_CUDA(h, cudaMemsetAsync(h->geom_flags.p, 0, 2 * sizeof(uint32_t), h->stream));
+  ShapeGenParams sp{};
+  sp.desc = *crystal;
+  sp.a1 = crystal->kind == 1u ? hb_pyramid_slope(crystal->wedge_upper_deg) : -1.0;
+  sp.a2 = crystal->kind == 1u ? hb_pyramid_slope(crystal->wedge_lower_deg) : -1.0;
+  sp.seed = seed ^ kNonceGeom;
+  sp.draw_base = draw_base;
+  sp.count = ph.shape_cnt;
+  sp.pop = population;
+  sp.shapes = L.shapes.p + ph.shape_base;
+  sp.planes = L.planes.p + static_cast<size_t>(ph.shape_base) * HB_MAX_FACES;
+  sp.axes = L.axes.p + static_cast<size_t>(ph.shape_base) * HB_MAX_FACES * 2;
+  sp.meta = L.shape_meta.p + ph.shape_base;
+  sp.fn = L.face_fn.p + static_cast<size_t>(ph.shape_base) * HB_MAX_FACES;
+  sp.ef = L.entry_faces.p + ph.shape_base;
+  sp.scalars = L.geom_scalars.p + static_cast<size_t>(ph.shape_base) * 10;
+  sp.flags = h->geom_flags.p;
+  resample_shapes_kernel<<<(sp.count + 63u) / 64u, 64, 0, h->stream>>>(sp);
+  h->ctr.kernel_launches++;
+  HB_CUDA(h, cudaGetLastError());
+  uint32_t flags[2] = { 0, 0 };
+  HB_CUDA(h, cudaMemcpyAsync(flags, h->geom_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  ph.p4 = flags[0] == 0u;
+  ph.device_pool = true;
+  L.p4 = true;
+  for (const PopHost& q : L.pops) L.p4 = L.p4 && q.p4;
+  if (rejected != nullptr) *rejected = flags[1];
+  return HB_OK;
+}
+
+int hb_export_shapes(HbEngine* h, uint32_t layer, uint32_t population, uint32_t cap, HbCrystalTables* tables,
+                     float* scalars10, uint32_t* count) {
+  if (h == nullptr || count == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->have_scene || layer >= h->layers.size() || population >= h->layers[layer]->pops.size())
+    return fail(h, HB_ERR_INVALID_ARG, "export_shapes: no such layer / population");
+  cudaSetDevice(h->device);
+  LayerDev& L = *h->layers[layer];
+  const PopHost& ph = L.pops[population];
+  *count = ph.shape_cnt;
+  if (tables == nullptr) return HB_OK;
+  if (cap < ph.shape_cnt) return fail(h, HB_ERR_CAPACITY, "export_shapes: caller buffer too small");
+  HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  HB_CUDA(h, cudaMemcpy(tables, L.shapes.p + ph.shape_base, ph.shape_cnt * sizeof(HbCrystalTables), cudaMemcpyDeviceToHost));
+  if (scalars10 != nullptr) {
+    if (ph.device_pool) {
+      HB_CUDA(h, cudaMemcpy(scalars10, L.geom_scalars.p + static_cast<size_t>(ph.shape_base) * 10,
+                            static_cast<size_t>(ph.shape_cnt) * 10 * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+      std::memset(scalars10, 0, static_cast<size_t>(ph.shape_cnt) * 10 * sizeof(float));
+    }
   }
   return HB_OK;
 }

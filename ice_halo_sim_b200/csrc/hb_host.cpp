@@ -16,6 +16,7 @@
 
 #include "halotrace_b200.h"
 #include "hb_filter.h"
+#include "hb_geometry.h"
 
 namespace hb {
 
@@ -31,219 +32,6 @@ constexpr float kPiF = 3.14159265359f;           // reference math::kPi (src/cor
 constexpr float kDeg2RadF = kPiF / 180.0f;       // math::kDegreeToRad
 constexpr float kSqrt3F = 1.73205080757f;        // math::kSqrt3
 constexpr float kFloatEps = 1e-5f;               // math::kFloatEps
-constexpr double kSqrt3Half = 0.86602540378443864676;
-// Hexagon face-normal directions (theta_i = i*60 deg) and corner directions (i*60 - 30 deg),
-// reference: geo3d_closedform.hpp:12-19.
-const double kFaceCos[6] = { 1.0, 0.5, -0.5, -1.0, -0.5, 0.5 };
-const double kFaceSin[6] = { 0.0, kSqrt3Half, kSqrt3Half, 0.0, -kSqrt3Half, -kSqrt3Half };
-const double kVtxCos[6] = { kSqrt3Half, kSqrt3Half, 0.0, -kSqrt3Half, -kSqrt3Half, 0.0 };
-const double kVtxSin[6] = { -0.5, 0.5, 1.0, 0.5, -0.5, -1.0 };
-
-struct V3 {
-  double x, y, z;
-};
-V3 operator+(V3 a, V3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
-V3 operator-(V3 a, V3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
-V3 operator*(V3 a, double s) { return { a.x * s, a.y * s, a.z * s }; }
-double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-V3 cross(V3 a, V3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
-
-// A convex crystal given as up to 20 half-spaces coef.(x,y,z,1) <= 0 in the reference's slot order
-// (0,1 basal; 2-7 prism; 8-13 upper pyramid; 14-19 lower pyramid; crystal.cpp:326-346).
-struct PlaneSet {
-  int slot_cnt = 0;
-  float coef[HB_MAX_FACES][4]{};
-  float unit_n[HB_MAX_FACES][3]{};
-  int face_number[HB_MAX_FACES]{};
-  bool candidate[HB_MAX_FACES]{};
-};
-
-// Clip a convex polygon (3-D points on a plane) by the half-space c.(p,1) <= 0 (Sutherland-Hodgman).
-void ClipPolygon(std::vector<V3>& poly, const double c[4], double tol) {
-  if (poly.empty()) return;
-  std::vector<V3> out;
-  size_t n = poly.size();
-  for (size_t i = 0; i < n; i++) {
-    V3 a = poly[i], b = poly[(i + 1) % n];
-    double fa = c[0] * a.x + c[1] * a.y + c[2] * a.z + c[3];
-    double fb = c[0] * b.x + c[1] * b.y + c[2] * b.z + c[3];
-    bool ina = fa <= tol, inb = fb <= tol;
-    if (ina) out.push_back(a);
-    if (ina != inb) {
-      double t = fa / (fa - fb);
-      out.push_back(a + (b - a) * t);
-    }
-  }
-  poly.swap(out);
-}
-
-void DedupRing(std::vector<V3>& poly, double tol) {
-  std::vector<V3> out;
-  for (const V3& p : poly) {
-    if (!out.empty()) {
-      V3 d = p - out.back();
-      if (std::sqrt(dot(d, d)) < tol) continue;
-    }
-    out.push_back(p);
-  }
-  while (out.size() > 1) {
-    V3 d = out.front() - out.back();
-    if (std::sqrt(dot(d, d)) < tol) out.pop_back(); else break;
-  }
-  poly.swap(out);
-}
-
-// Face polygons of the intersection of the candidate half-spaces, each CCW seen from outside.
-// Produces the compact present-face tables + the entry fan table (BuildEntrySubTris convention:
-// fan (0,k,k+1), raw-winding normal, area = |cross|/2; simulator.cpp:90-129).
-int BuildTablesFromPlanes(const PlaneSet& ps, HbCrystalTables* out) {
-  std::memset(out, 0, sizeof(*out));
-  uint32_t face = 0, tri = 0;
-  for (int s = 0; s < ps.slot_cnt; s++) {
-    if (!ps.candidate[s]) continue;
-    V3 n{ ps.coef[s][0], ps.coef[s][1], ps.coef[s][2] };
-    double mag = std::sqrt(dot(n, n));
-    if (!(mag > 0)) continue;
-    V3 nu = n * (1.0 / mag);
-    double d0 = ps.coef[s][3] / mag;
-    V3 origin = nu * (-d0);
-    V3 helper = std::fabs(nu.z) < 0.9 ? V3{ 0, 0, 1 } : V3{ 1, 0, 0 };
-    V3 t1 = cross(helper, nu);
-    t1 = t1 * (1.0 / std::sqrt(dot(t1, t1)));
-    V3 t2 = cross(nu, t1);  // t1 x t2 = nu  => (t1,t2)-CCW is CCW seen from outside
-    const double big = 1.0e3;
-    std::vector<V3> poly = { origin + t1 * (-big) + t2 * (-big), origin + t1 * big + t2 * (-big),
-                             origin + t1 * big + t2 * big, origin + t1 * (-big) + t2 * big };
-    for (int j = 0; j < ps.slot_cnt && !poly.empty(); j++) {
-      if (j == s || !ps.candidate[j]) continue;
-      double c[4] = { ps.coef[j][0], ps.coef[j][1], ps.coef[j][2], ps.coef[j][3] };
-      double cm = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
-      if (!(cm > 0)) continue;
-      for (double& v : c) v /= cm;
-      ClipPolygon(poly, c, 1e-12);
-    }
-    DedupRing(poly, 1e-7);
-    if (poly.size() < 3) continue;
-    double area2 = 0;
-    for (size_t k = 1; k + 1 < poly.size(); k++) {
-      V3 cr = cross(poly[k] - poly[0], poly[k + 1] - poly[0]);
-      area2 += dot(cr, nu);
-    }
-    if (!(area2 > 1e-10)) continue;
-    if (poly.size() > HB_MAX_FACE_VTX) {
-      global_error() = "crystal face has more than 12 corners";
-      return HB_ERR_CAPACITY;
-    }
-    // --- present face: plane entry (PopulateFromCfGeom, crystal.cpp:304-347) ---
-    out->plane[face][0] = ps.unit_n[s][0];
-    out->plane[face][1] = ps.unit_n[s][1];
-    out->plane[face][2] = ps.unit_n[s][2];
-    const float* cf = ps.coef[s];
-    float nrm = std::sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]);
-    out->plane[face][3] = nrm > kFloatEps ? cf[3] / nrm : 0.0f;
-    out->face_fn[face] = static_cast<uint8_t>(ps.face_number[s]);
-    // --- fan sub-triangles ---
-    std::vector<float> v(poly.size() * 3);
-    for (size_t k = 0; k < poly.size(); k++) {
-      v[k * 3 + 0] = static_cast<float>(poly[k].x);
-      v[k * 3 + 1] = static_cast<float>(poly[k].y);
-      v[k * 3 + 2] = static_cast<float>(poly[k].z);
-    }
-    for (size_t k = 1; k + 1 < poly.size(); k++) {
-      if (tri >= HB_MAX_SUBTRIS) {
-        global_error() = "crystal needs more than 64 entry sub-triangles";
-        return HB_ERR_CAPACITY;
-      }
-      float* tv = out->tri_v[tri];
-      std::memcpy(tv + 0, &v[0], 12);
-      std::memcpy(tv + 3, &v[k * 3], 12);
-      std::memcpy(tv + 6, &v[(k + 1) * 3], 12);
-      float e1[3] = { tv[3] - tv[0], tv[4] - tv[1], tv[5] - tv[2] };
-      float e2[3] = { tv[6] - tv[0], tv[7] - tv[1], tv[8] - tv[2] };
-      float cr[3] = { -e2[1] * e1[2] + e1[1] * e2[2], e2[0] * e1[2] - e1[0] * e2[2], -e2[0] * e1[1] + e1[0] * e2[1] };
-      float len = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
-      out->tri_area[tri] = len / 2.0f;
-      for (int q = 0; q < 3; q++) out->tri_n[tri][q] = len > 0.0f ? cr[q] / len : 0.0f;
-      out->tri_face[tri] = static_cast<uint8_t>(face);
-      tri++;
-    }
-    face++;
-  }
-  out->face_cnt = face;
-  out->subtri_cnt = tri;
-  if (face < 4) {  // not a solid: the reference returns an empty Crystal (crystal.cpp:80-100)
-    std::memset(out, 0, sizeof(*out));
-  }
-  return HB_OK;
-}
-
-// Largest inset m (in face-distance units) for which the hexagonal cross-section
-// { n_i . x <= (sqrt3/4)(dist_i - m) } is non-empty: a 3-variable LP solved by vertex enumeration.
-// This is the apex height parameter of a pyramidal segment (geo3d_closedform.cpp MaxFeasibleInsetLP).
-double ApexInset(const float dist[6]) {
-  const double k = 0.25 * 1.7320508075688772935;
-  double best = -std::numeric_limits<double>::infinity();
-  bool found = false;
-  for (int a = 0; a < 6; a++)
-    for (int b = a + 1; b < 6; b++)
-      for (int c = b + 1; c < 6; c++) {
-        int id[3] = { a, b, c };
-        double M[3][4];
-        for (int r = 0; r < 3; r++) {
-          M[r][0] = kFaceCos[id[r]];
-          M[r][1] = kFaceSin[id[r]];
-          M[r][2] = k;
-          M[r][3] = k * dist[id[r]];
-        }
-        double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
-                     M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
-        if (std::fabs(det) < 1e-12) continue;
-        auto det3 = [&](int col) {
-          double T[3][3];
-          for (int r = 0; r < 3; r++)
-            for (int q = 0; q < 3; q++) T[r][q] = q == col ? M[r][3] : M[r][q];
-          return T[0][0] * (T[1][1] * T[2][2] - T[1][2] * T[2][1]) - T[0][1] * (T[1][0] * T[2][2] - T[1][2] * T[2][0]) +
-                 T[0][2] * (T[1][0] * T[2][1] - T[1][1] * T[2][0]);
-        };
-        double u = det3(0) / det, v = det3(1) / det, m = det3(2) / det;
-        bool ok = true;
-        for (int i = 0; i < 6 && ok; i++) ok = kFaceCos[i] * u + kFaceSin[i] * v + k * m <= k * dist[i] + 1e-9;
-        if (ok && (!found || m > best)) {
-          best = m;
-          found = true;
-        }
-      }
-  return found ? std::max(best, 0.0) : 0.0;
-}
-
-void PrismPlanes(float h, const float dist[6], PlaneSet* ps) {
-  // geo3d_closedform.cpp ComputeClosedFormPrism: basal (0,0,+-1,-h/2); side i 0.5(cos,sin,0), d = -dist*sqrt3/8.
-  ps->slot_cnt = 8;
-  float hh = 0.5f * h;
-  float basal[2][4] = { { 0, 0, 1, -hh }, { 0, 0, -1, -hh } };
-  for (int s = 0; s < 2; s++) {
-    std::memcpy(ps->coef[s], basal[s], 16);
-    ps->unit_n[s][0] = 0;
-    ps->unit_n[s][1] = 0;
-    ps->unit_n[s][2] = basal[s][2];
-    ps->face_number[s] = s + 1;
-    ps->candidate[s] = true;
-  }
-  double kd = static_cast<double>(kSqrt3F) / 8.0;
-  for (int i = 0; i < 6; i++) {
-    int s = 2 + i;
-    ps->coef[s][0] = 0.5f * static_cast<float>(kFaceCos[i]);
-    ps->coef[s][1] = 0.5f * static_cast<float>(kFaceSin[i]);
-    ps->coef[s][2] = 0.0f;
-    ps->coef[s][3] = -static_cast<float>(kd * static_cast<double>(dist[i]));
-    ps->unit_n[s][0] = static_cast<float>(kFaceCos[i]);
-    ps->unit_n[s][1] = static_cast<float>(kFaceSin[i]);
-    ps->unit_n[s][2] = 0.0f;
-    ps->face_number[s] = 3 + i;
-    ps->candidate[s] = true;
-  }
-}
-
 }  // namespace
 }  // namespace hb
 
@@ -253,87 +41,29 @@ extern "C" {
 
 uint32_t hb_abi_version(void) { return HB_ABI_VERSION; }
 
+namespace {
+int GeometryStatus(int rc) {
+  if (rc == HB_ERR_CAPACITY) global_error() = "crystal face has more than 12 corners or the crystal needs more than 64 entry sub-triangles";
+  return rc;
+}
+}  // namespace
+
 int hb_make_prism(float h, const float dist6[6], HbCrystalTables* out) {
   if (out == nullptr || dist6 == nullptr) return HB_ERR_INVALID_ARG;
-  std::memset(out, 0, sizeof(*out));
-  if (!(h > kFloatEps)) return HB_OK;  // zero-volume: empty crystal (crystal.cpp:80-82)
-  PlaneSet ps;
-  PrismPlanes(h, dist6, &ps);
-  return BuildTablesFromPlanes(ps, out);
+  return GeometryStatus(hbg::MakePrism(h, dist6, out));
+}
+
+double hb_pyramid_slope(float alpha_deg) {
+  // geo3d_closedform.cpp ComputeClosedFormPyramidInner: a = (sqrt3/4)/tan(alpha) for alpha in [0.1, 89.9] deg
+  const float sqrt3_4 = kSqrt3F / 4.0f;
+  if (!(alpha_deg >= 0.1f && alpha_deg <= 89.9f)) return -1.0;
+  return static_cast<double>(sqrt3_4) / std::tan(static_cast<double>(alpha_deg) * static_cast<double>(kDeg2RadF));
 }
 
 int hb_make_pyramid(float upper_alpha, float lower_alpha, float h1, float h2, float h3, const float dist[6],
                     HbCrystalTables* out) {
   if (out == nullptr || dist == nullptr) return HB_ERR_INVALID_ARG;
-  std::memset(out, 0, sizeof(*out));
-  // geo3d_closedform.cpp ComputeClosedFormPyramid + ComputeClosedFormPyramidInner: a = (sqrt3/4)/tan(alpha)
-  // when the segment exists (h > eps and alpha in [0.1, 89.9] deg).
-  double a1 = -1.0, a2 = -1.0;
-  const float sqrt3_4 = kSqrt3F / 4.0f;
-  if (h1 > kFloatEps && upper_alpha >= 0.1f && upper_alpha <= 89.9f)
-    a1 = static_cast<double>(sqrt3_4) / std::tan(static_cast<double>(upper_alpha) * static_cast<double>(kDeg2RadF));
-  if (h3 > kFloatEps && lower_alpha >= 0.1f && lower_alpha <= 89.9f)
-    a2 = static_cast<double>(sqrt3_4) / std::tan(static_cast<double>(lower_alpha) * static_cast<double>(kDeg2RadF));
-  bool has_upper = a1 > 0, has_lower = a2 > 0;
-  const double h2_2 = 0.5 * static_cast<double>(h2);
-  if (!has_upper && !has_lower && h2 < kFloatEps) return HB_OK;
-
-  PlaneSet ps;
-  ps.slot_cnt = 20;
-  ps.face_number[0] = 1;
-  ps.face_number[1] = 2;
-  for (int i = 0; i < 6; i++) {
-    ps.face_number[2 + i] = 3 + i;
-    ps.face_number[8 + i] = 13 + i;
-    ps.face_number[14 + i] = 23 + i;
-    int i2 = (i + 1) % 6;
-    double x1 = 0.5 * kVtxCos[i], x2 = 0.5 * kVtxCos[i2], y1 = 0.5 * kVtxSin[i], y2 = 0.5 * kVtxSin[i2];
-    double det = x1 * y2 - x2 * y1;
-    float* c = ps.coef[2 + i];
-    c[0] = static_cast<float>(y2 - y1);
-    c[1] = static_cast<float>(x1 - x2);
-    c[2] = 0;
-    c[3] = static_cast<float>(-static_cast<double>(dist[i]) * det);
-    ps.candidate[2 + i] = h2 > 0.0f || true;
-    if (has_upper) {
-      float* u = ps.coef[8 + i];
-      u[0] = static_cast<float>(a1 * (y2 - y1));
-      u[1] = static_cast<float>(a1 * (x1 - x2));
-      u[2] = static_cast<float>(det);
-      u[3] = static_cast<float>(-(h2_2 + a1 * static_cast<double>(dist[i])) * det);
-      ps.candidate[8 + i] = true;
-    }
-    if (has_lower) {
-      float* l = ps.coef[14 + i];
-      l[0] = static_cast<float>(a2 * (y2 - y1));
-      l[1] = static_cast<float>(a2 * (x1 - x2));
-      l[2] = static_cast<float>(-det);
-      l[3] = static_cast<float>(-(h2_2 + a2 * static_cast<double>(dist[i])) * det);
-      ps.candidate[14 + i] = true;
-    }
-  }
-  double m_apex = (has_upper || has_lower) ? ApexInset(dist) : 0.0;
-  double m_top = has_upper ? std::min(static_cast<double>(h1) * m_apex, m_apex) : 0.0;
-  double m_bot = has_lower ? std::min(static_cast<double>(h3) * m_apex, m_apex) : 0.0;
-  double z_top = has_upper ? h2_2 + a1 * m_top : h2_2;
-  double z_bot = has_lower ? -h2_2 - a2 * m_bot : -h2_2;
-  float basal[2][4] = { { 0, 0, 1, static_cast<float>(-z_top) }, { 0, 0, -1, static_cast<float>(z_bot) } };
-  for (int s = 0; s < 2; s++) {
-    std::memcpy(ps.coef[s], basal[s], 16);
-    ps.candidate[s] = true;
-  }
-  ps.unit_n[0][2] = 1.0f;
-  ps.unit_n[1][2] = -1.0f;
-  for (int s = 2; s < 20; s++) {
-    double nx = ps.coef[s][0], ny = ps.coef[s][1], nz = ps.coef[s][2];
-    double mag = std::sqrt(nx * nx + ny * ny + nz * nz);
-    if (mag > 0) {
-      ps.unit_n[s][0] = static_cast<float>(nx / mag);
-      ps.unit_n[s][1] = static_cast<float>(ny / mag);
-      ps.unit_n[s][2] = static_cast<float>(nz / mag);
-    }
-  }
-  return BuildTablesFromPlanes(ps, out);
+  return GeometryStatus(hbg::MakePyramidFromSlopes(hb_pyramid_slope(upper_alpha), hb_pyramid_slope(lower_alpha), h1, h2, h3, dist, out));
 }
 
 // IceRefractiveIndex::Get, optics.cpp:180-198 (Sellmeier fit, valid 350..900 nm, float coefficients).
@@ -536,17 +266,10 @@ bool ShapeIsDeterministic(const HbCrystalDesc& c) {  // IsDeterministic, simulat
 }
 
 int MakeShape(std::mt19937& gen, const HbCrystalDesc& c, HbCrystalTables* out) {  // MakeCrystal, simulator.cpp:405-450
-  float dist[6];
-  if (c.kind == 0) {
-    float h = std::fabs(DrawDist(gen, c.height[0]));
-    for (int i = 0; i < 6; i++) dist[i] = DrawDist(gen, c.face_dist[i]);
-    return hb_make_prism(h, dist, out);
-  }
-  float h1 = std::fabs(DrawDist(gen, c.height[0]));
-  float h2 = std::fabs(DrawDist(gen, c.height[1]));
-  float h3 = std::fabs(DrawDist(gen, c.height[2]));
-  for (int i = 0; i < 6; i++) dist[i] = DrawDist(gen, c.face_dist[i]);
-  return hb_make_pyramid(c.wedge_upper_deg, c.wedge_lower_deg, h1, h2, h3, dist, out);
+  float hgt[3], dist[6];
+  hbg::SampleShapeScalars(c, [&](const HbDist& d) { return DrawDist(gen, d); }, hgt, dist);
+  if (c.kind == 0) return hb_make_prism(hgt[0], dist, out);
+  return hb_make_pyramid(c.wedge_upper_deg, c.wedge_lower_deg, hgt[0], hgt[1], hgt[2], dist, out);
 }
 
 // BuildDeviceFilterDesc, device_filter_desc.cpp:130-143 (+ crystal.cpp:710-730 D-symmetry helpers).

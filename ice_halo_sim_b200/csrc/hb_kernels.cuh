@@ -19,6 +19,7 @@
 
 #include "halotrace_b200.h"
 #include "hb_device.cuh"
+#include "hb_geometry.h"
 
 namespace hb {
 
@@ -746,6 +747,78 @@ struct EntryFaces {
 };
 static_assert(sizeof(EntryFaces) % 16 == 0, "EntryFaces is copied as uint4 words");
 
+// Face groups of one shape's entry fan table: runs of consecutive triangles that share the face id and the
+// normal; per triangle the cumulative area fraction inside its run. Host (upload_layer) and device
+// (derive_shapes_kernel) run this same code.
+__host__ __device__ inline void build_entry_faces(const HbCrystalTables& t, EntryFaces* out) {
+  EntryFaces& ef = *out;
+  memset(&ef, 0, sizeof(ef));
+  uint32_t g = 0;
+  for (uint32_t i = 0; i < t.subtri_cnt;) {
+    uint32_t j = i + 1;
+    while (j < t.subtri_cnt && t.tri_face[j] == t.tri_face[i] && fabsf(t.tri_n[j][0] - t.tri_n[i][0]) <= 1e-4f &&
+           fabsf(t.tri_n[j][1] - t.tri_n[i][1]) <= 1e-4f && fabsf(t.tri_n[j][2] - t.tri_n[i][2]) <= 1e-4f)
+      j++;
+    if (g == HB_MAX_FACES) {  // cannot happen for the reference's crystals; keep the triangle-level sampler
+      ef.group_cnt = 0;
+      return;
+    }
+    float area = 0.0f;
+    for (uint32_t k = i; k < j; k++) area += t.tri_area[k];
+    float run = 0.0f;
+    for (uint32_t k = i; k < j; k++) {
+      run += t.tri_area[k];
+      ef.cum[k] = area > 0.0f ? run / area : 1.0f;
+    }
+    ef.na[g] = make_float4(t.tri_n[i][0], t.tri_n[i][1], t.tri_n[i][2], area);
+    ef.first[g] = static_cast<uint8_t>(i);
+    ef.cnt[g] = static_cast<uint8_t>(j - i);
+    g++;
+    i = j;
+  }
+  ef.group_cnt = g;
+}
+
+// Everything the trace kernels read of one shape, derived from its HbCrystalTables: plane table, face numbers,
+// the paired-axis table of the slab scan (faces whose unit normals are exact negatives share one entry, see
+// slab_exit), meta word (face_cnt | population << 8 | axis_cnt << 16) and the entry face groups.
+// Returns true when the shape qualifies for the P4 kernels (exactly four axes, all paired).
+__host__ __device__ inline bool derive_shape_tables(const HbCrystalTables& t, uint32_t pop, float4* planes, uint8_t* fn,
+                                                    float4* axes, uint32_t* meta, EntryFaces* ef) {
+  for (uint32_t f = 0; f < HB_MAX_FACES; f++) {
+    planes[f] = make_float4(t.plane[f][0], t.plane[f][1], t.plane[f][2], t.plane[f][3]);
+    fn[f] = t.face_fn[f];
+    axes[2u * f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    axes[2u * f + 1u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  uint32_t axis_cnt = 0;
+  bool used[HB_MAX_FACES];
+  for (uint32_t f = 0; f < HB_MAX_FACES; f++) used[f] = false;
+  bool all_paired = true;
+  for (uint32_t f = 0; f < t.face_cnt && f < HB_MAX_FACES; f++) {
+    if (used[f]) continue;
+    used[f] = true;
+    uint32_t partner = 63u;  // kFaceInvalid
+    for (uint32_t g = f + 1; g < t.face_cnt && g < HB_MAX_FACES; g++) {
+      if (!used[g] && t.plane[g][0] == -t.plane[f][0] && t.plane[g][1] == -t.plane[f][1] && t.plane[g][2] == -t.plane[f][2]) {
+        partner = g;
+        used[g] = true;
+        break;
+      }
+    }
+    const uint32_t fbits = f | (partner << 8);
+    float fb;
+    memcpy(&fb, &fbits, 4);
+    axes[2u * axis_cnt] = make_float4(t.plane[f][0], t.plane[f][1], t.plane[f][2], t.plane[f][3]);
+    axes[2u * axis_cnt + 1u] = make_float4(partner == 63u ? 0.0f : t.plane[partner][3], fb, 0.f, 0.f);
+    axis_cnt++;
+    if (partner == 63u) all_paired = false;
+  }
+  *meta = t.face_cnt | (pop << 8) | (axis_cnt << 16);
+  build_entry_faces(t, ef);
+  return all_paired && axis_cnt == 4u;
+}
+
 constexpr uint32_t kFastGroups = 8;  // prism: 8 faces, weights kept in registers
 
 // Returns the chosen fan triangle. `ef` may point to shared or global memory (warp-uniform address).
@@ -911,6 +984,56 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
     gp.D[slot] = make_float4(dx, dy, dz, weight);
     gp.Q[slot] = q;
     if ((gp.flags & kFlagPath) && gp.path != nullptr) gp.path[slot] = static_cast<uint8_t>(face);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stochastic geometry pool on the device. One thread per shape: draw the shape scalars of the
+// population's CrystalConfig with the counter-based RNG (MakeCrystal's order, simulator.cpp:405-450: heights
+// first, then the six face distances), build the crystal tables with the SAME code the host builders run
+// (hb_geometry.h) and derive everything the trace kernels read (derive_shape_tables). The pool is overwritten
+// in place, so a fresh pool per session costs one small launch and no host work.
+// ------------------------------------------------------------------------------------------------
+struct ShapeGenParams {
+  HbCrystalDesc desc;
+  double a1, a2;               // pyramid slopes (sqrt3/4)/tan(alpha) from the host, <= 0: segment absent
+  uint32_t seed;               // session-independent geometry seed ^ kNonceGeom
+  uint32_t draw_base;          // stream index of shape 0
+  uint32_t count;
+  uint32_t pop;                // population index inside the layer (meta word)
+  HbCrystalTables* shapes;     // the population's slices of the layer tables
+  float4* planes;
+  float4* axes;
+  uint32_t* meta;
+  uint8_t* fn;
+  EntryFaces* ef;
+  float* scalars;              // [count][10] h1, h2, h3, d0..d5, builder status (parity export)
+  uint32_t* flags;             // [0]: number of shapes that are NOT P4, [1]: number of builder errors
+};
+
+__global__ void __launch_bounds__(64) resample_shapes_kernel(const ShapeGenParams sp) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= sp.count) return;
+  Stream s{ sp.seed, sp.draw_base + k, 0u };
+  float hgt[3], dist[6];
+  hbg::SampleShapeScalars(sp.desc, [&](const HbDist& d) { return get_dist(s, d.type, d.center, d.spread); }, hgt, dist);
+  HbCrystalTables* t = sp.shapes + k;
+  const int rc = sp.desc.kind == 0u ? hbg::MakePrism(hgt[0], dist, t)
+                                    : hbg::MakePyramidFromSlopes(sp.a1, sp.a2, hgt[0], hgt[1], hgt[2], dist, t);
+  if (rc != HB_OK) {
+    memset(t, 0, sizeof(*t));  // degenerate crystal: rays of this shape are discarded (zero sub-triangles)
+    atomicAdd(sp.flags + 1, 1u);
+  }
+  const bool p4 = derive_shape_tables(*t, sp.pop, sp.planes + k * HB_MAX_FACES, sp.fn + k * HB_MAX_FACES,
+                                      sp.axes + k * HB_MAX_FACES * 2u, sp.meta + k, sp.ef + k);
+  if (!p4) atomicAdd(sp.flags + 0, 1u);
+  if (sp.scalars != nullptr) {
+    float* o = sp.scalars + k * 10u;
+    o[0] = hgt[0];
+    o[1] = hgt[1];
+    o[2] = hgt[2];
+    for (int i = 0; i < 6; i++) o[3 + i] = dist[i];
+    o[9] = static_cast<float>(rc);
   }
 }
 

@@ -48,16 +48,33 @@ def trace_session(backend: B200TraceBackend, layer_cnt: int, spec: SessionSpec, 
         backend.EndSession()
 
 
+def stochastic_populations(desc: A.HbSceneDesc):
+    """(layer, population) of every population whose shape scalars are random (IsDeterministic, simulator.cpp:453-471)."""
+    out = []
+    for li in range(desc.layer_cnt):
+        layer = desc.layers[li]
+        for pi in range(layer.population_cnt):
+            c = layer.populations[pi].crystal
+            heights = c.height[:1] if c.kind == 0 else c.height[:3]
+            if any(d.type != 0 for d in list(heights) + list(c.face_dist)):
+                out.append((li, pi))
+    return out
+
+
 def render_config(cfg: SceneConfig, backend: Optional[B200TraceBackend] = None, seed: int = 42,
                   session_rays: int = 1 << 24, rank: int = 0, world: int = 1, geometry_seed: int = 1,
                   wl_pool_size: int = 64, srgb: bool = False, intensity_factor: float = 1.0,
-                  allreduce: bool = True) -> Dict[int, Frame]:
+                  allreduce: bool = True, device_geometry: bool = True) -> Dict[int, Frame]:
     """Trace `cfg` (from config.load_config) and return {renderer id: Frame}.
 
     Discrete spectrum: `rays_per_wavelength()` roots per wavelength, one single-entry pool per session
     (ray_num_semantics.hpp:12-16). Illuminant spectrum: all rays in sessions that carry the M-entry pool and
     draw a per-ray wavelength index (wl_pool.hpp:73-84). Ray indices are global: rank r of `world` traces its
     contiguous share of each wavelength's index range, so any world size traces the same set of rays.
+    Stochastic crystal shapes: with `device_geometry` every session gets a fresh pool (`cfg.desc.geom_pool_size`
+    shapes per population, one shape per 32 consecutive rays) drawn and built on the device
+    (hb_resample_shapes); the shape stream index follows the session's first global ray index, so the crystals
+    depend on the ray range only, not on the rank that traces it.
     """
     if not cfg.renders:
         raise ValueError("config has no renderer")
@@ -80,8 +97,12 @@ def render_config(cfg: SceneConfig, backend: Optional[B200TraceBackend] = None, 
             n = cfg.rays_per_wavelength()
             jobs = [([make_wl_entry(wl, w)], n) for wl, w in cfg.spectrum]
         index_base = 0
+        stochastic = stochastic_populations(cfg.desc) if device_geometry and cfg.desc.geom_pool_size > 1 else []
         for pool, total in jobs:
             for first, count in session_plan(total, rank, world, session_rays, index_base):
+                for li, pi in stochastic:
+                    be.ResampleShapes(li, pi, cfg.desc.layers[li].populations[pi].crystal, geometry_seed,
+                                      (first // 32) & 0xFFFFFFFF)
                 trace_session(be, cfg.desc.layer_cnt,
                               SessionSpec(seed=seed, wl=pool, ray_num=count, accumulate=True, ray_base=first), count)
             index_base += total

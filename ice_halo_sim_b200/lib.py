@@ -36,6 +36,9 @@ PROTOTYPES = {
     "hb_inject_rays": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "hb_export_roots": (C.c_int, [_vp, C.c_uint64] + [_vp] * 8),
     "hb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "hb_resample_shapes": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32, _vp]),
+    "hb_export_shapes": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
+    "hb_pyramid_slope": (C.c_double, [C.c_float]),
     "hb_get_counters": (C.c_int, [_vp, _vp]),
     "hb_synchronize": (C.c_int, [_vp]),
     "hb_image_device_ptr": (C.c_int, [_vp, _vp, _vp]),
@@ -86,7 +89,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError here = header/library drift
             fn.restype = res
             fn.argtypes = args
-        if lib.hb_abi_version() != 1:
+        if lib.hb_abi_version() != 2:
             raise ImportError("libhalotrace_b200.so ABI version mismatch")
         _lib = lib
     return _lib

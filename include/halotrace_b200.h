@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 1u
+#define HB_ABI_VERSION 2u
 
 /* Limits (reference: src/core/def.hpp:23-31, crystal.hpp:67,76, pcg_shared.h:71). */
 #define HB_MAX_FACES 20u      /* kCrystalGeomMaxFaces */
@@ -373,6 +373,11 @@ typedef struct HbCrystalDesc {
   HbDist face_dist[6];
   float wedge_upper_deg, wedge_lower_deg;
   HbDist latitude, azimuth, roll; /* AxisDistribution (latitude center = 90 - zenith), degrees */
+  /* Shape-scalar sync groups (crystal_config.hpp:29-43,62-76; SyncGroupSampler, simulator.cpp:341-393), in
+   * ShapeScalar order: [0] prism height, [1] upper_h, [2] prism_h, [3] lower_h, [4..9] face distances.
+   * 0 = independent; scalars sharing a non-zero id share ONE raw draw per crystal instance (taken with the
+   * distribution of the group's first member; heights fold it with |.| at their own use site). */
+  int32_t sync_group[10];
 } HbCrystalDesc;
 
 typedef struct HbSimpleFilterSpec {
@@ -432,6 +437,26 @@ typedef struct HbRenderDesc {
   int32_t visible_range, lens_shift_x, lens_shift_y;
   float overlap;
 } HbRenderDesc;
+
+/* ---------------------------------------------------------------------------
+ * Stochastic geometry pool on the device (reference: MakeCrystal per 32-ray batch on the CPU,
+ * simulator.cpp:405-450 + simulator.hpp:144-151, and the per-batch / per-K-rays geometry pool of the reference
+ * CUDA backend, cuda_trace_backend.cu:3617-3627). hb_resample_shapes redraws ALL shapes of one population's
+ * pool on the device: shape scalars (heights, face distances) from `crystal`'s distributions with the
+ * counter-based RNG (stream: seed, draw_base + shape index), crystal tables built by the same code as
+ * hb_make_prism / hb_make_pyramid (bit-identical for equal scalars), pool overwritten in place (its size was
+ * fixed by hb_set_scene). Legal between sessions only. A shape the builder rejects (face with more than 12
+ * corners) becomes an empty crystal whose rays are discarded; their number is returned in *rejected.
+ * hb_export_shapes copies the current pool back (parity harness): tables and, when the pool was drawn on the
+ * device, the ten scalars per shape {h1, h2, h3, d0..d5, builder status}.
+ * ------------------------------------------------------------------------- */
+int hb_resample_shapes(HbEngine* h, uint32_t layer, uint32_t population, const HbCrystalDesc* crystal,
+                       uint32_t seed, uint32_t draw_base, uint32_t* rejected);
+int hb_export_shapes(HbEngine* h, uint32_t layer, uint32_t population, uint32_t cap, HbCrystalTables* tables,
+                     float* scalars10, uint32_t* count);
+/* (sqrt3/4) / tan(alpha): slope parameter of a pyramidal segment, -1 when alpha is outside [0.1, 89.9] deg
+ * (geo3d_closedform.cpp ComputeClosedFormPyramidInner). */
+double hb_pyramid_slope(float alpha_deg);
 
 typedef struct HbSceneTables HbSceneTables;  /* owns an HbScene and all its storage */
 int hb_build_scene(const HbSceneDesc* desc, uint32_t geometry_seed, HbSceneTables** out);

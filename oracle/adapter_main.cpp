@@ -10,6 +10,8 @@
 // Scene 2 adds a raypath_color config (three classes over two layers): the per-class Y lanes read back through
 // TraceBackend::ReadbackClassLanes must match lanes built on the host from the CPU backend's
 // ExitRayRecord::component_mask (same battery per class).
+// Scene 3 is a stochastic-geometry population (sync-grouped face distances): the CPU backend samples crystals with
+// MakeCrystal, the B200 backend on the device (hb_resample_shapes); same battery.
 // Prints one JSON line; exit code 0 iff the battery passes.
 #include <algorithm>
 #include <cmath>
@@ -47,7 +49,24 @@ SceneConfig MakeScene(int which, size_t max_hits) {
     s.crystal_proportion_ = 1.0f;
     return s;
   };
-  if (which == 0) {  // BASELINE config 2 scene: column, zenith gauss(90, 0.3) => latitude gauss(0, 0.3)
+  if (which == 3) {
+    // Stochastic geometry (BASELINE config 5 family): irregular column, h ~ U(1.1, 1.5), face distances
+    // ~ N(1, 0.12) in two sync groups (faces 0/2/4 share one draw, faces 1/3/5 another: triangular habits),
+    // zenith gauss(90, 1). The CPU backend draws one crystal per session with MakeCrystal (mt19937); the B200
+    // backend redraws its 256-shape pool on the device every session (hb_resample_shapes).
+    MsInfo ms;
+    ms.prob_ = 0.0f;
+    ScatteringSetting s = prism(1.3f, Distribution{ DistributionType::kGaussian, 0.0f, 1.0f }, 5);
+    PrismCrystalParam p;
+    p.h_ = Distribution{ DistributionType::kUniform, 1.3f, 0.4f };
+    for (int i = 0; i < 6; i++) {
+      p.d_[i] = Distribution{ DistributionType::kGaussian, 1.0f, 0.12f };
+      p.sync_group_[kShapeScalarFace0 + i] = 1 + (i & 1);
+    }
+    s.crystal_.param_ = p;
+    ms.setting_.push_back(std::move(s));
+    scene.ms_.push_back(std::move(ms));
+  } else if (which == 0) {  // BASELINE config 2 scene: column, zenith gauss(90, 0.3) => latitude gauss(0, 0.3)
     MsInfo ms;
     ms.prob_ = 0.0f;
     ms.setting_.push_back(prism(1.3f, Distribution{ DistributionType::kGaussian, 0.0f, 0.3f }, 3));
@@ -221,8 +240,8 @@ int main(int argc, char** argv) {
   float cpu_landed = 0.0f;
   {
     CpuTraceBackend cpu;
-    RunSessions(cpu, scene, render, total, 4096, 42, &cpu_img, &cpu_landed, colors, colors ? &class_table : nullptr,
-                &cpu_lanes);
+    RunSessions(cpu, scene, render, total, mode == 3 ? 512 : 4096, 42, &cpu_img, &cpu_landed, colors,
+                colors ? &class_table : nullptr, &cpu_lanes);
   }
 
   std::vector<float> gpu_img(pix * 3, 0.0f);
@@ -233,7 +252,7 @@ int main(int argc, char** argv) {
       std::printf("{\"error\": \"backend refused the render config\"}\n");
       return 2;
     }
-    RunSessions(gpu, scene, render, total, 1 << 20, 42, nullptr, nullptr, colors);
+    RunSessions(gpu, scene, render, total, mode == 3 ? 1 << 17 : 1 << 20, 42, nullptr, nullptr, colors);
     XyzImageData xyz{ gpu_img.data(), w, h };
     gpu.ReadbackXyzAccum(xyz, gpu_landed);
     gpu.ReadbackClassLanes(gpu_lanes, gpu_ncls);

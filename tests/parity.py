@@ -290,7 +290,27 @@ def oracle_image(proj, wl_arr, exits):
     return img, mag, landed.value, cnt
 
 
-def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=7, tile_rays=None):
+def resample_pools_on_device(be, tables, seed, draw_base=0):
+    """Redraw every multi-shape pool of the scene on the device (hb_resample_shapes) and copy the device-built
+    tables over the host scene's, so the oracle replays exactly the crystals the engine traces.
+    Returns [(layer, population, tables, scalars)]."""
+    sc = tables.scene()
+    out = []
+    for li in range(sc.layer_cnt):
+        layer = sc.layers[li]
+        for pi in range(layer.population_cnt):
+            pop = layer.populations[pi]
+            if pop.shape_cnt <= 1:
+                continue
+            be.ResampleShapes(li, pi, tables.desc.layers[li].populations[pi].crystal, seed, draw_base)
+            tb, scal = be.ExportShapes(li, pi)
+            assert len(tb) == pop.shape_cnt
+            C.memmove(pop.shapes, tb, C.sizeof(A.HbCrystalTables) * len(tb))
+            out.append((li, pi, tb, scal))
+    return out
+
+
+def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=7, tile_rays=None, device_pool_seed=None):
     """Full protocol on one case; returns a dict of comparison results (all layers merged)."""
     desc = case["scene"]()
     rdescs = case["render"]()
@@ -305,6 +325,8 @@ def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=
     if tile_rays:
         be.SetOption("tile_rays", tile_rays)
     be.SetScene(tables)
+    if device_pool_seed is not None:
+        resample_pools_on_device(be, tables, device_pool_seed)
     be.SetOption("stream_base", 0)
     be.SetRenders(rdescs)
     projs = [B.make_proj_params(r) for r in rdescs]

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in L.PROTOTYPES, f"{n} has no ctypes prototype"
     assert sorted(L.PROTOTYPES) == names
-    assert lib.hb_abi_version() == 1
+    assert lib.hb_abi_version() == 2
 
 
 def test_struct_sizes_match_the_c_compiler():

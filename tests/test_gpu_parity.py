@@ -153,7 +153,7 @@ def test_reference_driver_through_adapter():
     exe = os.path.join(H.ROOT, "oracle", "_ref", "adapter_demo")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/adapter_demo not built (needs /root/reference at build time)")
-    for scene, rays in ((0, 1500000), (1, 600000), (2, 1500000)):
+    for scene, rays in ((0, 1500000), (1, 600000), (2, 1500000), (3, 1500000)):
         out = subprocess.run([exe, str(scene), str(rays)], capture_output=True, text=True, timeout=600)
         lines = [json.loads(x) for x in out.stdout.strip().splitlines()]
         res = lines[-1]
@@ -271,3 +271,62 @@ def test_driver_renders_whole_config_and_shards_by_rank(backend):
     ex["scene"]["ray_num"] = 400_000
     fr = render_config(load_config(ex), backend, seed=9)[4]
     assert fr.landed_weight > 0 and (fr.xyz[..., 0].sum() > 0 and fr.xyz[..., 2].sum() > 0)
+
+
+def test_device_geometry_pool_tables_equal_host_builder(backend):
+    """hb_resample_shapes: the shapes drawn and built on the device are byte-identical to what the
+    host builders (hb_make_prism / hb_make_pyramid, themselves pinned to the reference's MakeCrystal tables in
+    test_host_tables.py) make of the same scalars; the scalars follow the configured distributions; a second
+    draw range gives different shapes, the same range the same ones."""
+    import ctypes as C
+    import harness as H
+    from ice_halo_sim_b200 import backend as B
+    A = H.A
+    lib = B.load()
+    prism = parity.prism_pop(parity.dist("uniform", 1.2, 0.6), zenith=("uniform", 90, 360),
+                             face_dist=[parity.dist("gauss", 1.0, 0.15)] * 6)
+    prism.crystal.sync_group[4] = prism.crystal.sync_group[6] = 1   # faces 0 and 2 share one draw (SyncGroupSampler)
+    pyr = parity.pyramid_pop()
+    for k in range(3):
+        pyr.crystal.height[k] = parity.dist("uniform", pyr.crystal.height[k].center, 0.2)
+    for k in range(6):
+        pyr.crystal.face_dist[k] = parity.dist("gauss", 1.0, 0.1)
+    for pop, n_pool in ((prism, 512), (pyr, 128)):
+        tables = B.SceneTables(parity.scene([(0.0, [pop])], 6, pool=n_pool), 3)
+        backend.SetScene(tables)
+        assert backend.ResampleShapes(0, 0, pop.crystal, 77, 0) == 0
+        tb, sc = backend.ExportShapes(0, 0)
+        assert len(tb) == n_pool and (sc[:, 9] == 0).all()
+        want = A.HbCrystalTables()
+        dist6 = (C.c_float * 6)()
+        for k in range(n_pool):
+            for i in range(6):
+                dist6[i] = float(sc[k, 3 + i])
+            if pop.crystal.kind == 0:
+                assert lib.hb_make_prism(C.c_float(float(sc[k, 0])), dist6, C.byref(want)) == 0
+            else:
+                assert lib.hb_make_pyramid(C.c_float(pop.crystal.wedge_upper_deg), C.c_float(pop.crystal.wedge_lower_deg),
+                                           C.c_float(float(sc[k, 0])), C.c_float(float(sc[k, 1])), C.c_float(float(sc[k, 2])),
+                                           dist6, C.byref(want)) == 0
+            assert bytes(tb[k]) == bytes(want), (pop.crystal.kind, k)
+            assert tb[k].face_cnt >= 4
+        if pop.crystal.kind == 0:   # sync group: members identical, others independent
+            assert np.array_equal(sc[:, 3], sc[:, 5]) and not np.array_equal(sc[:, 3], sc[:, 4])
+        d = sc[:, 3:9].astype(np.float64)
+        spread = pop.crystal.face_dist[0].spread
+        assert abs(d.mean() - 1.0) < 4.5 * spread / np.sqrt(d.size)
+        assert abs(d.std() - spread) < 0.1 * spread
+        backend.ResampleShapes(0, 0, pop.crystal, 77, 0)
+        _, sc_same = backend.ExportShapes(0, 0)
+        backend.ResampleShapes(0, 0, pop.crystal, 77, n_pool)
+        _, sc_next = backend.ExportShapes(0, 0)
+        assert np.array_equal(sc, sc_same) and not np.array_equal(sc, sc_next)
+
+
+@pytest.mark.parametrize("name", ["stoch_config5"])
+def test_device_geometry_pool_traces_bit_exact(backend, name):
+    """Parity protocol on a pool that was drawn and built on the device (tables, axis tables, entry face groups
+    all derived by the device kernels): same bit-exact bar as the host-built pools."""
+    res = parity.run_case(parity.CASES[name], n_rays=20000, seed=5, backend=backend, device_pool_seed=1234)
+    assert res["paths_equal"] and res["dirs_bit_equal"] and res["weights_bit_equal"] and res["meta_equal"], res
+    assert res["image_ok"], res

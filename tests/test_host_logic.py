@@ -244,3 +244,44 @@ def test_two_rank_sharding_equals_single_rank(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "SHARD_OK" in outs[0]
+
+
+def test_shape_sync_groups_parse_and_sample():
+    """Crystal shape "sync_group" (crystal_config.cpp:47-146,179-205 + SyncGroupSampler, simulator.cpp:341-393):
+    singleton groups dissolve, survivors are renumbered by first appearance, members take the leader's
+    distribution, and the host pool builder draws ONE value per group and crystal."""
+    import ctypes as C
+    from ice_halo_sim_b200 import _abi as A
+    from ice_halo_sim_b200 import backend as B
+    from ice_halo_sim_b200 import config as cfgmod
+    g = {"type": "gauss", "mean": 1.0, "std": 0.2}
+    c = {"id": 1, "type": "prism",
+         "shape": {"height": 1.2, "face_distance": [g, g, {"type": "gauss", "mean": 1.0, "std": 0.05}, g, g, g],
+                   "sync_group": {"height": 9, "face_distance": [7, 3, 7, 0, 3, 5]}}}
+    d = cfgmod.crystal_desc(c)
+    assert list(d.sync_group) == [0, 0, 0, 0, 1, 2, 1, 0, 2, 0]          # height 9 and face 5 are singletons
+    assert abs(d.face_dist[2].spread - 0.2) < 1e-7                        # member takes the leader's distribution
+    pop = A.HbPopulationDesc()
+    pop.proportion = 1.0
+    pop.crystal = d
+    pop.crystal.latitude = A.HbDist(1, 90.0, 360.0)
+    pop.crystal.azimuth = pop.crystal.roll = A.HbDist(1, 0.0, 360.0)
+    pop.filter.simple.entry_fn = pop.filter.simple.exit_fn = -1
+    sd = A.HbSceneDesc()
+    sd.max_hits, sd.layer_cnt, sd.geom_pool_size = 4, 1, 64
+    sd.sun_altitude_deg, sd.sun_diameter_deg = 20.0, 0.5
+    sd.layers[0].prob, sd.layers[0].population_cnt = 0.0, 1
+    sd.layers[0].populations[0] = pop
+    tables = B.SceneTables(sd, 11)
+    p = tables.scene().layers[0].populations[0]
+    assert p.shape_cnt == 64
+    same02 = same14 = diff01 = 0
+    for k in range(64):
+        t = p.shapes[k]
+        if t.face_cnt != 8:
+            continue
+        d0 = {int(t.face_fn[f]): float(t.plane[f][3]) for f in range(8)}
+        same02 += d0[3] == d0[5]
+        same14 += d0[4] == d0[7]
+        diff01 += d0[3] != d0[4]
+    assert same02 >= 60 and same14 == same02 and diff01 >= 60
