@@ -50,7 +50,14 @@ class B200TraceBackend : public TraceBackend {
   }
   ~B200TraceBackend() override { hb_destroy(h_); }
 
-  bool SupportsDeviceXyzAccum() const override { return true; }
+  // Exit-seam egress (trace_backend.hpp:391-446). Default: the device-fused consumer (projection + XYZ accumulate
+  // on the GPU, DrainExits returns nothing). With SetExitEgress(true) the backend behaves like the CPU backend at
+  // the seam instead: no device image, every outgoing ray of every layer is materialised as a 96-byte
+  // ExitRayRecord {dir, weight, path (face numbers), crystal_id, ms_layer_idx, wl_idx, component_mask} and handed
+  // to the driver by DrainExits (destructive, grow-not-clamp) for its host consumers (show_rays, raypath
+  // statistics, GUI filters). Switch between sessions only.
+  void SetExitEgress(bool on) { egress_ = on; }
+  bool SupportsDeviceXyzAccum() const override { return !egress_; }
   bool SupportsThirdClockDrain() const override { return true; }
   uint32_t WlPoolSize() const override { return kWlPoolSizeDefault; }
   bool IsCompatible(const RenderConfig&) const override { return true; }  // all 11 lens types
@@ -81,8 +88,8 @@ class B200TraceBackend : public TraceBackend {
       s.wl_cnt = static_cast<uint32_t>(pool.size());
       s.wl = reinterpret_cast<const HbWlEntry*>(pool.data());
       s.ray_num = spec.ray_num;
-      s.record_exits = 0;
-      s.accumulate = 1;
+      s.record_exits = egress_ ? 2u : 0u;
+      s.accumulate = egress_ ? 0u : 1u;
       Check(hb_begin_session(h_, &s), "BeginSession");
       layer_cnt_ = spec.scene->ms_.size();
       layer_idx_ = 0;
@@ -112,9 +119,21 @@ class B200TraceBackend : public TraceBackend {
   }
 
   size_t DrainExits(std::vector<ExitRayRecord>& out) override {
-    out.clear();  // device-fused path: exits are reduced into the image, never materialised
-    return 0;
+    out.clear();
+    if (!egress_) {
+      return 0;  // device-fused path: exits are reduced into the image, never materialised
+    }
+    static_assert(sizeof(ExitRayRecord) == sizeof(HbExitRecord), "ExitRayRecord layout (exit_seam.hpp:40-53)");
+    uint64_t n = 0;
+    Check(hb_drain_exits(h_, nullptr, nullptr, 0, &n), "DrainExits");
+    out.resize(static_cast<size_t>(n));
+    if (n != 0) {
+      Check(hb_drain_exits(h_, reinterpret_cast<HbExitRecord*>(out.data()), nullptr, n, &n), "DrainExits");
+    }
+    return out.size();
   }
+  // Session-level egress of the older contract: here the same destructive drain (the driver calls one or the other).
+  size_t ReadbackExitRays(std::vector<ExitRayRecord>& out) override { return DrainExits(out); }
 
   void ReadbackXyzAccum(XyzImageData& xyz, float& landed_weight) override {
     Check(hb_readback_xyz(h_, xyz.data, &landed_weight), "ReadbackXyzAccum");
@@ -477,6 +496,7 @@ class B200TraceBackend : public TraceBackend {
   size_t layer_cnt_ = 0;
   size_t layer_idx_ = 0;
   size_t stochastic_shapes_last_upload_ = 0;
+  bool egress_ = false;
   static constexpr uint32_t kPoolShapes = 256;
   uint32_t geom_draws_ = 0;  // monotone shape-stream index: every session draws new crystals
 };

@@ -32,7 +32,8 @@ class SessionSpec:
     seed: int
     wl: List[tuple]
     ray_num: int = 0
-    record_exits: bool = False      # materialise ExitRayRecords (parity path); production = fused accumulate
+    record_exits: int = 0           # 1/True: ExitRayRecords + exported roots (parity); 2: records only (exit-seam
+                                    # egress, TraceBackend::DrainExits); 0: production = fused accumulate
     accumulate: bool = True
     ray_base: Optional[int] = None  # multi-GPU sharding: global index of this session's first root
 
@@ -188,7 +189,7 @@ class B200TraceBackend:
         s.wl_cnt = len(spec.wl)
         s.wl = wl
         s.ray_num = int(spec.ray_num)
-        s.record_exits = 1 if spec.record_exits else 0
+        s.record_exits = int(spec.record_exits)
         s.accumulate = 1 if spec.accumulate else 0
         if spec.ray_base is not None:
             s.ray_base = int(spec.ray_base)

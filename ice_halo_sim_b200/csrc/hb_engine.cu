@@ -542,7 +542,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   HB_CUDA(h, cudaGetLastError());
 
   // ---- parity export of the roots this tile starts from ----
-  if (h->spec.record_exits && !(li == 0 && h->injected)) {
+  if (h->spec.record_exits == 1u && !(li == 0 && h->injected)) {  // parity sessions only (2 = plain egress)
     std::vector<float4> hp(n), hd(n), hq(n);
     DevBuf<float> rot;
     HB_CUDA(h, rot.ensure(static_cast<size_t>(n) * 9));
@@ -1015,7 +1015,7 @@ int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats) {
     cudaEventRecord(e0, h->stream);
   }
   uint64_t tile = h->tile_rays;
-  if (flags & kFlagRecord) tile = std::min<uint64_t>(tile, 1u << 18);
+  if (flags & kFlagRecord) tile = std::min<uint64_t>(tile, h->spec.record_exits == 1u ? 1u << 18 : 1u << 20);
   for (uint64_t r0 = 0; r0 < n; r0 += tile) {
     const uint32_t cnt = static_cast<uint32_t>(std::min<uint64_t>(tile, n - r0));
     int rc = trace_tile(h, li, r0, cnt, pop_begin, flags, n);

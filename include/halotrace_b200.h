@@ -215,7 +215,9 @@ typedef struct HbSessionSpec {            /* reference: SessionSpec, trace_backe
   uint32_t wl_cnt;                        /* 1 = discrete wavelength session; >1 = per-ray pool draw */
   const HbWlEntry* wl;                    /* [wl_cnt] */
   uint64_t ray_num;                       /* hint (pool sizing) */
-  uint32_t record_exits;                  /* 1 => materialise exit records for hb_drain_exits (parity) */
+  uint32_t record_exits;                  /* 1 => materialise exit records for hb_drain_exits AND keep the generated
+                                             roots for hb_export_roots (parity harness); 2 => exit records only: the
+                                             exit-seam egress of TraceBackend::DrainExits (trace_backend.hpp:391-446) */
   uint32_t accumulate;                    /* 1 => fused projection + XYZ accumulate (production) */
   uint64_t ray_base;                      /* global index of this session's first root ray when
                                              use_ray_base != 0 (multi-GPU sharding: disjoint index ranges per

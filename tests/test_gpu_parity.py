@@ -153,12 +153,14 @@ def test_reference_driver_through_adapter():
     exe = os.path.join(H.ROOT, "oracle", "_ref", "adapter_demo")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/adapter_demo not built (needs /root/reference at build time)")
-    for scene, rays in ((0, 1500000), (1, 600000), (2, 1500000), (3, 1500000)):
+    for scene, rays in ((0, 1500000), (1, 600000), (2, 1500000), (3, 1500000), (4, 1000000), (5, 1000000)):
         out = subprocess.run([exe, str(scene), str(rays)], capture_output=True, text=True, timeout=600)
         lines = [json.loads(x) for x in out.stdout.strip().splitlines()]
         res = lines[-1]
         assert out.returncode == 0 and res["pass"], lines
         assert res["pearson_4x4"] >= 0.95 and abs(res["total_y_ratio"] - 1) <= 0.05
+        if scene == 4:   # exit-seam egress vs device-fused consumer of the same backend: the same rays
+            assert res["pearson_4x4"] >= 0.9999 and abs(res["total_y_ratio"] - 1) <= 2e-4
         if scene == 2:   # raypath colour: per-class Y lanes vs lanes built from the CPU backend's component masks
             lanes = [x for x in lines if "class" in x]
             assert len(lanes) == 3 and all(abs(x["ratio"] - 1) <= 0.05 and x["pearson_8x8"] >= 0.95 for x in lanes), lanes
