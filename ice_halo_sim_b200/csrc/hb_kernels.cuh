@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
       }
       if (LAST) {
         // no intersect pass follows the final interaction: classify the inside child here too
-        if (iw >= 0.0f) {
+        if (iw >= 0.0f && !near_child_surely_hits(axes, P4 ? 4u : axis_cnt, p4.x, p4.y, p4.z, ix, iy, iz)) {
           float nx, ny, nz;
           const uint32_t nf = P4 ? slab_exit_p4<false>(axes, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz)
                                  : slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);

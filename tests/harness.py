@@ -142,3 +142,65 @@ def sort_exits(recs, roots):
                                                      float(recs[i]["weight"])))
     idx = np.array(order, dtype=np.int64)
     return recs[idx], np.asarray(roots)[idx]
+
+
+def adversarial_roots(rng, t, n, n_idx):
+    """Entry rays that stress the rare branches of the exit-face search (ties, near-edge double continuation,
+    zero numerators, fast-test fallbacks): entry points exactly on polygon vertices / edges or 1e-6.5 .. 1e-3.5
+    inside an edge, and directions whose REFRACTED ray is aimed (to float rounding) at a vertex, an edge point
+    or the interior of another face (inverse Snell; directions that cannot be reached from outside are
+    injected as they are). Returns crystal-local (d, p, w, face) like roots_on_crystal."""
+    nf, nt = int(t.face_cnt), int(t.subtri_cnt)
+    planes = np.ctypeslib.as_array(t.plane)[:nf].astype(np.float64)
+    tri_v = np.ctypeslib.as_array(t.tri_v)[:nt].astype(np.float64).reshape(nt, 3, 3)
+    tri_face = np.ctypeslib.as_array(t.tri_face)[:nt]
+    polys = []
+    for k in range(nf):
+        tris = tri_v[tri_face == k]
+        polys.append(np.vstack([tris[0, 0][None], tris[:, 1], tris[-1, 2][None]]))
+
+    def point_on_face(k, kind):
+        poly = polys[k]
+        m = len(poly)
+        i = int(rng.integers(m))
+        a, b, cen = poly[i], poly[(i + 1) % m], poly.mean(axis=0)
+        if kind == 0:
+            return a.copy()
+        e = a + rng.random() * (b - a)
+        if kind == 1:
+            return e
+        if kind == 2:
+            return e + (cen - e) * 10.0 ** rng.uniform(-6.5, -3.5)
+        return e + (cen - e) * rng.uniform(0.05, 1.0)
+
+    d = np.zeros((n, 3), np.float32)
+    p = np.zeros((n, 3), np.float32)
+    f = np.zeros(n, np.uint16)
+    k = 0
+    while k < n:
+        fi = int(rng.integers(nf))
+        gi = int(rng.integers(nf))
+        if gi == fi:
+            continue
+        pp = point_on_face(fi, int(rng.integers(4)))
+        qq = point_on_face(gi, int(rng.integers(4)))
+        tdir = qq - pp
+        nrm = np.linalg.norm(tdir)
+        if nrm < 1e-3:
+            continue
+        tdir /= nrm
+        nvec = planes[fi, :3]
+        c = float(tdir @ nvec)
+        if c > -1e-3:
+            continue                     # must head into the crystal through face fi
+        tang = float(n_idx) * (tdir - c * nvec)
+        s2 = float(tang @ tang)
+        if s2 < 0.98 and rng.random() < 0.85:
+            din = tang - np.sqrt(1.0 - s2) * nvec     # refracts into tdir
+        else:
+            din = tdir                                  # taken as the incoming direction itself
+        d[k] = (din / np.linalg.norm(din)).astype(np.float32)
+        p[k] = pp.astype(np.float32)
+        f[k] = fi
+        k += 1
+    return d, p, np.ones(n, np.float32), f

@@ -332,3 +332,42 @@ def test_device_geometry_pool_traces_bit_exact(backend, name):
     res = parity.run_case(parity.CASES[name], n_rays=20000, seed=5, backend=backend, device_pool_seed=1234)
     assert res["paths_equal"] and res["dirs_bit_equal"] and res["weights_bit_equal"] and res["meta_equal"], res
     assert res["image_ok"], res
+
+
+def test_injected_adversarial_rays_bit_exact(backend):
+    """Rays that enter exactly on vertices / edges and are refracted onto vertices / edges of other faces
+    (harness.adversarial_roots): ties between planes, t ~ 0 candidates, near-edge double continuation (fork rays),
+    the fall-backs of the quick far-child / near-child tests and the reference-order tie scan, in the unrolled
+    prism kernels (P4) and the generic axis-loop kernels alike. Same bit-exact bar as the random rays; the oracle
+    is pinned to the reference on the same kind of rays in test_oracle_vs_reference.py."""
+    import harness as H
+    from ice_halo_sim_b200 import backend as B
+    from test_oracle_golden import oracle_trace_single
+    rng = np.random.default_rng(4242)
+    pops = [parity.prism_pop(1.3), parity.prism_pop(0.3),
+            parity.prism_pop(0.8, face_dist=[1.0, 0.7, 1.2, 0.9, 1.1, 0.8]),
+            parity.prism_pop(1.0, face_dist=[1.0, 2.4, 1.0, 1.0, 1.0, 1.0]),      # one prism face vanishes: generic kernels
+            parity.pyramid_pop(), parity.pyramid_pop(h=(0.6, 0.0, 0.6))]
+    wl = [B.make_wl_entry(550.0, 1.0)]
+    total = 0
+    for use_p4 in (1, 0):
+        backend.SetOption("prism_fast_path", use_p4)
+        for pop in pops[: (len(pops) if use_p4 else 2)]:
+            mh = 8
+            tables = B.SceneTables(parity.scene([(0.0, [pop])], mh), 1)
+            t = tables.scene().layers[0].populations[0].shapes[0]
+            assert t.face_cnt >= 4
+            n = 4000
+            d, p, w, f = H.adversarial_roots(rng, t, n, wl[0][0])
+            backend.SetScene(tables)
+            backend.SetOption("stream_base", 0)
+            backend.BeginSession(B.SessionSpec(seed=3, wl=wl, ray_num=n, record_exits=True, accumulate=False))
+            backend.TraceLayer(B.RootRaySource.FromHost(n, d, p, w, f))
+            g_ex, g_roots = backend.DrainExits(with_roots=True)
+            backend.EndSession()
+            o_ex, o_roots = oracle_trace_single(t, np.float32(wl[0][0]), mh, d, p, w, f)
+            r = parity.compare_exit_lists(g_ex, g_roots, o_ex, o_roots)
+            assert r["paths_equal"] and r["dirs_bit_equal"] and r["weights_bit_equal"], (use_p4, t.face_cnt, r)
+            total += len(g_ex)
+    backend.SetOption("prism_fast_path", 1)
+    assert total > 100000

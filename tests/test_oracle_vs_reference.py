@@ -75,6 +75,38 @@ def test_random_crystals_traced_bit_exact():
     assert total > 20000
 
 
+def test_adversarial_edge_and_vertex_rays_bit_exact():
+    """Rays entering exactly on vertices / edges and refracted onto vertices / edges of other faces (ties between
+    planes, t ~ 0 candidates, near-edge double continuation): reference CpuTraceBackend vs oracle, bit-exact."""
+    ref = H.ref()
+    rng = np.random.default_rng(77)
+    shapes = [H.ref_shape(0, (1.3, 0, 0), (1.0,) * 6), H.ref_shape(0, (0.3, 0, 0), (1.0,) * 6),
+              H.ref_shape(1, (0.3, 0.5, 0.4), (1.0,) * 6, (28.0, 28.0))] + [random_shape(rng) for _ in range(5)]
+    total = 0
+    for sh in shapes:
+        t = A.HbCrystalTables()
+        ref.ref_make_tables(C.byref(sh), C.byref(t))
+        if t.face_cnt < 4:
+            continue
+        n, mh = 1500, 8
+        n_idx = np.float32(1.3110129)
+        d, p, w, f = H.adversarial_roots(rng, t, n, n_idx)
+        cap = n * (mh + 2) * 2
+        ex = np.zeros(cap, H.EXIT_DTYPE)
+        er = np.zeros(cap, np.uint32)
+        ec = C.c_uint64()
+        assert ref.ref_trace_injected(C.byref(sh), float(n_idx), mh, n, H.ptr(d), H.ptr(p), H.ptr(w), H.ptr(f), cap,
+                                      H.ptr(ex), H.ptr(er), C.byref(ec)) == 0
+        o_ex, o_er = oracle_trace_single(t, n_idx, mh, d, p, w, f)
+        a, ar = H.sort_exits(ex[: ec.value], er[: ec.value])
+        b, br = H.sort_exits(o_ex, o_er)
+        assert len(a) == len(b) and np.array_equal(ar, br)
+        assert np.array_equal(a["path_len"], b["path_len"]) and np.array_equal(a["path"], b["path"])
+        assert np.array_equal(bits(a["dir"]), bits(b["dir"])) and np.array_equal(bits(a["weight"]), bits(b["weight"]))
+        total += len(a)
+    assert total > 20000
+
+
 def test_accumulate_matches_scatter_outgoing_to_xyz():
     """orc_accumulate == ScatterOutgoingToXyz (sequential fp32 adds in the same order => bit-exact)."""
     import sys, os
