@@ -67,10 +67,12 @@ class B200TraceBackend : public TraceBackend {
       raypath_color_ = spec.raypath_color;
       if (spec.scene != scene_ || raypath_color_ != color_uploaded_) {
         UploadScene(*spec.scene);
+        // Stochastic geometry: hand the populations' shape distributions to the engine's geometry clock. Every
+        // session then gets a fresh pool of kPoolShapes crystals per population, drawn and built on the device one
+        // session ahead (hb_auto_resample) -- the host no longer calls MakeCrystal per session.
+        StartGeometryClock(*spec.scene, spec.seed);
       }
-      // Stochastic geometry: a fresh pool of kPoolShapes crystals per population and session, drawn and built
-      // on the device (hb_resample_shapes) -- the host no longer calls MakeCrystal per session.
-      ResampleStochasticPools(*spec.scene, spec.seed);
+      stochastic_shapes_last_upload_ = stochastic_population_cnt_ * kPoolShapes;
       if (spec.render != render_ || render_snapshot_dirty_) {
         UploadRender(*spec.render);
       }
@@ -216,8 +218,8 @@ class B200TraceBackend : public TraceBackend {
     return d;
   }
 
-  void ResampleStochasticPools(const SceneConfig& scene, uint32_t seed) {
-    stochastic_shapes_last_upload_ = 0;
+  void StartGeometryClock(const SceneConfig& scene, uint32_t seed) {
+    stochastic_population_cnt_ = 0;
     for (size_t li = 0; li < scene.ms_.size(); li++) {
       for (size_t ci = 0; ci < scene.ms_[li].setting_.size(); ci++) {
         const ScatteringSetting& st = scene.ms_[li].setting_[ci];
@@ -225,11 +227,9 @@ class B200TraceBackend : public TraceBackend {
           continue;
         }
         const HbCrystalDesc desc = ToCrystalDesc(st.crystal_);
-        uint32_t rejected = 0;
-        Check(hb_resample_shapes(h_, static_cast<uint32_t>(li), static_cast<uint32_t>(ci), &desc, seed, geom_draws_, &rejected),
-              "ResampleShapes");
-        geom_draws_ += kPoolShapes;
-        stochastic_shapes_last_upload_ += kPoolShapes;
+        Check(hb_auto_resample(h_, static_cast<uint32_t>(li), static_cast<uint32_t>(ci), &desc, seed, geom_draws_), "AutoResample");
+        geom_draws_ += 1u << 24;  // disjoint shape-stream ranges per population and upload
+        stochastic_population_cnt_++;
       }
     }
   }
@@ -498,7 +498,8 @@ class B200TraceBackend : public TraceBackend {
   size_t stochastic_shapes_last_upload_ = 0;
   bool egress_ = false;
   static constexpr uint32_t kPoolShapes = 256;
-  uint32_t geom_draws_ = 0;  // monotone shape-stream index: every session draws new crystals
+  uint32_t geom_draws_ = 0;  // shape-stream base handed to the engine's geometry clock
+  size_t stochastic_population_cnt_ = 0;
 };
 
 }  // namespace lumice

@@ -56,7 +56,8 @@ WORKLOADS = {
                          "fisheye_equal_area 1920x1080; every exit of layer 0 re-enters layer 1"),
     "config5": dict(case="stoch_config5", rays_per_wl=50_000_000, session=SESSION_RAYS,
                     what="BASELINE configs[4]: bench_config_stoch.json prism h=1 d_i~gauss(1,0.15) full-sphere axis, "
-                         "max_hits 8, rectangular 2048x1024 full sky"),
+                         "max_hits 8, rectangular 2048x1024 full sky; 256-shape pool redrawn on the device every session, "
+                         "one shape per 32 consecutive rays"),
 }
 
 
@@ -204,7 +205,7 @@ def main():
     import torch.distributed as dist
     from ice_halo_sim_b200 import _abi as A
     from ice_halo_sim_b200 import backend as B
-    from ice_halo_sim_b200.driver import trace_session
+    from ice_halo_sim_b200.driver import stochastic_populations, trace_session
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -214,6 +215,9 @@ def main():
     desc, rdesc = workload_desc(args.workload)
     if args.geom_pool:
         desc.geom_pool_size = args.geom_pool
+    elif args.workload == "config5":
+        desc.geom_pool_size = 256   # the adapter's pool size; redrawn on the device at every session (below)
+    stochastic = stochastic_populations(desc) if desc.geom_pool_size > 1 else []
     max_hits = int(desc.max_hits)
     layer_cnt = int(desc.layer_cnt)
     session_rays = wk["session"]
@@ -227,6 +231,11 @@ def main():
         be.SetOption(k, int(v))
     be.SetScene(tables)
     be.SetRender(rdesc)
+
+    def start_geometry_clock():   # stochastic geometry: a fresh shape pool per session, built on the device one session ahead
+        for k, (li, pi) in enumerate(stochastic):
+            be.AutoResample(li, pi, desc.layers[li].populations[pi].crystal, 7, ((rank * 64 + k) << 22) & 0xFFFFFFFF)
+    start_geometry_clock()
     stream = torch.cuda.ExternalStream(be._lib.hb_stream(be._h), device=torch.device("cuda", local_rank))
     if world > 1:
         ids = [B.comm_unique_id() if rank == 0 else None]
@@ -245,6 +254,7 @@ def main():
         if e2e:  # host tables travel every step
             be.SetScene(tables)
             be.SetRender(rdesc)
+            start_geometry_clock()
         for wi, wl in enumerate(wl_entries):
             done = 0
             while done < rays_per_wl:

@@ -309,6 +309,12 @@ class B200TraceBackend:
                                                  int(draw_base), C.byref(rejected)))
         return rejected.value
 
+    def AutoResample(self, layer, population, crystal: Optional[A.HbCrystalDesc], seed=0, draw_base=0):
+        """Geometry clock run by the engine (hb_auto_resample): a fresh device-built pool for every session,
+        prepared one session ahead. crystal=None switches it off."""
+        self._check(self._lib.hb_auto_resample(self._h, int(layer), int(population),
+                                               C.byref(crystal) if crystal is not None else None, int(seed), int(draw_base)))
+
     def ExportShapes(self, layer, population):
         """Parity helper: (HbCrystalTables array, scalars [n, 10] = h1, h2, h3, d0..d5, builder status)."""
         cnt = C.c_uint32()

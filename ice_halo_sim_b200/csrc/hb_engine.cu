@@ -57,8 +57,41 @@ struct PopHost {
   uint32_t shape_base, shape_cnt;
   AxisParams axis;
   bool has_filter;
-  bool p4;  // every shape of this population's pool is a full hexagonal prism
-  bool device_pool;  // pool last drawn by hb_resample_shapes (scalars available for export)
+  bool device_pool;  // pool last drawn on the device (scalars available for export)
+  // geometry clock (hb_auto_resample): the pool is redrawn on the device for every session, one session ahead
+  bool auto_geom;
+  HbCrystalDesc auto_desc;
+  uint32_t auto_seed;
+  uint32_t auto_draws;  // shape-stream index of the next pool
+};
+
+// Everything the kernels read of a layer's crystal shapes. Two copies exist once a population's pool is redrawn
+// ahead of time: the trace reads sb[cur] while the next session's pool is built into sb[cur ^ 1].
+struct ShapeBufs {
+  DevBuf<float4> planes;
+  DevBuf<float4> axes;
+  DevBuf<uint32_t> shape_meta;
+  DevBuf<uint8_t> face_fn;
+  DevBuf<HbCrystalTables> shapes;
+  DevBuf<EntryFaces> entry_faces;  // [shape] face groups of the entry fan table
+  DevBuf<float> geom_scalars;      // [shape][10] scalars of device-drawn shapes (parity export)
+  std::vector<uint8_t> pop_p4;     // [pop] every shape of the population's pool is a full hexagonal prism
+  bool allocated = false;
+  bool p4() const {
+    for (uint8_t v : pop_p4)
+      if (!v) return false;
+    return true;
+  }
+  void release() {
+    planes.release();
+    axes.release();
+    shape_meta.release();
+    face_fn.release();
+    shapes.release();
+    entry_faces.release();
+    geom_scalars.release();
+    allocated = false;
+  }
 };
 
 struct LayerDev {
@@ -67,20 +100,38 @@ struct LayerDev {
   std::vector<double> carry;  // PartitionCrystalRayNum carry (simulator.cpp:519-582)
   uint32_t shape_cnt = 0;
   bool any_filter = false;
-  bool p4 = false;  // every shape is a full hexagonal prism (four paired axes): unrolled kernel variants
-  DevBuf<float4> planes;
-  DevBuf<float4> axes;
-  DevBuf<uint32_t> shape_meta;
-  DevBuf<uint8_t> face_fn;
-  DevBuf<HbCrystalTables> shapes;
-  DevBuf<EntryFaces> entry_faces;  // [shape] face groups of the entry fan table
-  DevBuf<float> geom_scalars;      // [shape][10] scalars of device-drawn shapes (hb_resample_shapes; parity export)
+  ShapeBufs sb[2];
+  int cur = 0;
+  ShapeBufs& b() { return sb[cur]; }
+  // geometry prefetch state (see prefetch_geometry)
+  bool any_auto = false;
+  bool shadow_pending = false;
+  cudaEvent_t shadow_event = nullptr;
+  cudaEvent_t main_event = nullptr;  // "everything enqueued on the trace stream so far" marker for the geometry stream
+  DevBuf<uint32_t> geom_flags_dev;   // [pop][2]: shapes that are not P4, shapes the builder rejected
+  uint32_t* geom_flags_host = nullptr;  // pinned mirror
   DevBuf<HbFilterDesc> filters;
   DevBuf<uint32_t> pop_crystal_id;
   DevBuf<float> luts;  // [pop][3][257]
   bool any_color = false;              // some population carries colour predicates
   DevBuf<HbColorGroup> color_groups;   // [pop][HB_MAX_COLOR_GROUPS]
   DevBuf<uint32_t> color_group_cnt;    // [pop]
+  void release() {
+    sb[0].release();
+    sb[1].release();
+    geom_flags_dev.release();
+    if (geom_flags_host) cudaFreeHost(geom_flags_host);
+    geom_flags_host = nullptr;
+    if (shadow_event) cudaEventDestroy(shadow_event);
+    shadow_event = nullptr;
+    if (main_event) cudaEventDestroy(main_event);
+    main_event = nullptr;
+    filters.release();
+    pop_crystal_id.release();
+    luts.release();
+    color_groups.release();
+    color_group_cnt.release();
+  }
 };
 
 struct EventPair {
@@ -181,7 +232,8 @@ struct HbEngine {
   size_t ev_used = 0;
   int blocks_per_sm = 8;
   int blocks_per_sm_override = 0;
-  DevBuf<uint32_t> geom_flags;
+  cudaStream_t geom_stream = nullptr;  // geometry-clock redraws run here, beside the trace stream
+  uint64_t geom_rejected = 0;   // shapes the device builder rejected since hb_set_scene (empty crystals)
   bool p4_enable = true;  // option "prism_fast_path": 0 forces the generic axis-loop kernels (A/B tests)
   bool pixel_cache = true;
 #ifdef HB_WITH_NCCL
@@ -358,7 +410,9 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   std::vector<uint32_t> cgroup_cnt;
   L->any_filter = false;
   L->any_color = false;
-  L->p4 = true;  // every shape: four axes, all paired (hexagonal prism with all eight faces)
+  ShapeBufs& B0 = L->sb[0];
+  L->cur = 0;
+  B0.pop_p4.clear();
   for (uint32_t ci = 0; ci < src.population_cnt; ci++) {
     const HbCrystalPopulation& p = src.populations[ci];
     if (p.shape_cnt == 0 || p.shapes == nullptr) return fail(h, HB_ERR_INVALID_ARG, "population without shapes");
@@ -370,7 +424,7 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
     ph.axis = AxisParams{ p.axis.lat_path, p.axis.lat_mean, p.axis.lat_std, p.axis.az_type, p.axis.az_mean, p.axis.az_std,
                           p.axis.roll_type, p.axis.roll_mean, p.axis.roll_std, p.axis.lut_n };
     ph.has_filter = p.filter.kind != 0;
-    ph.p4 = true;
+    bool pop_p4 = true;  // every shape: four axes, all paired (hexagonal prism with all eight faces)
     L->any_filter = L->any_filter || ph.has_filter;
     for (uint32_t s = 0; s < p.shape_cnt; s++) {
       const HbCrystalTables& t = p.shapes[s];
@@ -383,9 +437,9 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
       entry_faces.emplace_back();
       if (!derive_shape_tables(t, ci, &planes[planes.size() - HB_MAX_FACES], &fn[fn.size() - HB_MAX_FACES],
                                &axes[axes.size() - HB_MAX_FACES * 2], &meta.back(), &entry_faces.back()))
-        ph.p4 = false;
+        pop_p4 = false;
     }
-    L->p4 = L->p4 && ph.p4;
+    B0.pop_p4.push_back(pop_p4 ? 1 : 0);
     filters.push_back(p.filter);
     cid.push_back(p.crystal_id);
     if (p.color_group_cnt > HB_MAX_COLOR_GROUPS) return fail(h, HB_ERR_INVALID_ARG, "population: too many colour groups");
@@ -400,21 +454,23 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   if (shapes.size() > 65535) return fail(h, HB_ERR_CAPACITY, "more than 65535 crystal shapes in one layer");
   L->shape_cnt = static_cast<uint32_t>(shapes.size());
   L->carry.assign(L->pops.size(), 0.0);
-  HB_CUDA(h, L->planes.ensure(planes.size()));
-  HB_CUDA(h, L->axes.ensure(axes.size()));
-  HB_CUDA(h, L->shape_meta.ensure(meta.size()));
-  HB_CUDA(h, L->face_fn.ensure(fn.size()));
-  HB_CUDA(h, L->shapes.ensure(shapes.size()));
+  HB_CUDA(h, B0.planes.ensure(planes.size()));
+  HB_CUDA(h, B0.axes.ensure(axes.size()));
+  HB_CUDA(h, B0.shape_meta.ensure(meta.size()));
+  HB_CUDA(h, B0.face_fn.ensure(fn.size()));
+  HB_CUDA(h, B0.shapes.ensure(shapes.size()));
+  HB_CUDA(h, B0.geom_scalars.ensure(shapes.size() * 10));
+  B0.allocated = true;
   HB_CUDA(h, L->filters.ensure(filters.size()));
   HB_CUDA(h, L->pop_crystal_id.ensure(cid.size()));
   HB_CUDA(h, L->luts.ensure(luts.size()));
-  HB_CUDA(h, cudaMemcpy(L->planes.p, planes.data(), planes.size() * sizeof(float4), cudaMemcpyHostToDevice));
-  HB_CUDA(h, cudaMemcpy(L->axes.p, axes.data(), axes.size() * sizeof(float4), cudaMemcpyHostToDevice));
-  HB_CUDA(h, cudaMemcpy(L->shape_meta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
-  HB_CUDA(h, cudaMemcpy(L->face_fn.p, fn.data(), fn.size(), cudaMemcpyHostToDevice));
-  HB_CUDA(h, cudaMemcpy(L->shapes.p, shapes.data(), shapes.size() * sizeof(HbCrystalTables), cudaMemcpyHostToDevice));
-  HB_CUDA(h, L->entry_faces.ensure(entry_faces.size()));
-  HB_CUDA(h, cudaMemcpy(L->entry_faces.p, entry_faces.data(), entry_faces.size() * sizeof(EntryFaces), cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(B0.planes.p, planes.data(), planes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(B0.axes.p, axes.data(), axes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(B0.shape_meta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(B0.face_fn.p, fn.data(), fn.size(), cudaMemcpyHostToDevice));
+  HB_CUDA(h, cudaMemcpy(B0.shapes.p, shapes.data(), shapes.size() * sizeof(HbCrystalTables), cudaMemcpyHostToDevice));
+  HB_CUDA(h, B0.entry_faces.ensure(entry_faces.size()));
+  HB_CUDA(h, cudaMemcpy(B0.entry_faces.p, entry_faces.data(), entry_faces.size() * sizeof(EntryFaces), cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->filters.p, filters.data(), filters.size() * sizeof(HbFilterDesc), cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->pop_crystal_id.p, cid.data(), cid.size() * 4, cudaMemcpyHostToDevice));
   HB_CUDA(h, cudaMemcpy(L->luts.p, luts.data(), luts.size() * 4, cudaMemcpyHostToDevice));
@@ -502,8 +558,8 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
       gp.seed = h->spec.seed ^ (li == 0 ? kNonceGen : kNonceTransit);
       gp.axis = ph.axis;
       gp.lut = L.luts.p + ci * 3 * HB_LUT_NODES;
-      gp.shapes = L.shapes.p + ph.shape_base;
-      gp.entry_faces = L.entry_faces.p + ph.shape_base;
+      gp.shapes = L.b().shapes.p + ph.shape_base;
+      gp.entry_faces = L.b().entry_faces.p + ph.shape_base;
       gp.shape_base = ph.shape_base;
       gp.shape_cnt = ph.shape_cnt;
       gp.wl = h->wl_cur;
@@ -586,7 +642,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.cap = cap;
   tp.fork_cap = fork_cap;
   tp.root_base = static_cast<uint32_t>(root0);
-  tp.lt = LayerTables{ L.planes.p, L.axes.p, L.shape_meta.p, L.face_fn.p, L.shapes.p, L.filters.p, L.pop_crystal_id.p,
+  tp.lt = LayerTables{ L.b().planes.p, L.b().axes.p, L.b().shape_meta.p, L.b().face_fn.p, L.b().shapes.p, L.filters.p, L.pop_crystal_id.p,
                        L.shape_cnt, static_cast<uint32_t>(L.pops.size()), L.any_filter ? 1u : 0u,
                        L.any_color ? L.color_groups.p : nullptr, L.color_group_cnt.p };
   tp.wl = h->wl_cur;
@@ -629,14 +685,14 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
     tp.hit = hit;
     const bool last = hit + 1 == h->max_hits;
     EventPair* ev = begin_event(h, 1, n);
-    launch_optics(h, general, last, in_smem, L.p4 && h->p4_enable, smem + kStageBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
+    launch_optics(h, general, last, in_smem, L.b().p4() && h->p4_enable, smem + kStageBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
     end_event(h, ev);
     h->ctr.kernel_launches++;
     h->ctr.optics_launches++;
     h->ctr.optics_rays += n;
     if (!last) {
       ev = begin_event(h, 2, n);
-      launch_intersect(h, general, in_smem, L.p4 && h->p4_enable, smem, tp);
+      launch_intersect(h, general, in_smem, L.b().p4() && h->p4_enable, smem, tp);
       end_event(h, ev);
       h->ctr.kernel_launches++;
       h->ctr.intersect_launches++;
@@ -730,18 +786,11 @@ void hb_destroy(HbEngine* h) {
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
   }
-  for (auto& L : h->layers) {
-    L->planes.release();
-    L->axes.release();
-    L->entry_faces.release();
-    L->geom_scalars.release();
-    L->shape_meta.release();
-    L->face_fn.release();
-    L->shapes.release();
-    L->filters.release();
-    L->pop_crystal_id.release();
-    L->luts.release();
+  if (h->geom_stream) {
+    cudaStreamSynchronize(h->geom_stream);
+    cudaStreamDestroy(h->geom_stream);
   }
+  for (auto& L : h->layers) L->release();
   h->image.release();
   h->master.release();
   h->extra_dev.release();
@@ -783,6 +832,8 @@ int hb_set_scene(HbEngine* h, const HbScene* s) {
     return fail(h, HB_ERR_INVALID_ARG, "scene: layer_cnt must be 1..8 and max_hits 1..64");
   cudaSetDevice(h->device);
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->geom_stream) HB_CUDA(h, cudaStreamSynchronize(h->geom_stream));
+  for (auto& L : h->layers) L->release();
   h->layers.clear();
   for (uint32_t li = 0; li < s->layer_cnt; li++) {
     auto L = std::make_unique<LayerDev>();
@@ -850,6 +901,10 @@ int hb_set_renders(HbEngine* h, uint32_t n, const HbProjParams* p) {
 
 int hb_set_render(HbEngine* h, const HbProjParams* p) { return hb_set_renders(h, 1, p); }
 
+namespace {
+int prefetch_geometry(HbEngine* h, LayerDev& L);  // defined with the geometry-pool API below
+}
+
 int hb_begin_session(HbEngine* h, const HbSessionSpec* spec) {
   if (h == nullptr || spec == nullptr) return HB_ERR_INVALID_ARG;
   if (h->in_session) return fail(h, HB_ERR_STATE, "BeginSession on an already-open session");
@@ -905,6 +960,11 @@ int hb_begin_session(HbEngine* h, const HbSessionSpec* spec) {
     h->wl_cur = h->wl_cache[hit].dev.p;
     h->wl2_cur = h->wl_cache[hit].dev2.p;
     h->wl0 = h->wl_cache[hit].host2[0];
+  }
+  for (auto& L : h->layers) {  // geometry clock: swap in the pool drawn one session ahead, enqueue the next one
+    if (!L->any_auto) continue;
+    int rc = prefetch_geometry(h, *L);
+    if (rc != HB_OK) return rc;
   }
   if (spec->use_ray_base) h->gen_base = spec->ray_base;
   h->layer_idx = 0;
@@ -1234,6 +1294,122 @@ int hb_set_option(HbEngine* h, const char* key, int64_t value) {
   return HB_OK;
 }
 
+namespace {
+
+int ensure_geom_state(HbEngine* h, LayerDev& L) {
+  HB_CUDA(h, L.geom_flags_dev.ensure(L.pops.size() * 2));
+  if (L.geom_flags_host == nullptr) HB_CUDA(h, cudaMallocHost(&L.geom_flags_host, HB_MAX_CRYSTALS * 2 * sizeof(uint32_t)));
+  if (L.shadow_event == nullptr) HB_CUDA(h, cudaEventCreateWithFlags(&L.shadow_event, cudaEventDisableTiming));
+  if (L.main_event == nullptr) HB_CUDA(h, cudaEventCreateWithFlags(&L.main_event, cudaEventDisableTiming));
+  if (h->geom_stream == nullptr) HB_CUDA(h, cudaStreamCreateWithFlags(&h->geom_stream, cudaStreamNonBlocking));
+  return HB_OK;
+}
+
+// Second copy of the layer's shape tables (allocated on first use, filled device-to-device from the live one:
+// deterministic populations never change, stochastic ones are overwritten by every redraw).
+int ensure_shadow(HbEngine* h, LayerDev& L) {
+  ShapeBufs& src = L.sb[L.cur];
+  ShapeBufs& dst = L.sb[L.cur ^ 1];
+  if (dst.allocated) return HB_OK;
+  HB_CUDA(h, dst.planes.ensure(src.planes.n));
+  HB_CUDA(h, dst.axes.ensure(src.axes.n));
+  HB_CUDA(h, dst.shape_meta.ensure(src.shape_meta.n));
+  HB_CUDA(h, dst.face_fn.ensure(src.face_fn.n));
+  HB_CUDA(h, dst.shapes.ensure(src.shapes.n));
+  HB_CUDA(h, dst.entry_faces.ensure(src.entry_faces.n));
+  HB_CUDA(h, dst.geom_scalars.ensure(src.geom_scalars.n));
+  const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+  HB_CUDA(h, cudaMemcpyAsync(dst.planes.p, src.planes.p, src.planes.n * sizeof(float4), k, h->stream));
+  HB_CUDA(h, cudaMemcpyAsync(dst.axes.p, src.axes.p, src.axes.n * sizeof(float4), k, h->stream));
+  HB_CUDA(h, cudaMemcpyAsync(dst.shape_meta.p, src.shape_meta.p, src.shape_meta.n * sizeof(uint32_t), k, h->stream));
+  HB_CUDA(h, cudaMemcpyAsync(dst.face_fn.p, src.face_fn.p, src.face_fn.n, k, h->stream));
+  HB_CUDA(h, cudaMemcpyAsync(dst.shapes.p, src.shapes.p, src.shapes.n * sizeof(HbCrystalTables), k, h->stream));
+  HB_CUDA(h, cudaMemcpyAsync(dst.entry_faces.p, src.entry_faces.p, src.entry_faces.n * sizeof(EntryFaces), k, h->stream));
+  HB_CUDA(h, cudaMemcpyAsync(dst.geom_scalars.p, src.geom_scalars.p, src.geom_scalars.n * sizeof(float), k, h->stream));
+  dst.pop_p4 = src.pop_p4;
+  dst.allocated = true;
+  return HB_OK;
+}
+
+// Enqueue the redraw of one population's pool into buffer `buf` of the layer (no synchronisation).
+int launch_resample(HbEngine* h, LayerDev& L, uint32_t population, int buf, const HbCrystalDesc& crystal, uint32_t seed,
+                    uint32_t draw_base, cudaStream_t stream) {
+  const PopHost& ph = L.pops[population];
+  ShapeBufs& B = L.sb[buf];
+  HB_CUDA(h, cudaMemsetAsync(L.geom_flags_dev.p + population * 2, 0, 2 * sizeof(uint32_t), stream));
+  ShapeGenParams sp{};
+  sp.desc = crystal;
+  sp.a1 = crystal.kind == 1u ? hb_pyramid_slope(crystal.wedge_upper_deg) : -1.0;
+  sp.a2 = crystal.kind == 1u ? hb_pyramid_slope(crystal.wedge_lower_deg) : -1.0;
+  sp.seed = seed ^ kNonceGeom;
+  sp.draw_base = draw_base;
+  sp.count = ph.shape_cnt;
+  sp.pop = population;
+  sp.shapes = B.shapes.p + ph.shape_base;
+  sp.planes = B.planes.p + static_cast<size_t>(ph.shape_base) * HB_MAX_FACES;
+  sp.axes = B.axes.p + static_cast<size_t>(ph.shape_base) * HB_MAX_FACES * 2;
+  sp.meta = B.shape_meta.p + ph.shape_base;
+  sp.fn = B.face_fn.p + static_cast<size_t>(ph.shape_base) * HB_MAX_FACES;
+  sp.ef = B.entry_faces.p + ph.shape_base;
+  sp.scalars = B.geom_scalars.p + static_cast<size_t>(ph.shape_base) * 10;
+  sp.flags = L.geom_flags_dev.p + population * 2;
+  resample_shapes_kernel<<<(sp.count + 63u) / 64u, 64, 0, stream>>>(sp);
+  h->ctr.kernel_launches++;
+  HB_CUDA(h, cudaGetLastError());
+  return HB_OK;
+}
+
+// Geometry clock, one session ahead. Called by hb_begin_session for every layer with hb_auto_resample
+// populations: (1) the pool that was enqueued during the PREVIOUS BeginSession -- i.e. before that session's
+// kernels, so it finished long ago and waiting for its event does not drain the stream -- becomes the live
+// one; (2) the redraw of the next pool is enqueued into the buffer that just became free. The host learns the
+// P4 flag of the new live pool from a pinned copy of the builder's counters. Only the very first session
+// waits for its own redraw.
+int prefetch_geometry(HbEngine* h, LayerDev& L) {
+  int rc = ensure_geom_state(h, L);
+  if (rc != HB_OK) return rc;
+  rc = ensure_shadow(h, L);
+  if (rc != HB_OK) return rc;
+  // The redraw runs on its own stream, concurrently with the trace kernels of the session that is about to
+  // start: it only has to wait for what is ALREADY enqueued on the trace stream (the previous session, which
+  // still reads the buffer that is about to be overwritten).
+  auto enqueue_shadow = [&]() -> int {
+    const int buf = L.cur ^ 1;
+    HB_CUDA(h, cudaEventRecord(L.main_event, h->stream));
+    HB_CUDA(h, cudaStreamWaitEvent(h->geom_stream, L.main_event, 0));
+    for (uint32_t pi = 0; pi < L.pops.size(); pi++) {
+      PopHost& ph = L.pops[pi];
+      if (!ph.auto_geom) continue;
+      int r = launch_resample(h, L, pi, buf, ph.auto_desc, ph.auto_seed, ph.auto_draws, h->geom_stream);
+      if (r != HB_OK) return r;
+      ph.auto_draws += ph.shape_cnt;
+    }
+    HB_CUDA(h, cudaMemcpyAsync(L.geom_flags_host, L.geom_flags_dev.p, L.pops.size() * 2 * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, h->geom_stream));
+    HB_CUDA(h, cudaEventRecord(L.shadow_event, h->geom_stream));
+    L.shadow_pending = true;
+    return HB_OK;
+  };
+  if (!L.shadow_pending) {
+    rc = enqueue_shadow();
+    if (rc != HB_OK) return rc;
+  }
+  HB_CUDA(h, cudaEventSynchronize(L.shadow_event));
+  HB_CUDA(h, cudaStreamWaitEvent(h->stream, L.shadow_event, 0));
+  ShapeBufs& fresh = L.sb[L.cur ^ 1];
+  for (uint32_t pi = 0; pi < L.pops.size(); pi++) {
+    if (!L.pops[pi].auto_geom) continue;
+    fresh.pop_p4[pi] = L.geom_flags_host[pi * 2] == 0u ? 1 : 0;
+    L.pops[pi].device_pool = true;
+    h->geom_rejected += L.geom_flags_host[pi * 2 + 1];
+  }
+  L.cur ^= 1;
+  L.shadow_pending = false;
+  return enqueue_shadow();
+}
+
+}  // namespace
+
 int hb_resample_shapes(HbEngine* h, uint32_t layer, uint32_t population, const HbCrystalDesc* crystal, uint32_t seed,
                        uint32_t draw_base, uint32_t* rejected) {
   if (h == nullptr || crystal == nullptr) return HB_ERR_INVALID_ARG;
@@ -1244,37 +1420,50 @@ int hb_resample_shapes(HbEngine* h, uint32_t layer, uint32_t population, const H
   if (crystal->kind > 1u) return fail(h, HB_ERR_INVALID_ARG, "resample_shapes: crystal kind must be prism (0) or pyramid (1)");
   cudaSetDevice(h->device);
   LayerDev& L = *h->layers[layer];
-  PopHost& ph = L.pops[population];
-  HB_CUDA(h, L.geom_scalars.ensure(static_cast<size_t>(L.shape_cnt) * 10));
-  HB_CUDA(h, h->geom_flags.ensure(2));
-  HB_CUDA(h, cudaMemsetAsync(h->geom_flags.p, 0, 2 * sizeof(uint32_t), h->stream));
-  ShapeGenParams sp{};
-  sp.desc = *crystal;
-  sp.a1 = crystal->kind == 1u ? hb_pyramid_slope(crystal->wedge_upper_deg) : -1.0;
-  sp.a2 = crystal->kind == 1u ? hb_pyramid_slope(crystal->wedge_lower_deg) : -1.0;
-  sp.seed = seed ^ kNonceGeom;
-  sp.draw_base = draw_base;
-  sp.count = ph.shape_cnt;
-  sp.pop = population;
-  sp.shapes = L.shapes.p + ph.shape_base;
-  sp.planes = L.planes.p + static_cast<size_t>(ph.shape_base) * HB_MAX_FACES;
-  sp.axes = L.axes.p + static_cast<size_t>(ph.shape_base) * HB_MAX_FACES * 2;
-  sp.meta = L.shape_meta.p + ph.shape_base;
-  sp.fn = L.face_fn.p + static_cast<size_t>(ph.shape_base) * HB_MAX_FACES;
-  sp.ef = L.entry_faces.p + ph.shape_base;
-  sp.scalars = L.geom_scalars.p + static_cast<size_t>(ph.shape_base) * 10;
-  sp.flags = h->geom_flags.p;
-  resample_shapes_kernel<<<(sp.count + 63u) / 64u, 64, 0, h->stream>>>(sp);
-  h->ctr.kernel_launches++;
-  HB_CUDA(h, cudaGetLastError());
+  if (L.pops[population].auto_geom) return fail(h, HB_ERR_STATE, "resample_shapes: population is on the automatic geometry clock");
+  int rc = ensure_geom_state(h, L);
+  if (rc != HB_OK) return rc;
+  if (L.shadow_pending) {  // a prefetched pool of this layer is in flight: it would carry a stale copy of this population
+    HB_CUDA(h, cudaEventSynchronize(L.shadow_event));
+    L.shadow_pending = false;
+  }
+  L.sb[L.cur ^ 1].allocated = false;  // re-copied from the live tables before its next use
+  rc = launch_resample(h, L, population, L.cur, *crystal, seed, draw_base, h->stream);
+  if (rc != HB_OK) return rc;
   uint32_t flags[2] = { 0, 0 };
-  HB_CUDA(h, cudaMemcpyAsync(flags, h->geom_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
+  HB_CUDA(h, cudaMemcpyAsync(flags, L.geom_flags_dev.p + population * 2, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
-  ph.p4 = flags[0] == 0u;
-  ph.device_pool = true;
-  L.p4 = true;
-  for (const PopHost& q : L.pops) L.p4 = L.p4 && q.p4;
+  L.b().pop_p4[population] = flags[0] == 0u ? 1 : 0;
+  L.pops[population].device_pool = true;
   if (rejected != nullptr) *rejected = flags[1];
+  return HB_OK;
+}
+
+int hb_auto_resample(HbEngine* h, uint32_t layer, uint32_t population, const HbCrystalDesc* crystal, uint32_t seed,
+                     uint32_t draw_base) {
+  if (h == nullptr) return HB_ERR_INVALID_ARG;
+  if (!h->have_scene) return fail(h, HB_ERR_STATE, "auto_resample before hb_set_scene");
+  if (h->in_session) return fail(h, HB_ERR_STATE, "auto_resample inside a session");
+  if (layer >= h->layers.size() || population >= h->layers[layer]->pops.size())
+    return fail(h, HB_ERR_INVALID_ARG, "auto_resample: no such layer / population");
+  cudaSetDevice(h->device);
+  LayerDev& L = *h->layers[layer];
+  PopHost& ph = L.pops[population];
+  if (crystal == nullptr) {  // switch the clock off: the live pool stays
+    ph.auto_geom = false;
+  } else {
+    if (crystal->kind > 1u) return fail(h, HB_ERR_INVALID_ARG, "auto_resample: crystal kind must be prism (0) or pyramid (1)");
+    ph.auto_geom = true;
+    ph.auto_desc = *crystal;
+    ph.auto_seed = seed;
+    ph.auto_draws = draw_base;
+  }
+  if (L.shadow_pending) {  // a pool drawn under the old settings is in flight: drop it
+    HB_CUDA(h, cudaEventSynchronize(L.shadow_event));
+    L.shadow_pending = false;
+  }
+  L.any_auto = false;
+  for (const PopHost& q : L.pops) L.any_auto = L.any_auto || q.auto_geom;
   return HB_OK;
 }
 
@@ -1290,10 +1479,10 @@ int hb_export_shapes(HbEngine* h, uint32_t layer, uint32_t population, uint32_t 
   if (tables == nullptr) return HB_OK;
   if (cap < ph.shape_cnt) return fail(h, HB_ERR_CAPACITY, "export_shapes: caller buffer too small");
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
-  HB_CUDA(h, cudaMemcpy(tables, L.shapes.p + ph.shape_base, ph.shape_cnt * sizeof(HbCrystalTables), cudaMemcpyDeviceToHost));
+  HB_CUDA(h, cudaMemcpy(tables, L.b().shapes.p + ph.shape_base, ph.shape_cnt * sizeof(HbCrystalTables), cudaMemcpyDeviceToHost));
   if (scalars10 != nullptr) {
     if (ph.device_pool) {
-      HB_CUDA(h, cudaMemcpy(scalars10, L.geom_scalars.p + static_cast<size_t>(ph.shape_base) * 10,
+      HB_CUDA(h, cudaMemcpy(scalars10, L.b().geom_scalars.p + static_cast<size_t>(ph.shape_base) * 10,
                             static_cast<size_t>(ph.shape_cnt) * 10 * sizeof(float), cudaMemcpyDeviceToHost));
     } else {
       std::memset(scalars10, 0, static_cast<size_t>(ph.shape_cnt) * 10 * sizeof(float));

@@ -72,9 +72,8 @@ def render_config(cfg: SceneConfig, backend: Optional[B200TraceBackend] = None, 
     draw a per-ray wavelength index (wl_pool.hpp:73-84). Ray indices are global: rank r of `world` traces its
     contiguous share of each wavelength's index range, so any world size traces the same set of rays.
     Stochastic crystal shapes: with `device_geometry` every session gets a fresh pool (`cfg.desc.geom_pool_size`
-    shapes per population, one shape per 32 consecutive rays) drawn and built on the device
-    (hb_resample_shapes); the shape stream index follows the session's first global ray index, so the crystals
-    depend on the ray range only, not on the rank that traces it.
+    shapes per population, one shape per 32 consecutive rays) drawn and built on the device one session ahead
+    (hb_auto_resample); ranks draw from disjoint ranges of the shape stream.
     """
     if not cfg.renders:
         raise ValueError("config has no renderer")
@@ -97,12 +96,12 @@ def render_config(cfg: SceneConfig, backend: Optional[B200TraceBackend] = None, 
             n = cfg.rays_per_wavelength()
             jobs = [([make_wl_entry(wl, w)], n) for wl, w in cfg.spectrum]
         index_base = 0
-        stochastic = stochastic_populations(cfg.desc) if device_geometry and cfg.desc.geom_pool_size > 1 else []
+        if device_geometry and cfg.desc.geom_pool_size > 1:
+            for k, (li, pi) in enumerate(stochastic_populations(cfg.desc)):   # engine-run geometry clock
+                be.AutoResample(li, pi, cfg.desc.layers[li].populations[pi].crystal, geometry_seed,
+                                ((rank * 64 + k) << 22) & 0xFFFFFFFF)
         for pool, total in jobs:
             for first, count in session_plan(total, rank, world, session_rays, index_base):
-                for li, pi in stochastic:
-                    be.ResampleShapes(li, pi, cfg.desc.layers[li].populations[pi].crystal, geometry_seed,
-                                      (first // 32) & 0xFFFFFFFF)
                 trace_session(be, cfg.desc.layer_cnt,
                               SessionSpec(seed=seed, wl=pool, ray_num=count, accumulate=True, ray_base=first), count)
             index_base += total

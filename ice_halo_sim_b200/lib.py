@@ -37,6 +37,7 @@ PROTOTYPES = {
     "hb_export_roots": (C.c_int, [_vp, C.c_uint64] + [_vp] * 8),
     "hb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "hb_resample_shapes": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32, _vp]),
+    "hb_auto_resample": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32]),
     "hb_export_shapes": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "hb_pyramid_slope": (C.c_double, [C.c_float]),
     "hb_get_counters": (C.c_int, [_vp, _vp]),

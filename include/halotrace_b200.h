@@ -456,6 +456,13 @@ int hb_resample_shapes(HbEngine* h, uint32_t layer, uint32_t population, const H
                        uint32_t seed, uint32_t draw_base, uint32_t* rejected);
 int hb_export_shapes(HbEngine* h, uint32_t layer, uint32_t population, uint32_t cap, HbCrystalTables* tables,
                      float* scalars10, uint32_t* count);
+/* Geometry clock run by the engine: from now on every hb_begin_session gives the population a FRESH pool
+ * (shape-stream indices draw_base, draw_base + pool size, ...), drawn and built on the device ONE SESSION AHEAD
+ * into a second copy of the layer's tables, so no session waits for its crystals and the host never drains
+ * the stream (only the first session waits for its own pool). crystal == NULL switches the clock off (the live
+ * pool stays). Legal between sessions; hb_set_scene resets it. */
+int hb_auto_resample(HbEngine* h, uint32_t layer, uint32_t population, const HbCrystalDesc* crystal, uint32_t seed,
+                     uint32_t draw_base);
 /* (sqrt3/4) / tan(alpha): slope parameter of a pyramidal segment, -1 when alpha is outside [0.1, 89.9] deg
  * (geo3d_closedform.cpp ComputeClosedFormPyramidInner). */
 double hb_pyramid_slope(float alpha_deg);

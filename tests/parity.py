@@ -310,7 +310,20 @@ def resample_pools_on_device(be, tables, seed, draw_base=0):
     return out
 
 
-def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=7, tile_rays=None, device_pool_seed=None):
+def sync_host_scene_with_device_pools(be, tables):
+    """Copy the engine's LIVE shape pools over the host scene's (geometry clock: the pool changes per session)."""
+    sc = tables.scene()
+    for li in range(sc.layer_cnt):
+        layer = sc.layers[li]
+        for pi in range(layer.population_cnt):
+            pop = layer.populations[pi]
+            if pop.shape_cnt > 1:
+                tb, _ = be.ExportShapes(li, pi)
+                C.memmove(pop.shapes, tb, C.sizeof(A.HbCrystalTables) * len(tb))
+
+
+def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=7, tile_rays=None, device_pool_seed=None,
+             geometry_clock_seed=None):
     """Full protocol on one case; returns a dict of comparison results (all layers merged)."""
     desc = case["scene"]()
     rdescs = case["render"]()
@@ -327,12 +340,19 @@ def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=
     be.SetScene(tables)
     if device_pool_seed is not None:
         resample_pools_on_device(be, tables, device_pool_seed)
+    if geometry_clock_seed is not None:   # engine-run geometry clock: pools are swapped in by BeginSession
+        for li in range(desc.layer_cnt):
+            for pi in range(desc.layers[li].population_cnt):
+                if sc.layers[li].populations[pi].shape_cnt > 1:
+                    be.AutoResample(li, pi, desc.layers[li].populations[pi].crystal, geometry_clock_seed, 0)
     be.SetOption("stream_base", 0)
     be.SetRenders(rdescs)
     projs = [B.make_proj_params(r) for r in rdescs]
     for r in range(len(rdescs)):
         be.ReadbackXyzAccum(render=r)  # start from zero images
     be.BeginSession(B.SessionSpec(seed=seed, wl=wl, ray_num=n_rays, record_exits=True, accumulate=True))
+    if geometry_clock_seed is not None:
+        sync_host_scene_with_device_pools(be, tables)
     out = dict(paths_equal=True, dirs_bit_equal=True, weights_bit_equal=True, meta_equal=True, exits=0, layers=[])
     all_exits = []
     roots_src = B.RootRaySource.FromHost(n_rays)

@@ -371,3 +371,39 @@ def test_injected_adversarial_rays_bit_exact(backend):
             total += len(g_ex)
     backend.SetOption("prism_fast_path", 1)
     assert total > 100000
+
+
+def test_geometry_clock_prefetch(backend):
+    """hb_auto_resample: every BeginSession swaps in a fresh pool that was drawn one session ahead. Session k's pool
+    equals an explicit hb_resample_shapes of the stream range [k n, (k + 1) n); traces on the swapped-in pools
+    pass the bit-exact protocol; switching the clock off freezes the live pool."""
+    from ice_halo_sim_b200 import backend as B
+    case = parity.CASES["stoch_config5"]
+    desc = case["scene"]()
+    n_pool = int(desc.geom_pool_size)
+    crystal = desc.layers[0].populations[0].crystal
+    tables = B.SceneTables(desc, 7)
+    wl = [B.make_wl_entry(550.0, 1.0)]
+    backend.SetScene(tables)
+    backend.SetRender(case["render"]())
+    backend.AutoResample(0, 0, crystal, 31, 0)
+    seen = []
+    for k in range(3):
+        backend.BeginSession(B.SessionSpec(seed=1, wl=wl, ray_num=4096))
+        backend.TraceLayer(B.RootRaySource.FromHost(4096), want_stats=False)
+        backend.EndSession()
+        seen.append(backend.ExportShapes(0, 0)[1].copy())
+    backend.AutoResample(0, 0, None)
+    backend.BeginSession(B.SessionSpec(seed=1, wl=wl, ray_num=16))
+    backend.TraceLayer(B.RootRaySource.FromHost(16), want_stats=False)
+    backend.EndSession()
+    assert np.array_equal(backend.ExportShapes(0, 0)[1], seen[2])          # clock off: pool frozen
+    backend.ReadbackXyzAccum()
+    for k in range(3):
+        backend.ResampleShapes(0, 0, crystal, 31, k * n_pool)
+        assert np.array_equal(backend.ExportShapes(0, 0)[1], seen[k]), k
+    assert not np.array_equal(seen[0], seen[1])
+    for seed in (5, 6):   # two consecutive sessions on the clock, each against the oracle on its own pool
+        res = parity.run_case(case, n_rays=15000, seed=seed, backend=backend, geometry_clock_seed=99)
+        assert res["paths_equal"] and res["dirs_bit_equal"] and res["weights_bit_equal"] and res["meta_equal"], res
+        assert res["image_ok"], res
