@@ -407,3 +407,30 @@ def test_geometry_clock_prefetch(backend):
         res = parity.run_case(case, n_rays=15000, seed=seed, backend=backend, geometry_clock_seed=99)
         assert res["paths_equal"] and res["dirs_bit_equal"] and res["weights_bit_equal"] and res["meta_equal"], res
         assert res["image_ok"], res
+
+
+def test_driver_stochastic_config_device_geometry(backend):
+    """driver.render_config on a bench_config_stoch.json-shaped config (prism, face distances ~ N(1, 0.15), full-sphere
+    axis, rectangular full-sky lens): the engine-run geometry clock (fresh device-built pool per session) and the
+    host-drawn pool give statistically the same frame."""
+    from ice_halo_sim_b200 import load_config, render_config
+    g = {"type": "gauss", "mean": 1.0, "std": 0.15}
+    u360 = {"type": "uniform", "mean": 0.0, "std": 360.0}
+    cfg_json = {
+        "crystal": [{"id": 1, "type": "prism", "shape": {"height": 1.0, "face_distance": [g] * 6},
+                     "axis": {"zenith": u360, "azimuth": u360, "roll": u360}}],
+        "filter": [],
+        "render": [{"id": 1, "lens": {"type": "rectangular", "fov": 180.0}, "resolution": [1024, 512],
+                    "view": {"azimuth": 0.0, "elevation": 0.0, "roll": 0.0}, "visible": "full"}],
+        "scene": {"id": 1, "light_source": {"type": "sun", "altitude": 20.0, "azimuth": 0.0, "diameter": 0.5,
+                                            "spectrum": [{"wavelength": 550.0, "weight": 1.0}]},
+                  "ray_num": 3_000_000, "max_hits": 8,
+                  "scattering": [{"prob": 0.0, "entries": [{"crystal": 1, "proportion": 1.0}]}]},
+    }
+    cfg = load_config(cfg_json, geom_pool_size=128)
+    dev = render_config(cfg, backend, seed=3, session_rays=1 << 18, device_geometry=True)[1]
+    host = render_config(cfg, backend, seed=3, session_rays=1 << 18, device_geometry=False)[1]
+    assert dev.landed_weight > 0 and abs(dev.landed_weight / host.landed_weight - 1.0) < 0.02
+    a = dev.xyz[..., 1].reshape(32, 16, 64, 16).mean(axis=(1, 3)).ravel()
+    b = host.xyz[..., 1].reshape(32, 16, 64, 16).mean(axis=(1, 3)).ravel()
+    assert np.corrcoef(a, b)[0, 1] > 0.95
