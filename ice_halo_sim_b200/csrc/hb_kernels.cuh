@@ -537,6 +537,12 @@ HB_DEV void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+#ifndef HB_OPTICS_MINB_GENERAL
+#define HB_OPTICS_MINB_GENERAL 4
+#endif
+#ifndef HB_INTERSECT_MINB_GENERAL
+#define HB_INTERSECT_MINB_GENERAL 4
+#endif
 #ifndef HB_OPTICS_MINB
 #define HB_OPTICS_MINB 4
 #endif
@@ -544,7 +550,7 @@ HB_DEV void cp_async_wait() {
 #define HB_INTERSECT_MINB 5
 #endif
 template <bool GENERAL, bool LAST, bool SMEM, bool MULTI, bool P4 = false>
-__global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const TraceParams tp) {
+__global__ void __launch_bounds__(256, GENERAL ? HB_OPTICS_MINB_GENERAL : HB_OPTICS_MINB) optics_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Tally tally;
   const bool use_cache = (tp.flags & kFlagPixelCache) != 0u;
@@ -670,7 +676,7 @@ __global__ void __launch_bounds__(256, HB_OPTICS_MINB) optics_kernel(const Trace
 // intersect kernel: slab exit-face search for the inside child
 // ------------------------------------------------------------------------------------------------
 template <bool GENERAL, bool SMEM, bool MULTI, bool P4 = false>
-__global__ void __launch_bounds__(256, HB_INTERSECT_MINB) intersect_kernel(const TraceParams tp) {
+__global__ void __launch_bounds__(256, GENERAL ? HB_INTERSECT_MINB_GENERAL : HB_INTERSECT_MINB) intersect_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw, GENERAL);
   const uint32_t forks = *tp.fork_count;
