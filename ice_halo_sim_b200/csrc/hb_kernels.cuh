@@ -261,6 +261,12 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
     }
     uint8_t fn_path[HB_MAX_HITS];
     const uint32_t len = tp.hit + 1u;
+    if (tp.lt.any_filter) {
+      // A filter_in raypath filter only admits paths of its own length: everything else fails before the path
+      // is even gathered (len is uniform over the launch, so whole hit levels skip the matcher).
+      const HbFilterDesc& f = tp.lt.filters[pop];
+      if (f.kind == 1u && f.action == 0u && len != f.simple.path_len) return;
+    }
     if (tp.flags & kFlagPath) {
       for (uint32_t k = 0; k < len; k++)
         fn_path[k] = static_cast<uint8_t>(tb.face_fn(shape, tp.path[static_cast<size_t>(k) * tp.cap + slot]));
