@@ -327,11 +327,11 @@ uint32_t resident_grid(const HbEngine* h, K kernel, size_t smem, uint64_t n) {
 
 template <bool G, bool L, bool S, bool M = false, bool P = false>
 void launch_optics_t(HbEngine* h, size_t smem, const TraceParams& tp) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device: function attributes live in the device's context
+  if (!attr_set[h->device & 63]) {
     cudaFuncSetAttribute(optics_kernel<G, L, S, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(shared_tables_bytes(kSmemShapes) + kCacheBytes + kStageBytes));
-    attr_set = true;
+    attr_set[h->device & 63] = true;
   }
   const uint32_t grid = resident_grid(h, optics_kernel<G, L, S, M, P>, smem, tp.cap);
   optics_kernel<G, L, S, M, P><<<grid, 256, smem, h->stream>>>(tp);
