@@ -75,12 +75,17 @@ struct ShapeBufs {
   DevBuf<HbCrystalTables> shapes;
   DevBuf<EntryFaces> entry_faces;  // [shape] face groups of the entry fan table
   DevBuf<float> geom_scalars;      // [shape][10] scalars of device-drawn shapes (parity export)
-  std::vector<uint8_t> pop_p4;     // [pop] every shape of the population's pool is a full hexagonal prism
+  std::vector<uint32_t> pop_p4;    // [pop] number of shapes of the pool that are full hexagonal prisms (kMetaP4)
+  std::vector<uint32_t> pop_shapes;  // [pop] pool size
   bool allocated = false;
-  bool p4() const {
-    for (uint8_t v : pop_p4)
-      if (!v) return false;
-    return true;
+  // kernel variant of the layer: 1 = every shape is P4 (unrolled forms only), 2 = some are (per-ray choice), 0 = none
+  int p4_mode() const {
+    uint32_t p4 = 0, all = 0;
+    for (size_t i = 0; i < pop_p4.size(); i++) {
+      p4 += pop_p4[i];
+      all += pop_shapes[i];
+    }
+    return p4 == all ? 1 : (p4 != 0 ? 2 : 0);
   }
   void release() {
     planes.release();
@@ -325,7 +330,7 @@ uint32_t resident_grid(const HbEngine* h, K kernel, size_t smem, uint64_t n) {
   return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(blocks, static_cast<uint64_t>(h->sm_count) * per_sm)));
 }
 
-template <bool G, bool L, bool S, bool M = false, bool P = false>
+template <bool G, bool L, bool S, bool M = false, int P = 0>
 void launch_optics_t(HbEngine* h, size_t smem, const TraceParams& tp) {
   static bool attr_set[64] = {};  // per device: function attributes live in the device's context
   if (!attr_set[h->device & 63]) {
@@ -336,19 +341,23 @@ void launch_optics_t(HbEngine* h, size_t smem, const TraceParams& tp) {
   const uint32_t grid = resident_grid(h, optics_kernel<G, L, S, M, P>, smem, tp.cap);
   optics_kernel<G, L, S, M, P><<<grid, 256, smem, h->stream>>>(tp);
 }
-void launch_optics(HbEngine* h, bool general, bool last, bool in_smem, bool p4, size_t smem, const TraceParams& tp) {
+template <int P>
+void launch_optics_p(HbEngine* h, int key, size_t smem, const TraceParams& tp) {
+  switch (key) {
+    case 0: launch_optics_t<false, false, false, false, P>(h, smem, tp); break;
+    case 1: launch_optics_t<false, false, true, false, P>(h, smem, tp); break;
+    case 2: launch_optics_t<false, true, false, false, P>(h, smem, tp); break;
+    case 3: launch_optics_t<false, true, true, false, P>(h, smem, tp); break;
+    case 4: launch_optics_t<true, false, false, false, P>(h, smem, tp); break;
+    case 5: launch_optics_t<true, false, true, false, P>(h, smem, tp); break;
+    case 6: launch_optics_t<true, true, false, false, P>(h, smem, tp); break;
+    default: launch_optics_t<true, true, true, false, P>(h, smem, tp); break;
+  }
+}
+void launch_optics(HbEngine* h, bool general, bool last, bool in_smem, int p4, size_t smem, const TraceParams& tp) {
   const int key = (general ? 4 : 0) | (last ? 2 : 0) | (in_smem ? 1 : 0);
-  if (p4 && tp.extra_cnt == 0u && tp.color_on == 0u) {  // hexagonal-prism layers: unrolled paired-axis forms
-    switch (key) {
-      case 0: launch_optics_t<false, false, false, false, true>(h, smem, tp); break;
-      case 1: launch_optics_t<false, false, true, false, true>(h, smem, tp); break;
-      case 2: launch_optics_t<false, true, false, false, true>(h, smem, tp); break;
-      case 3: launch_optics_t<false, true, true, false, true>(h, smem, tp); break;
-      case 4: launch_optics_t<true, false, false, false, true>(h, smem, tp); break;
-      case 5: launch_optics_t<true, false, true, false, true>(h, smem, tp); break;
-      case 6: launch_optics_t<true, true, false, false, true>(h, smem, tp); break;
-      default: launch_optics_t<true, true, true, false, true>(h, smem, tp); break;
-    }
+  if (p4 != 0 && tp.extra_cnt == 0u && tp.color_on == 0u) {  // hexagonal prisms: unrolled paired-axis forms
+    if (p4 == 1) launch_optics_p<1>(h, key, smem, tp); else launch_optics_p<2>(h, key, smem, tp);
     return;
   }
   if (tp.extra_cnt != 0u || tp.color_on != 0u) {  // N projections per trace / raypath colour: extended GENERAL kernels
@@ -371,18 +380,22 @@ void launch_optics(HbEngine* h, bool general, bool last, bool in_smem, bool p4, 
     default: launch_optics_t<true, true, true>(h, smem, tp); break;
   }
 }
-template <bool G, bool S, bool M = false, bool P = false>
+template <bool G, bool S, bool M = false, int P = 0>
 void launch_intersect_t(HbEngine* h, size_t smem, const TraceParams& tp) {
   const uint32_t grid = resident_grid(h, intersect_kernel<G, S, M, P>, smem, tp.cap);
   intersect_kernel<G, S, M, P><<<grid, 256, smem, h->stream>>>(tp);
 }
-void launch_intersect(HbEngine* h, bool general, bool in_smem, bool p4, size_t smem, const TraceParams& tp) {
-  if (p4 && tp.extra_cnt == 0u && tp.color_on == 0u) {
-    if (general) {
-      if (in_smem) launch_intersect_t<true, true, false, true>(h, smem, tp); else launch_intersect_t<true, false, false, true>(h, smem, tp);
-    } else {
-      if (in_smem) launch_intersect_t<false, true, false, true>(h, smem, tp); else launch_intersect_t<false, false, false, true>(h, smem, tp);
-    }
+template <int P>
+void launch_intersect_p(HbEngine* h, bool general, bool in_smem, size_t smem, const TraceParams& tp) {
+  if (general) {
+    if (in_smem) launch_intersect_t<true, true, false, P>(h, smem, tp); else launch_intersect_t<true, false, false, P>(h, smem, tp);
+  } else {
+    if (in_smem) launch_intersect_t<false, true, false, P>(h, smem, tp); else launch_intersect_t<false, false, false, P>(h, smem, tp);
+  }
+}
+void launch_intersect(HbEngine* h, bool general, bool in_smem, int p4, size_t smem, const TraceParams& tp) {
+  if (p4 != 0 && tp.extra_cnt == 0u && tp.color_on == 0u) {
+    if (p4 == 1) launch_intersect_p<1>(h, general, in_smem, smem, tp); else launch_intersect_p<2>(h, general, in_smem, smem, tp);
   } else if (tp.extra_cnt != 0u || tp.color_on != 0u) {
     if (in_smem) launch_intersect_t<true, true, true>(h, smem, tp); else launch_intersect_t<true, false, true>(h, smem, tp);
   } else if (general) {
@@ -413,6 +426,7 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   ShapeBufs& B0 = L->sb[0];
   L->cur = 0;
   B0.pop_p4.clear();
+  B0.pop_shapes.clear();
   for (uint32_t ci = 0; ci < src.population_cnt; ci++) {
     const HbCrystalPopulation& p = src.populations[ci];
     if (p.shape_cnt == 0 || p.shapes == nullptr) return fail(h, HB_ERR_INVALID_ARG, "population without shapes");
@@ -424,7 +438,7 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
     ph.axis = AxisParams{ p.axis.lat_path, p.axis.lat_mean, p.axis.lat_std, p.axis.az_type, p.axis.az_mean, p.axis.az_std,
                           p.axis.roll_type, p.axis.roll_mean, p.axis.roll_std, p.axis.lut_n };
     ph.has_filter = p.filter.kind != 0;
-    bool pop_p4 = true;  // every shape: four axes, all paired (hexagonal prism with all eight faces)
+    uint32_t pop_p4 = 0;  // shapes with four axes, all paired (hexagonal prism with all eight faces)
     L->any_filter = L->any_filter || ph.has_filter;
     for (uint32_t s = 0; s < p.shape_cnt; s++) {
       const HbCrystalTables& t = p.shapes[s];
@@ -435,11 +449,12 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
       axes.resize(axes.size() + HB_MAX_FACES * 2);
       meta.push_back(0u);
       entry_faces.emplace_back();
-      if (!derive_shape_tables(t, ci, &planes[planes.size() - HB_MAX_FACES], &fn[fn.size() - HB_MAX_FACES],
-                               &axes[axes.size() - HB_MAX_FACES * 2], &meta.back(), &entry_faces.back()))
-        pop_p4 = false;
+      if (derive_shape_tables(t, ci, &planes[planes.size() - HB_MAX_FACES], &fn[fn.size() - HB_MAX_FACES],
+                              &axes[axes.size() - HB_MAX_FACES * 2], &meta.back(), &entry_faces.back()))
+        pop_p4++;
     }
-    B0.pop_p4.push_back(pop_p4 ? 1 : 0);
+    B0.pop_p4.push_back(pop_p4);
+    B0.pop_shapes.push_back(p.shape_cnt);
     filters.push_back(p.filter);
     cid.push_back(p.crystal_id);
     if (p.color_group_cnt > HB_MAX_COLOR_GROUPS) return fail(h, HB_ERR_INVALID_ARG, "population: too many colour groups");
@@ -685,14 +700,14 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
     tp.hit = hit;
     const bool last = hit + 1 == h->max_hits;
     EventPair* ev = begin_event(h, 1, n);
-    launch_optics(h, general, last, in_smem, L.b().p4() && h->p4_enable, smem + kStageBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
+    launch_optics(h, general, last, in_smem, h->p4_enable ? L.b().p4_mode() : 0, smem + kStageBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
     end_event(h, ev);
     h->ctr.kernel_launches++;
     h->ctr.optics_launches++;
     h->ctr.optics_rays += n;
     if (!last) {
       ev = begin_event(h, 2, n);
-      launch_intersect(h, general, in_smem, L.b().p4() && h->p4_enable, smem, tp);
+      launch_intersect(h, general, in_smem, h->p4_enable ? L.b().p4_mode() : 0, smem, tp);
       end_event(h, ev);
       h->ctr.kernel_launches++;
       h->ctr.intersect_launches++;
@@ -1327,6 +1342,7 @@ int ensure_shadow(HbEngine* h, LayerDev& L) {
   HB_CUDA(h, cudaMemcpyAsync(dst.entry_faces.p, src.entry_faces.p, src.entry_faces.n * sizeof(EntryFaces), k, h->stream));
   HB_CUDA(h, cudaMemcpyAsync(dst.geom_scalars.p, src.geom_scalars.p, src.geom_scalars.n * sizeof(float), k, h->stream));
   dst.pop_p4 = src.pop_p4;
+  dst.pop_shapes = src.pop_shapes;
   dst.allocated = true;
   return HB_OK;
 }
@@ -1399,7 +1415,7 @@ int prefetch_geometry(HbEngine* h, LayerDev& L) {
   ShapeBufs& fresh = L.sb[L.cur ^ 1];
   for (uint32_t pi = 0; pi < L.pops.size(); pi++) {
     if (!L.pops[pi].auto_geom) continue;
-    fresh.pop_p4[pi] = L.geom_flags_host[pi * 2] == 0u ? 1 : 0;
+    fresh.pop_p4[pi] = L.pops[pi].shape_cnt - std::min(L.pops[pi].shape_cnt, L.geom_flags_host[pi * 2]);
     L.pops[pi].device_pool = true;
     h->geom_rejected += L.geom_flags_host[pi * 2 + 1];
   }
@@ -1433,7 +1449,7 @@ int hb_resample_shapes(HbEngine* h, uint32_t layer, uint32_t population, const H
   uint32_t flags[2] = { 0, 0 };
   HB_CUDA(h, cudaMemcpyAsync(flags, L.geom_flags_dev.p + population * 2, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
-  L.b().pop_p4[population] = flags[0] == 0u ? 1 : 0;
+  L.b().pop_p4[population] = L.pops[population].shape_cnt - std::min(L.pops[population].shape_cnt, flags[0]);
   L.pops[population].device_pool = true;
   if (rejected != nullptr) *rejected = flags[1];
   return HB_OK;

@@ -26,6 +26,8 @@ namespace hb {
 // ------------------------------------------------------------------------------------------------
 // Kernel parameter blocks
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t kMetaP4 = 1u << 24;  // shape meta word: the shape is a full hexagonal prism (four paired axes)
+
 struct LayerTables {            // device pointers, one scattering layer
   const float4* planes;         // [shape_cnt][HB_MAX_FACES]
   const float4* axes;           // [shape_cnt][HB_MAX_FACES][2] paired-plane axis table (see slab_exit)
@@ -555,7 +557,10 @@ HB_DEV void cp_async_wait() {
 #ifndef HB_INTERSECT_MINB
 #define HB_INTERSECT_MINB 5
 #endif
-template <bool GENERAL, bool LAST, bool SMEM, bool MULTI, bool P4 = false>
+// P4: 0 = generic axis loop, 1 = every shape of the layer is a full hexagonal prism (unrolled forms only),
+// 2 = mixed layer: chosen per ray from the shape's meta word (kMetaP4). Shapes are uniform over 32-ray blocks
+// and populations occupy contiguous index ranges, so the choice is warp-uniform except at block boundaries.
+template <bool GENERAL, bool LAST, bool SMEM, bool MULTI, int P4 = 0>
 __global__ void __launch_bounds__(256, GENERAL ? HB_OPTICS_MINB_GENERAL : HB_OPTICS_MINB) optics_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Tally tally;
@@ -618,6 +623,7 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_OPTICS_MINB_GENERAL : HB_OPT
       const uint32_t meta = tb.meta(shape);
       const AxisRow<SMEM> axes = tb.axes(shape);
       const uint32_t axis_cnt = (meta >> 16) & 255u;
+      const bool shape_p4 = (meta & kMetaP4) != 0u;
       float n_idx = tp.wl0.n_idx, inv_n = tp.wl0.inv_n;
       if (tp.wl_cnt != 1u) {
         const float2 nn = __ldg(reinterpret_cast<const float2*>(tp.wl2 + bits_wl(bits)));
@@ -636,7 +642,7 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_OPTICS_MINB_GENERAL : HB_OPT
       if (ow >= 0.0f) {
         float nx = 0.f, ny = 0.f, nz = 0.f;
         uint32_t nf = kFaceInvalid;
-        if (P4) {
+        if (P4 == 1 || (P4 == 2 && shape_p4)) {
           if (!far_child_surely_exits_p4(axes, pl, p4.x, p4.y, p4.z, ox, oy, oz))
             nf = slab_exit_p4<true>(axes, face, p4.x, p4.y, p4.z, ox, oy, oz, nx, ny, nz);
         } else {
@@ -651,10 +657,11 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_OPTICS_MINB_GENERAL : HB_OPT
       }
       if (LAST) {
         // no intersect pass follows the final interaction: classify the inside child here too
-        if (iw >= 0.0f && !near_child_surely_hits(axes, P4 ? 4u : axis_cnt, p4.x, p4.y, p4.z, ix, iy, iz)) {
+        if (iw >= 0.0f && !near_child_surely_hits(axes, P4 == 1 ? 4u : axis_cnt, p4.x, p4.y, p4.z, ix, iy, iz)) {
           float nx, ny, nz;
-          const uint32_t nf = P4 ? slab_exit_p4<false>(axes, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz)
-                                 : slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+          uint32_t nf;
+          if (P4 == 1 || (P4 == 2 && shape_p4)) nf = slab_exit_p4<false>(axes, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+          else nf = slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
           if (nf == kFaceInvalid) emit_exit<GENERAL, MULTI>(tp, i, bits, HB_LOAD_Q(), ix, iy, iz, iw, /*role=*/1u, tb, tally);
         }
       } else {
@@ -681,7 +688,7 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_OPTICS_MINB_GENERAL : HB_OPT
 // ------------------------------------------------------------------------------------------------
 // intersect kernel: slab exit-face search for the inside child
 // ------------------------------------------------------------------------------------------------
-template <bool GENERAL, bool SMEM, bool MULTI, bool P4 = false>
+template <bool GENERAL, bool SMEM, bool MULTI, int P4 = 0>
 __global__ void __launch_bounds__(256, GENERAL ? HB_INTERSECT_MINB_GENERAL : HB_INTERSECT_MINB) intersect_kernel(const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw, GENERAL);
@@ -712,9 +719,11 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_INTERSECT_MINB_GENERAL : HB_
         const uint32_t shape = bits_shape(bits);
         const uint32_t meta = tb.meta(shape);
         float nx, ny, nz;
-        const uint32_t nf = P4 ? slab_exit_p4<false>(tb.axes(shape), face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz)
-                               : slab_exit<false>(tb.axes(shape), (meta >> 16) & 255u, face, p4.x, p4.y, p4.z, d4.x, d4.y,
-                                                  d4.z, nx, ny, nz);
+        uint32_t nf;
+        if (P4 == 1 || (P4 == 2 && (meta & kMetaP4) != 0u))
+          nf = slab_exit_p4<false>(tb.axes(shape), face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz);
+        else
+          nf = slab_exit<false>(tb.axes(shape), (meta >> 16) & 255u, face, p4.x, p4.y, p4.z, d4.x, d4.y, d4.z, nx, ny, nz);
         if (nf == kFaceInvalid) {
           // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
           emit_exit<GENERAL, MULTI>(tp, i, bits, tp.Q[i], d4.x, d4.y, d4.z, d4.w, /*role=*/1u, tb, tally);
@@ -793,7 +802,7 @@ __host__ __device__ inline void build_entry_faces(const HbCrystalTables& t, Entr
 
 // Everything the trace kernels read of one shape, derived from its HbCrystalTables: plane table, face numbers,
 // the paired-axis table of the slab scan (faces whose unit normals are exact negatives share one entry, see
-// slab_exit), meta word (face_cnt | population << 8 | axis_cnt << 16) and the entry face groups.
+// slab_exit), meta word (face_cnt | population << 8 | axis_cnt << 16 | kMetaP4) and the entry face groups.
 // Returns true when the shape qualifies for the P4 kernels (exactly four axes, all paired).
 __host__ __device__ inline bool derive_shape_tables(const HbCrystalTables& t, uint32_t pop, float4* planes, uint8_t* fn,
                                                     float4* axes, uint32_t* meta, EntryFaces* ef) {
@@ -826,9 +835,10 @@ __host__ __device__ inline bool derive_shape_tables(const HbCrystalTables& t, ui
     axis_cnt++;
     if (partner == 63u) all_paired = false;
   }
-  *meta = t.face_cnt | (pop << 8) | (axis_cnt << 16);
+  const bool p4 = all_paired && axis_cnt == 4u;
+  *meta = t.face_cnt | (pop << 8) | (axis_cnt << 16) | (p4 ? kMetaP4 : 0u);
   build_entry_faces(t, ef);
-  return all_paired && axis_cnt == 4u;
+  return p4;
 }
 
 constexpr uint32_t kFastGroups = 8;  // prism: 8 faces, weights kept in registers
