@@ -55,8 +55,23 @@ def test_generated_roots_match_oracle_generator(backend):
     import harness as H
     from ice_halo_sim_b200 import backend as B
     A = H.A
-    for name in ("column_config2", "stoch_config5", "pyramid"):
-        case = parity.CASES[name]
+    # every latitude path of the sampler (full sphere, fixed, legacy Gauss, inverse-CDF LUT of each distribution
+    # type) and the azimuth / roll distribution types, beyond what the named cases use
+    extra = {
+        "lat_none_roll_gauss": dict(scene=lambda: parity.scene([(0.0, [parity.prism_pop(
+            0.4, zenith=("none", 35.0, 0.0), azimuth=("gauss", 40.0, 10.0), roll=("gauss", 10.0, 5.0))])], 5), wl=[550.0]),
+        "lat_gauss_legacy": dict(scene=lambda: parity.scene([(0.0, [parity.prism_pop(
+            1.5, zenith=("gauss_legacy", 80.0, 6.0), roll=("none", 30.0, 0.0))])], 5), wl=[550.0]),
+        "lat_laplacian": dict(scene=lambda: parity.scene([(0.0, [parity.prism_pop(
+            0.3, zenith=("laplacian", 10.0, 3.0), azimuth=("laplacian", 90.0, 20.0), roll=("zigzag", 0.0, 15.0))])], 5),
+            wl=[550.0]),
+        "lat_zigzag": dict(scene=lambda: parity.scene([(0.0, [parity.prism_pop(
+            1.0, zenith=("zigzag", 90.0, 25.0), roll=("uniform", 0.0, 60.0))])], 5), wl=[550.0]),
+        "lat_uniform_band": dict(scene=lambda: parity.scene([(0.0, [parity.prism_pop(
+            1.0, zenith=("uniform", 60.0, 40.0), azimuth=("zigzag", 0.0, 30.0))])], 5), wl=[550.0]),
+    }
+    for name in ("column_config2", "stoch_config5", "pyramid") + tuple(sorted(extra)):
+        case = parity.CASES[name] if name in parity.CASES else extra[name]
         desc = case["scene"]()
         tables = B.SceneTables(desc, 7)
         wl = [B.make_wl_entry(x, 1.0) for x in case["wl"]]
