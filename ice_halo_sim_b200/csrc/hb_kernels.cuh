@@ -165,7 +165,10 @@ struct Tally {
 // direct-mapped table of kCacheSlots pixels in shared memory (first come, first claimed): contributions to a
 // cached pixel are summed in shared memory and reduced into the global image once, when the CTA retires.
 // Everything else goes straight to the L2 with one red.global.add.v4.f32.
-constexpr uint32_t kCacheSlots = 512;
+#ifndef HB_CACHE_SLOTS_LOG2
+#define HB_CACHE_SLOTS_LOG2 9
+#endif
+constexpr uint32_t kCacheSlots = 1u << HB_CACHE_SLOTS_LOG2;
 constexpr uint32_t kCacheEmpty = 0xFFFFFFFFu;
 constexpr size_t kCacheBytes = kCacheSlots * (sizeof(uint32_t) + 4 * sizeof(float));
 
@@ -204,7 +207,7 @@ HB_DEV void smem_add_f4(uint32_t addr, float x, float y, float z, float w) {
 
 HB_DEV void accumulate_pixel(const TraceParams& tp, const Tally& tally, uint32_t pix, float x, float y, float z, float lw) {
   if (tally.cache_keys != nullptr) {
-    const uint32_t slot = (pix * 2654435761u) >> 23;  // top 9 bits
+    const uint32_t slot = (pix * 2654435761u) >> (32 - HB_CACHE_SLOTS_LOG2);  // multiplicative hash, top bits
     uint32_t k = tally.cache_keys[slot];
     if (k == kCacheEmpty) {
       k = atomicCAS(&tally.cache_keys[slot], kCacheEmpty, pix);
