@@ -449,3 +449,33 @@ def test_driver_stochastic_config_device_geometry(backend):
     a = dev.xyz[..., 1].reshape(32, 16, 64, 16).mean(axis=(1, 3)).ravel()
     b = host.xyz[..., 1].reshape(32, 16, 64, 16).mean(axis=(1, 3)).ravel()
     assert np.corrcoef(a, b)[0, 1] > 0.95
+
+
+def test_two_layer_full_size_invariants(backend):
+    """BASELINE config 4 shape (two layers, prob 1.0) at 4 Mi roots, properties that need no oracle: every exit of
+    layer 0 continues (LayerStats: continuations == exits, nothing lands from layer 0), layer 1 traces exactly those
+    continuations, energy only decreases, and total Y == cmf_y x landed weight after both layers."""
+    from ice_halo_sim_b200 import backend as B
+    case = parity.CASES["two_layer_config4"]
+    backend.SetScene(B.SceneTables(case["scene"](), 7))
+    backend.SetRender(case["render"]())
+    backend.ReadbackXyzAccum()
+    wl = [B.make_wl_entry(550.0, 1.0)]
+    n = 1 << 22
+    backend.BeginSession(B.SessionSpec(seed=21, wl=wl, ray_num=n, accumulate=True))
+    h0 = backend.TraceLayer(B.RootRaySource.FromHost(n), want_stats=True)
+    assert h0.root_count == n
+    assert h0.continuation_count == h0.exit_count and 4.0 * n < h0.exit_count < 8.0 * n
+    assert h0.exit_w_sum <= n * (1 + 1e-6)                      # Fresnel splitting never creates energy
+    _, landed_mid = backend.ReadbackXyzAccum()
+    assert landed_mid == 0.0                                     # prob 1.0: nothing of layer 0 reaches the image
+    roots = backend.Recombine(h0, shuffle=True)
+    assert roots.is_device and roots.count == h0.continuation_count
+    h1 = backend.TraceLayer(roots, want_stats=True)
+    backend.EndSession()
+    assert h1.root_count == h0.continuation_count and h1.continuation_count == 0
+    assert h1.exit_w_sum <= h0.exit_w_sum * (1 + 1e-6)
+    img, landed = backend.ReadbackXyzAccum()
+    assert 0 < landed <= h1.exit_w_sum * (1 + 1e-5)              # "upper" view: only part of the sky lands
+    y = img[..., 1].astype(np.float64).sum()
+    assert abs(y - wl[0][3] * landed) <= 2e-4 * y
