@@ -38,6 +38,12 @@ BYTES_OPTICS_LAST = 48          # final interaction writes no state
 BYTES_EXIT = 16
 BYTES_INTERSECT = 48            # read P,D (32) + write P (16)
 BYTES_GEN = 48
+# fused bounce kernel (one launch per interaction): read P,D (32) + write P,D (32); per emitted exit the
+# orientation quaternion is read (16) and one v4 reduction goes to the image (16); the final interaction writes no state
+BYTES_BOUNCE = 64
+BYTES_BOUNCE_LAST = 32
+BYTES_BOUNCE_EXIT = 32
+TRAFFIC_FILE = "traffic_r2.json"
 EXITS_PER_ROOT = 4.7            # measured on this scene (reference CPU: 4.69-4.71)
 
 
@@ -344,36 +350,40 @@ def main():
             peaks = json.load(open(pk_path))
             hbm_peak = float(peaks.get("hbm_gbs", hbm_peak))
             peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-        o_l = c1.optics_launches - c0.optics_launches
-        i_l = c1.intersect_launches - c0.intersect_launches
-        o_ms = (c1.optics_ms - c0.optics_ms) / max(1, o_l)
-        i_ms = (c1.intersect_ms - c0.intersect_ms) / max(1, i_l)
-        g_ms = (c1.gen_ms - c0.gen_ms) / max(1, c1.gen_launches - c0.gen_launches)
-        tile = (c1.optics_rays - c0.optics_rays) / max(1, o_l)
-        opt_bytes = tile * ((BYTES_OPTICS * (max_hits - 1) + BYTES_OPTICS_LAST) / max_hits +
-                            BYTES_EXIT * exits_per_root / max_hits)
-        int_bytes = tile * BYTES_INTERSECT
-        opt_total = (c1.optics_ms - c0.optics_ms)
-        int_total = (c1.intersect_ms - c0.intersect_ms)
-        dom = "optics" if opt_total >= int_total else "intersect"
-        ach_o = opt_bytes / (o_ms * 1e-3) / 1e9 if o_ms > 0 else 0.0
-        ach_i = int_bytes / (i_ms * 1e-3) / 1e9 if i_ms > 0 else 0.0
+        epb = exits_per_root / max_hits          # exits per ray-bounce
+        fam = {}
+        for name, ms, launches, rays, bytes_per_ray in (
+                ("bounce", c1.bounce_ms - c0.bounce_ms, c1.bounce_launches - c0.bounce_launches,
+                 c1.bounce_rays - c0.bounce_rays,
+                 (BYTES_BOUNCE * (max_hits - 1) + BYTES_BOUNCE_LAST) / max_hits + BYTES_BOUNCE_EXIT * epb),
+                ("optics", c1.optics_ms - c0.optics_ms, c1.optics_launches - c0.optics_launches,
+                 c1.optics_rays - c0.optics_rays,
+                 (BYTES_OPTICS * (max_hits - 1) + BYTES_OPTICS_LAST) / max_hits + BYTES_EXIT * epb),
+                ("intersect", c1.intersect_ms - c0.intersect_ms, c1.intersect_launches - c0.intersect_launches,
+                 c1.intersect_rays - c0.intersect_rays, BYTES_INTERSECT)):
+            if launches == 0:
+                continue
+            avg_ms = ms / launches
+            tile = rays / launches
+            ach = tile * bytes_per_ray / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+            fam[name] = {"avg_ms": avg_ms, "launches": int(launches), "rays_per_launch": tile,
+                         "algorithmic_bytes_per_ray_bounce": bytes_per_ray, "achieved_gbs": ach,
+                         "frac": ach / hbm_peak, "total_ms": ms}
+        gen_ms = c1.gen_ms - c0.gen_ms
+        gen_l = c1.gen_launches - c0.gen_launches
+        all_ms = sum(f["total_ms"] for f in fam.values()) + gen_ms
+        dom = max(fam, key=lambda k: fam[k]["total_ms"])
         traffic = None
-        tr_path = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        tr_path = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
         if os.path.exists(tr_path):  # DRAM bytes per ray-bounce from the committed ncu --set full capture
             tr = json.load(open(tr_path))["dram_bytes_per_ray_bounce"]
-            traffic = tr[dom] * tile
-        roof = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": ach_o if dom == "optics" else ach_i,
-                "peak": hbm_peak, "unit": "GB/s", "frac": (ach_o if dom == "optics" else ach_i) / hbm_peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": opt_bytes if dom == "optics" else int_bytes,
-                "peak_source": peak_src,
-                "per_kernel": {"optics": {"avg_ms": o_ms, "launches": o_l, "achieved_gbs": ach_o,
-                                          "frac": ach_o / hbm_peak, "rays_per_launch": tile},
-                               "intersect": {"avg_ms": i_ms, "launches": i_l, "achieved_gbs": ach_i,
-                                             "frac": ach_i / hbm_peak, "rays_per_launch": tile},
-                               "gen": {"avg_ms": g_ms}},
-                "share_of_step": {"optics": opt_total / max(1e-9, opt_total + int_total + (c1.gen_ms - c0.gen_ms)),
-                                  "intersect": int_total / max(1e-9, opt_total + int_total + (c1.gen_ms - c0.gen_ms))}}
+            if dom in tr:
+                traffic = tr[dom] * fam[dom]["rays_per_launch"]
+        roof = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": fam[dom]["achieved_gbs"],
+                "peak": hbm_peak, "unit": "GB/s", "frac": fam[dom]["frac"], "traffic": traffic,
+                "algorithmic_bytes_per_launch": fam[dom]["algorithmic_bytes_per_ray_bounce"] * fam[dom]["rays_per_launch"],
+                "peak_source": peak_src, "per_kernel": dict(fam, gen={"avg_ms": gen_ms / max(1, gen_l), "launches": int(gen_l)}),
+                "share_of_step": {k: f["total_ms"] / max(1e-9, all_ms) for k, f in fam.items()}}
         total_rays = rays_per_step * world * args.steps
         value = total_rays / (dev_ms * 1e-3) / 1e6
         e2e_val = total_rays / (e2e_ms * 1e-3) / 1e6

@@ -122,7 +122,8 @@ class HbCounters(C.Structure):
     _fields_ = [("kernel_launches", u64), ("rays_traced", u64), ("last_layer_ms", f64),
                 ("intersect_ms", f64), ("optics_ms", f64), ("gen_ms", f64),
                 ("intersect_launches", u64), ("optics_launches", u64), ("gen_launches", u64),
-                ("intersect_rays", u64), ("optics_rays", u64)]
+                ("intersect_rays", u64), ("optics_rays", u64),
+                ("bounce_ms", f64), ("bounce_launches", u64), ("bounce_rays", u64)]
 
 
 class HbDist(C.Structure):

@@ -25,6 +25,7 @@ std::string& global_error();  // hb_host.cpp
 }  // namespace hb
 
 #include "hb_kernels.cuh"
+#include "hb_launch.cuh"
 
 namespace hb {
 
@@ -141,7 +142,7 @@ struct LayerDev {
 
 struct EventPair {
   cudaEvent_t a, b;
-  int family;       // 0 gen, 1 optics, 2 intersect
+  int family;       // 0 gen, 1 optics, 2 intersect, 3 fused bounce
   uint64_t rays;
 };
 
@@ -210,7 +211,7 @@ struct HbEngine {
   DevBuf<float4> P, D, Q;
   DevBuf<uint8_t> path;
   DevBuf<uint32_t> fork_root, fork_code;
-  DevBuf<uint32_t> counters;    // [0] fork_count [1] fork_snapshot [2] cont_count [3] exit_count [4] error
+  DevBuf<uint32_t> counters;    // [0] fork_count [1] fork_snapshot [2] cont_count [3] exit_count [4] error [5] done_count
   DevBuf<unsigned long long> stat_cnt;
   DevBuf<double> stat_sum;
   DevBuf<float4> cont_dw[2];
@@ -241,6 +242,7 @@ struct HbEngine {
   uint64_t geom_rejected = 0;   // shapes the device builder rejected since hb_set_scene (empty crystals)
   bool p4_enable = true;  // option "prism_fast_path": 0 forces the generic axis-loop kernels (A/B tests)
   bool pixel_cache = true;
+  bool fused_bounce = true;  // option "fused_bounce": 0 runs the split optics + intersect pipeline
 #ifdef HB_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
@@ -274,8 +276,10 @@ void flush_events(HbEngine* h) {
         h->ctr.gen_ms += ms;
       } else if (e.family == 1) {
         h->ctr.optics_ms += ms;
-      } else {
+      } else if (e.family == 2) {
         h->ctr.intersect_ms += ms;
+      } else {
+        h->ctr.bounce_ms += ms;
       }
     }
   }
@@ -319,91 +323,7 @@ void fold_arena(HbEngine* h) {
   h->rays_since_fold = 0;
 }
 
-// Persistent grid-stride launch: exactly as many CTAs as are co-resident (occupancy x SM count), so there is
-// no partially filled second wave.
-template <typename K>
-uint32_t resident_grid(const HbEngine* h, K kernel, size_t smem, uint64_t n) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
-  if (h->blocks_per_sm_override > 0) per_sm = h->blocks_per_sm_override;
-  const uint64_t blocks = (n + 255) / 256;
-  return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(blocks, static_cast<uint64_t>(h->sm_count) * per_sm)));
-}
-
-template <bool G, bool L, bool S, bool M = false, int P = 0>
-void launch_optics_t(HbEngine* h, size_t smem, const TraceParams& tp) {
-  static bool attr_set[64] = {};  // per device: function attributes live in the device's context
-  if (!attr_set[h->device & 63]) {
-    cudaFuncSetAttribute(optics_kernel<G, L, S, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(shared_tables_bytes(kSmemShapes) + kCacheBytes + kStageBytes));
-    attr_set[h->device & 63] = true;
-  }
-  const uint32_t grid = resident_grid(h, optics_kernel<G, L, S, M, P>, smem, tp.cap);
-  optics_kernel<G, L, S, M, P><<<grid, 256, smem, h->stream>>>(tp);
-}
-template <int P>
-void launch_optics_p(HbEngine* h, int key, size_t smem, const TraceParams& tp) {
-  switch (key) {
-    case 0: launch_optics_t<false, false, false, false, P>(h, smem, tp); break;
-    case 1: launch_optics_t<false, false, true, false, P>(h, smem, tp); break;
-    case 2: launch_optics_t<false, true, false, false, P>(h, smem, tp); break;
-    case 3: launch_optics_t<false, true, true, false, P>(h, smem, tp); break;
-    case 4: launch_optics_t<true, false, false, false, P>(h, smem, tp); break;
-    case 5: launch_optics_t<true, false, true, false, P>(h, smem, tp); break;
-    case 6: launch_optics_t<true, true, false, false, P>(h, smem, tp); break;
-    default: launch_optics_t<true, true, true, false, P>(h, smem, tp); break;
-  }
-}
-void launch_optics(HbEngine* h, bool general, bool last, bool in_smem, int p4, size_t smem, const TraceParams& tp) {
-  const int key = (general ? 4 : 0) | (last ? 2 : 0) | (in_smem ? 1 : 0);
-  if (p4 != 0 && tp.extra_cnt == 0u && tp.color_on == 0u) {  // hexagonal prisms: unrolled paired-axis forms
-    if (p4 == 1) launch_optics_p<1>(h, key, smem, tp); else launch_optics_p<2>(h, key, smem, tp);
-    return;
-  }
-  if (tp.extra_cnt != 0u || tp.color_on != 0u) {  // N projections per trace / raypath colour: extended GENERAL kernels
-    switch (key & 3) {
-      case 0: launch_optics_t<true, false, false, true>(h, smem, tp); break;
-      case 1: launch_optics_t<true, false, true, true>(h, smem, tp); break;
-      case 2: launch_optics_t<true, true, false, true>(h, smem, tp); break;
-      default: launch_optics_t<true, true, true, true>(h, smem, tp); break;
-    }
-    return;
-  }
-  switch (key) {
-    case 0: launch_optics_t<false, false, false>(h, smem, tp); break;
-    case 1: launch_optics_t<false, false, true>(h, smem, tp); break;
-    case 2: launch_optics_t<false, true, false>(h, smem, tp); break;
-    case 3: launch_optics_t<false, true, true>(h, smem, tp); break;
-    case 4: launch_optics_t<true, false, false>(h, smem, tp); break;
-    case 5: launch_optics_t<true, false, true>(h, smem, tp); break;
-    case 6: launch_optics_t<true, true, false>(h, smem, tp); break;
-    default: launch_optics_t<true, true, true>(h, smem, tp); break;
-  }
-}
-template <bool G, bool S, bool M = false, int P = 0>
-void launch_intersect_t(HbEngine* h, size_t smem, const TraceParams& tp) {
-  const uint32_t grid = resident_grid(h, intersect_kernel<G, S, M, P>, smem, tp.cap);
-  intersect_kernel<G, S, M, P><<<grid, 256, smem, h->stream>>>(tp);
-}
-template <int P>
-void launch_intersect_p(HbEngine* h, bool general, bool in_smem, size_t smem, const TraceParams& tp) {
-  if (general) {
-    if (in_smem) launch_intersect_t<true, true, false, P>(h, smem, tp); else launch_intersect_t<true, false, false, P>(h, smem, tp);
-  } else {
-    if (in_smem) launch_intersect_t<false, true, false, P>(h, smem, tp); else launch_intersect_t<false, false, false, P>(h, smem, tp);
-  }
-}
-void launch_intersect(HbEngine* h, bool general, bool in_smem, int p4, size_t smem, const TraceParams& tp) {
-  if (p4 != 0 && tp.extra_cnt == 0u && tp.color_on == 0u) {
-    if (p4 == 1) launch_intersect_p<1>(h, general, in_smem, smem, tp); else launch_intersect_p<2>(h, general, in_smem, smem, tp);
-  } else if (tp.extra_cnt != 0u || tp.color_on != 0u) {
-    if (in_smem) launch_intersect_t<true, true, true>(h, smem, tp); else launch_intersect_t<true, false, true>(h, smem, tp);
-  } else if (general) {
-    if (in_smem) launch_intersect_t<true, true>(h, smem, tp); else launch_intersect_t<true, false>(h, smem, tp);
-  } else {
-    if (in_smem) launch_intersect_t<false, true>(h, smem, tp); else launch_intersect_t<false, false>(h, smem, tp);
-  }
-}
+LaunchCtx launch_ctx(const HbEngine* h) { return LaunchCtx{ h->device, h->sm_count, h->blocks_per_sm_override, h->stream }; }
 
 size_t trace_smem(const LayerDev& L) { return shared_tables_bytes(L.shape_cnt); }
 
@@ -653,6 +573,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.fork_code = h->fork_code.p;
   tp.fork_count = h->counters.p + 0;
   tp.fork_snapshot = h->counters.p + 1;
+  tp.done_count = h->counters.p + 5;
   tp.n_main = n;
   tp.cap = cap;
   tp.fork_cap = fork_cap;
@@ -699,15 +620,25 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   for (uint32_t hit = 0; hit < h->max_hits; hit++) {
     tp.hit = hit;
     const bool last = hit + 1 == h->max_hits;
+    if (h->fused_bounce) {  // one launch per interaction (DESIGN.md "kernels")
+      EventPair* ev = begin_event(h, 3, n);
+      launch_bounce(launch_ctx(h), general, last, in_smem, h->p4_enable ? L.b().p4_mode() : 0,
+                    smem + kStage2Bytes + kQueueBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
+      end_event(h, ev);
+      h->ctr.kernel_launches++;
+      h->ctr.bounce_launches++;
+      h->ctr.bounce_rays += n;
+      continue;
+    }
     EventPair* ev = begin_event(h, 1, n);
-    launch_optics(h, general, last, in_smem, h->p4_enable ? L.b().p4_mode() : 0, smem + kStageBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
+    launch_optics(launch_ctx(h), general, last, in_smem, h->p4_enable ? L.b().p4_mode() : 0, smem + kStageBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
     end_event(h, ev);
     h->ctr.kernel_launches++;
     h->ctr.optics_launches++;
     h->ctr.optics_rays += n;
     if (!last) {
       ev = begin_event(h, 2, n);
-      launch_intersect(h, general, in_smem, h->p4_enable ? L.b().p4_mode() : 0, smem, tp);
+      launch_intersect(launch_ctx(h), general, in_smem, h->p4_enable ? L.b().p4_mode() : 0, smem, tp);
       end_event(h, ev);
       h->ctr.kernel_launches++;
       h->ctr.intersect_launches++;
@@ -1072,7 +1003,7 @@ int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats) {
   HB_CUDA(h, h->counters.ensure(8));
   HB_CUDA(h, h->stat_cnt.ensure(1));
   HB_CUDA(h, h->stat_sum.ensure(1));
-  HB_CUDA(h, cudaMemsetAsync(h->counters.p + 2, 0, 3 * sizeof(uint32_t), h->stream));  // cont_count, exit_count, error
+  HB_CUDA(h, cudaMemsetAsync(h->counters.p + 2, 0, 4 * sizeof(uint32_t), h->stream));  // cont_count, exit_count, error, done_count
   HB_CUDA(h, cudaMemsetAsync(h->stat_cnt.p, 0, sizeof(unsigned long long), h->stream));
   HB_CUDA(h, cudaMemsetAsync(h->stat_sum.p, 0, sizeof(double), h->stream));
   if (flags & kFlagGate) {
@@ -1294,6 +1225,8 @@ int hb_set_option(HbEngine* h, const char* key, int64_t value) {
     h->p4_enable = value != 0;
   } else if (k == "pixel_cache") {
     h->pixel_cache = value != 0;
+  } else if (k == "fused_bounce") {
+    h->fused_bounce = value != 0;
   } else if (k == "fold_rays") {
     if (value < 1024) return fail(h, HB_ERR_INVALID_ARG, "fold_rays out of range");
     h->fold_rays = static_cast<uint64_t>(value);

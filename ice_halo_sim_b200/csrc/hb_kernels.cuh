@@ -80,7 +80,8 @@ struct TraceParams {
   uint32_t* fork_root;          // [fork_cap] layer-root index of fork rays
   uint32_t* fork_code;          // [fork_cap] branch code of fork rays
   uint32_t* fork_count;         // rays appended behind the main slots (near-edge double continuation)
-  uint32_t* fork_snapshot;      // fork_count as of the last intersect kernel
+  uint32_t* fork_snapshot;      // fork_count as of the last intersect kernel (split) / the last bounce kernel (fused)
+  uint32_t* done_count;         // CTAs of the running bounce kernel that have retired (publish_fork_snapshot)
   uint32_t n_main, cap, fork_cap;
   uint32_t root_base;           // layer-root index of slot 0 of this tile
   LayerTables lt;
@@ -495,16 +496,18 @@ HB_DEV Tables<true> stage_tables<true>(const LayerTables& lt, unsigned char* sme
   return Tables<true>{ base, base + ax_off, base + meta_off, base + meta_off + n * 4u };
 }
 
+// `advanced`: the split pipeline marks a fork ray so that the intersect pass that follows skips it (it was advanced
+// when it was created); the fused bounce kernel picks fork rays up at the next interaction and needs no mark.
 template <bool GENERAL>
 HB_DEV void fork_append(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float px, float py, float pz,
-                        float dx, float dy, float dz, float w, uint32_t new_face) {
+                        float dx, float dy, float dz, float w, uint32_t new_face, uint32_t advanced = 1u) {
   const uint32_t k = atomicAdd(tp.fork_count, 1u);
   if (k >= tp.fork_cap) {
     *tp.error_flag = 3u;
     return;
   }
   const uint32_t dst = tp.n_main + k;
-  const uint32_t nb = bits_with_face(bits, new_face) | (1u << 30);
+  const uint32_t nb = bits_with_face(bits, new_face) | (advanced << 30);
   tp.P[dst] = make_float4(px, py, pz, __uint_as_float(nb));
   tp.D[dst] = make_float4(dx, dy, dz, w);
   tp.Q[dst] = q;
@@ -746,6 +749,241 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_INTERSECT_MINB_GENERAL : HB_
     atomicAdd(tp.stat_exit_count, tally.exits);
     atomicAdd(tp.stat_w_sum, tally.w_sum);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused bounce kernel: one whole surface interaction per launch (the optics and the intersect pass in one), with
+// a per-warp EXIT QUEUE in shared memory.
+//
+// Why a queue. In the split optics kernel a lane whose far-side child leaves the crystal walks the whole emission
+// path (orientation matrix, world rotation, visibility, projection, image reduction: ~130 instructions) while the
+// lanes of the same warp whose ray was totally reflected (a third of them after the entry interaction) idle:
+// ncu counted 19.5 of 32 lanes active per instruction at hit 1. Here a leaving child is only PUSHED (ballot +
+// prefix + two shared-memory stores) and the warp emits 32 queued exits at a time with all lanes busy; whatever
+// is left when the warp runs out of rays is emitted at the end of the kernel.
+//
+// Why fused. The near-side child's slab scan needs the same point-to-plane offsets as the far-side child's quick
+// classification (bounce_axes_p4 evaluates them once), the child's direction never travels through HBM between
+// the two passes, and one launch replaces two: read P, D (32 B) + Q of the exits, write P, D (32 B) per
+// ray-bounce instead of 112 B.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kQueueSlots = 96u;                                  // < 32 pending + up to 2 x 32 new per iteration
+constexpr uint32_t kQueueWarpBytes = kQueueSlots * 16u + kQueueSlots * 8u;  // float4 (local dir, w) + uint2 (slot|role, bits)
+constexpr uint32_t kQueueBytes = 8u * kQueueWarpBytes;                 // 8 warps per CTA
+constexpr uint32_t kStage2Bytes = 2u * 2u * 256u * 16u;                // two stages x (D, P) x 256 threads x 16 B
+
+HB_DEV void sts128(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+HB_DEV void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+HB_DEV uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+struct ExitQueue {
+  uint32_t addr;    // shared-space address of this warp's queue
+  uint32_t count;   // warp-uniform
+};
+
+// All 32 lanes call this together. `meta0` = tile slot | role << 31.
+HB_DEV void queue_push(ExitQueue& xq, bool has, float x, float y, float z, float w, uint32_t meta0, uint32_t bits) {
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
+  if (m == 0u) return;
+  if (has) {
+    const uint32_t pos = xq.count + __popc(m & ((1u << (threadIdx.x & 31u)) - 1u));
+    sts128(xq.addr + pos * 16u, x, y, z, w);
+    sts64(xq.addr + kQueueSlots * 16u + pos * 8u, meta0, bits);
+  }
+  xq.count += __popc(m);
+  __syncwarp();
+}
+
+// Emit queued exits, 32 at a time (`all`: whatever is left, with the lanes that still have an entry).
+template <bool GENERAL, bool MULTI, typename TablesT>
+HB_DEV void queue_drain(ExitQueue& xq, bool all, const TraceParams& tp, const TablesT& tb, Tally& tally) {
+  const uint32_t lane = threadIdx.x & 31u;
+  while (xq.count >= 32u || (all && xq.count != 0u)) {
+    const uint32_t n = min(xq.count, 32u), first = xq.count - n;
+    if (lane < n) {
+      const float4 e = lds128(xq.addr + (first + lane) * 16u);
+      const uint2 m = lds64(xq.addr + kQueueSlots * 16u + (first + lane) * 8u);
+      const uint32_t slot = m.x & 0x7FFFFFFFu;
+      emit_exit<GENERAL, MULTI>(tp, slot, m.y, __ldg(tp.Q + slot), e.x, e.y, e.z, e.w, m.x >> 31, tb, tally);
+    }
+    xq.count = first;
+    __syncwarp();
+  }
+}
+
+// The last CTA to retire publishes the number of fork rays appended so far: the next bounce launch traces
+// [0, n_main + snapshot). (The split pipeline lets its intersect pass take the snapshot.)
+HB_DEV void publish_fork_snapshot(const TraceParams& tp) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t prev = atomicAdd(tp.done_count, 1u);
+    if (prev + 1u == gridDim.x) {
+      __threadfence();
+      *tp.fork_snapshot = min(atomicAdd(tp.fork_count, 0u), tp.fork_cap);
+      *tp.done_count = 0u;
+    }
+  }
+}
+
+// One interaction of one live ray in registers. Outputs: up to two leaving children (e0: far side, role 0;
+// e1: near side, role 1) and the ray's next state (written by the caller unless LAST).
+template <bool GENERAL, bool LAST, bool SMEM, int P4>
+HB_DEV void bounce_ray(const TraceParams& tp, const Tables<SMEM>& tb, uint32_t i, float4 p4, float4 d4, bool& has0,
+                       float4& e0, bool& has1, float4& e1) {
+  const uint32_t bits = __float_as_uint(p4.w);
+  const uint32_t face = bits_face(bits);
+  const uint32_t shape = bits_shape(bits);
+  const uint32_t meta = tb.meta(shape);
+  const AxisRow<SMEM> axes = tb.axes(shape);
+  const uint32_t axis_cnt = (meta >> 16) & 255u;
+  const bool shape_p4 = P4 == 1 || (P4 == 2 && (meta & kMetaP4) != 0u);
+  float n_idx = tp.wl0.n_idx, inv_n = tp.wl0.inv_n;
+  if (tp.wl_cnt != 1u) {
+    const float2 nn = __ldg(reinterpret_cast<const float2*>(tp.wl2 + bits_wl(bits)));
+    n_idx = nn.x;
+    inv_n = nn.y;
+  }
+  const float4 pl = tb.plane(shape, face);
+  const Split s = hit_surface(pl, n_idx, inv_n, d4.x, d4.y, d4.z, d4.w);
+  const bool internal = s.cos_in > 0.0f;  // internal hit: the refracted child leaves; entry: the reflected one
+  const float ox = internal ? s.tx : s.rx, oy = internal ? s.ty : s.ry, oz = internal ? s.tz : s.rz;
+  const float ow = internal ? s.tw : s.rw;
+  const float ix = internal ? s.rx : s.tx, iy = internal ? s.ry : s.ty, iz = internal ? s.rz : s.tz;
+  const float iw = internal ? s.rw : s.tw;
+
+  // ---- both children against the crystal ----
+  bool far_exits;
+  float nx = p4.x, ny = p4.y, nz = p4.z;   // near child's next point
+  uint32_t nf = kFaceInvalid;              // ... and face
+  bool near_done = false;                  // LAST: the near child provably stays inside, nothing to do
+  if (shape_p4) {
+    if (LAST) {
+      far_exits = far_child_surely_exits_p4(axes, pl, p4.x, p4.y, p4.z, ox, oy, oz);
+      near_done = iw < 0.0f || near_child_surely_hits(axes, 4u, p4.x, p4.y, p4.z, ix, iy, iz);
+      if (!near_done) nf = slab_exit_p4<false>(axes, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+    } else {
+      nf = bounce_axes_p4(axes, face, pl, p4.x, p4.y, p4.z, ox, oy, oz, ix, iy, iz, far_exits, nx, ny, nz);
+    }
+  } else {
+    far_exits = far_child_surely_exits(axes, axis_cnt, face, pl, p4.x, p4.y, p4.z, ox, oy, oz);
+    if (LAST) {
+      near_done = iw < 0.0f || near_child_surely_hits(axes, axis_cnt, p4.x, p4.y, p4.z, ix, iy, iz);
+      if (!near_done) nf = slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+    } else {
+      nf = slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+    }
+  }
+  // far-side child: leaves (the common case), or stays inside within ~1e-7 of an edge (fork ray)
+  if (ow >= 0.0f) {
+    uint32_t ff = kFaceInvalid;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (!far_exits) {
+      if (shape_p4) ff = slab_exit_p4<true>(axes, face, p4.x, p4.y, p4.z, ox, oy, oz, fx, fy, fz);
+      else ff = slab_exit<true>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ox, oy, oz, fx, fy, fz);
+    }
+    if (ff == kFaceInvalid) {
+      has0 = true;
+      e0 = make_float4(ox, oy, oz, ow);
+    } else if (!LAST) {
+      fork_append<GENERAL>(tp, i, bits, tp.Q[i], fx, fy, fz, ox, oy, oz, ow, ff, /*advanced=*/0u);
+    }
+  }
+  // near-side child
+  if (LAST) {
+    if (!near_done && nf == kFaceInvalid) {
+      has1 = true;
+      e1 = make_float4(ix, iy, iz, iw);
+    }
+  } else if (iw < 0.0f) {
+    tp.D[i] = make_float4(ix, iy, iz, iw);  // TIR sentinel: the ray ends (entry-side refraction never does)
+  } else if (nf == kFaceInvalid) {
+    // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
+    has1 = true;
+    e1 = make_float4(ix, iy, iz, iw);
+    tp.D[i] = make_float4(ix, iy, iz, -1.0f);
+  } else {
+    tp.D[i] = make_float4(ix, iy, iz, iw);
+    tp.P[i] = make_float4(nx, ny, nz, __uint_as_float(bits_with_face(bits, nf)));
+    if (GENERAL && (tp.flags & kFlagPath) && tp.hit + 1u < tp.max_hits)
+      tp.path[static_cast<size_t>(tp.hit + 1u) * tp.cap + i] = static_cast<uint8_t>(nf);
+  }
+}
+
+#ifndef HB_BOUNCE_MINB
+#define HB_BOUNCE_MINB 4
+#endif
+#ifndef HB_BOUNCE_MINB_GENERAL
+#define HB_BOUNCE_MINB_GENERAL 4
+#endif
+// dynamic shared memory: [pixel cache] [ray staging D, P x 2] [exit queues] [crystal tables]
+template <bool GENERAL, bool LAST, bool SMEM, bool MULTI, int P4 = 0>
+__global__ void __launch_bounds__(256, GENERAL ? HB_BOUNCE_MINB_GENERAL : HB_BOUNCE_MINB) bounce_kernel(const TraceParams tp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tally tally;
+  const bool use_cache = (tp.flags & kFlagPixelCache) != 0u;
+  if (use_cache) cache_init(tally, smem_raw);
+  const uint32_t stage_off = use_cache ? static_cast<uint32_t>(kCacheBytes) : 0u;
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + stage_off + kStage2Bytes + kQueueBytes, GENERAL);
+  if (!SMEM && use_cache) __syncthreads();
+  const uint32_t total = tp.n_main + *tp.fork_snapshot;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
+  ExitQueue xq{ smem_base + stage_off + kStage2Bytes + (threadIdx.x >> 5) * kQueueWarpBytes, 0u };
+  const uint32_t stage0 = smem_base + stage_off + threadIdx.x * 16u;
+  uint32_t stage = 0u;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t warp_first = i - (threadIdx.x & 31u);  // the loop runs while the WARP has a ray: pushes are warp-wide
+  if (i < total) {
+    cp_async16(stage0, tp.D + i);
+    cp_async16(stage0 + 4096u, tp.P + i);
+  }
+  cp_async_commit();
+  // One emission site: the loop body runs once more after the warp's last ray to flush the queue, so the (large)
+  // emission code is instantiated once and nothing of the trace state is live across it.
+  for (;;) {
+    const bool more = warp_first < total;
+    if (more) {
+      const uint32_t i_next = i + stride;
+      const uint32_t cur = stage0 + stage * 8192u, nxt = stage0 + (stage ^ 1u) * 8192u;
+      if (i_next < total) {
+        cp_async16(nxt, tp.D + i_next);
+        cp_async16(nxt + 4096u, tp.P + i_next);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();
+      bool has0 = false, has1 = false;
+      float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+      uint32_t bits = 0u;
+      if (i < total) {
+        const float4 d4 = lds128(cur), p4 = lds128(cur + 4096u);
+        bits = __float_as_uint(p4.w);
+        if (d4.w >= 0.0f && bits_face(bits) != kFaceInvalid)  // else: terminated ray
+          bounce_ray<GENERAL, LAST, SMEM, P4>(tp, tb, i, p4, d4, has0, e0, has1, e1);
+      }
+      queue_push(xq, has0, e0.x, e0.y, e0.z, e0.w, i, bits);
+      queue_push(xq, has1, e1.x, e1.y, e1.z, e1.w, i | 0x80000000u, bits);
+      stage ^= 1u;
+      i = i_next;
+      warp_first += stride;
+    }
+    if (xq.count >= 32u || !more) queue_drain<GENERAL, MULTI>(xq, !more, tp, tb, tally);
+    if (!more) break;
+  }
+  if (use_cache) cache_flush(tp, tally);
+  if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
+    atomicAdd(tp.stat_exit_count, tally.exits);
+    atomicAdd(tp.stat_w_sum, tally.w_sum);
+  }
+  if (!LAST) publish_fork_snapshot(tp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1012,6 +1250,7 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
   }
 }
 
+#ifndef HB_TU  // non-template kernels: defined once, in the engine translation unit (hb_tu.cu slices skip them)
 // ------------------------------------------------------------------------------------------------
 // Stochastic geometry pool on the device. One thread per shape: draw the shape scalars of the
 // population's CrystalConfig with the counter-based RNG (MakeCrystal's order, simulator.cpp:405-450: heights
@@ -1195,6 +1434,8 @@ __global__ void quat_to_rot_kernel(const float4* Q, float* rot9, uint32_t n) {
   for (int k = 0; k < 9; k++) rot9[static_cast<size_t>(i) * 9 + k] = r.m[k];
 }
 
+
+#endif  // HB_TU
 
 }  // namespace hb
 

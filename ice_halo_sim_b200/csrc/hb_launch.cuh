@@ -1,0 +1,55 @@
+// hb_launch.cuh — host-side launch entry points of the trace kernels. The kernel templates (hb_kernels.cuh) are
+// instantiated in several translation units (hb_tu.cu compiled with -DHB_TU=n, see the Makefile) so the library
+// builds in parallel; hb_engine.cu only sees these declarations.
+#ifndef HB_LAUNCH_CUH_
+#define HB_LAUNCH_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hb_kernels.cuh"
+
+namespace hb {
+
+struct LaunchCtx {
+  int device;
+  int sm_count;
+  int blocks_per_sm_override;  // option "blocks_per_sm" (experiments); 0 = occupancy
+  cudaStream_t stream;
+};
+
+// key = general << 2 | last << 1 | tables_in_smem; p4 = 0 generic axis loop, 1 all hexagonal prisms, 2 per ray.
+// Sessions with extra renders or raypath colour run the MULTI instantiations.
+void launch_optics(const LaunchCtx& c, bool general, bool last, bool in_smem, int p4, size_t smem, const TraceParams& tp);
+void launch_intersect(const LaunchCtx& c, bool general, bool in_smem, int p4, size_t smem, const TraceParams& tp);
+void launch_bounce(const LaunchCtx& c, bool general, bool last, bool in_smem, int p4, size_t smem, const TraceParams& tp);
+
+// per-TU pieces
+void launch_optics_p0(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_optics_p1(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_optics_p2(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_optics_multi(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_intersect_p0(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_intersect_p1(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_intersect_p2(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_intersect_multi(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_bounce_p0(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_bounce_p1(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_bounce_p2(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+void launch_bounce_multi(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
+
+// Persistent grid-stride launch: exactly as many CTAs as are co-resident (occupancy x SM count), so there is
+// no partially filled second wave.
+template <typename K>
+uint32_t resident_grid(const LaunchCtx& c, K kernel, size_t smem, uint64_t n) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
+  if (c.blocks_per_sm_override > 0) per_sm = c.blocks_per_sm_override;
+  const uint64_t blocks = (n + 255) / 256;
+  const uint64_t cap = static_cast<uint64_t>(c.sm_count) * per_sm;
+  return static_cast<uint32_t>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace hb
+
+#endif  // HB_LAUNCH_CUH_

@@ -241,6 +241,8 @@ typedef struct HbCounters {               /* measurement helpers (bench.py) */
   double intersect_ms, optics_ms, gen_ms; /* accumulated per-kernel-family CUDA-event time (profiling mode) */
   uint64_t intersect_launches, optics_launches, gen_launches;
   uint64_t intersect_rays, optics_rays;   /* ray-bounces processed by each family */
+  double bounce_ms;                       /* fused bounce kernels (one launch per interaction; gen + entry interaction included) */
+  uint64_t bounce_launches, bounce_rays;
 } HbCounters;
 
 typedef struct HbEngine HbEngine;         /* opaque; one per TraceBackend instance / GPU */

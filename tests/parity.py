@@ -205,6 +205,34 @@ CASES = {
         scene=lambda: scene([(0.0, [prism_pop(1.3, zenith=("gauss", 90, 0.3), cid=3, proportion=10.0),
                                     pyramid_pop(proportion=3.0)])], 6),
         render=lambda: render("linear", 40.0, (640, 480), (-50.0, 30.0, 0.0)), wl=[490.0]),
+    # ---- the lens types no other case reaches (projection_shared.h:196-375) ----
+    "lens_stereographic": dict(scene=lambda: scene([(0.0, [prism_pop(1.3, zenith=("gauss", 90, 0.3), cid=3)])], 6),
+                               render=lambda: render("fisheye_stereographic", 140.0, (800, 800), (0.0, 60.0, 0.0)),
+                               wl=[550.0]),
+    "lens_dual_equidistant": dict(scene=lambda: scene([(0.0, [prism_pop(0.3, zenith=("gauss", 0, 1.0), cid=6)])], 6),
+                                  render=lambda: render("dual_fisheye_equidistant", 180.0, (1024, 512), visible="full",
+                                                        overlap=0.05), wl=[490.0]),
+    "lens_dual_stereographic": dict(scene=lambda: scene([(0.0, [prism_pop(1.0, zenith=("uniform", 90, 360))])], 6),
+                                    render=lambda: render("dual_fisheye_stereographic", 180.0, (1024, 512),
+                                                          visible="full", overlap=0.1), wl=[610.0]),
+    "lens_dual_orthographic": dict(scene=lambda: scene([(0.0, [prism_pop(1.3, zenith=("gauss", 90, 0.3), cid=3)])], 6),
+                                   render=lambda: render("dual_fisheye_orthographic", 180.0, (1024, 512), visible="full",
+                                                         overlap=0.08), wl=[570.0]),
+    "lens_globe": dict(scene=lambda: scene([(0.0, [prism_pop(1.0, zenith=("uniform", 90, 360))])], 6),
+                       render=lambda: render("globe", 60.0, (900, 900), (30.0, 20.0, 10.0), visible="full"), wl=[530.0]),
+    # filter_out action (action 1: the filter REMOVES what it matches) on a raypath filter with full symmetry
+    "filter_out_raypath": dict(
+        scene=lambda: scene([(0.0, [prism_pop(1.3, zenith=("gauss", 90, 5.0), cid=3,
+                                              filt=raypath_filter([3, 5], "PBD", action=1))])], 6),
+        render=lambda: render(res=(960, 540)), wl=[550.0]),
+    # D-symmetry PHYSICAL filters: raypath and entry-exit under the dihedral reduction only / with P and B
+    "filter_d_symmetry": dict(
+        scene=lambda: scene([(0.0, [prism_pop(1.3, zenith=("gauss", 90, 10.0), cid=3, proportion=2.0,
+                                              filt=raypath_filter([3, 1, 5], "D")),
+                                    prism_pop(0.4, zenith=("gauss", 0, 10.0), roll=("gauss", 60.0, 20.0), cid=6,
+                                              proportion=1.0, filt=complex_filter([[dict(kind=2, entry=1, exit=4)],
+                                                                   [dict(kind=1, path=[4, 2, 6])]], "BD"))])], 6),
+        render=lambda: render(res=(960, 540)), wl=[550.0]),
     "partial_prob": dict(
         scene=lambda: scene([(0.5, [prism_pop(1.0, zenith=("uniform", 90, 360), cid=1)]),
                              (0.0, [prism_pop(0.5, zenith=("gauss", 0, 2.0), cid=2)])], 5),
@@ -323,7 +351,7 @@ def sync_host_scene_with_device_pools(be, tables):
 
 
 def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=7, tile_rays=None, device_pool_seed=None,
-             geometry_clock_seed=None):
+             geometry_clock_seed=None, fused_bounce=None):
     """Full protocol on one case; returns a dict of comparison results (all layers merged)."""
     desc = case["scene"]()
     rdescs = case["render"]()
@@ -337,6 +365,8 @@ def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=
     be = backend or B.B200TraceBackend(device)
     if tile_rays:
         be.SetOption("tile_rays", tile_rays)
+    if fused_bounce is not None:   # 1: one bounce kernel per interaction (default), 0: split optics + intersect kernels
+        be.SetOption("fused_bounce", int(fused_bounce))
     be.SetScene(tables)
     if device_pool_seed is not None:
         resample_pools_on_device(be, tables, device_pool_seed)

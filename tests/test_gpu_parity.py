@@ -7,11 +7,17 @@ import parity
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("pipeline", ["fused", "split"])
 @pytest.mark.parametrize("name", sorted(parity.CASES))
-def test_case_bit_exact(backend, name):
+def test_case_bit_exact(backend, name, pipeline):
     """Face-number sequences, world exit directions and weights bit-exact against the oracle replay of
-    the engine's own roots; image within IMG_RTOL of the oracle accumulation of the same exits."""
-    res = parity.run_case(parity.CASES[name], n_rays=30000, seed=42, backend=backend)
+    the engine's own roots; image within IMG_RTOL of the oracle accumulation of the same exits. Both kernel
+    pipelines: the fused bounce kernels (default) and the split optics + intersect kernels."""
+    try:
+        res = parity.run_case(parity.CASES[name], n_rays=30000, seed=42, backend=backend,
+                              fused_bounce=pipeline == "fused")
+    finally:
+        backend.SetOption("fused_bounce", 1)
     assert res["exits"] > 0
     assert res["paths_equal"], res
     assert res["dirs_bit_equal"], res
@@ -21,6 +27,8 @@ def test_case_bit_exact(backend, name):
     assert res["image_ok"], res
     assert res["landed_rel_err"] < 1e-5, res
     assert res["masks_equal"], res
+    if name in ("filter_out_raypath", "filter_d_symmetry"):
+        assert 0 < res["exits"] < 30000 * 5          # the filter is selective, not empty and not everything
     if name == "color_classes":
         assert res["mask_bits_seen"] == 0b1111111, bin(res["mask_bits_seen"])   # every predicate fired somewhere
         assert res["lanes_shape_ok"] and res["lanes_ok"], res
