@@ -43,6 +43,11 @@ BYTES_GEN = 48
 BYTES_BOUNCE = 64
 BYTES_BOUNCE_LAST = 32
 BYTES_BOUNCE_EXIT = 32
+# root generation fused with the entry interaction: writes P, D, Q once (48); the external reflection of every
+# root leaves at hit 0 (1 exit per root: Q is still in flight, only the 16-byte reduction reaches the image)
+BYTES_GENBOUNCE = 48
+BYTES_GENBOUNCE_EXIT = 16
+EXITS_AT_ENTRY = 1.0
 TRAFFIC_FILE = "traffic_r2.json"
 EXITS_PER_ROOT = 4.7            # measured on this scene (reference CPU: 4.69-4.71)
 
@@ -355,7 +360,13 @@ def main():
         for name, ms, launches, rays, bytes_per_ray in (
                 ("bounce", c1.bounce_ms - c0.bounce_ms, c1.bounce_launches - c0.bounce_launches,
                  c1.bounce_rays - c0.bounce_rays,
+                 # with the entry interaction inside genbounce the bounce kernels run hits 1 .. H-1
+                 ((BYTES_BOUNCE * (max_hits - 2) + BYTES_BOUNCE_LAST) / (max_hits - 1) +
+                  BYTES_BOUNCE_EXIT * (exits_per_root - EXITS_AT_ENTRY) / (max_hits - 1))
+                 if c1.genbounce_launches > c0.genbounce_launches and max_hits > 1 else
                  (BYTES_BOUNCE * (max_hits - 1) + BYTES_BOUNCE_LAST) / max_hits + BYTES_BOUNCE_EXIT * epb),
+                ("genbounce", c1.genbounce_ms - c0.genbounce_ms, c1.genbounce_launches - c0.genbounce_launches,
+                 c1.genbounce_rays - c0.genbounce_rays, BYTES_GENBOUNCE + BYTES_GENBOUNCE_EXIT * EXITS_AT_ENTRY),
                 ("optics", c1.optics_ms - c0.optics_ms, c1.optics_launches - c0.optics_launches,
                  c1.optics_rays - c0.optics_rays,
                  (BYTES_OPTICS * (max_hits - 1) + BYTES_OPTICS_LAST) / max_hits + BYTES_EXIT * epb),

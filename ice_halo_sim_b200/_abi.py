@@ -123,7 +123,8 @@ class HbCounters(C.Structure):
                 ("intersect_ms", f64), ("optics_ms", f64), ("gen_ms", f64),
                 ("intersect_launches", u64), ("optics_launches", u64), ("gen_launches", u64),
                 ("intersect_rays", u64), ("optics_rays", u64),
-                ("bounce_ms", f64), ("bounce_launches", u64), ("bounce_rays", u64)]
+                ("bounce_ms", f64), ("bounce_launches", u64), ("bounce_rays", u64),
+                ("genbounce_ms", f64), ("genbounce_launches", u64), ("genbounce_rays", u64)]
 
 
 class HbDist(C.Structure):

@@ -142,7 +142,7 @@ struct LayerDev {
 
 struct EventPair {
   cudaEvent_t a, b;
-  int family;       // 0 gen, 1 optics, 2 intersect, 3 fused bounce
+  int family;       // 0 gen, 1 optics, 2 intersect, 3 fused bounce, 4 gen + entry interaction
   uint64_t rays;
 };
 
@@ -243,6 +243,13 @@ struct HbEngine {
   bool p4_enable = true;  // option "prism_fast_path": 0 forces the generic axis-loop kernels (A/B tests)
   bool pixel_cache = true;
   bool fused_bounce = true;  // option "fused_bounce": 0 runs the split optics + intersect pipeline
+  bool fused_gen = true;     // option "fused_gen": 0 keeps root generation in its own kernel
+  // Device error word (fork-slot / continuation-pool / exit-record overflow): sticky on the device until it has
+  // been REPORTED to the caller. Every TraceLayer enqueues a copy into this pinned mirror; every entry point that
+  // synchronises the stream anyway (readback, snapshot, stats, drain, hb_synchronize) checks it.
+  uint32_t* err_host = nullptr;
+  uint64_t fork_cap_override = 0;   // option "fork_cap" (tests: force an overflow)
+  uint64_t cont_cap_override = 0;   // option "cont_cap"
 #ifdef HB_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
@@ -267,6 +274,17 @@ int fail(HbEngine* h, int code, const std::string& msg) {
   return code;
 }
 
+// After a stream synchronisation: report a pending device overflow exactly once, then re-arm the flag.
+int check_device_error(HbEngine* h) {
+  if (h->err_host == nullptr || *h->err_host == 0u) return HB_OK;
+  const uint32_t code = *h->err_host;
+  *h->err_host = 0u;
+  if (h->counters.p) cudaMemsetAsync(h->counters.p + 4, 0, sizeof(uint32_t), h->stream);
+  const char* what = code == 1u ? "continuation pool" : code == 2u ? "exit record buffer" : "fork-ray slots";
+  return fail(h, HB_ERR_CAPACITY, std::string("device buffer overflow: ") + what + " (code " + std::to_string(code) +
+                                      "); rays were dropped, the frame is incomplete");
+}
+
 void flush_events(HbEngine* h) {
   for (size_t i = 0; i < h->ev_used; i++) {
     float ms = 0.0f;
@@ -278,8 +296,10 @@ void flush_events(HbEngine* h) {
         h->ctr.optics_ms += ms;
       } else if (e.family == 2) {
         h->ctr.intersect_ms += ms;
-      } else {
+      } else if (e.family == 3) {
         h->ctr.bounce_ms += ms;
+      } else {
+        h->ctr.genbounce_ms += ms;
       }
     }
   }
@@ -347,6 +367,8 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
   L->cur = 0;
   B0.pop_p4.clear();
   B0.pop_shapes.clear();
+  if (src.population_cnt == 0 || src.population_cnt > HB_MAX_CRYSTALS || src.populations == nullptr)
+    return fail(h, HB_ERR_INVALID_ARG, "layer: population_cnt must be 1..HB_MAX_CRYSTALS");
   for (uint32_t ci = 0; ci < src.population_cnt; ci++) {
     const HbCrystalPopulation& p = src.populations[ci];
     if (p.shape_cnt == 0 || p.shapes == nullptr) return fail(h, HB_ERR_INVALID_ARG, "population without shapes");
@@ -448,7 +470,7 @@ int ensure_tile(HbEngine* h, uint64_t cap, uint64_t fork_cap, uint32_t flags) {
 int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::vector<uint64_t>& pop_begin,
                uint32_t flags, uint64_t layer_total) {
   LayerDev& L = *h->layers[li];
-  const uint32_t fork_cap = std::max<uint32_t>(4096u, n / 64u);
+  const uint32_t fork_cap = h->fork_cap_override ? static_cast<uint32_t>(h->fork_cap_override) : std::max<uint32_t>(4096u, n / 64u);
   const uint32_t cap = n + fork_cap;
   int rc = ensure_tile(h, cap, fork_cap, flags);
   if (rc != HB_OK) return rc;
@@ -463,107 +485,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
     HB_CUDA(h, cudaMemsetAsync(h->counters.p + 3, 0, sizeof(uint32_t), h->stream));
   }
 
-  // ---- roots ----
-  if (li == 0 && h->injected) {
-    HB_CUDA(h, cudaMemcpyAsync(h->P.p, h->inj_P.data() + root0, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-    HB_CUDA(h, cudaMemcpyAsync(h->D.p, h->inj_D.data() + root0, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-    HB_CUDA(h, cudaMemcpyAsync(h->Q.p, h->inj_Q.data() + root0, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-    if (flags & kFlagPath) {
-      std::vector<uint8_t> p0(n);
-      for (uint32_t i = 0; i < n; i++) p0[i] = static_cast<uint8_t>(bits_face_host(h->inj_P[root0 + i]));
-      HB_CUDA(h, cudaMemcpyAsync(h->path.p, p0.data(), n, cudaMemcpyHostToDevice, h->stream));
-      HB_CUDA(h, cudaStreamSynchronize(h->stream));
-    }
-  } else {
-    for (size_t ci = 0; ci < L.pops.size(); ci++) {
-      const uint64_t b = std::max<uint64_t>(pop_begin[ci], root0), e = std::min<uint64_t>(pop_begin[ci + 1], root0 + n);
-      if (b >= e) continue;
-      const PopHost& ph = L.pops[ci];
-      GenParams gp{};
-      gp.P = h->P.p;
-      gp.D = h->D.p;
-      gp.Q = h->Q.p;
-      gp.path = h->path.p;
-      gp.slot0 = static_cast<uint32_t>(b - root0);
-      gp.count = static_cast<uint32_t>(e - b);
-      gp.cap = cap;
-      const uint64_t base = (li == 0 ? h->gen_base : h->transit_base) + b;
-      gp.idx_lo = static_cast<uint32_t>(base);
-      gp.idx_hi = static_cast<uint32_t>(base >> 32);
-      gp.seed = h->spec.seed ^ (li == 0 ? kNonceGen : kNonceTransit);
-      gp.axis = ph.axis;
-      gp.lut = L.luts.p + ci * 3 * HB_LUT_NODES;
-      gp.shapes = L.b().shapes.p + ph.shape_base;
-      gp.entry_faces = L.b().entry_faces.p + ph.shape_base;
-      gp.shape_base = ph.shape_base;
-      gp.shape_cnt = ph.shape_cnt;
-      gp.wl = h->wl_cur;
-      gp.wl_cnt = h->wl_cnt;
-      gp.sun_lon = h->sun_lon;
-      gp.sun_lat = h->sun_lat;
-      gp.sun_half = h->sun_half;
-      gp.sun_c_cap = std::cos(h->sun_half);
-      gp.sun_c_lon = std::cos(h->sun_lon);
-      gp.sun_s_lon = std::sin(h->sun_lon);
-      gp.sun_c_lat = std::cos(h->sun_lat);
-      gp.sun_s_lat = std::sin(h->sun_lat);
-      gp.flags = flags;
-      EventPair* ev = begin_event(h, 0, gp.count);
-      if (li == 0) {
-        gen_kernel<false><<<grid_for(h, gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
-      } else {
-        const int src = h->cont_cur ^ 1;
-        gp.cont_dw = h->cont_dw[src].p;
-        gp.cont_meta = h->cont_meta[src].p;
-        if (color_on) {
-          gp.cont_mask = h->cont_mask[src].p;
-          gp.M = h->mask_tile.p;
-        }
-        gp.cont_n = static_cast<uint32_t>(layer_total);
-        gp.cont_first = static_cast<uint32_t>(b);
-        gp.shuffle = h->cont_shuffle ? 1u : 0u;
-        gp.shuffle_seed = pcg_hash_host(h->spec.seed ^ kNonceShuffle ^ h->shuffle_round);
-        gen_kernel<true><<<grid_for(h, gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
-      }
-      end_event(h, ev);
-      h->ctr.kernel_launches++;
-      h->ctr.gen_launches++;
-    }
-  }
-  HB_CUDA(h, cudaGetLastError());
-
-  // ---- parity export of the roots this tile starts from ----
-  if (h->spec.record_exits == 1u && !(li == 0 && h->injected)) {  // parity sessions only (2 = plain egress)
-    std::vector<float4> hp(n), hd(n), hq(n);
-    DevBuf<float> rot;
-    HB_CUDA(h, rot.ensure(static_cast<size_t>(n) * 9));
-    quat_to_rot_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->Q.p, rot.p, n);
-    std::vector<float> hr(static_cast<size_t>(n) * 9);
-    HB_CUDA(h, cudaMemcpyAsync(hp.data(), h->P.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
-    HB_CUDA(h, cudaMemcpyAsync(hd.data(), h->D.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
-    HB_CUDA(h, cudaMemcpyAsync(hr.data(), rot.p, hr.size() * 4, cudaMemcpyDeviceToHost, h->stream));
-    HB_CUDA(h, cudaStreamSynchronize(h->stream));
-    rot.release();
-    for (uint32_t i = 0; i < n; i++) {
-      uint32_t bits;
-      std::memcpy(&bits, &hp[i].w, 4);
-      h->exp_p.insert(h->exp_p.end(), { hp[i].x, hp[i].y, hp[i].z });
-      h->exp_d.insert(h->exp_d.end(), { hd[i].x, hd[i].y, hd[i].z });
-      h->exp_w.push_back(hd[i].w);
-      const uint32_t f = bits & 63u;
-      h->exp_face.push_back(f == kFaceInvalid ? static_cast<uint16_t>(HB_INVALID_FACE) : static_cast<uint16_t>(f));
-      h->exp_shape.push_back((bits >> 14) & 65535u);
-      h->exp_wl.push_back((bits >> 6) & 255u);
-    }
-    h->exp_rot.insert(h->exp_rot.end(), hr.begin(), hr.end());
-    if (color_on) {  // component masks the roots carry in from earlier layers
-      const size_t old = h->exp_mask.size();
-      h->exp_mask.resize(old + n, 0ull);
-      if (li > 0) HB_CUDA(h, cudaMemcpy(h->exp_mask.data() + old, h->mask_tile.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    }
-  }
-
-  // ---- hit loop ----
+  // ---- kernel parameters of the hit loop ----
   TraceParams tp{};
   tp.P = h->P.p;
   tp.D = h->D.p;
@@ -617,12 +539,135 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
 
   const size_t smem = trace_smem(L);
   const bool in_smem = L.shape_cnt <= kSmemShapes;
-  for (uint32_t hit = 0; hit < h->max_hits; hit++) {
+  const int p4_mode = h->p4_enable ? L.b().p4_mode() : 0;
+  // Root generation fused with the entry interaction (genbounce_kernel). Parity sessions export the roots
+  // between generation and hit 0 and injected rays skip generation: both take the separate gen kernel.
+  const bool fused_gen = h->fused_bounce && h->fused_gen && h->max_hits > 1 && !(li == 0 && h->injected) &&
+                         h->spec.record_exits != 1u;
+
+  // ---- roots ----
+  if (li == 0 && h->injected) {
+    HB_CUDA(h, cudaMemcpyAsync(h->P.p, h->inj_P.data() + root0, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(h->D.p, h->inj_D.data() + root0, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(h->Q.p, h->inj_Q.data() + root0, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    if (flags & kFlagPath) {
+      std::vector<uint8_t> p0(n);
+      for (uint32_t i = 0; i < n; i++) p0[i] = static_cast<uint8_t>(bits_face_host(h->inj_P[root0 + i]));
+      HB_CUDA(h, cudaMemcpyAsync(h->path.p, p0.data(), n, cudaMemcpyHostToDevice, h->stream));
+      HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+  } else {
+    for (size_t ci = 0; ci < L.pops.size(); ci++) {
+      const uint64_t b = std::max<uint64_t>(pop_begin[ci], root0), e = std::min<uint64_t>(pop_begin[ci + 1], root0 + n);
+      if (b >= e) continue;
+      const PopHost& ph = L.pops[ci];
+      GenParams gp{};
+      gp.P = h->P.p;
+      gp.D = h->D.p;
+      gp.Q = h->Q.p;
+      gp.path = h->path.p;
+      gp.slot0 = static_cast<uint32_t>(b - root0);
+      gp.count = static_cast<uint32_t>(e - b);
+      gp.cap = cap;
+      const uint64_t base = (li == 0 ? h->gen_base : h->transit_base) + b;
+      gp.idx_lo = static_cast<uint32_t>(base);
+      gp.idx_hi = static_cast<uint32_t>(base >> 32);
+      gp.seed = h->spec.seed ^ (li == 0 ? kNonceGen : kNonceTransit);
+      gp.axis = ph.axis;
+      gp.lut = L.luts.p + ci * 3 * HB_LUT_NODES;
+      gp.shapes = L.b().shapes.p + ph.shape_base;
+      gp.entry_faces = L.b().entry_faces.p + ph.shape_base;
+      gp.shape_base = ph.shape_base;
+      gp.shape_cnt = ph.shape_cnt;
+      gp.wl = h->wl_cur;
+      gp.wl_cnt = h->wl_cnt;
+      gp.sun_lon = h->sun_lon;
+      gp.sun_lat = h->sun_lat;
+      gp.sun_half = h->sun_half;
+      gp.sun_c_cap = std::cos(h->sun_half);
+      gp.sun_c_lon = std::cos(h->sun_lon);
+      gp.sun_s_lon = std::sin(h->sun_lon);
+      gp.sun_c_lat = std::cos(h->sun_lat);
+      gp.sun_s_lat = std::sin(h->sun_lat);
+      gp.flags = flags;
+      EventPair* ev = begin_event(h, fused_gen ? 4 : 0, gp.count);
+      const size_t gb_smem = kGenSharedBytes + kQueueBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0) + smem;
+      if (li == 0) {
+        if (fused_gen) {
+          tp.hit = 0;
+          launch_genbounce(launch_ctx(h), false, general, in_smem, p4_mode, gb_smem, gp, tp);
+        } else {
+          gen_kernel<false><<<grid_for(h, gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
+        }
+      } else {
+        const int src = h->cont_cur ^ 1;
+        gp.cont_dw = h->cont_dw[src].p;
+        gp.cont_meta = h->cont_meta[src].p;
+        if (color_on) {
+          gp.cont_mask = h->cont_mask[src].p;
+          gp.M = h->mask_tile.p;
+        }
+        gp.cont_n = static_cast<uint32_t>(layer_total);
+        gp.cont_first = static_cast<uint32_t>(b);
+        gp.shuffle = h->cont_shuffle ? 1u : 0u;
+        gp.shuffle_seed = pcg_hash_host(h->spec.seed ^ kNonceShuffle ^ h->shuffle_round);
+        if (fused_gen) {
+          tp.hit = 0;
+          launch_genbounce(launch_ctx(h), true, general, in_smem, p4_mode, gb_smem, gp, tp);
+        } else {
+          gen_kernel<true><<<grid_for(h, gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
+        }
+      }
+      end_event(h, ev);
+      h->ctr.kernel_launches++;
+      if (fused_gen) {
+        h->ctr.genbounce_launches++;
+        h->ctr.genbounce_rays += gp.count;
+      } else {
+        h->ctr.gen_launches++;
+      }
+    }
+  }
+  HB_CUDA(h, cudaGetLastError());
+
+  // ---- parity export of the roots this tile starts from ----
+  if (h->spec.record_exits == 1u && !(li == 0 && h->injected)) {  // parity sessions only (2 = plain egress)
+    std::vector<float4> hp(n), hd(n), hq(n);
+    DevBuf<float> rot;
+    HB_CUDA(h, rot.ensure(static_cast<size_t>(n) * 9));
+    quat_to_rot_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->Q.p, rot.p, n);
+    std::vector<float> hr(static_cast<size_t>(n) * 9);
+    HB_CUDA(h, cudaMemcpyAsync(hp.data(), h->P.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(hd.data(), h->D.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(hr.data(), rot.p, hr.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    rot.release();
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t bits;
+      std::memcpy(&bits, &hp[i].w, 4);
+      h->exp_p.insert(h->exp_p.end(), { hp[i].x, hp[i].y, hp[i].z });
+      h->exp_d.insert(h->exp_d.end(), { hd[i].x, hd[i].y, hd[i].z });
+      h->exp_w.push_back(hd[i].w);
+      const uint32_t f = bits & 63u;
+      h->exp_face.push_back(f == kFaceInvalid ? static_cast<uint16_t>(HB_INVALID_FACE) : static_cast<uint16_t>(f));
+      h->exp_shape.push_back((bits >> 14) & 65535u);
+      h->exp_wl.push_back((bits >> 6) & 255u);
+    }
+    h->exp_rot.insert(h->exp_rot.end(), hr.begin(), hr.end());
+    if (color_on) {  // component masks the roots carry in from earlier layers
+      const size_t old = h->exp_mask.size();
+      h->exp_mask.resize(old + n, 0ull);
+      if (li > 0) HB_CUDA(h, cudaMemcpy(h->exp_mask.data() + old, h->mask_tile.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+  }
+
+  // ---- hit loop ----
+  for (uint32_t hit = fused_gen ? 1u : 0u; hit < h->max_hits; hit++) {
     tp.hit = hit;
     const bool last = hit + 1 == h->max_hits;
     if (h->fused_bounce) {  // one launch per interaction (DESIGN.md "kernels")
       EventPair* ev = begin_event(h, 3, n);
-      launch_bounce(launch_ctx(h), general, last, in_smem, h->p4_enable ? L.b().p4_mode() : 0,
+      launch_bounce(launch_ctx(h), general, last, in_smem, p4_mode,
                     smem + kStage2Bytes + kQueueBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
       end_event(h, ev);
       h->ctr.kernel_launches++;
@@ -631,14 +676,14 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
       continue;
     }
     EventPair* ev = begin_event(h, 1, n);
-    launch_optics(launch_ctx(h), general, last, in_smem, h->p4_enable ? L.b().p4_mode() : 0, smem + kStageBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
+    launch_optics(launch_ctx(h), general, last, in_smem, p4_mode, smem + kStageBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
     end_event(h, ev);
     h->ctr.kernel_launches++;
     h->ctr.optics_launches++;
     h->ctr.optics_rays += n;
     if (!last) {
       ev = begin_event(h, 2, n);
-      launch_intersect(launch_ctx(h), general, in_smem, h->p4_enable ? L.b().p4_mode() : 0, smem, tp);
+      launch_intersect(launch_ctx(h), general, in_smem, p4_mode, smem, tp);
       end_event(h, ev);
       h->ctr.kernel_launches++;
       h->ctr.intersect_launches++;
@@ -720,6 +765,12 @@ int hb_create(int device, HbEngine** out) {
     g_create_error = "cudaStreamCreate failed";
     return HB_ERR_CUDA;
   }
+  if (h->counters.ensure(8) != cudaSuccess || cudaMemset(h->counters.p, 0, 8 * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMallocHost(&h->err_host, sizeof(uint32_t)) != cudaSuccess) {
+    g_create_error = "device counter allocation failed";
+    return HB_ERR_CUDA;
+  }
+  *h->err_host = 0u;
   *out = h.release();
   return HB_OK;
 }
@@ -747,7 +798,10 @@ void hb_destroy(HbEngine* h) {
   h->rgb_stage.release();
   h->xyz_stage.release();
   h->landed_dev.release();
-  for (auto& s : h->wl_cache) s.dev.release();
+  for (auto& s : h->wl_cache) {
+    s.dev.release();
+    s.dev2.release();
+  }
   h->P.release();
   h->D.release();
   h->Q.release();
@@ -764,6 +818,7 @@ void hb_destroy(HbEngine* h) {
   }
   h->exits_dev.release();
   h->exit_root_dev.release();
+  if (h->err_host) cudaFreeHost(h->err_host);
 #ifdef HB_WITH_NCCL
   if (h->comm) ncclCommDestroy(h->comm);
 #endif
@@ -779,19 +834,25 @@ int hb_set_scene(HbEngine* h, const HbScene* s) {
   cudaSetDevice(h->device);
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->geom_stream) HB_CUDA(h, cudaStreamSynchronize(h->geom_stream));
+  if (s->color_classes.class_cnt > HB_MAX_COLOR_CLASSES) return fail(h, HB_ERR_INVALID_ARG, "scene: more than 16 colour classes");
   for (auto& L : h->layers) L->release();
   h->layers.clear();
+  h->have_scene = false;  // a failed upload leaves the engine without a scene, not with half of the old one
   for (uint32_t li = 0; li < s->layer_cnt; li++) {
     auto L = std::make_unique<LayerDev>();
     int rc = upload_layer(h, s->layers[li], L.get());
-    if (rc != HB_OK) return rc;
+    if (rc != HB_OK) {
+      L->release();
+      for (auto& K : h->layers) K->release();
+      h->layers.clear();
+      return rc;
+    }
     h->layers.push_back(std::move(L));
   }
   h->max_hits = s->max_hits;
   h->sun_lon = s->sun_lon;
   h->sun_lat = s->sun_lat;
   h->sun_half = s->sun_half_angle;
-  if (s->color_classes.class_cnt > HB_MAX_COLOR_CLASSES) return fail(h, HB_ERR_INVALID_ARG, "scene: more than 16 colour classes");
   h->classes = s->color_classes;
   h->have_scene = true;
   return HB_OK;
@@ -912,7 +973,19 @@ int hb_begin_session(HbEngine* h, const HbSessionSpec* spec) {
     int rc = prefetch_geometry(h, *L);
     if (rc != HB_OK) return rc;
   }
-  if (spec->use_ray_base) h->gen_base = spec->ray_base;
+  if (spec->use_ray_base) {
+    // Sharded sessions (multi-GPU): EVERY stream of the session is keyed by the global ray index, not
+    // only root generation -- ranks tracing disjoint root ranges must also draw disjoint gate and transit streams,
+    // or the second-layer samples would be replicated across ranks. A root spawns at most (max_hits + 1) exits per
+    // layer, so `span` stream indices per root are enough for all layers of the session.
+    h->gen_base = spec->ray_base;
+    uint64_t span = 0, per = 1;
+    for (size_t l = 0; l < h->layers.size(); l++) {
+      span += per;
+      per *= static_cast<uint64_t>(h->max_hits) + 1u;
+    }
+    h->gate_base = h->transit_base = spec->ray_base * span;
+  }
   h->layer_idx = 0;
   h->layer_traced = false;
   h->cont_n = 0;
@@ -926,6 +999,7 @@ int hb_begin_session(HbEngine* h, const HbSessionSpec* spec) {
   h->exp_face.clear();
   h->exp_shape.clear();
   h->exp_wl.clear();
+  h->exp_mask.clear();
   h->in_session = true;
   return HB_OK;
 }
@@ -998,16 +1072,21 @@ int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats) {
     hb_partition_rays(prop.data(), static_cast<uint32_t>(prop.size()), n, L.carry.data(), counts.data());
   }
   for (size_t i = 0; i < counts.size(); i++) pop_begin[i + 1] = pop_begin[i] + counts[i];
+  // All proportions <= 0 assign no ray at all (the reference traces nothing then): trace what was assigned, never
+  // the stale state of slots no generator wrote.
+  n = pop_begin.back();
 
   // continuation pool of this layer (only when its exits can continue)
   HB_CUDA(h, h->counters.ensure(8));
   HB_CUDA(h, h->stat_cnt.ensure(1));
   HB_CUDA(h, h->stat_sum.ensure(1));
-  HB_CUDA(h, cudaMemsetAsync(h->counters.p + 2, 0, 4 * sizeof(uint32_t), h->stream));  // cont_count, exit_count, error, done_count
+  HB_CUDA(h, cudaMemsetAsync(h->counters.p + 2, 0, 2 * sizeof(uint32_t), h->stream));  // cont_count, exit_count
+  HB_CUDA(h, cudaMemsetAsync(h->counters.p + 5, 0, sizeof(uint32_t), h->stream));      // done_count (the error word [4] stays)
   HB_CUDA(h, cudaMemsetAsync(h->stat_cnt.p, 0, sizeof(unsigned long long), h->stream));
   HB_CUDA(h, cudaMemsetAsync(h->stat_sum.p, 0, sizeof(double), h->stream));
   if (flags & kFlagGate) {
-    const uint64_t ccap = std::min<uint64_t>(n * (h->max_hits + 1) + 4096, 0xFFFFFFF0ull);
+    uint64_t ccap = std::min<uint64_t>(n * (h->max_hits + 1) + 4096, 0xFFFFFFF0ull);
+    if (h->cont_cap_override) ccap = std::min<uint64_t>(ccap, h->cont_cap_override);
     HB_CUDA(h, h->cont_dw[h->cont_cur].ensure(ccap));
     HB_CUDA(h, h->cont_meta[h->cont_cur].ensure(ccap));
     if (h->classes.class_cnt != 0) HB_CUDA(h, h->cont_mask[h->cont_cur].ensure(ccap));
@@ -1042,7 +1121,10 @@ int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats) {
     HB_CUDA(h, cudaMemcpyAsync(&ws, h->stat_sum.p, 8, cudaMemcpyDeviceToHost, h->stream));
     HB_CUDA(h, cudaStreamSynchronize(h->stream));
     if (h->profile) flush_events(h);
-    if (c[2] != 0) return fail(h, HB_ERR_CAPACITY, "device buffer overflow (code " + std::to_string(c[2]) + ")");
+    if (c[2] != 0) {
+      *h->err_host = c[2];
+      return check_device_error(h);
+    }
     h->cont_n = c[0];
     if (stats != nullptr) {
       float ms = 0.0f;
@@ -1057,6 +1139,8 @@ int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats) {
     }
   } else {
     h->cont_n = 0;
+    // no synchronisation here: mirror the error word; the next synchronising entry point reports it
+    HB_CUDA(h, cudaMemcpyAsync(h->err_host, h->counters.p + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   }
   return HB_OK;
 }
@@ -1081,7 +1165,9 @@ int hb_end_session(HbEngine* h) {
   h->layer_traced = false;
   h->layer_idx = 0;
   h->injected = false;
-  return HB_OK;
+  // Non-blocking: an overflow whose mirror copy has already landed is reported here, otherwise by the next
+  // synchronising call (ReadbackXyzAccum at the latest); it is never cleared unreported.
+  return check_device_error(h);
 }
 
 int hb_readback_xyz_render(HbEngine* h, uint32_t render, float* xyz, float* landed) {
@@ -1101,7 +1187,7 @@ int hb_readback_xyz_render(HbEngine* h, uint32_t render, float* xyz, float* land
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->profile) flush_events(h);
   *landed += static_cast<float>(l);
-  return HB_OK;
+  return check_device_error(h);
 }
 
 int hb_readback_xyz(HbEngine* h, float* xyz, float* landed) { return hb_readback_xyz_render(h, 0, xyz, landed); }
@@ -1116,7 +1202,7 @@ int hb_readback_class_lanes(HbEngine* h, float* lanes, uint64_t cap_floats, uint
   HB_CUDA(h, cudaMemsetAsync(h->lanes.p, 0, h->lanes_floats * sizeof(float), h->stream));
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
   *class_count = h->classes.class_cnt;
-  return HB_OK;
+  return check_device_error(h);
 }
 
 int hb_snapshot(HbEngine* h, uint32_t render, const HbSnapshotDesc* desc, uint8_t* rgb8, float* xyz, float* intensity) {
@@ -1137,6 +1223,10 @@ int hb_snapshot(HbEngine* h, uint32_t render, const HbSnapshotDesc* desc, uint8_
   if (xyz)
     HB_CUDA(h, cudaMemcpyAsync(xyz, h->xyz_stage.p, static_cast<size_t>(pix) * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
+  {
+    int rc = check_device_error(h);
+    if (rc != HB_OK) return rc;
+  }
   const float snapshot_intensity = static_cast<float>(l);
   if (intensity) *intensity = snapshot_intensity;
   if (rgb8 != nullptr) {
@@ -1163,6 +1253,12 @@ int hb_snapshot(HbEngine* h, uint32_t render, const HbSnapshotDesc* desc, uint8_
 int hb_drain_exits(HbEngine* h, HbExitRecord* out, uint32_t* root_ids, uint64_t cap, uint64_t* count) {
   if (h == nullptr || count == nullptr) return HB_ERR_INVALID_ARG;
   if (!h->in_session) return fail(h, HB_ERR_STATE, "DrainExits outside a session");
+  if (h->spec.record_exits) {  // record sessions are synchronous per tile already: make the error word current
+    cudaSetDevice(h->device);
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    int rc = check_device_error(h);
+    if (rc != HB_OK) return rc;
+  }
   *count = h->exits_host.size();
   if (out == nullptr) return HB_OK;
   if (cap < h->exits_host.size()) return fail(h, HB_ERR_CAPACITY, "DrainExits: caller buffer too small (grow, not clamp)");
@@ -1227,6 +1323,14 @@ int hb_set_option(HbEngine* h, const char* key, int64_t value) {
     h->pixel_cache = value != 0;
   } else if (k == "fused_bounce") {
     h->fused_bounce = value != 0;
+  } else if (k == "fused_gen") {
+    h->fused_gen = value != 0;
+  } else if (k == "fork_cap") {   // fork-ray slots per tile (0 = automatic: max(4096, n / 64)); tests force overflows
+    if (value < 0 || value > (1ll << 30)) return fail(h, HB_ERR_INVALID_ARG, "fork_cap out of range");
+    h->fork_cap_override = static_cast<uint64_t>(value);
+  } else if (k == "cont_cap") {   // continuation-pool capacity (0 = automatic: n (max_hits + 1) + 4096)
+    if (value < 0) return fail(h, HB_ERR_INVALID_ARG, "cont_cap out of range");
+    h->cont_cap_override = static_cast<uint64_t>(value);
   } else if (k == "fold_rays") {
     if (value < 1024) return fail(h, HB_ERR_INVALID_ARG, "fold_rays out of range");
     h->fold_rays = static_cast<uint64_t>(value);
@@ -1451,10 +1555,9 @@ int hb_synchronize(HbEngine* h) {
   cudaSetDevice(h->device);
   HB_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->profile) flush_events(h);
-  uint32_t err = 0;
   if (h->counters.p) {
-    HB_CUDA(h, cudaMemcpy(&err, h->counters.p + 4, 4, cudaMemcpyDeviceToHost));
-    if (err != 0) return fail(h, HB_ERR_CAPACITY, "device buffer overflow (code " + std::to_string(err) + ")");
+    HB_CUDA(h, cudaMemcpy(h->err_host, h->counters.p + 4, 4, cudaMemcpyDeviceToHost));
+    return check_device_error(h);
   }
   return HB_OK;
 }

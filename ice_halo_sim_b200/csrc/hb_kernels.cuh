@@ -784,6 +784,8 @@ HB_DEV uint2 lds64(uint32_t addr) {
   return v;
 }
 
+HB_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct ExitQueue {
   uint32_t addr;    // shared-space address of this warp's queue
   uint32_t count;   // warp-uniform
@@ -812,7 +814,7 @@ HB_DEV void queue_drain(ExitQueue& xq, bool all, const TraceParams& tp, const Ta
       const float4 e = lds128(xq.addr + (first + lane) * 16u);
       const uint2 m = lds64(xq.addr + kQueueSlots * 16u + (first + lane) * 8u);
       const uint32_t slot = m.x & 0x7FFFFFFFu;
-      emit_exit<GENERAL, MULTI>(tp, slot, m.y, __ldg(tp.Q + slot), e.x, e.y, e.z, e.w, m.x >> 31, tb, tally);
+      emit_exit<GENERAL, MULTI>(tp, slot, m.y, tp.Q[slot], e.x, e.y, e.z, e.w, m.x >> 31, tb, tally);
     }
     xq.count = first;
     __syncwarp();
@@ -835,10 +837,11 @@ HB_DEV void publish_fork_snapshot(const TraceParams& tp) {
 }
 
 // One interaction of one live ray in registers. Outputs: up to two leaving children (e0: far side, role 0;
-// e1: near side, role 1) and the ray's next state (written by the caller unless LAST).
+// e1: near side, role 1) and the ray's next state: d_out always (w < 0: the ray ends), p_out when `moved`
+// (the near child reached a face). The caller stores them (nothing is stored after the LAST interaction).
 template <bool GENERAL, bool LAST, bool SMEM, int P4>
 HB_DEV void bounce_ray(const TraceParams& tp, const Tables<SMEM>& tb, uint32_t i, float4 p4, float4 d4, bool& has0,
-                       float4& e0, bool& has1, float4& e1) {
+                       float4& e0, bool& has1, float4& e1, float4& d_out, float4& p_out, bool& moved) {
   const uint32_t bits = __float_as_uint(p4.w);
   const uint32_t face = bits_face(bits);
   const uint32_t shape = bits_shape(bits);
@@ -898,28 +901,34 @@ HB_DEV void bounce_ray(const TraceParams& tp, const Tables<SMEM>& tb, uint32_t i
     }
   }
   // near-side child
+  moved = false;
+  d_out = make_float4(ix, iy, iz, iw);  // iw < 0: TIR sentinel, the ray ends (entry-side refraction never does)
+  p_out = p4;
   if (LAST) {
     if (!near_done && nf == kFaceInvalid) {
       has1 = true;
       e1 = make_float4(ix, iy, iz, iw);
     }
-  } else if (iw < 0.0f) {
-    tp.D[i] = make_float4(ix, iy, iz, iw);  // TIR sentinel: the ray ends (entry-side refraction never does)
-  } else if (nf == kFaceInvalid) {
-    // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
-    has1 = true;
-    e1 = make_float4(ix, iy, iz, iw);
-    tp.D[i] = make_float4(ix, iy, iz, -1.0f);
-  } else {
-    tp.D[i] = make_float4(ix, iy, iz, iw);
-    tp.P[i] = make_float4(nx, ny, nz, __uint_as_float(bits_with_face(bits, nf)));
-    if (GENERAL && (tp.flags & kFlagPath) && tp.hit + 1u < tp.max_hits)
-      tp.path[static_cast<size_t>(tp.hit + 1u) * tp.cap + i] = static_cast<uint8_t>(nf);
+  } else if (iw >= 0.0f) {
+    if (nf == kFaceInvalid) {
+      // the inside child found no face: it is outgoing (CollectData branch 1) and the ray ends here
+      has1 = true;
+      e1 = make_float4(ix, iy, iz, iw);
+      d_out.w = -1.0f;
+    } else {
+      moved = true;
+      p_out = make_float4(nx, ny, nz, __uint_as_float(bits_with_face(bits, nf)));
+      if (GENERAL && (tp.flags & kFlagPath) && tp.hit + 1u < tp.max_hits)
+        tp.path[static_cast<size_t>(tp.hit + 1u) * tp.cap + i] = static_cast<uint8_t>(nf);
+    }
   }
 }
 
 #ifndef HB_BOUNCE_MINB
 #define HB_BOUNCE_MINB 4
+#endif
+#ifndef HB_PREFETCH_Q
+#define HB_PREFETCH_Q 1
 #endif
 #ifndef HB_BOUNCE_MINB_GENERAL
 #define HB_BOUNCE_MINB_GENERAL 4
@@ -966,9 +975,19 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_BOUNCE_MINB_GENERAL : HB_BOU
       if (i < total) {
         const float4 d4 = lds128(cur), p4 = lds128(cur + 4096u);
         bits = __float_as_uint(p4.w);
-        if (d4.w >= 0.0f && bits_face(bits) != kFaceInvalid)  // else: terminated ray
-          bounce_ray<GENERAL, LAST, SMEM, P4>(tp, tb, i, p4, d4, has0, e0, has1, e1);
+        if (d4.w >= 0.0f && bits_face(bits) != kFaceInvalid) {  // else: terminated ray
+          float4 d_out, p_out;
+          bool moved;
+          bounce_ray<GENERAL, LAST, SMEM, P4>(tp, tb, i, p4, d4, has0, e0, has1, e1, d_out, p_out, moved);
+          if (!LAST) {
+            tp.D[i] = d_out;
+            if (moved) tp.P[i] = p_out;
+          }
+        }
       }
+#if HB_PREFETCH_Q
+      if (has0 || has1) prefetch_l1(tp.Q + i);  // the emission (some iterations later, another lane) reads the orientation
+#endif
       queue_push(xq, has0, e0.x, e0.y, e0.z, e0.w, i, bits);
       queue_push(xq, has1, e1.x, e1.y, e1.z, e1.w, i | 0x80000000u, bits);
       stage ^= 1u;
@@ -1170,10 +1189,7 @@ struct GenShared {
   EntryFaces ef0;                // ... and its face groups
 };
 
-template <bool TRANSIT>
-__global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  GenShared* gs = reinterpret_cast<GenShared*>(smem_raw);
+HB_DEV void stage_gen_shared(const GenParams& gp, GenShared* gs) {
   if (gp.axis.lat_path == HB_LAT_LUT) {
     for (uint32_t i = threadIdx.x; i < 3 * HB_LUT_NODES; i += blockDim.x) gs->lut[i] = gp.lut[i];
   }
@@ -1185,69 +1201,152 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
     uint4* edst = reinterpret_cast<uint4*>(&gs->ef0);
     for (uint32_t i = threadIdx.x; i < sizeof(EntryFaces) / 16; i += blockDim.x) edst[i] = esrc[i];
   }
+}
+
+// Root ray k of a launch (InitRay_*, simulator.cpp:133-339 with the counter-based streams of pcg_shared.h): wavelength
+// draw / continuation gather, orientation, sun-cone direction, shape pick, entry point. Returns the ray state.
+template <bool TRANSIT>
+HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float4& p_out, float4& d_out, float4& q_out) {
+  const uint32_t lo = gp.idx_lo + k;
+  const uint32_t hi = gp.idx_hi + (lo < gp.idx_lo ? 1u : 0u);
+  const uint32_t s0 = seed_with_high(gp.seed, hi);
+  uint32_t wl_i = 0u;
+  float wx, wy, wz, weight;
+  if (TRANSIT) {
+    uint32_t src = gp.cont_first + k;
+    if (gp.shuffle) src = feistel(src, gp.cont_n, gp.shuffle_seed);
+    const float4 c = gp.cont_dw[src];
+    wx = c.x;
+    wy = c.y;
+    wz = c.z;
+    weight = c.w;
+    wl_i = gp.cont_meta[src] & 255u;
+    if (gp.cont_mask != nullptr) gp.M[gp.slot0 + k] = gp.cont_mask[src];
+  } else if (gp.wl_cnt > 1u) {
+    wl_i = min(static_cast<uint32_t>(draw(s0 ^ kNonceWl, lo, 0u) * static_cast<float>(gp.wl_cnt)), gp.wl_cnt - 1u);
+  }
+  Stream s{ s0, lo, 0u };
+  float lon, lat, roll;
+  sample_lon_lat_roll(s, gp.axis, gs->lut, lon, lat, roll);
+  const float4 q = quat_from_angles(lon, lat, roll);
+  const Rot r = rot_from_quat(q);
+  if (!TRANSIT) {
+    // sample_sph_cap (pcg_shared.h:514-529) with the per-launch trigonometry hoisted to the host
+    const float u = s.next();
+    const float x = u + (1.0f - u) * gp.sun_c_cap;
+    const float rr = sqrtf(fmaxf(1.0f - x * x, 0.0f));
+    float sp, cp;
+    sincosf(s.next() * 2.0f * kPiF, &sp, &cp);
+    const float y = cp * rr, z = sp * rr;
+    wx = gp.sun_c_lon * gp.sun_c_lat * x - gp.sun_s_lon * y - gp.sun_c_lon * gp.sun_s_lat * z;
+    wy = gp.sun_s_lon * gp.sun_c_lat * x + gp.sun_c_lon * y - gp.sun_s_lon * gp.sun_s_lat * z;
+    wz = gp.sun_s_lat * x + gp.sun_c_lat * z;
+    weight = gp.wl[wl_i].spd_weight;
+  }
+  float dx, dy, dz;
+  rot_apply_t(r.m, wx, wy, wz, dx, dy, dz);
+  // Geometry clock: one shape of the pool serves a block of 32 consecutive ray indices, as on the reference's
+  // CPU path (kSmallBatchRayNum, simulator.hpp:144-151). A warp therefore reads ONE shape's tables in every
+  // kernel of the hit loop (uniform addresses: broadcast loads) instead of 32 different ones.
+  uint32_t sh = 0u;
+  if (gp.shape_cnt > 1u) {
+    sh = min(static_cast<uint32_t>(draw(s0 ^ kNonceShape, lo >> 5, 0u) * static_cast<float>(gp.shape_cnt)), gp.shape_cnt - 1u);
+  }
+  const HbCrystalTables* tab = gp.shape_cnt == 1u ? &gs->shape0 : gp.shapes + sh;
+  const EntryFaces* ef = gp.shape_cnt == 1u ? &gs->ef0 : gp.entry_faces + sh;
+  float px = 0.0f, py = 0.0f, pz = 0.0f;
+  uint32_t face = kFaceInvalid;
+  if (tab->subtri_cnt == 0u) {
+    weight = -1.0f;  // degenerate crystal: nothing to trace (zero-weight discard, simulator.cpp:149-159)
+  } else {
+    if (ef->group_cnt != 0u) sample_entry_faces(s, ef, tab, dx, dy, dz, px, py, pz, face);
+    else sample_entry(s, tab, dx, dy, dz, px, py, pz, face);
+  }
+  p_out = make_float4(px, py, pz, __uint_as_float(pack_bits(face, wl_i, gp.shape_base + sh, 0u)));
+  d_out = make_float4(dx, dy, dz, weight);
+  q_out = q;
+}
+
+template <bool TRANSIT>
+__global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenShared* gs = reinterpret_cast<GenShared*>(smem_raw);
+  stage_gen_shared(gp, gs);
   __syncthreads();
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gp.count; k += gridDim.x * blockDim.x) {
-    const uint32_t lo = gp.idx_lo + k;
-    const uint32_t hi = gp.idx_hi + (lo < gp.idx_lo ? 1u : 0u);
-    const uint32_t s0 = seed_with_high(gp.seed, hi);
-    uint32_t wl_i = 0u;
-    float wx, wy, wz, weight;
-    if (TRANSIT) {
-      uint32_t src = gp.cont_first + k;
-      if (gp.shuffle) src = feistel(src, gp.cont_n, gp.shuffle_seed);
-      const float4 c = gp.cont_dw[src];
-      wx = c.x;
-      wy = c.y;
-      wz = c.z;
-      weight = c.w;
-      wl_i = gp.cont_meta[src] & 255u;
-      if (gp.cont_mask != nullptr) gp.M[gp.slot0 + k] = gp.cont_mask[src];
-    } else if (gp.wl_cnt > 1u) {
-      wl_i = min(static_cast<uint32_t>(draw(s0 ^ kNonceWl, lo, 0u) * static_cast<float>(gp.wl_cnt)), gp.wl_cnt - 1u);
-    }
-    Stream s{ s0, lo, 0u };
-    float lon, lat, roll;
-    sample_lon_lat_roll(s, gp.axis, gs->lut, lon, lat, roll);
-    const float4 q = quat_from_angles(lon, lat, roll);
-    const Rot r = rot_from_quat(q);
-    if (!TRANSIT) {
-      // sample_sph_cap (pcg_shared.h:514-529) with the per-launch trigonometry hoisted to the host
-      const float u = s.next();
-      const float x = u + (1.0f - u) * gp.sun_c_cap;
-      const float rr = sqrtf(fmaxf(1.0f - x * x, 0.0f));
-      float sp, cp;
-      sincosf(s.next() * 2.0f * kPiF, &sp, &cp);
-      const float y = cp * rr, z = sp * rr;
-      wx = gp.sun_c_lon * gp.sun_c_lat * x - gp.sun_s_lon * y - gp.sun_c_lon * gp.sun_s_lat * z;
-      wy = gp.sun_s_lon * gp.sun_c_lat * x + gp.sun_c_lon * y - gp.sun_s_lon * gp.sun_s_lat * z;
-      wz = gp.sun_s_lat * x + gp.sun_c_lat * z;
-      weight = gp.wl[wl_i].spd_weight;
-    }
-    float dx, dy, dz;
-    rot_apply_t(r.m, wx, wy, wz, dx, dy, dz);
-    // Geometry clock: one shape of the pool serves a block of 32 consecutive ray indices, as on the reference's
-    // CPU path (kSmallBatchRayNum, simulator.hpp:144-151). A warp therefore reads ONE shape's tables in every
-    // kernel of the hit loop (uniform addresses: broadcast loads) instead of 32 different ones.
-    uint32_t sh = 0u;
-    if (gp.shape_cnt > 1u) {
-      sh = min(static_cast<uint32_t>(draw(s0 ^ kNonceShape, lo >> 5, 0u) * static_cast<float>(gp.shape_cnt)), gp.shape_cnt - 1u);
-    }
-    const HbCrystalTables* tab = gp.shape_cnt == 1u ? &gs->shape0 : gp.shapes + sh;
-    const EntryFaces* ef = gp.shape_cnt == 1u ? &gs->ef0 : gp.entry_faces + sh;
-    float px = 0.0f, py = 0.0f, pz = 0.0f;
-    uint32_t face = kFaceInvalid;
-    if (tab->subtri_cnt == 0u) {
-      weight = -1.0f;  // degenerate crystal: nothing to trace (zero-weight discard, simulator.cpp:149-159)
-    } else {
-      if (ef->group_cnt != 0u) sample_entry_faces(s, ef, tab, dx, dy, dz, px, py, pz, face);
-      else sample_entry(s, tab, dx, dy, dz, px, py, pz, face);
-    }
+    float4 p4, d4, q;
+    gen_root<TRANSIT>(gp, gs, k, p4, d4, q);
     const uint32_t slot = gp.slot0 + k;
-    gp.P[slot] = make_float4(px, py, pz, __uint_as_float(pack_bits(face, wl_i, gp.shape_base + sh, 0u)));
-    gp.D[slot] = make_float4(dx, dy, dz, weight);
+    gp.P[slot] = p4;
+    gp.D[slot] = d4;
     gp.Q[slot] = q;
-    if ((gp.flags & kFlagPath) && gp.path != nullptr) gp.path[slot] = static_cast<uint8_t>(face);
+    if ((gp.flags & kFlagPath) && gp.path != nullptr) gp.path[slot] = static_cast<uint8_t>(bits_face(__float_as_uint(p4.w)));
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Root generation fused with the ENTRY interaction (InitRay_* + the first pass of the hit loop,
+// simulator.cpp:133-259,1308-1336): the root never travels through HBM between the generator and hit 0 --
+// the state after the entry interaction is written once (P, D, Q: 48 B per root instead of 48 written +
+// 32..48 read + 32 written), and a session needs one launch less. The external reflection goes through the
+// same per-warp exit queue as in bounce_kernel.
+// dynamic shared memory: [GenShared] [pixel cache] [exit queues] [crystal tables]
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kGenSharedBytes = (static_cast<uint32_t>(sizeof(GenShared)) + 15u) & ~15u;
+
+template <bool TRANSIT, bool GENERAL, bool SMEM, bool MULTI, int P4 = 0>
+__global__ void __launch_bounds__(256, 4) genbounce_kernel(const GenParams gp, const TraceParams tp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenShared* gs = reinterpret_cast<GenShared*>(smem_raw);
+  stage_gen_shared(gp, gs);
+  Tally tally;
+  const bool use_cache = (tp.flags & kFlagPixelCache) != 0u;
+  if (use_cache) cache_init(tally, smem_raw + kGenSharedBytes);
+  const uint32_t q_off = kGenSharedBytes + (use_cache ? static_cast<uint32_t>(kCacheBytes) : 0u);
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + q_off + kQueueBytes, GENERAL);
+  if (!SMEM) __syncthreads();
+  const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
+  ExitQueue xq{ smem_base + q_off + (threadIdx.x >> 5) * kQueueWarpBytes, 0u };
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t warp_first = k - (threadIdx.x & 31u);
+  for (;;) {
+    const bool more = warp_first < gp.count;
+    if (more) {
+      bool has0 = false, has1 = false;
+      float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+      uint32_t bits = 0u;
+      const uint32_t slot = gp.slot0 + k;
+      if (k < gp.count) {
+        float4 p4, d4, q;
+        gen_root<TRANSIT>(gp, gs, k, p4, d4, q);
+        bits = __float_as_uint(p4.w);
+        gp.Q[slot] = q;
+        if (GENERAL && (gp.flags & kFlagPath) && gp.path != nullptr) gp.path[slot] = static_cast<uint8_t>(bits_face(bits));
+        if (d4.w >= 0.0f && bits_face(bits) != kFaceInvalid) {
+          float4 d_out, p_out;
+          bool moved;
+          bounce_ray<GENERAL, false, SMEM, P4>(tp, tb, slot, p4, d4, has0, e0, has1, e1, d_out, p_out, moved);
+          d4 = d_out;
+          p4 = p_out;
+        }
+        gp.P[slot] = p4;
+        gp.D[slot] = d4;
+      }
+      queue_push(xq, has0, e0.x, e0.y, e0.z, e0.w, slot, bits);
+      queue_push(xq, has1, e1.x, e1.y, e1.z, e1.w, slot | 0x80000000u, bits);
+      k += stride;
+      warp_first += stride;
+    }
+    if (xq.count >= 32u || !more) queue_drain<GENERAL, MULTI>(xq, !more, tp, tb, tally);
+    if (!more) break;
+  }
+  if (use_cache) cache_flush(tp, tally);
+  if (GENERAL && (tp.flags & kFlagStats) && tally.exits != 0ull) {
+    atomicAdd(tp.stat_exit_count, tally.exits);
+    atomicAdd(tp.stat_w_sum, tally.w_sum);
+  }
+  publish_fork_snapshot(tp);
 }
 
 #ifndef HB_TU  // non-template kernels: defined once, in the engine translation unit (hb_tu.cu slices skip them)

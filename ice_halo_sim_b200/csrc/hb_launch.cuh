@@ -24,7 +24,15 @@ void launch_optics(const LaunchCtx& c, bool general, bool last, bool in_smem, in
 void launch_intersect(const LaunchCtx& c, bool general, bool in_smem, int p4, size_t smem, const TraceParams& tp);
 void launch_bounce(const LaunchCtx& c, bool general, bool last, bool in_smem, int p4, size_t smem, const TraceParams& tp);
 
+// Root generation fused with the entry interaction (genbounce_kernel); the caller continues the hit loop at hit 1.
+void launch_genbounce(const LaunchCtx& c, bool transit, bool general, bool in_smem, int p4, size_t smem, const GenParams& gp,
+                      const TraceParams& tp);
+
 // per-TU pieces
+void launch_genbounce_p0(const LaunchCtx& c, int key, size_t smem, const GenParams& gp, const TraceParams& tp);
+void launch_genbounce_p1(const LaunchCtx& c, int key, size_t smem, const GenParams& gp, const TraceParams& tp);
+void launch_genbounce_p2(const LaunchCtx& c, int key, size_t smem, const GenParams& gp, const TraceParams& tp);
+void launch_genbounce_multi(const LaunchCtx& c, int key, size_t smem, const GenParams& gp, const TraceParams& tp);
 void launch_optics_p0(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
 void launch_optics_p1(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
 void launch_optics_p2(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);

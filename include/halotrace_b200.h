@@ -241,8 +241,10 @@ typedef struct HbCounters {               /* measurement helpers (bench.py) */
   double intersect_ms, optics_ms, gen_ms; /* accumulated per-kernel-family CUDA-event time (profiling mode) */
   uint64_t intersect_launches, optics_launches, gen_launches;
   uint64_t intersect_rays, optics_rays;   /* ray-bounces processed by each family */
-  double bounce_ms;                       /* fused bounce kernels (one launch per interaction; gen + entry interaction included) */
+  double bounce_ms;                       /* fused bounce kernels (one launch per interaction) */
   uint64_t bounce_launches, bounce_rays;
+  double genbounce_ms;                    /* root generation fused with the entry interaction */
+  uint64_t genbounce_launches, genbounce_rays;
 } HbCounters;
 
 typedef struct HbEngine HbEngine;         /* opaque; one per TraceBackend instance / GPU */

@@ -487,3 +487,130 @@ def test_two_layer_full_size_invariants(backend):
     assert 0 < landed <= h1.exit_w_sum * (1 + 1e-5)              # "upper" view: only part of the sky lands
     y = img[..., 1].astype(np.float64).sum()
     assert abs(y - wl[0][3] * landed) <= 2e-4 * y
+
+
+def _fused_image(backend, case, n, seed, want_stats, opts):
+    """Single-layer accumulate-only session under engine options `opts`; returns (image, landed)."""
+    from ice_halo_sim_b200 import backend as B
+    for k, v in opts.items():
+        backend.SetOption(k, v)
+    try:
+        tables = B.SceneTables(case["scene"](), 7)
+        backend.SetScene(tables)
+        backend.SetOption("stream_base", 0)
+        backend.SetRender(case["render"]())
+        backend.ReadbackXyzAccum()
+        wl = [B.make_wl_entry(x, 1.0) for x in case["wl"]]
+        backend.BeginSession(B.SessionSpec(seed=seed, wl=wl, ray_num=n))
+        backend.TraceLayer(B.RootRaySource.FromHost(n), want_stats=want_stats)
+        backend.EndSession()
+        return backend.ReadbackXyzAccum()
+    finally:
+        for k in opts:
+            backend.SetOption(k, 1)
+
+
+@pytest.mark.parametrize("name", ["column_config2", "stoch_config5", "pyramid", "two_populations"])
+def test_production_kernels_equal_parity_kernels(backend, name):
+    """The kernels a production session runs (no exit records: fast non-general instantiations, root generation
+    fused with the entry interaction) trace the same rays as the general kernels the bit-exact protocol runs on:
+    same seed => same exits => the same image up to the order of the float additions. Covers every pipeline
+    variant: gen fused / separate, bounce fused / split optics + intersect."""
+    case = parity.CASES[name]
+    n = 300000
+    backend.SetOption("tile_rays", 1 << 15)   # small tiles folded into the fp64 master: fp32 absorption cannot blur the comparison
+    backend.SetOption("fold_rays", 1 << 15)
+    try:
+        ref_img, ref_landed = _fused_image(backend, case, n, 17, True, {"fused_gen": 0})   # general kernels (LayerStats)
+        assert ref_landed > 0
+        scale = float(np.abs(ref_img).max())
+        for opts in ({}, {"fused_gen": 0}, {"fused_bounce": 0}):
+            img, landed = _fused_image(backend, case, n, 17, False, opts)
+            assert abs(landed - ref_landed) <= 1e-5 * ref_landed, (name, opts)
+            assert np.allclose(img, ref_img, rtol=5e-5, atol=2e-6 * scale), (name, opts)
+            assert abs(float(img.astype(np.float64).sum()) / float(ref_img.astype(np.float64).sum()) - 1.0) < 3e-6
+    finally:
+        backend.SetOption("tile_rays", 1 << 24)
+        backend.SetOption("fold_rays", 1 << 21)
+
+
+def test_device_overflow_is_reported_not_dropped(backend):
+    """Fork-slot and continuation-pool overflow (forced through the `fork_cap` / `cont_cap` options) in the
+    production call sequence -- no LayerStats, no hb_synchronize -- surface as HB_ERR_CAPACITY at the next
+    synchronising call (ReadbackXyzAccum at the latest) and are reported once; the session after is clean."""
+    from ice_halo_sim_b200 import backend as B
+    from ice_halo_sim_b200.lib import HaloTraceError
+    wl = [B.make_wl_entry(550.0, 1.0)]
+    # (a) continuation pool: two layers, prob 1.0, pool capped at 1000 records
+    case = parity.CASES["two_layer_config4"]
+    backend.SetScene(B.SceneTables(case["scene"](), 7))
+    backend.SetRender(case["render"]())
+    backend.ReadbackXyzAccum()
+    backend.SetOption("cont_cap", 1000)
+    try:
+        backend.BeginSession(B.SessionSpec(seed=5, wl=wl, ray_num=100000))
+        with pytest.raises(HaloTraceError) as ei:
+            backend.TraceLayer(B.RootRaySource.FromHost(100000), want_stats=False)   # the gate layer reads its count: sync
+        assert ei.value.status == -5 and "continuation" in str(ei.value)
+        backend.EndSession()
+    finally:
+        backend.SetOption("cont_cap", 0)
+    backend.ReadbackXyzAccum()       # reported once: the accumulator is readable again
+    # (b) fork slots: single layer, one fork slot; ~1e-6 of the ray-bounces fork
+    case = parity.CASES["column_config2"]
+    backend.SetScene(B.SceneTables(case["scene"](), 7))
+    backend.SetRender(case["render"]())
+    backend.SetOption("fork_cap", 1)
+    try:
+        n = 1 << 23
+        backend.BeginSession(B.SessionSpec(seed=5, wl=wl, ray_num=n))
+        backend.TraceLayer(B.RootRaySource.FromHost(n), want_stats=False)             # no sync, no error yet
+        try:
+            backend.EndSession()                                                     # may already see the mirror
+            with pytest.raises(HaloTraceError) as ei:
+                backend.ReadbackXyzAccum()
+        except HaloTraceError as e:
+            ei = type("E", (), {"value": e})
+        assert ei.value.status == -5 and "fork" in str(ei.value)
+    finally:
+        backend.SetOption("fork_cap", 0)
+    backend.ReadbackXyzAccum()
+    n = 1 << 20
+    backend.BeginSession(B.SessionSpec(seed=5, wl=wl, ray_num=n))
+    backend.TraceLayer(B.RootRaySource.FromHost(n), want_stats=False)
+    backend.EndSession()
+    img, landed = backend.ReadbackXyzAccum()                                          # clean again
+    assert landed > 0
+
+
+def test_sharded_sessions_draw_disjoint_layer_streams(backend):
+    """Multi-GPU sharding: sessions that start at different global ray indices (two ranks' shards)
+    must draw different transit / gate streams in layers >= 1 too, not only different roots; the same index range
+    replays exactly."""
+    from ice_halo_sim_b200 import backend as B
+    case = parity.CASES["partial_prob"]
+    tables = B.SceneTables(case["scene"](), 7)
+    wl = [B.make_wl_entry(530.0, 1.0)]
+    backend.SetScene(tables)
+    n = 4000
+
+    def layer1_roots(ray_base):
+        backend.BeginSession(B.SessionSpec(seed=3, wl=wl, ray_num=n, record_exits=True, accumulate=False, ray_base=ray_base))
+        h = backend.TraceLayer(B.RootRaySource.FromHost(n))
+        backend.DrainExits()
+        backend.ExportRoots()
+        src = backend.Recombine(h, shuffle=True)
+        backend.TraceLayer(src)
+        backend.DrainExits()
+        r = backend.ExportRoots()
+        backend.EndSession()
+        return h.continuation_count, r
+
+    c0, r0 = layer1_roots(0)
+    c1, r1 = layer1_roots(n)          # the neighbouring rank's shard
+    c0b, r0b = layer1_roots(0)
+    assert c0 > 100 and c1 > 100
+    m = min(c0, c1)
+    assert not np.array_equal(r0["rot"][:m], r1["rot"][:m])            # different orientation draws
+    assert (np.abs(r0["rot"][:m] - r1["rot"][:m]).max(axis=1) > 1e-3).mean() > 0.99
+    assert c0 == c0b and np.array_equal(r0["rot"], r0b["rot"]) and np.array_equal(r0["p"], r0b["p"])
