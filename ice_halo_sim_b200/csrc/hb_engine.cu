@@ -106,6 +106,7 @@ struct LayerDev {
   std::vector<double> carry;  // PartitionCrystalRayNum carry (simulator.cpp:519-582)
   uint32_t shape_cnt = 0;
   bool any_filter = false;
+  uint32_t hit_bound = 0xFFFFFFFFu;  // longest path any population's filter can admit (filter_max_len)
   ShapeBufs sb[2];
   int cur = 0;
   ShapeBufs& b() { return sb[cur]; }
@@ -243,10 +244,14 @@ struct HbEngine {
   bool p4_enable = true;  // option "prism_fast_path": 0 forces the generic axis-loop kernels (A/B tests)
   bool pixel_cache = true;
   bool fused_bounce = true;  // option "fused_bounce": 0 runs the split optics + intersect pipeline
-  bool fused_gen = true;     // option "fused_gen": 0 keeps root generation in its own kernel
+  // option "fused_gen": 1 fuses root generation with the entry interaction (genbounce_kernel). Off by default: the
+  // path is instruction-issue bound, the fusion only saves the 80 B/root round trip through HBM and runs the
+  // generator at the bounce kernel's lower occupancy (measured 1.06 ms against 0.58 + 0.38 ms per 16 Mi roots).
+  bool fused_gen = false;
   // Device error word (fork-slot / continuation-pool / exit-record overflow): sticky on the device until it has
   // been REPORTED to the caller. Every TraceLayer enqueues a copy into this pinned mirror; every entry point that
   // synchronises the stream anyway (readback, snapshot, stats, drain, hb_synchronize) checks it.
+  bool filter_hit_bound = true;  // option "filter_hit_bound": 0 traces all max_hits interactions of filtered layers too
   uint32_t* err_host = nullptr;
   uint64_t fork_cap_override = 0;   // option "fork_cap" (tests: force an overflow)
   uint64_t cont_cap_override = 0;   // option "cont_cap"
@@ -398,6 +403,10 @@ int upload_layer(HbEngine* h, const HbLayer& src, LayerDev* L) {
     B0.pop_p4.push_back(pop_p4);
     B0.pop_shapes.push_back(p.shape_cnt);
     filters.push_back(p.filter);
+    {
+      const uint32_t b = filter_max_len(p.filter);
+      L->hit_bound = ci == 0 ? b : std::max(L->hit_bound, b);
+    }
     cid.push_back(p.crystal_id);
     if (p.color_group_cnt > HB_MAX_COLOR_GROUPS) return fail(h, HB_ERR_INVALID_ARG, "population: too many colour groups");
     cgroup_cnt.push_back(p.color_group_cnt);
@@ -529,6 +538,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.cont_root = h->spec.record_exits ? h->cont_root[h->cont_cur].p : nullptr;
   tp.cont_count = h->counters.p + 2;
   tp.cont_cap = static_cast<uint32_t>(h->cont_dw[h->cont_cur].n);
+  if (h->cont_cap_override) tp.cont_cap = static_cast<uint32_t>(std::min<uint64_t>(tp.cont_cap, h->cont_cap_override));
   tp.exits = h->exits_dev.p;
   tp.exit_root = h->exit_root_dev.p;
   tp.exit_count = h->counters.p + 3;
@@ -542,7 +552,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   const int p4_mode = h->p4_enable ? L.b().p4_mode() : 0;
   // Root generation fused with the entry interaction (genbounce_kernel). Parity sessions export the roots
   // between generation and hit 0 and injected rays skip generation: both take the separate gen kernel.
-  const bool fused_gen = h->fused_bounce && h->fused_gen && h->max_hits > 1 && !(li == 0 && h->injected) &&
+  const bool fused_gen = h->fused_bounce && h->fused_gen && h->max_hits > 1 && (!h->filter_hit_bound || L.hit_bound > 1u) && !(li == 0 && h->injected) &&
                          h->spec.record_exits != 1u;
 
   // ---- roots ----
@@ -662,9 +672,12 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   }
 
   // ---- hit loop ----
-  for (uint32_t hit = fused_gen ? 1u : 0u; hit < h->max_hits; hit++) {
+  // A layer whose every population carries a length-bounded filter_in filter stops at that length: deeper
+  // interactions can only produce exits the filter rejects (hb_filter.h, filter_max_len).
+  const uint32_t hits = h->filter_hit_bound ? std::min<uint32_t>(h->max_hits, std::max<uint32_t>(1u, L.hit_bound)) : h->max_hits;
+  for (uint32_t hit = fused_gen ? 1u : 0u; hit < hits; hit++) {
     tp.hit = hit;
-    const bool last = hit + 1 == h->max_hits;
+    const bool last = hit + 1 == hits;
     if (h->fused_bounce) {  // one launch per interaction (DESIGN.md "kernels")
       EventPair* ev = begin_event(h, 3, n);
       launch_bounce(launch_ctx(h), general, last, in_smem, p4_mode,
@@ -1325,6 +1338,8 @@ int hb_set_option(HbEngine* h, const char* key, int64_t value) {
     h->fused_bounce = value != 0;
   } else if (k == "fused_gen") {
     h->fused_gen = value != 0;
+  } else if (k == "filter_hit_bound") {
+    h->filter_hit_bound = value != 0;
   } else if (k == "fork_cap") {   // fork-ray slots per tile (0 = automatic: max(4096, n / 64)); tests force overflows
     if (value < 0 || value > (1ll << 30)) return fail(h, HB_ERR_INVALID_ARG, "fork_cap out of range");
     h->fork_cap_override = static_cast<uint64_t>(value);

@@ -142,6 +142,32 @@ HB_HD bool filter_check(const HbFilterDesc& f, const uint8_t* fn_path, uint32_t 
   return f.action == 0u ? m : !m;
 }
 
+// Longest path (number of interactions) an exit may have and still be ADMITTED by filter `f`; 0xFFFFFFFF = unbounded.
+// A filter_in raypath filter admits only paths of its own length, an entry-exit filter with max_len only paths up to
+// it; a complex filter admits what any OR-term admits, a term what all of its AND-factors admit. filter_out and the
+// direction / crystal filters bound nothing. The engine ends a layer's hit loop at the largest bound of its
+// populations: later interactions can only produce exits the filter rejects (filter-fail terminates,
+// simulator.cpp:678-730), so results are unchanged.
+HB_HD uint32_t filter_factor_max_len(const HbSimpleFilter& s) {
+  if (s.kind == 1u) return s.path_len;
+  if (s.kind == 2u && s.max_len != 0u) return s.max_len;
+  return 0xFFFFFFFFu;
+}
+HB_HD uint32_t filter_max_len(const HbFilterDesc& f) {
+  if (f.kind == 0u || f.action != 0u) return 0xFFFFFFFFu;
+  if (f.kind != 5u) return filter_factor_max_len(f.simple);
+  uint32_t best = 0u;
+  for (uint32_t o = 0; o < f.term_cnt; ++o) {
+    uint32_t term = 0xFFFFFFFFu;
+    for (uint32_t a = 0; a < f.term_len[o]; ++a) {
+      const uint32_t b = filter_factor_max_len(f.terms[o][a]);
+      term = b < term ? b : term;
+    }
+    best = term > best ? term : best;
+  }
+  return best;
+}
+
 }  // namespace hb
 
 #endif  // HB_FILTER_H_

@@ -85,7 +85,7 @@ def load():
         if not os.path.exists(SO_PATH):
             raise ImportError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(the engine has no CPU fallback)")
-        lib = C.CDLL(SO_PATH)
+        lib = C.CDLL(os.environ.get("HALOTRACE_B200_LIB", SO_PATH))   # override: A/B builds in experiments
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)  # AttributeError here = header/library drift
             fn.restype = res

@@ -489,6 +489,9 @@ def test_two_layer_full_size_invariants(backend):
     assert abs(y - wl[0][3] * landed) <= 2e-4 * y
 
 
+ENGINE_DEFAULTS = {"fused_bounce": 1, "fused_gen": 0, "filter_hit_bound": 1}
+
+
 def _fused_image(backend, case, n, seed, want_stats, opts):
     """Single-layer accumulate-only session under engine options `opts`; returns (image, landed)."""
     from ice_halo_sim_b200 import backend as B
@@ -507,7 +510,7 @@ def _fused_image(backend, case, n, seed, want_stats, opts):
         return backend.ReadbackXyzAccum()
     finally:
         for k in opts:
-            backend.SetOption(k, 1)
+            backend.SetOption(k, ENGINE_DEFAULTS[k])
 
 
 @pytest.mark.parametrize("name", ["column_config2", "stoch_config5", "pyramid", "two_populations"])
@@ -521,10 +524,10 @@ def test_production_kernels_equal_parity_kernels(backend, name):
     backend.SetOption("tile_rays", 1 << 15)   # small tiles folded into the fp64 master: fp32 absorption cannot blur the comparison
     backend.SetOption("fold_rays", 1 << 15)
     try:
-        ref_img, ref_landed = _fused_image(backend, case, n, 17, True, {"fused_gen": 0})   # general kernels (LayerStats)
+        ref_img, ref_landed = _fused_image(backend, case, n, 17, True, {})   # general kernels (LayerStats)
         assert ref_landed > 0
         scale = float(np.abs(ref_img).max())
-        for opts in ({}, {"fused_gen": 0}, {"fused_bounce": 0}):
+        for opts in ({}, {"fused_gen": 1}, {"fused_bounce": 0}):
             img, landed = _fused_image(backend, case, n, 17, False, opts)
             assert abs(landed - ref_landed) <= 1e-5 * ref_landed, (name, opts)
             assert np.allclose(img, ref_img, rtol=5e-5, atol=2e-6 * scale), (name, opts)
@@ -614,3 +617,33 @@ def test_sharded_sessions_draw_disjoint_layer_streams(backend):
     assert not np.array_equal(r0["rot"][:m], r1["rot"][:m])            # different orientation draws
     assert (np.abs(r0["rot"][:m] - r1["rot"][:m]).max(axis=1) > 1e-3).mean() > 0.99
     assert c0 == c0b and np.array_equal(r0["rot"], r0b["rot"]) and np.array_equal(r0["p"], r0b["p"])
+
+
+@pytest.mark.parametrize("name", ["plate_filter_config3", "complex_filter", "filter_d_symmetry", "filter_out_raypath"])
+def test_filter_hit_bound_changes_nothing(backend, name):
+    """A layer whose populations all carry a length-bounded filter_in filter ends its hit loop at that length
+    (filter_max_len): interactions beyond it can only produce exits the filter rejects. Same image, same landed
+    weight and the same LayerStats as tracing all max_hits interactions."""
+    from ice_halo_sim_b200 import backend as B
+    case = parity.CASES[name]
+    n = 400000
+    backend.SetOption("tile_rays", 1 << 15)
+    backend.SetOption("fold_rays", 1 << 15)
+    try:
+        full_img, full_landed = _fused_image(backend, case, n, 23, False, {"filter_hit_bound": 0})
+        c0 = backend.Counters()
+        img, landed = _fused_image(backend, case, n, 23, False, {})
+        c1 = backend.Counters()
+        assert full_landed > 0 and abs(landed - full_landed) <= 1e-5 * full_landed
+        scale = float(np.abs(full_img).max())
+        assert np.allclose(img, full_img, rtol=5e-5, atol=2e-6 * scale)
+        launches = (c1.bounce_launches - c0.bounce_launches)
+        tiles = -(-n // (1 << 15))
+        max_hits = int(case["scene"]().max_hits)
+        if name == "plate_filter_config3":
+            assert launches == 2 * tiles          # raypath [3, 5]: two interactions instead of seven
+        if name == "filter_out_raypath":
+            assert launches == max_hits * tiles   # filter_out bounds nothing
+    finally:
+        backend.SetOption("tile_rays", 1 << 24)
+        backend.SetOption("fold_rays", 1 << 21)
