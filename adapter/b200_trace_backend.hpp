@@ -43,12 +43,31 @@ class B200LayerHandle : public LayerHandle {
 
 class B200TraceBackend : public TraceBackend {
  public:
-  explicit B200TraceBackend(int device_ordinal = 0) : rng_(0) {
-    if (hb_create(device_ordinal, &h_) != HB_OK) {
-      throw BackendUnavailableError(std::string("B200TraceBackend: ") + hb_last_error(nullptr));
+  explicit B200TraceBackend(int device_ordinal = 0) : B200TraceBackend(std::vector<int>{ device_ordinal }) {}
+  // Several devices behind ONE backend instance: the reference's GPU route runs a single Simulator
+  // thread (server.cpp:451-454), so scaling over the GPUs of a node has to happen behind the seam. Every session is
+  // split into contiguous shares of the global ray-index range, one per device; the engines' calls are asynchronous,
+  // so this one host thread keeps all devices busy; at drain time device 0 adds the other devices' accumulators out
+  // of their memory (hb_merge_from_peer: P2P loads over NVLink) and is the only one read back.
+  explicit B200TraceBackend(const std::vector<int>& devices) : rng_(0) {
+    if (devices.empty()) {
+      throw BackendUnavailableError("B200TraceBackend: empty device list");
     }
+    for (int d : devices) {
+      HbEngine* h = nullptr;
+      if (hb_create(d, &h) != HB_OK) {
+        for (HbEngine* e : hs_) hb_destroy(e);
+        throw BackendUnavailableError(std::string("B200TraceBackend: ") + hb_last_error(nullptr));
+      }
+      hs_.push_back(h);
+    }
+    h_ = hs_[0];
+    share_.assign(hs_.size(), 0);
   }
-  ~B200TraceBackend() override { hb_destroy(h_); }
+  ~B200TraceBackend() override {
+    for (HbEngine* e : hs_) hb_destroy(e);
+  }
+  size_t DeviceCount() const { return hs_.size(); }
 
   // Exit-seam egress (trace_backend.hpp:391-446). Default: the device-fused consumer (projection + XYZ accumulate
   // on the GPU, DrainExits returns nothing). With SetExitEgress(true) the backend behaves like the CPU backend at
@@ -89,14 +108,28 @@ class B200TraceBackend : public TraceBackend {
       s.seed = spec.seed;
       s.wl_cnt = static_cast<uint32_t>(pool.size());
       s.wl = reinterpret_cast<const HbWlEntry*>(pool.data());
-      s.ray_num = spec.ray_num;
       s.record_exits = egress_ ? 2u : 0u;
       s.accumulate = egress_ ? 0u : 1u;
-      Check(hb_begin_session(h_, &s), "BeginSession");
+      // contiguous shares of the session's global ray-index range [ray_base_, ray_base_ + ray_num)
+      const size_t R = hs_.size();
+      size_t first = 0;
+      for (size_t r = 0; r < R; r++) {
+        share_[r] = spec.ray_num / R + (r < spec.ray_num % R ? 1 : 0);
+        s.ray_num = share_[r];
+        if (R > 1) {  // every stream of the share is keyed by its global index (hb_begin_session)
+          s.use_ray_base = 1;
+          s.ray_base = ray_base_ + first;
+        }
+        Check(hb_begin_session(hs_[r], &s), "BeginSession", hs_[r]);
+        first += share_[r];
+      }
+      ray_base_ += spec.ray_num;
       layer_cnt_ = spec.scene->ms_.size();
       layer_idx_ = 0;
+      layer_roots_ = spec.ray_num;
+      orientation_draws_ = 0;
     } catch (...) {
-      hb_end_session(h_);  // leave the instance un-sessioned (trace_backend.hpp:149-153)
+      for (HbEngine* e : hs_) hb_end_session(e);  // leave the instance un-sessioned (trace_backend.hpp:149-153)
       throw;
     }
   }
@@ -104,16 +137,32 @@ class B200TraceBackend : public TraceBackend {
   LayerHandlePtr TraceLayer(const RootRaySource& roots) override {
     auto handle = std::make_unique<B200LayerHandle>();
     const bool last = layer_idx_ + 1 == layer_cnt_;
-    // The final layer needs no host-visible counter: launch and return (no synchronisation).
-    Check(hb_trace_layer(h_, roots.is_device ? 0 : roots.host.count, last ? nullptr : &handle->stats_), "TraceLayer");
+    if (layer_idx_ < layer_axis_stochastic_.size() && layer_axis_stochastic_[layer_idx_]) {
+      orientation_draws_ += layer_roots_;
+    }
+    // The final layer needs no host-visible counter: launch and return (no synchronisation), so the devices of a
+    // multi-device backend all run at once; a gated layer reads each device's continuation count in turn.
+    for (size_t r = 0; r < hs_.size(); r++) {
+      HbLayerStats st{};
+      Check(hb_trace_layer(hs_[r], roots.is_device ? 0 : share_[r], last ? nullptr : &st), "TraceLayer", hs_[r]);
+      handle->stats_.root_count += st.root_count;
+      handle->stats_.continuation_count += st.continuation_count;
+      handle->stats_.exit_count += st.exit_count;
+      handle->stats_.exit_w_sum += st.exit_w_sum;
+    }
     return handle;
   }
 
   RootRaySource Recombine(LayerHandlePtr handle, const RecombineSpec& spec) override {
     (void)handle;
     uint64_t n = 0;
-    Check(hb_recombine(h_, spec.shuffle ? 1 : 0, &n), "Recombine");
+    for (HbEngine* e : hs_) {  // continuations stay on the device that produced them
+      uint64_t k = 0;
+      Check(hb_recombine(e, spec.shuffle ? 1 : 0, &k), "Recombine", e);
+      n += k;
+    }
     layer_idx_++;
+    layer_roots_ = static_cast<size_t>(n);
     DeviceRayBatch dev;
     dev.backend_ptr = h_;
     dev.count = static_cast<size_t>(n);
@@ -126,11 +175,14 @@ class B200TraceBackend : public TraceBackend {
       return 0;  // device-fused path: exits are reduced into the image, never materialised
     }
     static_assert(sizeof(ExitRayRecord) == sizeof(HbExitRecord), "ExitRayRecord layout (exit_seam.hpp:40-53)");
-    uint64_t n = 0;
-    Check(hb_drain_exits(h_, nullptr, nullptr, 0, &n), "DrainExits");
-    out.resize(static_cast<size_t>(n));
-    if (n != 0) {
-      Check(hb_drain_exits(h_, reinterpret_cast<HbExitRecord*>(out.data()), nullptr, n, &n), "DrainExits");
+    for (HbEngine* e : hs_) {
+      uint64_t n = 0;
+      Check(hb_drain_exits(e, nullptr, nullptr, 0, &n), "DrainExits", e);
+      const size_t old = out.size();
+      out.resize(old + static_cast<size_t>(n));
+      if (n != 0) {
+        Check(hb_drain_exits(e, reinterpret_cast<HbExitRecord*>(out.data() + old), nullptr, n, &n), "DrainExits", e);
+      }
     }
     return out.size();
   }
@@ -138,6 +190,8 @@ class B200TraceBackend : public TraceBackend {
   size_t ReadbackExitRays(std::vector<ExitRayRecord>& out) override { return DrainExits(out); }
 
   void ReadbackXyzAccum(XyzImageData& xyz, float& landed_weight) override {
+    MergeDevices();
+    landed_weight = 0.0f;  // the seam's contract is "copies the running scalar out" (trace_backend.hpp), the C ABI adds
     Check(hb_readback_xyz(h_, xyz.data, &landed_weight), "ReadbackXyzAccum");
   }
 
@@ -150,21 +204,44 @@ class B200TraceBackend : public TraceBackend {
     const size_t pix = static_cast<size_t>(render_->resolution_[0]) * static_cast<size_t>(render_->resolution_[1]);
     lane_data.resize(raypath_color_->classes_.size() * pix);
     uint32_t n = 0;
+    MergeDevices();
     Check(hb_readback_class_lanes(h_, lane_data.data(), lane_data.size(), &n), "ReadbackClassLanes");
     class_count = n;
     lane_data.resize(static_cast<size_t>(n) * pix);
   }
 
-  void EndSession() override { Check(hb_end_session(h_), "EndSession"); }
+  void EndSession() override {
+    int first_bad = HB_OK;
+    HbEngine* bad = nullptr;
+    for (HbEngine* e : hs_) {  // close every device's session even when one reports an error
+      const int rc = hb_end_session(e);
+      if (rc != HB_OK && first_bad == HB_OK) {
+        first_bad = rc;
+        bad = e;
+      }
+    }
+    Check(first_bad, "EndSession", bad);
+  }
 
   size_t GetLastBatchStochasticCrystalSampleCount() const override { return stochastic_shapes_last_upload_; }
+  // Orientations are drawn per ray on the device: every root of layer 0 and every continuation that enters a later
+  // layer draws one, so the count is the number of rays traced through layers whose axis is not deterministic
+  // (AxisDistribution::IsAxisDeterministic, the seam's single predicate, trace_backend.hpp:589-625).
+  size_t GetLastBatchStochasticOrientationSampleCount() const override { return orientation_draws_; }
 
  private:
-  void Check(int status, const char* what) {
+  // Device 0 gathers the other devices' accumulators (asynchronous; ordered by events on the engines' streams).
+  void MergeDevices() {
+    for (size_t r = 1; r < hs_.size(); r++) {
+      Check(hb_merge_from_peer(hs_[0], hs_[r]), "MergeDevices", hs_[0]);
+    }
+  }
+
+  void Check(int status, const char* what, HbEngine* which = nullptr) {
     if (status == HB_OK) {
       return;
     }
-    std::string msg = std::string("B200TraceBackend::") + what + ": " + hb_last_error(h_);
+    std::string msg = std::string("B200TraceBackend::") + what + ": " + hb_last_error(which ? which : h_);
     if (status == HB_ERR_NO_DEVICE || status == HB_ERR_CUDA) {
       throw BackendUnavailableError(msg);
     }
@@ -227,8 +304,10 @@ class B200TraceBackend : public TraceBackend {
           continue;
         }
         const HbCrystalDesc desc = ToCrystalDesc(st.crystal_);
-        Check(hb_auto_resample(h_, static_cast<uint32_t>(li), static_cast<uint32_t>(ci), &desc, seed, geom_draws_), "AutoResample");
-        geom_draws_ += 1u << 24;  // disjoint shape-stream ranges per population and upload
+        for (HbEngine* e : hs_) {
+          Check(hb_auto_resample(e, static_cast<uint32_t>(li), static_cast<uint32_t>(ci), &desc, seed, geom_draws_), "AutoResample", e);
+          geom_draws_ += 1u << 24;  // disjoint shape-stream ranges per population, device and upload
+        }
         stochastic_population_cnt_++;
       }
     }
@@ -429,7 +508,17 @@ class B200TraceBackend : public TraceBackend {
         s.color_classes.combine_all_mask |= 1u << c;
       }
     }
-    Check(hb_set_scene(h_, &s), "UploadScene");
+    for (HbEngine* e : hs_) {
+      Check(hb_set_scene(e, &s), "UploadScene", e);
+    }
+    layer_axis_stochastic_.assign(scene.ms_.size(), false);
+    for (size_t li = 0; li < scene.ms_.size(); li++) {
+      for (const auto& st : scene.ms_[li].setting_) {
+        if (!st.crystal_.axis_.IsAxisDeterministic()) {
+          layer_axis_stochastic_[li] = true;
+        }
+      }
+    }
     scene_ = &scene;
     color_uploaded_ = raypath_color_;
   }
@@ -449,7 +538,9 @@ class B200TraceBackend : public TraceBackend {
     for (const RenderConfig* extra : extra_renders_) {
       all.push_back(ToProj(*extra));
     }
-    Check(hb_set_renders(h_, static_cast<uint32_t>(all.size()), all.data()), "UploadRender");
+    for (HbEngine* e : hs_) {
+      Check(hb_set_renders(e, static_cast<uint32_t>(all.size()), all.data()), "UploadRender", e);
+    }
     render_ = &render;
     render_snapshot_dirty_ = false;
   }
@@ -467,6 +558,8 @@ class B200TraceBackend : public TraceBackend {
   }
   // ReadbackXyzAccum for renderer `index` (0 = the session's own, 1.. = SetExtraRenders order).
   void ReadbackXyzAccumOf(uint32_t index, XyzImageData& xyz, float& landed_weight) {
+    MergeDevices();
+    landed_weight = 0.0f;
     Check(hb_readback_xyz_render(h_, index, xyz.data, &landed_weight), "ReadbackXyzAccumOf");
   }
   // RenderConsumer::PrepareSnapshot + PostSnapshot on the device: 8-bit sRGB frame of renderer `index`,
@@ -479,13 +572,20 @@ class B200TraceBackend : public TraceBackend {
       d.background[j] = cfg.background_[j];
     }
     float intensity = 0.0f;
+    MergeDevices();
     Check(hb_snapshot(h_, index, &d, rgb8, nullptr, &intensity), "SnapshotSrgb");
     return intensity;
   }
 
  private:
 
-  HbEngine* h_ = nullptr;
+  HbEngine* h_ = nullptr;              // device 0 of hs_: the one that is read back
+  std::vector<HbEngine*> hs_;          // one engine per device
+  std::vector<size_t> share_;          // root rays of the current session per device
+  uint64_t ray_base_ = 0;              // global index of the next session's first root (multi-device sessions)
+  std::vector<bool> layer_axis_stochastic_;  // per layer: some population draws its orientation
+  size_t layer_roots_ = 0;             // rays entering the layer about to be traced
+  size_t orientation_draws_ = 0;       // GetLastBatchStochasticOrientationSampleCount of the current session
   RandomNumberGenerator rng_;
   const SceneConfig* scene_ = nullptr;
   const RenderConfig* render_ = nullptr;

@@ -345,11 +345,25 @@ class B200TraceBackend:
         return ptr.value, n.value
 
     def AllReduceImage(self):
+        """Sum of all ranks' accumulators on EVERY rank (refuses to run twice on the same accumulation)."""
         self._check(self._lib.hb_allreduce_image(self._h))
+
+    def ReduceImage(self, root=0):
+        """Frame end: fp32 ncclReduce of the accumulators (all renders + colour lanes) to `root`; the other ranks'
+        accumulators are zero afterwards, so only the root reads back."""
+        self._check(self._lib.hb_reduce_image(self._h, int(root)))
+
+    def MergeFromPeer(self, other: "B200TraceBackend"):
+        """Same process, another device: add `other`'s accumulators into this engine's (P2P loads) and zero them."""
+        self._check(self._lib.hb_merge_from_peer(self._h, other._h))
+
+    def HasComm(self) -> bool:
+        return getattr(self, "_comm_ranks", 1) > 1
 
     def CommInit(self, unique_id: bytes, rank: int, nranks: int):
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self._lib.hb_comm_init(self._h, buf, rank, nranks))
+        self._comm_ranks = int(nranks)
 
 
 def comm_unique_id() -> bytes:

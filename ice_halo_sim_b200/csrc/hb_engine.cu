@@ -182,6 +182,9 @@ struct HbEngine {
   uint64_t fold_rays = 1u << 21;
   DevBuf<float> xyz_stage;
   DevBuf<double> landed_dev;
+  DevBuf<float4> reduce_stage;         // fp32 (X, Y, Z, landed) of the arena for the NCCL reduce
+  bool allreduced = false;             // the master holds an all-reduced sum (a second all-reduce would multiply it)
+  cudaEvent_t merge_event = nullptr;   // hb_merge_from_peer hand-shake
 
   // session
   bool in_session = false;
@@ -601,7 +604,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
       gp.sun_s_lat = std::sin(h->sun_lat);
       gp.flags = flags;
       EventPair* ev = begin_event(h, fused_gen ? 4 : 0, gp.count);
-      const size_t gb_smem = kGenSharedBytes + kQueueBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0) + smem;
+      const size_t gb_smem = kGenSharedBytes + kQueueBytes + kQueue2Bytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0) + smem;
       if (li == 0) {
         if (fused_gen) {
           tp.hit = 0;
@@ -681,7 +684,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
     if (h->fused_bounce) {  // one launch per interaction (DESIGN.md "kernels")
       EventPair* ev = begin_event(h, 3, n);
       launch_bounce(launch_ctx(h), general, last, in_smem, p4_mode,
-                    smem + kStage2Bytes + kQueueBytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
+                    smem + kStage2Bytes + kQueueBytes + kQueue2Bytes + ((flags & kFlagPixelCache) ? kCacheBytes : 0), tp);
       end_event(h, ev);
       h->ctr.kernel_launches++;
       h->ctr.bounce_launches++;
@@ -719,6 +722,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
     }
   }
   h->ctr.rays_traced += n;
+  h->allreduced = false;
   if (flags & kFlagAccum) {
     h->rays_since_fold += n;
     if (h->rays_since_fold >= h->fold_rays) fold_arena(h);
@@ -811,6 +815,8 @@ void hb_destroy(HbEngine* h) {
   h->rgb_stage.release();
   h->xyz_stage.release();
   h->landed_dev.release();
+  h->reduce_stage.release();
+  if (h->merge_event) cudaEventDestroy(h->merge_event);
   for (auto& s : h->wl_cache) {
     s.dev.release();
     s.dev2.release();
@@ -1192,6 +1198,7 @@ int hb_readback_xyz_render(HbEngine* h, uint32_t render, float* xyz, float* land
   fold_arena(h);
   drain_image_kernel<<<grid_for(h, pix), 256, 0, h->stream>>>(h->master.p + h->render_off[render], h->xyz_stage.p,
                                                               h->landed_dev.p, pix);
+  h->allreduced = false;
   h->ctr.kernel_launches++;
   double l = 0.0;
   HB_CUDA(h, cudaMemcpyAsync(xyz, h->xyz_stage.p, static_cast<size_t>(pix) * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1619,20 +1626,108 @@ int hb_comm_init(HbEngine* h, const void* id128, int rank, int nranks) {
 #endif
 }
 
-int hb_allreduce_image(HbEngine* h) {
-  if (h == nullptr) return HB_ERR_INVALID_ARG;
+namespace {
+
 #ifdef HB_WITH_NCCL
+// Frame-end reduction over the NCCL communicator; root < 0: all-reduce. fp32 (X, Y, Z, landed) per pixel of the
+// whole arena + the colour-class lanes.
+int reduce_over_comm(HbEngine* h, int root) {
   if (h->comm == nullptr) return fail(h, HB_ERR_STATE, "hb_comm_init not called");
   cudaSetDevice(h->device);
   if (!h->have_render) return fail(h, HB_ERR_STATE, "no render set");
-  const size_t cnt = static_cast<size_t>(h->arena_pix) * 4;
+  if (root >= h->nranks) return fail(h, HB_ERR_INVALID_ARG, "reduce: root rank out of range");
+  if (root < 0 && h->allreduced) {
+    return fail(h, HB_ERR_STATE, "hb_allreduce_image called twice on the same accumulation: every rank already holds the sum "
+                                 "(trace or drain first, or use hb_reduce_image)");
+  }
   fold_arena(h);
-  if (ncclAllReduce(h->master.p, h->master.p, cnt, ncclDouble, ncclSum, h->comm, h->stream) != ncclSuccess)
-    return fail(h, HB_ERR_COMM, "ncclAllReduce failed");
+  HB_CUDA(h, h->reduce_stage.ensure(h->arena_pix));
+  pack_master_kernel<<<grid_for(h, h->arena_pix), 256, 0, h->stream>>>(h->master.p, h->reduce_stage.p, h->arena_pix);
+  h->ctr.kernel_launches++;
+  const size_t cnt = static_cast<size_t>(h->arena_pix) * 4;
+  const bool lanes = h->classes.class_cnt != 0 && h->lanes_floats != 0;
+  ncclResult_t rc = ncclGroupStart();
+  if (rc == ncclSuccess) {
+    rc = root < 0 ? ncclAllReduce(h->reduce_stage.p, h->reduce_stage.p, cnt, ncclFloat, ncclSum, h->comm, h->stream)
+                  : ncclReduce(h->reduce_stage.p, h->reduce_stage.p, cnt, ncclFloat, ncclSum, root, h->comm, h->stream);
+  }
+  if (rc == ncclSuccess && lanes) {
+    rc = root < 0 ? ncclAllReduce(h->lanes.p, h->lanes.p, h->lanes_floats, ncclFloat, ncclSum, h->comm, h->stream)
+                  : ncclReduce(h->lanes.p, h->lanes.p, h->lanes_floats, ncclFloat, ncclSum, root, h->comm, h->stream);
+  }
+  if (rc == ncclSuccess) rc = ncclGroupEnd();
+  if (rc != ncclSuccess) return fail(h, HB_ERR_COMM, std::string("NCCL reduce failed: ") + ncclGetErrorString(rc));
+  if (root < 0 || root == h->rank) {
+    unpack_master_kernel<<<grid_for(h, h->arena_pix), 256, 0, h->stream>>>(h->reduce_stage.p, h->master.p, h->arena_pix);
+    h->ctr.kernel_launches++;
+  } else {  // this rank's contribution now lives on the root
+    HB_CUDA(h, cudaMemsetAsync(h->master.p, 0, static_cast<size_t>(h->arena_pix) * sizeof(double4), h->stream));
+    if (lanes) HB_CUDA(h, cudaMemsetAsync(h->lanes.p, 0, h->lanes_floats * sizeof(float), h->stream));
+  }
+  h->allreduced = root < 0;
   return HB_OK;
+}
+#endif
+
+}  // namespace
+
+int hb_allreduce_image(HbEngine* h) {
+  if (h == nullptr) return HB_ERR_INVALID_ARG;
+#ifdef HB_WITH_NCCL
+  return reduce_over_comm(h, -1);
 #else
   return fail(h, HB_ERR_UNSUPPORTED, "library built without NCCL");
 #endif
+}
+
+int hb_reduce_image(HbEngine* h, int root) {
+  if (h == nullptr || root < 0) return HB_ERR_INVALID_ARG;
+#ifdef HB_WITH_NCCL
+  return reduce_over_comm(h, root);
+#else
+  return fail(h, HB_ERR_UNSUPPORTED, "library built without NCCL");
+#endif
+}
+
+int hb_merge_from_peer(HbEngine* dst, HbEngine* src) {
+  if (dst == nullptr || src == nullptr || dst == src) return HB_ERR_INVALID_ARG;
+  if (!dst->have_render || !src->have_render || dst->arena_pix != src->arena_pix || dst->lanes_floats != src->lanes_floats)
+    return fail(dst, HB_ERR_STATE, "merge_from_peer: the two engines do not hold the same renders");
+  if (dst->in_session || src->in_session) return fail(dst, HB_ERR_STATE, "merge_from_peer inside a session");
+  if (dst->device != src->device) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, dst->device, src->device);
+    if (!can) return fail(dst, HB_ERR_UNSUPPORTED, "merge_from_peer: no peer access between the two devices");
+    cudaSetDevice(dst->device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+      dst->error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+      return HB_ERR_CUDA;
+    }
+    (void)cudaGetLastError();
+  }
+  // src: fold, then signal; dst: wait, add the peer's master (P2P loads), signal; src: wait, zero.
+  cudaSetDevice(src->device);
+  fold_arena(src);
+  if (src->merge_event == nullptr) HB_CUDA(src, cudaEventCreateWithFlags(&src->merge_event, cudaEventDisableTiming));
+  HB_CUDA(src, cudaEventRecord(src->merge_event, src->stream));
+  cudaSetDevice(dst->device);
+  fold_arena(dst);
+  if (dst->merge_event == nullptr) HB_CUDA(dst, cudaEventCreateWithFlags(&dst->merge_event, cudaEventDisableTiming));
+  HB_CUDA(dst, cudaStreamWaitEvent(dst->stream, src->merge_event, 0));
+  merge_peer_kernel<<<grid_for(dst, dst->arena_pix), 256, 0, dst->stream>>>(dst->master.p, src->master.p, dst->arena_pix,
+                                                                           dst->lanes.p, src->lanes.p, dst->lanes_floats);
+  dst->ctr.kernel_launches++;
+  HB_CUDA(dst, cudaGetLastError());
+  HB_CUDA(dst, cudaEventRecord(dst->merge_event, dst->stream));
+  cudaSetDevice(src->device);
+  HB_CUDA(src, cudaStreamWaitEvent(src->stream, dst->merge_event, 0));
+  HB_CUDA(src, cudaMemsetAsync(src->master.p, 0, static_cast<size_t>(src->arena_pix) * sizeof(double4), src->stream));
+  if (src->lanes_floats != 0) HB_CUDA(src, cudaMemsetAsync(src->lanes.p, 0, src->lanes_floats * sizeof(float), src->stream));
+  // the source's device error word travels with its image
+  HB_CUDA(src, cudaMemcpyAsync(src->err_host, src->counters.p + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, src->stream));
+  cudaSetDevice(dst->device);
+  return HB_OK;
 }
 
 }  // extern "C"

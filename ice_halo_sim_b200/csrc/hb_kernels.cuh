@@ -167,7 +167,10 @@ struct Tally {
 // cached pixel are summed in shared memory and reduced into the global image once, when the CTA retires.
 // Everything else goes straight to the L2 with one red.global.add.v4.f32.
 #ifndef HB_CACHE_SLOTS_LOG2
-#define HB_CACHE_SLOTS_LOG2 9
+#define HB_CACHE_SLOTS_LOG2 8
+#endif
+#ifndef HB_EXIT_STAGES
+#define HB_EXIT_STAGES 2   // 2: exits are projected from a second, visibility-culled queue (see queue_drain)
 #endif
 constexpr uint32_t kCacheSlots = 1u << HB_CACHE_SLOTS_LOG2;
 constexpr uint32_t kCacheEmpty = 0xFFFFFFFFu;
@@ -245,15 +248,18 @@ HB_DEV void cache_flush(const TraceParams& tp, const Tally& tally) {
   }
 }
 
+// Emission, first half: crystal-local direction -> world, then everything that decides the exit's fate (filter,
+// colour predicates, gate, continuation append, exit record, stats). Returns true when the exit goes on to the
+// image (second half: emit_project) with its world direction and component mask.
 template <bool GENERAL, bool MULTI, typename TablesT>
-HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float lx, float ly, float lz,
-                      float w, uint32_t role, const TablesT& tb, Tally& tally) {
+HB_DEV bool emit_world(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float lx, float ly, float lz,
+                       float w, uint32_t role, const TablesT& tb, Tally& tally, float& wx, float& wy, float& wz,
+                       uint64_t& mask) {
   const Rot r = rot_from_quat(q);
-  float wx, wy, wz;
   rot_apply(r, lx, ly, lz, wx, wy, wz);
   const uint32_t wl_i = bits_wl(bits);
   bool to_next_layer = false;
-  uint64_t mask = 0ull;  // component mask (raypath colour)
+  mask = 0ull;  // component mask (raypath colour)
   if (GENERAL) {
     const uint32_t shape = bits_shape(bits);
     const uint32_t pop = (tp.lt.shape_meta[shape] >> 8) & 255u;
@@ -271,7 +277,7 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
       // A filter_in raypath filter only admits paths of its own length: everything else fails before the path
       // is even gathered (len is uniform over the launch, so whole hit levels skip the matcher).
       const HbFilterDesc& f = tp.lt.filters[pop];
-      if (f.kind == 1u && f.action == 0u && len != f.simple.path_len) return;
+      if (f.kind == 1u && f.action == 0u && len != f.simple.path_len) return false;
     }
     if (tp.flags & kFlagPath) {
       for (uint32_t k = 0; k < len; k++)
@@ -280,7 +286,7 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
         const HbFilterDesc& f = tp.lt.filters[pop];
         if (f.kind != 0u) {
           const float dir[3] = { wx, wy, wz };
-          if (!filter_check(f, fn_path, len, dir, tp.lt.pop_crystal_id[pop])) return;  // filter-fail terminates
+          if (!filter_check(f, fn_path, len, dir, tp.lt.pop_crystal_id[pop])) return false;  // filter-fail terminates
         }
       }
     }
@@ -335,7 +341,7 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
       } else {
         *tp.error_flag = 1u;
       }
-      return;
+      return false;
     }
     if (tp.flags & kFlagRecord) {
       const uint32_t dst = atomicAdd(tp.exit_count, 1u);
@@ -358,8 +364,29 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
         *tp.error_flag = 2u;
       }
     }
-    if (!(tp.flags & kFlagAccum)) return;
+    if (!(tp.flags & kFlagAccum)) return false;
   }
+  return true;
+}
+
+// Exact "this direction reaches no pixel of render 0" test for the lenses that cull (same expressions as
+// project_exit evaluates first); false = project it. Lets the emission drop invisible exits (about half of them
+// for a one-hemisphere view) before they take a slot of the projection stage.
+HB_DEV bool project_culls(const HbProjParams& p, float wx, float wy, float wz) {
+  const int t = p.proj_type;
+  if (t == HB_LENS_LINEAR || t == HB_LENS_FISHEYE_EQUAL_AREA || t == HB_LENS_FISHEYE_EQUIDISTANT ||
+      t == HB_LENS_FISHEYE_STEREOGRAPHIC || t == HB_LENS_FISHEYE_ORTHOGRAPHIC) {
+    if ((p.visible_range == HB_VISIBLE_UPPER && wz > 0.0f) || (p.visible_range == HB_VISIBLE_LOWER && wz < 0.0f)) return true;
+    return dot3(p.rot[2], p.rot[5], p.rot[8], -wx, -wy, -wz) <= 0.0f;  // cz of rot_apply_t(p.rot, -w)
+  }
+  if (t == HB_LENS_GLOBE) return dot3(p.rot[2], p.rot[5], p.rot[8], -wx, -wy, -wz) >= dvd(-1.0f, 4.0f);
+  return false;
+}
+
+// Emission, second half: projection through every render of the trace + image reduction (+ colour lanes).
+template <bool MULTI>
+HB_DEV void emit_project(const TraceParams& tp, uint32_t wl_i, float wx, float wy, float wz, float w, uint64_t mask,
+                         Tally& tally) {
   const PixelHits h = project_exit(tp.proj, wx, wy, wz);
   const WlDev we = load_wl(tp.wl0, tp.wl2, tp.wl_cnt, wl_i);
 #pragma unroll
@@ -402,6 +429,15 @@ HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float
       }
     }
   }
+}
+
+template <bool GENERAL, bool MULTI, typename TablesT>
+HB_DEV void emit_exit(const TraceParams& tp, uint32_t slot, uint32_t bits, float4 q, float lx, float ly, float lz,
+                      float w, uint32_t role, const TablesT& tb, Tally& tally) {
+  float wx, wy, wz;
+  uint64_t mask;
+  if (emit_world<GENERAL, MULTI>(tp, slot, bits, q, lx, ly, lz, w, role, tb, tally, wx, wy, wz, mask))
+    emit_project<MULTI>(tp, bits_wl(bits), wx, wy, wz, w, mask, tally);
 }
 
 // Shared-memory staging of the per-layer crystal tables.
@@ -804,21 +840,89 @@ HB_DEV void queue_push(ExitQueue& xq, bool has, float x, float y, float z, float
   __syncwarp();
 }
 
-// Emit queued exits, 32 at a time (`all`: whatever is left, with the lanes that still have an entry).
+// Emit queued exits, 32 at a time (`all`: whatever is left, with the lanes that still have an entry), in two
+// converged stages:
+//   stage 1  orientation matrix, world rotation, filter / gate / record (emit_world), then the exact visibility
+//            cull of render 0 (project_culls) -- for a one-hemisphere view about half of the exits end here;
+//   stage 2  the survivors are compacted into the warp's second queue (world direction, weight, wavelength) and
+//            projected + reduced into the image 32 at a time (emit_project).
+// MULTI kernels (extra renders, colour lanes: per-exit masks and several lenses) project straight from stage 1.
+struct ExitQueue2 {
+  uint32_t addr;
+  uint32_t count;
+};
+constexpr uint32_t kQueue2Slots = 64u;                                      // < 32 pending + up to 32 new per stage-1 pass
+constexpr uint32_t kQueue2WarpBytes = kQueue2Slots * 16u + kQueue2Slots * 4u;  // float4 (world dir, w) + u32 wavelength index
+#if HB_EXIT_STAGES == 2
+constexpr uint32_t kQueue2Bytes = 8u * kQueue2WarpBytes;
+#else
+constexpr uint32_t kQueue2Bytes = 0u;
+#endif
+
+template <bool MULTI>
+HB_DEV void queue2_drain(ExitQueue2& q2, bool all, const TraceParams& tp, Tally& tally) {
+  const uint32_t lane = threadIdx.x & 31u;
+  while (q2.count >= 32u || (all && q2.count != 0u)) {
+    const uint32_t n = min(q2.count, 32u), first = q2.count - n;
+    if (lane < n) {
+      const float4 e = lds128(q2.addr + (first + lane) * 16u);
+      uint32_t wl_i;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wl_i) : "r"(q2.addr + kQueue2Slots * 16u + (first + lane) * 4u));
+      emit_project<MULTI>(tp, wl_i, e.x, e.y, e.z, e.w, 0ull, tally);
+    }
+    q2.count = first;
+    __syncwarp();
+  }
+}
+
 template <bool GENERAL, bool MULTI, typename TablesT>
-HB_DEV void queue_drain(ExitQueue& xq, bool all, const TraceParams& tp, const TablesT& tb, Tally& tally) {
+HB_DEV void queue_drain(ExitQueue& xq, ExitQueue2& q2, bool all, const TraceParams& tp, const TablesT& tb, Tally& tally) {
   const uint32_t lane = threadIdx.x & 31u;
   while (xq.count >= 32u || (all && xq.count != 0u)) {
     const uint32_t n = min(xq.count, 32u), first = xq.count - n;
+    bool keep = false;
+    float wx = 0.f, wy = 0.f, wz = 0.f, w = 0.f;
+    uint32_t wl_i = 0u;
     if (lane < n) {
       const float4 e = lds128(xq.addr + (first + lane) * 16u);
       const uint2 m = lds64(xq.addr + kQueueSlots * 16u + (first + lane) * 8u);
       const uint32_t slot = m.x & 0x7FFFFFFFu;
-      emit_exit<GENERAL, MULTI>(tp, slot, m.y, tp.Q[slot], e.x, e.y, e.z, e.w, m.x >> 31, tb, tally);
+#if HB_EXIT_STAGES == 2
+      if constexpr (!MULTI) {
+        uint64_t mask;
+        w = e.w;
+        wl_i = bits_wl(m.y);
+        keep = emit_world<GENERAL, MULTI>(tp, slot, m.y, tp.Q[slot], e.x, e.y, e.z, e.w, m.x >> 31, tb, tally, wx, wy, wz, mask) &&
+               !project_culls(tp.proj, wx, wy, wz);
+      } else
+#endif
+      {
+        emit_exit<GENERAL, MULTI>(tp, slot, m.y, tp.Q[slot], e.x, e.y, e.z, e.w, m.x >> 31, tb, tally);
+      }
     }
     xq.count = first;
     __syncwarp();
+#if HB_EXIT_STAGES == 2
+    if constexpr (!MULTI) {
+      const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+      if (km != 0u) {
+        if (keep) {
+          const uint32_t pos = q2.count + __popc(km & ((1u << lane) - 1u));
+          sts128(q2.addr + pos * 16u, wx, wy, wz, w);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(q2.addr + kQueue2Slots * 16u + pos * 4u), "r"(wl_i) : "memory");
+        }
+        q2.count += __popc(km);
+        __syncwarp();
+        queue2_drain<MULTI>(q2, false, tp, tally);
+      }
+    }
+#endif
   }
+#if HB_EXIT_STAGES == 2
+  if constexpr (!MULTI) {
+    if (all) queue2_drain<MULTI>(q2, true, tp, tally);
+  }
+#endif
 }
 
 // The last CTA to retire publishes the number of fork rays appended so far: the next bounce launch traces
@@ -941,12 +1045,13 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_BOUNCE_MINB_GENERAL : HB_BOU
   const bool use_cache = (tp.flags & kFlagPixelCache) != 0u;
   if (use_cache) cache_init(tally, smem_raw);
   const uint32_t stage_off = use_cache ? static_cast<uint32_t>(kCacheBytes) : 0u;
-  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + stage_off + kStage2Bytes + kQueueBytes, GENERAL);
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + stage_off + kStage2Bytes + kQueueBytes + kQueue2Bytes, GENERAL);
   if (!SMEM && use_cache) __syncthreads();
   const uint32_t total = tp.n_main + *tp.fork_snapshot;
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
   ExitQueue xq{ smem_base + stage_off + kStage2Bytes + (threadIdx.x >> 5) * kQueueWarpBytes, 0u };
+  ExitQueue2 q2{ smem_base + stage_off + kStage2Bytes + kQueueBytes + (threadIdx.x >> 5) * kQueue2WarpBytes, 0u };
   const uint32_t stage0 = smem_base + stage_off + threadIdx.x * 16u;
   uint32_t stage = 0u;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -994,7 +1099,7 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_BOUNCE_MINB_GENERAL : HB_BOU
       i = i_next;
       warp_first += stride;
     }
-    if (xq.count >= 32u || !more) queue_drain<GENERAL, MULTI>(xq, !more, tp, tb, tally);
+    if (xq.count >= 32u || !more) queue_drain<GENERAL, MULTI>(xq, q2, !more, tp, tb, tally);
     if (!more) break;
   }
   if (use_cache) cache_flush(tp, tally);
@@ -1303,10 +1408,11 @@ __global__ void __launch_bounds__(256, 4) genbounce_kernel(const GenParams gp, c
   const bool use_cache = (tp.flags & kFlagPixelCache) != 0u;
   if (use_cache) cache_init(tally, smem_raw + kGenSharedBytes);
   const uint32_t q_off = kGenSharedBytes + (use_cache ? static_cast<uint32_t>(kCacheBytes) : 0u);
-  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + q_off + kQueueBytes, GENERAL);
+  const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + q_off + kQueueBytes + kQueue2Bytes, GENERAL);
   if (!SMEM) __syncthreads();
   const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
   ExitQueue xq{ smem_base + q_off + (threadIdx.x >> 5) * kQueueWarpBytes, 0u };
+  ExitQueue2 q2{ smem_base + q_off + kQueueBytes + (threadIdx.x >> 5) * kQueue2WarpBytes, 0u };
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t warp_first = k - (threadIdx.x & 31u);
@@ -1338,7 +1444,7 @@ __global__ void __launch_bounds__(256, 4) genbounce_kernel(const GenParams gp, c
       k += stride;
       warp_first += stride;
     }
-    if (xq.count >= 32u || !more) queue_drain<GENERAL, MULTI>(xq, !more, tp, tb, tally);
+    if (xq.count >= 32u || !more) queue_drain<GENERAL, MULTI>(xq, q2, !more, tp, tb, tally);
     if (!more) break;
   }
   if (use_cache) cache_flush(tp, tally);
@@ -1522,6 +1628,45 @@ __global__ void __launch_bounds__(256) snapshot_srgb_kernel(const double4* maste
       v = fminf(fmaxf(v, 0.0f), 1.0f);
       rgb8[3u * i + j] = static_cast<uint8_t>(mul(linear_to_srgb(v), 255.0f));
     }
+  }
+}
+
+// ---- multi-GPU frame end ---------------------------------------------------------------------------------
+// Cross-process reduce (NCCL): the fp64 master is packed to fp32 (X, Y, Z, landed) -- the precision of the frame the
+// caller reads anyway -- so 16 instead of 32 bytes per pixel cross NVLink; after the reduce the root's master is
+// REPLACED by the sum and every other rank's master is zero, which makes a repeated reduce harmless.
+__global__ void __launch_bounds__(256) pack_master_kernel(const double4* master, float4* out, uint32_t pixels) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const double4 v = master[i];
+    out[i] = make_float4(static_cast<float>(v.x), static_cast<float>(v.y), static_cast<float>(v.z), static_cast<float>(v.w));
+  }
+}
+__global__ void __launch_bounds__(256) unpack_master_kernel(const float4* in, double4* master, uint32_t pixels) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    master[i] = make_double4(static_cast<double>(v.x), static_cast<double>(v.y), static_cast<double>(v.z), static_cast<double>(v.w));
+  }
+}
+// In-process merge (one host thread driving several devices behind the seam): the destination device adds a peer's
+// fp64 master straight out of the peer's memory -- P2P loads over NVLink inside the kernel, no staging copy, no
+// packing -- and the peer's colour lanes likewise; the source zeroes its accumulators afterwards.
+__global__ void __launch_bounds__(256) merge_peer_kernel(double4* master, const double4* peer_master, uint32_t pixels,
+                                                         float* lanes, const float* peer_lanes, uint64_t lane_floats) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += stride) {
+    const double4 v = peer_master[i];
+    if (v.x != 0.0 || v.y != 0.0 || v.z != 0.0 || v.w != 0.0) {
+      double4 m = master[i];
+      m.x += v.x;
+      m.y += v.y;
+      m.z += v.z;
+      m.w += v.w;
+      master[i] = m;
+    }
+  }
+  for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < lane_floats; i += stride) {
+    const float v = peer_lanes[i];
+    if (v != 0.0f) lanes[i] += v;
   }
 }
 

@@ -36,7 +36,7 @@ void launch_bounce_t(const LaunchCtx& c, size_t smem, const TraceParams& tp) {
   static bool attr_set[64] = {};
   if (!attr_set[c.device & 63]) {
     cudaFuncSetAttribute(bounce_kernel<G, L, S, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(shared_tables_bytes(kSmemShapes) + kCacheBytes + kStage2Bytes + kQueueBytes));
+                         static_cast<int>(shared_tables_bytes(kSmemShapes) + kCacheBytes + kStage2Bytes + kQueueBytes + kQueue2Bytes));
     attr_set[c.device & 63] = true;
   }
   const uint32_t grid = resident_grid(c, bounce_kernel<G, L, S, M, P>, smem, tp.cap);
@@ -48,7 +48,7 @@ void launch_genbounce_t(const LaunchCtx& c, size_t smem, const GenParams& gp, co
   static bool attr_set[64] = {};
   if (!attr_set[c.device & 63]) {
     cudaFuncSetAttribute(genbounce_kernel<T, G, S, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(kGenSharedBytes + shared_tables_bytes(kSmemShapes) + kCacheBytes + kQueueBytes));
+                         static_cast<int>(kGenSharedBytes + shared_tables_bytes(kSmemShapes) + kCacheBytes + kQueueBytes + kQueue2Bytes));
     attr_set[c.device & 63] = true;
   }
   const uint32_t grid = resident_grid(c, genbounce_kernel<T, G, S, M, P>, smem, gp.count);

@@ -10,7 +10,7 @@ bracket per batch and wavelength, simulator.cpp:1498-1560), the server's dispatc
 * projects every exit through ALL renderers of the config in the same trace (hb_set_renders) instead of
   refusing multi-renderer configs (server.cpp:402-437);
 * shards the global ray-index range over ranks (sharding.session_plan) and sums the accumulators with one
-  NCCL all-reduce at frame end (SURVEY 8(e));
+  NCCL reduce to rank 0 at frame end (SURVEY 8(e)); only rank 0 returns frames;
 * hands back either raw XYZ (ReadbackXyzAccum semantics) or the 8-bit sRGB frame rendered on the device
   (hb_snapshot = PrepareSnapshot + PostSnapshot).
 """
@@ -46,6 +46,21 @@ def trace_session(backend: B200TraceBackend, layer_cnt: int, spec: SessionSpec, 
             roots = backend.Recombine(handle, shuffle=True)
     finally:
         backend.EndSession()
+
+
+def ensure_comm(backend: B200TraceBackend, rank: int, world: int):
+    """Create the engine's NCCL communicator for a `world`-rank frame (hb_comm_init) unless it has one. The unique id
+    travels over torch.distributed, whose process group the launcher (torchrun) has initialised."""
+    if world <= 1 or backend.HasComm():
+        return
+    import torch.distributed as dist
+    from .backend import comm_unique_id
+    if not dist.is_available() or not dist.is_initialized():
+        raise RuntimeError("render_config(world > 1): initialise torch.distributed first (the NCCL unique id is "
+                           "broadcast over it), or call backend.CommInit yourself")
+    ids = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    backend.CommInit(ids[0], rank, world)
 
 
 def stochastic_populations(desc: A.HbSceneDesc):
@@ -105,8 +120,12 @@ def render_config(cfg: SceneConfig, backend: Optional[B200TraceBackend] = None, 
                 trace_session(be, cfg.desc.layer_cnt,
                               SessionSpec(seed=seed, wl=pool, ray_num=count, accumulate=True, ray_base=first), count)
             index_base += total
-        if world > 1 and allreduce:
-            be.AllReduceImage()
+        if world > 1 and allreduce:   # frame end: one fp32 reduce to rank 0, which alone reads the frame back
+            ensure_comm(be, rank, world)
+            be.ReduceImage(0)
+            if rank != 0:
+                be.Synchronize()
+                return {}
         frames = {}
         for r, rid in enumerate(ids):
             rgb = None

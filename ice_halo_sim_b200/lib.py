@@ -47,6 +47,8 @@ PROTOTYPES = {
     "hb_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "hb_comm_unique_id": (C.c_int, [_vp]),
     "hb_allreduce_image": (C.c_int, [_vp]),
+    "hb_reduce_image": (C.c_int, [_vp, C.c_int]),
+    "hb_merge_from_peer": (C.c_int, [_vp, _vp]),
     "hb_make_prism": (C.c_int, [C.c_float, _vp, _vp]),
     "hb_make_pyramid": (C.c_int, [C.c_float] * 5 + [_vp, _vp]),
     "hb_make_axis_sampler": (C.c_int, [C.c_uint32, C.c_float, C.c_float] * 3 + [_vp]),

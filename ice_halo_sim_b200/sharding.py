@@ -1,8 +1,11 @@
 """Ray-index sharding for multi-GPU runs.
 
 Root rays are i.i.d. and the engine's RNG is counter-based on the global ray index, so R ranks tracing
-disjoint contiguous index ranges produce exactly the rays of a 1-rank run; the only exchange is one sum
-all-reduce of the XYZ accumulator at frame end.
+disjoint contiguous index ranges of a single-population layer generate exactly the roots of a 1-rank run (and,
+with the gate / transit streams keyed by the same index, statistically independent continuation layers); the only
+exchange is one sum reduce of the XYZ accumulator at frame end. With several populations the population of a
+global index depends on the session split (PartitionCrystalRayNum works on session-local counts), so such frames
+are statistically, not ray-for-ray, equal across world sizes.
 """
 
 

@@ -335,6 +335,17 @@ void* hb_stream(HbEngine* h);             /* cudaStream_t the engine launches on
 int hb_comm_init(HbEngine* h, const void* nccl_unique_id_128B, int rank, int nranks);
 int hb_comm_unique_id(void* out_128B);
 int hb_allreduce_image(HbEngine* h);
+/* Frame end, preferred form: ncclReduce of fp32 (X, Y, Z, landed) per pixel (+ the colour-class lanes) to rank
+ * `root`; afterwards the root's accumulator holds the sum of all ranks and every other rank's accumulator is
+ * zero (its contribution moved), so only the root reads back and a repeated call changes nothing.
+ * hb_allreduce_image leaves the sum on EVERY rank and therefore refuses (HB_ERR_STATE) to run twice on the same
+ * accumulation. */
+int hb_reduce_image(HbEngine* h, int root);
+/* Several engines in ONE process (one host thread driving R devices behind the seam): add `src`'s
+ * accumulators (all renders + colour lanes) into `dst`'s and zero `src`'s. Different devices: the kernel runs on
+ * dst's device and reads src's fp64 master through peer access (NVLink P2P loads); asynchronous, ordered by events
+ * on the two engines' streams. Both engines must hold the same renders; call between sessions. */
+int hb_merge_from_peer(HbEngine* dst, HbEngine* src);
 
 /* ---------------------------------------------------------------------------
  * Host-side table builders (no GPU needed). The reference adapter uses the

@@ -15,6 +15,8 @@
 // Scenes 4 (one layer: identical rays, agreement to summation order) and 5 (two layers, statistical) drive the B200
 // backend twice: exit-seam egress (DrainExits -> ExitRayRecords -> the reference's host ScatterOutgoingToXyz) against
 // its own device-fused image.
+// Mode 6 = scene 1 (two layers) and mode 7 = scene 0 with the B200 backend fanned out over argv[3] devices behind the one
+// seam instance (B200TraceBackend(devices)) against the CPU backend: same battery.
 // Prints one JSON line; exit code 0 iff the battery passes.
 #include <algorithm>
 #include <cmath>
@@ -222,7 +224,10 @@ std::vector<double> BlockMeansY(const std::vector<float>& img, int w, int h, int
 
 int main(int argc, char** argv) {
   const int mode = argc > 1 ? std::atoi(argv[1]) : 0;
-  const int which = (mode == 2 || mode == 5) ? 1 : (mode == 4 ? 0 : mode);
+  const int which = (mode == 2 || mode == 5 || mode == 6) ? 1 : ((mode == 4 || mode == 7) ? 0 : mode);
+  const int ndev = argc > 3 ? std::atoi(argv[3]) : 1;
+  std::vector<int> devices;
+  for (int d = 0; d < std::max(1, ndev); d++) devices.push_back(d);
   const size_t total = argc > 2 ? static_cast<size_t>(std::atoll(argv[2])) : 2000000;
   const int w = 480, h = 270;
   SceneConfig scene = MakeScene(which, 7);
@@ -267,7 +272,7 @@ int main(int argc, char** argv) {
   std::vector<float> gpu_img(pix * 3, 0.0f);
   float gpu_landed = 0.0f;
   try {
-    B200TraceBackend gpu(0);
+    B200TraceBackend gpu(devices);
     if (!gpu.SupportsDeviceXyzAccum() || !gpu.IsCompatible(render)) {
       std::printf("{\"error\": \"backend refused the render config\"}\n");
       return 2;
@@ -315,8 +320,8 @@ int main(int argc, char** argv) {
       ok = ok && tc > 0 && std::fabs(lr - 1.0) <= 0.05 && rc >= 0.95;
     }
   }
-  std::printf("{\"scene\": %d, \"rays\": %zu, \"pearson_4x4\": %.5f, \"total_y_ratio\": %.5f, \"landed_ratio\": %.5f, "
+  std::printf("{\"scene\": %d, \"devices\": %zu, \"rays\": %zu, \"pearson_4x4\": %.5f, \"total_y_ratio\": %.5f, \"landed_ratio\": %.5f, "
               "\"cpu_landed\": %.3f, \"gpu_landed\": %.3f, \"pass\": %s}\n",
-              mode, total, r, ratio, landed_ratio, cpu_landed, gpu_landed, ok ? "true" : "false");
+              mode, devices.size(), total, r, ratio, landed_ratio, cpu_landed, gpu_landed, ok ? "true" : "false");
   return ok ? 0 : 1;
 }

@@ -762,4 +762,97 @@ int ref_legacy_bench(const HbSceneDesc* sd, const HbRenderDesc* rd, const float*
   return 0;
 }
 
+// Simulator::Run on its TraceBackend route (SimulateOneWavelengthWithBackend + third-clock drain), unmodified.
+// Which backend CreateBackend() hands out is decided by how this library was BUILT (oracle/Makefile):
+//   libhalo_ref*.so      no LUMICE_CUDA_ENABLED: kCuda falls back to the legacy CPU path (backend_used = 0)
+//   libhalo_refcuda.so   the reference's own CudaTraceBackend (cuda_trace_backend.cu compiled for sm_100a)
+//   libhalo_refb200.so   oracle/shim: this repo's B200TraceBackend behind the same name
+// One Simulator thread, as the reference's GPU route runs (server.cpp:451-454); `dispatch_rays` per SimBatch
+// (kDefaultCudaDispatchRayNum = 262144 is the reference's CUDA default). The consumer sums the drained device images.
+int ref_backend_bench(const HbSceneDesc* sd, const HbRenderDesc* rd, const float* wl, const float* wl_weight,
+                      uint32_t wl_cnt, uint64_t rays_per_wl, uint64_t dispatch_rays, uint32_t seed, float* xyz_wh3,
+                      double* landed_out, double* rays_per_sec, double* seconds, uint32_t* backend_used) {
+  std::vector<WlParam> spectrum;
+  for (uint32_t i = 0; i < wl_cnt; i++) {
+    spectrum.push_back(WlParam{ wl[i], wl_weight[i] });
+  }
+  auto scene = std::make_shared<const SceneConfig>(ToScene(*sd, spectrum));
+  auto renders = std::make_shared<const std::vector<RenderConfig>>(std::vector<RenderConfig>{ ToRender(*rd) });
+  const RenderConfig& render = (*renders)[0];
+  Rotation cam = MakeCameraRotation(render);
+  const size_t pix = static_cast<size_t>(render.resolution_[0]) * render.resolution_[1];
+  std::vector<double> img(pix * 3, 0.0);
+  std::vector<float> host_img(pix * 3, 0.0f);
+
+  auto scene_q = std::make_shared<Queue<SimBatch>>();
+  auto data_q = std::make_shared<Queue<SimData>>();
+  scene_q->Start();
+  data_q->Start();
+  for (uint64_t committed = 0; committed < rays_per_wl; committed += dispatch_rays) {
+    SimBatch sb;
+    sb.ray_num_ = std::min<uint64_t>(dispatch_rays, rays_per_wl - committed);
+    sb.scene_ = scene;
+    sb.renders_ = renders;
+    sb.generation_ = 1;
+    scene_q->Emplace(std::move(sb));
+  }
+  scene_q->Emplace(SimBatch{});  // termination signal
+
+  Simulator sim(scene_q, data_q, seed);
+  sim.SetPreferredBackend(BackendKind::kCuda);
+
+  std::atomic<uint64_t> roots{ 0 };
+  std::atomic<uint64_t> fused{ 0 };
+  std::atomic<bool> done{ false };
+  double landed = 0.0;
+  float host_landed = 0.0f;
+  std::thread consumer([&]() {
+    while (true) {
+      SimData data = data_q->Get();
+      if (data.root_ray_count_ == 0 && data.outgoing_w_.empty() && data.xyz_pixel_data_.empty()) {
+        if (done.load()) {
+          break;
+        }
+        continue;
+      }
+      if (!data.xyz_pixel_data_.empty()) {  // device-fused window (ConsumeDeviceFused's payload)
+        for (size_t i = 0; i < data.xyz_pixel_data_.size() && i < img.size(); i++) {
+          img[i] += data.xyz_pixel_data_[i];
+        }
+        landed += data.xyz_landed_weight_;
+        fused++;
+      } else if (!data.outgoing_w_.empty()) {  // legacy / exit-seam payload: host projection
+        ScatterOutgoingToXyz(data.outgoing_d_.data(), data.outgoing_w_.data(), data.outgoing_w_.size(), render, cam,
+                             data.curr_wl_, host_img.data(), &host_landed);
+      }
+      roots += data.root_ray_count_;
+    }
+  });
+
+  auto t0 = std::chrono::steady_clock::now();
+  sim.Run();
+  const uint64_t expect = rays_per_wl * wl_cnt;
+  while (roots.load() < expect) {
+    std::this_thread::sleep_for(std::chrono::microseconds(200));
+    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 3600.0) {
+      break;
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  done = true;
+  data_q->Shutdown();
+  consumer.join();
+  const double sec = std::chrono::duration<double>(t1 - t0).count();
+  if (xyz_wh3 != nullptr) {
+    for (size_t i = 0; i < img.size(); i++) {
+      xyz_wh3[i] = static_cast<float>(img[i] + host_img[i]);
+    }
+  }
+  if (landed_out != nullptr) *landed_out = landed + host_landed;
+  if (seconds != nullptr) *seconds = sec;
+  if (rays_per_sec != nullptr) *rays_per_sec = static_cast<double>(roots.load()) / sec;
+  if (backend_used != nullptr) *backend_used = fused.load() != 0 ? 1u : 0u;
+  return 0;
+}
+
 }  // extern "C"

@@ -78,6 +78,13 @@ int ref_legacy_bench(const HbSceneDesc* scene, const HbRenderDesc* render, const
                      double* rays_per_sec, double* seconds, uint64_t* exits);
 uint32_t ref_physical_cores(void);
 
+/* --- the reference driver's TraceBackend route: unmodified Simulator::Run (one thread) + third-clock drain; the
+ * backend is fixed by the build (see ref_driver.cpp): legacy CPU fallback / the reference CudaTraceBackend /
+ * this repo's B200TraceBackend through oracle/shim. xyz_wh3 receives the sum of all drained images. --- */
+int ref_backend_bench(const HbSceneDesc* scene, const HbRenderDesc* render, const float* wl, const float* wl_weight,
+                      uint32_t wl_cnt, uint64_t rays_per_wl, uint64_t dispatch_rays, uint32_t seed, float* xyz_wh3,
+                      double* landed, double* rays_per_sec, double* seconds, uint32_t* backend_used);
+
 #ifdef __cplusplus
 }
 #endif

@@ -647,3 +647,88 @@ def test_filter_hit_bound_changes_nothing(backend, name):
     finally:
         backend.SetOption("tile_rays", 1 << 24)
         backend.SetOption("fold_rays", 1 << 21)
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_multi_device_backend_behind_the_seam():
+    """One B200TraceBackend instance fanned out over 2 devices (adapter ctor with a device list): the reference's
+    host code drives it through the seam exactly as the single-device one; device 0 gathers the peer's accumulator
+    (hb_merge_from_peer, P2P loads) at ReadbackXyzAccum. Same cross-backend battery against CpuTraceBackend, one
+    layer and two layers. Needs 2 GPUs (gpurun --gpus 2)."""
+    import json
+    import os
+    import subprocess
+    import harness as H
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(H.ROOT, "oracle", "_ref", "adapter_demo")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/adapter_demo not built")
+    for mode, rays in ((7, 1500000), (6, 600000)):
+        out = subprocess.run([exe, str(mode), str(rays), "2"], capture_output=True, text=True, timeout=600)
+        lines = [json.loads(x) for x in out.stdout.strip().splitlines()]
+        res = lines[-1]
+        assert out.returncode == 0 and res["pass"] and res["devices"] == 2, (lines, out.stderr[-500:])
+        assert res["pearson_4x4"] >= 0.95 and abs(res["total_y_ratio"] - 1) <= 0.05
+
+
+def test_two_engines_merge_equals_one_engine(backend):
+    """hb_merge_from_peer: two engines (two devices when the box has them, else the same device twice) trace the two
+    halves of an index range; after the merge engine 0 holds the image a single engine accumulates for the whole
+    range and the peer's accumulator is zero."""
+    from ice_halo_sim_b200 import B200TraceBackend
+    from ice_halo_sim_b200 import backend as B
+    case = parity.CASES["column_config2"]
+    tables = B.SceneTables(case["scene"](), 7)
+    wl = [B.make_wl_entry(550.0, 1.0)]
+    n = 1 << 20
+    other = B200TraceBackend(1 if _gpu_count() >= 2 else 0)
+    try:
+        for be in (backend, other):
+            be.SetScene(tables)
+            be.SetRender(case["render"]())
+            be.ReadbackXyzAccum()
+        backend.BeginSession(B.SessionSpec(seed=31, wl=wl, ray_num=n, ray_base=0))
+        backend.TraceLayer(B.RootRaySource.FromHost(n), want_stats=False)
+        backend.EndSession()
+        whole, whole_landed = backend.ReadbackXyzAccum()
+        for be, base in ((backend, 0), (other, n // 2)):
+            be.BeginSession(B.SessionSpec(seed=31, wl=wl, ray_num=n // 2, ray_base=base))
+            be.TraceLayer(B.RootRaySource.FromHost(n // 2), want_stats=False)
+            be.EndSession()
+        backend.MergeFromPeer(other)
+        merged, merged_landed = backend.ReadbackXyzAccum()
+        rest, rest_landed = other.ReadbackXyzAccum()
+        assert rest_landed == 0.0 and not rest.any()
+        assert abs(merged_landed - whole_landed) <= 1e-5 * whole_landed
+        scale = float(np.abs(whole).max())
+        assert np.allclose(merged, whole, rtol=2e-4, atol=2e-6 * scale)
+        assert abs(float(merged.astype(np.float64).sum()) / float(whole.astype(np.float64).sum()) - 1.0) < 1e-5
+    finally:
+        other.close()
+
+
+def test_two_rank_reduce_equals_single_rank():
+    """Frame end on hardware (needs 2 GPUs): two ranks' shards reduced with hb_reduce_image == one rank's image of the
+    same index range; the reduce is idempotent, the all-reduce refuses a second call, and the ranks draw disjoint
+    layer-1 streams. See tests/mp_reduce_check.py."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import harness as H
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(H.ROOT, "tests", "mp_reduce_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [x for x in p.stdout.splitlines() if x.startswith("{")]
+    assert p.returncode == 0 and lines, (p.stdout[-1000:], p.stderr[-2000:])
+    res = json.loads(lines[-1])
+    assert res["reduce_image_ok"] and res["reduce_landed_rel"] < 1e-5 and res["reduce_sum_rel"] < 1e-5, res
+    assert res["peer_zero"] and res["allreduce_refuses_second_call"] and res["allreduce_landed_rel"] < 1e-5, res
+    assert res["layer1_orientations_differ"], res
