@@ -637,6 +637,56 @@ uint32_t orc_feistel(uint32_t i, uint32_t n, uint32_t seed) {
   return cur % n;
 }
 
+// ---- the generator's building blocks one by one (pinned against lm_pcg::* of the reference through
+// oracle/ref_driver.cpp: tests/test_oracle_vs_reference.py::test_sampler_twin_matches_reference_pcg) ----
+uint32_t orc_seed_with_high(uint32_t seed, uint32_t hi) { return SeedWithHigh(seed, hi); }
+void orc_uniforms(uint32_t seed, uint32_t idx, uint32_t slot0, uint32_t n, float* out) {
+  Stream s{ seed, idx, slot0 };
+  for (uint32_t i = 0; i < n; i++) out[i] = s.Next();
+}
+void orc_get_dist(uint32_t seed, uint32_t idx0, uint32_t n, uint32_t type, float mean, float stdv, float* out) {
+  for (uint32_t i = 0; i < n; i++) {
+    Stream s{ seed, idx0 + i, 0u };
+    out[i] = GetDist(s, type, mean, stdv);
+  }
+}
+void orc_lat_lon_roll(const HbAxisSampler* a, uint32_t seed, uint32_t idx0, uint32_t n, float* lon_lat_roll3,
+                      uint32_t* slots_used) {
+  for (uint32_t i = 0; i < n; i++) {
+    Stream s{ seed, idx0 + i, 0u };
+    SampleLonLatRoll(s, *a, lon_lat_roll3[i * 3], lon_lat_roll3[i * 3 + 1], lon_lat_roll3[i * 3 + 2]);
+    if (slots_used != nullptr) slots_used[i] = s.slot;
+  }
+}
+void orc_rotation9(uint64_t n, const float* lon_lat_roll3, float* rot9) {  // quaternion form of BuildCrystalRotation
+  for (uint64_t i = 0; i < n; i++) {
+    float q[4];
+    QuatFromAngles(lon_lat_roll3[i * 3], lon_lat_roll3[i * 3 + 1], lon_lat_roll3[i * 3 + 2], q);
+    QuatToRot(q, rot9 + i * 9);
+  }
+}
+void orc_sph_cap(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, float lon, float lat, float half, float* d3) {
+  for (uint32_t i = 0; i < n; i++) {
+    Stream s{ seed, idx0 + i, slot0 };
+    SampleSphCap(s, lon, lat, half, d3 + i * 3);
+  }
+}
+void orc_triangle(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, const float* vtx9, float* p3) {
+  for (uint32_t i = 0; i < n; i++) {
+    Stream s{ seed, idx0 + i, slot0 };
+    float u = s.Next();
+    float v = s.Next();
+    if (u + v > 1.0f) {
+      u = 1.0f - u;
+      v = 1.0f - v;
+    }
+    for (int k = 0; k < 3; k++) {
+      float a = vtx9[k], b = vtx9[3 + k], c = vtx9[6 + k];
+      p3[i * 3 + k] = u * (b - a) + v * (c - a) + a;
+    }
+  }
+}
+
 int orc_gen_roots(const HbScene* scene, uint32_t layer, uint32_t pop_i, uint32_t shape_base, const HbWlEntry* wl,
                   uint32_t wl_cnt, uint32_t seed, uint64_t ray_base, uint64_t n, float* d3, float* p3, float* w,
                   uint16_t* face, float* quat4, float* rot9, uint32_t* shape_idx, uint32_t* wl_idx) {

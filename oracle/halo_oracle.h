@@ -43,6 +43,15 @@ typedef struct OrcLayerParams {
 uint32_t orc_pcg_hash(uint32_t x);
 float orc_draw(uint32_t seed, uint32_t idx, uint32_t slot);
 uint32_t orc_feistel(uint32_t i, uint32_t n, uint32_t seed);
+/* the generator's building blocks (twins of lm_pcg::*, pcg_shared.h:193-624) */
+uint32_t orc_seed_with_high(uint32_t seed, uint32_t hi);
+void orc_uniforms(uint32_t seed, uint32_t idx, uint32_t slot0, uint32_t n, float* out);
+void orc_get_dist(uint32_t seed, uint32_t idx0, uint32_t n, uint32_t type, float mean, float stdv, float* out);
+void orc_lat_lon_roll(const HbAxisSampler* a, uint32_t seed, uint32_t idx0, uint32_t n, float* lon_lat_roll3,
+                      uint32_t* slots_used);
+void orc_rotation9(uint64_t n, const float* lon_lat_roll3, float* rot9);
+void orc_sph_cap(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, float lon, float lat, float half, float* d3);
+void orc_triangle(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, const float* vtx9, float* p3);
 
 /* Root generation (engine stream spec, DESIGN.md "RNG streams"; samplers restate pcg_shared.h). */
 int orc_gen_roots(const HbScene* scene, uint32_t layer, uint32_t pop, uint32_t shape_base, const HbWlEntry* wl,

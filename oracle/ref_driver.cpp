@@ -23,6 +23,7 @@
 #include "core/optics.hpp"
 #include "core/scatter_accum.hpp"
 #include "core/shared/lat_path_selection.hpp"
+#include "core/shared/pcg_shared.h"
 #include "core/shared/projection_shared.h"
 #include "core/simulator.hpp"
 #include "core/trace_ops.hpp"
@@ -760,6 +761,70 @@ int ref_legacy_bench(const HbSceneDesc* sd, const HbRenderDesc* rd, const float*
   *rays_per_sec = static_cast<double>(roots.load()) / sec;
   *exits_out = exits.load();
   return 0;
+}
+
+// --- the reference's counter-based sampler (core/shared/pcg_shared.h, host-compilable: the code its GPU backends run) ---
+// Every function below CALLS lm_pcg::*; the oracle's twin generator is pinned against them bit-for-bit on integers
+// and to libm-equal floats (tests/test_oracle_vs_reference.py::test_sampler_twin_matches_reference_pcg).
+uint32_t ref_pcg_hash(uint32_t x) { return lm_pcg::pcg_hash(x); }
+uint32_t ref_pcg_seed_with_high(uint32_t seed, uint32_t hi) { return lm_pcg::pcg_seed_with_high(seed, hi); }
+void ref_pcg_uniforms(uint32_t seed, uint32_t idx, uint32_t slot0, uint32_t n, float* out) {
+  lm_pcg::PcgStream s{ seed, idx, slot0 };
+  for (uint32_t i = 0; i < n; i++) out[i] = lm_pcg::pcg_uniform(s);
+}
+void ref_pcg_get_dist(uint32_t seed, uint32_t idx0, uint32_t n, uint32_t type, float mean, float stdv, float* out) {
+  for (uint32_t i = 0; i < n; i++) {
+    lm_pcg::PcgStream s{ seed, idx0 + i, 0u };
+    out[i] = lm_pcg::pcg_get_dist(s, type, mean, stdv);
+  }
+}
+// sample_lat_lon_roll with the wire struct filled from an HbAxisSampler (same fields the backends upload)
+void ref_pcg_lat_lon_roll(const HbAxisSampler* a, uint32_t seed, uint32_t idx0, uint32_t n, float* lon_lat_roll3,
+                          uint32_t* slots_used) {
+  lm_pcg::GenRootKernelParams gp{};
+  gp.lat_path = a->lat_path;
+  gp.lat_mean_rad = a->lat_mean;
+  gp.lat_std_rad = a->lat_std;
+  gp.lat_rejection_m = 1.0f;
+  gp.lat_lut_n = a->lut_n;
+  gp.az_type = a->az_type;
+  gp.az_mean_rad = a->az_mean;
+  gp.az_std_rad = a->az_std;
+  gp.roll_type = a->roll_type;
+  gp.roll_mean_rad = a->roll_mean;
+  gp.roll_std_rad = a->roll_std;
+  for (uint32_t i = 0; i < n; i++) {
+    lm_pcg::PcgStream s{ seed, idx0 + i, 0u };
+    float lon, lat, roll;
+    lm_pcg::sample_lat_lon_roll(s, gp, a->lut_theta, a->lut_cdf, a->lut_flip, lon, lat, roll, nullptr);
+    lon_lat_roll3[i * 3 + 0] = lon;
+    lon_lat_roll3[i * 3 + 1] = lat;
+    lon_lat_roll3[i * 3 + 2] = roll;
+    if (slots_used != nullptr) slots_used[i] = s.slot;
+  }
+}
+void ref_pcg_rotation9(uint64_t n, const float* lon_lat_roll3, float* rot9) {
+  for (uint64_t i = 0; i < n; i++) {
+    lm_pcg::build_crystal_rotation_9(lon_lat_roll3[i * 3], lon_lat_roll3[i * 3 + 1], lon_lat_roll3[i * 3 + 2], rot9 + i * 9);
+  }
+}
+void ref_pcg_sph_cap(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, float lon, float lat, float half, float* d3) {
+  for (uint32_t i = 0; i < n; i++) {
+    lm_pcg::PcgStream s{ seed, idx0 + i, slot0 };
+    lm_pcg::sample_sph_cap(s, lon, lat, half, d3 + i * 3);
+  }
+}
+void ref_pcg_triangle(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, const float* vtx9, float* p3) {
+  for (uint32_t i = 0; i < n; i++) {
+    lm_pcg::PcgStream s{ seed, idx0 + i, slot0 };
+    lm_pcg::sample_triangle(s, vtx9, p3 + i * 3);
+  }
+}
+void ref_pcg_feistel(uint32_t n, uint32_t seed, uint32_t* out) {
+  for (uint32_t i = 0; i < n; i++) out[i] = lm_pcg::feistel_bijection(i, n, seed);
+}
+void ref_pcg_categorical(const float* weights, uint32_t n, const float* u, uint32_t m, uint32_t* out) {
+  for (uint32_t i = 0; i < m; i++) out[i] = lm_pcg::categorical_sample(weights, n, u[i]);
 }
 
 // Simulator::Run on its TraceBackend route (SimulateOneWavelengthWithBackend + third-clock drain), unmodified.

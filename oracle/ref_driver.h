@@ -78,6 +78,19 @@ int ref_legacy_bench(const HbSceneDesc* scene, const HbRenderDesc* render, const
                      double* rays_per_sec, double* seconds, uint64_t* exits);
 uint32_t ref_physical_cores(void);
 
+/* --- the reference's counter-based sampler, core/shared/pcg_shared.h (lm_pcg::*), called as is --- */
+uint32_t ref_pcg_hash(uint32_t x);
+uint32_t ref_pcg_seed_with_high(uint32_t seed, uint32_t hi);
+void ref_pcg_uniforms(uint32_t seed, uint32_t idx, uint32_t slot0, uint32_t n, float* out);
+void ref_pcg_get_dist(uint32_t seed, uint32_t idx0, uint32_t n, uint32_t type, float mean, float stdv, float* out);
+void ref_pcg_lat_lon_roll(const HbAxisSampler* a, uint32_t seed, uint32_t idx0, uint32_t n, float* lon_lat_roll3,
+                          uint32_t* slots_used);
+void ref_pcg_rotation9(uint64_t n, const float* lon_lat_roll3, float* rot9);    /* build_crystal_rotation_9 */
+void ref_pcg_sph_cap(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, float lon, float lat, float half, float* d3);
+void ref_pcg_triangle(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, const float* vtx9, float* p3);
+void ref_pcg_feistel(uint32_t n, uint32_t seed, uint32_t* out);                /* feistel_bijection(i, n, seed), i < n */
+void ref_pcg_categorical(const float* weights, uint32_t n, const float* u, uint32_t m, uint32_t* out);
+
 /* --- the reference driver's TraceBackend route: unmodified Simulator::Run (one thread) + third-clock drain; the
  * backend is fixed by the build (see ref_driver.cpp): legacy CPU fallback / the reference CudaTraceBackend /
  * this repo's B200TraceBackend through oracle/shim. xyz_wh3 receives the sum of all drained images. --- */

@@ -62,8 +62,55 @@ def oracle():
         lib.orc_post_snapshot.argtypes = [_vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp]
         lib.orc_filter_check.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64] + [_vp] * 4
         lib.orc_quat_to_rot9.argtypes = [_vp, _vp]
+        _sampler_prototypes(lib, "orc_")
         _oracle = lib
     return _oracle
+
+
+def _sampler_prototypes(lib, prefix):
+    """The generator's building blocks, same signatures on both sides (oracle: orc_*, reference: ref_pcg_*)."""
+    u32, f32 = C.c_uint32, C.c_float
+    getattr(lib, prefix + "seed_with_high").restype = u32
+    getattr(lib, prefix + "seed_with_high").argtypes = [u32, u32]
+    getattr(lib, prefix + "uniforms").argtypes = [u32, u32, u32, u32, _vp]
+    getattr(lib, prefix + "get_dist").argtypes = [u32, u32, u32, u32, f32, f32, _vp]
+    getattr(lib, prefix + "lat_lon_roll").argtypes = [_vp, u32, u32, u32, _vp, _vp]
+    getattr(lib, prefix + "rotation9").argtypes = [C.c_uint64, _vp, _vp]
+    getattr(lib, prefix + "sph_cap").argtypes = [u32, u32, u32, u32, f32, f32, f32, _vp]
+    getattr(lib, prefix + "triangle").argtypes = [u32, u32, u32, u32, _vp, _vp]
+
+
+def sampler_vectors(lib, prefix, axis_samplers):
+    """Run every building block of the generator on fixed inputs; returns {name: array}. `axis_samplers`:
+    [(name, HbAxisSampler)]."""
+    out = {}
+    n = 4096
+    hash_fn = lib.orc_pcg_hash if prefix == "orc_" else lib.ref_pcg_hash
+    xs = np.concatenate([np.arange(0, 2048, dtype=np.uint64), np.linspace(0, 2 ** 32 - 1, 2048).astype(np.uint64)])
+    out["hash"] = np.array([hash_fn(int(x)) for x in xs], np.uint32)
+    out["seed_hi"] = np.array([getattr(lib, prefix + "seed_with_high")(0x1234ABCD, h) for h in (0, 1, 2, 77, 2 ** 31)], np.uint32)
+    u = np.zeros(256, np.float32)
+    getattr(lib, prefix + "uniforms")(0xC0FFEE, 123456789, 3, 256, ptr(u))
+    out["uniforms"] = u
+    for t in range(6):
+        g = np.zeros(n, np.float32)
+        getattr(lib, prefix + "get_dist")(99 + t, 5000, n, t, 0.3, 0.7, ptr(g))
+        out[f"dist{t}"] = g
+    for name, ax in axis_samplers:
+        llr = np.zeros((n, 3), np.float32)
+        slots = np.zeros(n, np.uint32)
+        getattr(lib, prefix + "lat_lon_roll")(C.byref(ax), 0xBEEF, 4_000_000_000, n, ptr(llr), ptr(slots))
+        rot = np.zeros((n, 9), np.float32)
+        getattr(lib, prefix + "rotation9")(n, ptr(llr), ptr(rot))
+        out[f"llr_{name}"], out[f"slots_{name}"], out[f"rot_{name}"] = llr, slots, rot
+    d = np.zeros((n, 3), np.float32)
+    getattr(lib, prefix + "sph_cap")(7, 100, 5, n, 3.3, -0.35, 0.00436, ptr(d))
+    out["sph_cap"] = d
+    vtx = np.array([0.1, -0.2, 0.65, 0.9, 0.3, 0.65, -0.4, 0.8, 0.65], np.float32)
+    p = np.zeros((n, 3), np.float32)
+    getattr(lib, prefix + "triangle")(8, 200, 9, n, ptr(vtx), ptr(p))
+    out["triangle"] = p
+    return out
 
 
 def have_ref():
@@ -101,6 +148,11 @@ def ref():
         lib.ref_legacy_bench.argtypes = [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32] + \
             [_vp] * 3
         lib.ref_physical_cores.restype = C.c_uint32
+        _sampler_prototypes(lib, "ref_pcg_")
+        lib.ref_pcg_hash.restype = C.c_uint32
+        lib.ref_pcg_hash.argtypes = [C.c_uint32]
+        lib.ref_pcg_feistel.argtypes = [C.c_uint32, C.c_uint32, _vp]
+        lib.ref_pcg_categorical.argtypes = [_vp, C.c_uint32, _vp, C.c_uint32, _vp]
         _ref = lib
     return _ref
 

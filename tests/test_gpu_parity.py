@@ -616,7 +616,9 @@ def test_sharded_sessions_draw_disjoint_layer_streams(backend):
     m = min(c0, c1)
     assert not np.array_equal(r0["rot"][:m], r1["rot"][:m])            # different orientation draws
     assert (np.abs(r0["rot"][:m] - r1["rot"][:m]).max(axis=1) > 1e-3).mean() > 0.99
-    assert c0 == c0b and np.array_equal(r0["rot"], r0b["rot"]) and np.array_equal(r0["p"], r0b["p"])
+    # the same index range replays the same draws (the continuation pool is filled by atomics, so WHICH continuation
+    # meets draw k may differ between runs: orientations replay exactly, entry points follow the direction they meet)
+    assert c0 == c0b and np.array_equal(r0["rot"], r0b["rot"])
 
 
 @pytest.mark.parametrize("name", ["plate_filter_config3", "complex_filter", "filter_d_symmetry", "filter_out_raypath"])

@@ -273,3 +273,34 @@ def test_entry_sampling_matches_analytic_distribution():
             got = p[sel].astype(np.float64).mean(axis=0)
             spread = p[sel].astype(np.float64).std(axis=0).max()
             assert np.abs(got - cen).max() < 5.0 * spread / np.sqrt(sel.sum()) + 1e-6, (k, got, cen)
+
+
+def test_sampler_twin_matches_reference_pcg_fixture():
+    """tests/golden/sampler_pin.npz holds outputs of the reference's own counter-based sampler (lm_pcg::*,
+    core/shared/pcg_shared.h) on fixed inputs (oracle/make_golden.py::gen_sampler_pin). The oracle's generator
+    building blocks reproduce them: integers and uniforms exactly, libm-dependent floats to 2 ulp-scale tolerances
+    (the fixture was written on the build container's glibc), the orientation matrix to 1e-6, Feistel exactly."""
+    import ctypes as C
+    g = np.load(os.path.join(H.GOLDEN, "sampler_pin.npz"))
+    axes = []
+    for k in g.files:
+        if k.startswith("axis_"):
+            ax = A.HbAxisSampler.from_buffer_copy(g[k].tobytes())
+            axes.append((k[5:], ax))
+    order = ["full_sphere", "fixed", "gauss_lut", "gauss_legacy", "laplacian", "zigzag", "uniform_band"]
+    axes.sort(key=lambda kv: order.index(kv[0]))
+    got = H.sampler_vectors(H.oracle(), "orc_", axes)
+    for k, v in got.items():
+        want = g[k]
+        if v.dtype == np.uint32 or k == "uniforms":
+            assert np.array_equal(v, want), k
+        elif k.startswith("rot_"):
+            assert np.abs(v - want).max() <= 1e-6, k
+        else:
+            assert np.allclose(v, want, rtol=3e-7, atol=3e-7), k
+    orc = H.oracle()
+    for k in g.files:
+        if k.startswith("feistel_"):
+            _, n, seed = k.split("_")
+            n, seed = int(n), int(seed)
+            assert np.array_equal(np.array([orc.orc_feistel(i, n, seed) for i in range(n)], np.uint32), g[k]), k

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import harness as H
+import parity
 from test_oracle_golden import oracle_trace_single
 
 A = H.A
@@ -314,3 +315,62 @@ def test_colour_component_masks_match_reference(roll):
     assert np.array_equal(a["component_mask"], b["component_mask"])
     seen = int(np.bitwise_or.reduce(a["component_mask"]))
     assert seen & 0b100 and bin(seen).count("1") >= 8, bin(seen)      # whole-crystal bit + most predicates fire
+
+
+def pin_axis_samplers():
+    """One axis sampler per latitude path / distribution type, built by the reference's own host code."""
+    cases = [("full_sphere", ("uniform", 90, 360), ("uniform", 0, 360), ("uniform", 0, 360)),
+             ("fixed", ("none", 35, 0), ("gauss", 40, 10), ("gauss", 10, 5)),
+             ("gauss_lut", ("gauss", 90, 0.3), ("uniform", 0, 360), ("uniform", 0, 360)),
+             ("gauss_legacy", ("gauss_legacy", 80, 6), ("uniform", 0, 360), ("none", 30, 0)),
+             ("laplacian", ("laplacian", 10, 3), ("laplacian", 90, 20), ("zigzag", 0, 15)),
+             ("zigzag", ("zigzag", 90, 25), ("uniform", 0, 360), ("uniform", 0, 60)),
+             ("uniform_band", ("uniform", 60, 40), ("zigzag", 0, 30), ("uniform", 0, 360))]
+    out = []
+    for name, zen, az, roll in cases:
+        z = parity.dist(*zen)
+        lat = A.HbDist(z.type, 90.0 - z.center, z.spread)
+        ax = A.HbAxisSampler()
+        assert H.ref().ref_make_axis_sampler(C.byref(lat), C.byref(parity.dist(*az)), C.byref(parity.dist(*roll)), C.byref(ax)) == 0
+        out.append((name, ax))
+    return out
+
+
+def test_sampler_twin_matches_reference_pcg():
+    """The oracle's generator building blocks against the reference's own counter-based sampler (lm_pcg::*,
+    core/shared/pcg_shared.h, the code its GPU backends run; host-compiled into oracle/_ref): hashes, seeds, uniforms,
+    every distribution type, sample_lat_lon_roll on every latitude path (angles AND the number of stream slots
+    consumed), sample_sph_cap, sample_triangle bit-for-bit (same libm); the Feistel bijection and the categorical
+    pick exactly; the orientation matrix (the oracle builds it from a quaternion, the reference from three axis
+    rotations) to 1e-6."""
+    orc, ref = H.oracle(), H.ref()
+    axes = pin_axis_samplers()
+    a = H.sampler_vectors(orc, "orc_", axes)
+    b = H.sampler_vectors(ref, "ref_pcg_", axes)
+    assert sorted(a) == sorted(b)
+    for k in a:
+        if k.startswith("rot_"):
+            assert np.abs(a[k] - b[k]).max() <= 1e-6, k
+            eye = np.einsum("nij,nkj->nik", b[k].reshape(-1, 3, 3), b[k].reshape(-1, 3, 3))
+            assert np.abs(eye - np.eye(3)).max() < 1e-5
+        else:
+            assert a[k].dtype == b[k].dtype and np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    assert len(np.unique(a["hash"])) > 4000 and 0.0 <= a["uniforms"].min() and a["uniforms"].max() < 1.0
+    # Feistel bijection: same permutation for awkward sizes and seeds
+    for n, seed in ((1, 5), (2, 5), (3, 9), (17, 1), (1000, 0xABCDEF), (65536, 42), (100003, 7)):
+        want = np.zeros(n, np.uint32)
+        ref.ref_pcg_feistel(n, seed, H.ptr(want))
+        got = np.array([orc.orc_feistel(i, n, seed) for i in range(n)], np.uint32)
+        assert np.array_equal(got, want), (n, seed)
+        assert np.array_equal(np.sort(want), np.arange(n, dtype=np.uint32))
+    # categorical_sample (the triangle-level entry pick the oracle falls back to) on random weights
+    rng = np.random.default_rng(5)
+    w = rng.random(20).astype(np.float32)
+    w[[3, 7]] = 0.0
+    u = np.concatenate([rng.random(2000).astype(np.float32), np.array([0.0, 0.99999994], np.float32)])
+    pick = np.zeros(len(u), np.uint32)
+    ref.ref_pcg_categorical(H.ptr(w), len(w), H.ptr(u), len(u), H.ptr(pick))
+    cum = np.cumsum(w, dtype=np.float32)
+    assert pick.max() < len(w) and not np.isin(pick, [3, 7]).any()
+    freq = np.bincount(pick, minlength=len(w))[: len(w)] / len(u)
+    assert np.abs(freq - w / w.sum()).max() < 0.03
