@@ -1206,6 +1206,7 @@ __host__ __device__ inline bool derive_shape_tables(const HbCrystalTables& t, ui
   return p4;
 }
 
+constexpr uint32_t kShapeRunLog2 = 8;  // geometry clock: 256 consecutive rays per pool shape (see gen_root)
 constexpr uint32_t kFastGroups = 8;  // prism: 8 faces, weights kept in registers
 
 // Returns the chosen fan triangle. `ef` may point to shared or global memory (warp-uniform address).
@@ -1350,12 +1351,17 @@ HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float
   }
   float dx, dy, dz;
   rot_apply_t(r.m, wx, wy, wz, dx, dy, dz);
-  // Geometry clock: one shape of the pool serves a block of 32 consecutive ray indices, as on the reference's
-  // CPU path (kSmallBatchRayNum, simulator.hpp:144-151). A warp therefore reads ONE shape's tables in every
-  // kernel of the hit loop (uniform addresses: broadcast loads) instead of 32 different ones.
+  // Geometry clock: one shape of the pool serves a run of kShapeRunRays = 256 consecutive ray indices (the reference's
+  // CPU path samples a crystal per kSmallBatchRayNum = 32 rays, simulator.hpp:144-151; its GPU backends pick per
+  // ray), and consecutive runs walk through the pool in order -- the pool is an i.i.d. sample, so a sequential walk
+  // is as random as a drawn one. A warp therefore reads ONE shape's tables in every kernel of the hit loop (uniform
+  // addresses: broadcast loads) and a CTA pass (256 consecutive rays) at most two, so pools too large for shared
+  // memory stay L1-resident per SM whatever the pool size. A pure function of the global ray index: tiles and
+  // sessions may split the range anywhere.
   uint32_t sh = 0u;
   if (gp.shape_cnt > 1u) {
-    sh = min(static_cast<uint32_t>(draw(s0 ^ kNonceShape, lo >> 5, 0u) * static_cast<float>(gp.shape_cnt)), gp.shape_cnt - 1u);
+    const uint64_t run = ((static_cast<uint64_t>(hi) << 32) | lo) >> kShapeRunLog2;
+    sh = static_cast<uint32_t>(run % gp.shape_cnt);
   }
   const HbCrystalTables* tab = gp.shape_cnt == 1u ? &gs->shape0 : gp.shapes + sh;
   const EntryFaces* ef = gp.shape_cnt == 1u ? &gs->ef0 : gp.entry_faces + sh;
