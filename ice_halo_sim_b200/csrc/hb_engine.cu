@@ -1691,7 +1691,10 @@ int hb_reduce_image(HbEngine* h, int root) {
 
 int hb_merge_from_peer(HbEngine* dst, HbEngine* src) {
   if (dst == nullptr || src == nullptr || dst == src) return HB_ERR_INVALID_ARG;
-  if (!dst->have_render || !src->have_render || dst->arena_pix != src->arena_pix || dst->lanes_floats != src->lanes_floats)
+  // colour lanes exist only while the scene has colour classes (a stale allocation of an earlier scene does not count)
+  const uint64_t dst_lanes = dst->classes.class_cnt != 0 ? dst->lanes_floats : 0;
+  const uint64_t src_lanes = src->classes.class_cnt != 0 ? src->lanes_floats : 0;
+  if (!dst->have_render || !src->have_render || dst->arena_pix != src->arena_pix || dst_lanes != src_lanes)
     return fail(dst, HB_ERR_STATE, "merge_from_peer: the two engines do not hold the same renders");
   if (dst->in_session || src->in_session) return fail(dst, HB_ERR_STATE, "merge_from_peer inside a session");
   if (dst->device != src->device) {
@@ -1716,14 +1719,14 @@ int hb_merge_from_peer(HbEngine* dst, HbEngine* src) {
   if (dst->merge_event == nullptr) HB_CUDA(dst, cudaEventCreateWithFlags(&dst->merge_event, cudaEventDisableTiming));
   HB_CUDA(dst, cudaStreamWaitEvent(dst->stream, src->merge_event, 0));
   merge_peer_kernel<<<grid_for(dst, dst->arena_pix), 256, 0, dst->stream>>>(dst->master.p, src->master.p, dst->arena_pix,
-                                                                           dst->lanes.p, src->lanes.p, dst->lanes_floats);
+                                                                           dst->lanes.p, src->lanes.p, dst_lanes);
   dst->ctr.kernel_launches++;
   HB_CUDA(dst, cudaGetLastError());
   HB_CUDA(dst, cudaEventRecord(dst->merge_event, dst->stream));
   cudaSetDevice(src->device);
   HB_CUDA(src, cudaStreamWaitEvent(src->stream, dst->merge_event, 0));
   HB_CUDA(src, cudaMemsetAsync(src->master.p, 0, static_cast<size_t>(src->arena_pix) * sizeof(double4), src->stream));
-  if (src->lanes_floats != 0) HB_CUDA(src, cudaMemsetAsync(src->lanes.p, 0, src->lanes_floats * sizeof(float), src->stream));
+  if (src_lanes != 0) HB_CUDA(src, cudaMemsetAsync(src->lanes.p, 0, src_lanes * sizeof(float), src->stream));
   // the source's device error word travels with its image
   HB_CUDA(src, cudaMemcpyAsync(src->err_host, src->counters.p + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, src->stream));
   cudaSetDevice(dst->device);

@@ -804,7 +804,9 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_INTERSECT_MINB_GENERAL : HB_
 // ray-bounce instead of 112 B.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kQueueSlots = 96u;                                  // < 32 pending + up to 2 x 32 new per iteration
-constexpr uint32_t kQueueWarpBytes = kQueueSlots * 16u + kQueueSlots * 8u;  // float4 (local dir, w) + uint2 (slot|role, bits)
+// float4 (local dir, w) + u32 (tile slot | role << 31). The ray's packed bits (wavelength index, shape) never change
+// during a layer, so the emission re-reads them from P[slot] when it needs them (several wavelengths, GENERAL).
+constexpr uint32_t kQueueWarpBytes = kQueueSlots * 16u + kQueueSlots * 4u;
 constexpr uint32_t kQueueBytes = 8u * kQueueWarpBytes;                 // 8 warps per CTA
 constexpr uint32_t kStage2Bytes = 2u * 2u * 256u * 16u;                // two stages x (D, P) x 256 threads x 16 B
 
@@ -828,13 +830,13 @@ struct ExitQueue {
 };
 
 // All 32 lanes call this together. `meta0` = tile slot | role << 31.
-HB_DEV void queue_push(ExitQueue& xq, bool has, float x, float y, float z, float w, uint32_t meta0, uint32_t bits) {
+HB_DEV void queue_push(ExitQueue& xq, bool has, float x, float y, float z, float w, uint32_t meta0) {
   const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
   if (m == 0u) return;
   if (has) {
     const uint32_t pos = xq.count + __popc(m & ((1u << (threadIdx.x & 31u)) - 1u));
     sts128(xq.addr + pos * 16u, x, y, z, w);
-    sts64(xq.addr + kQueueSlots * 16u + pos * 8u, meta0, bits);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(xq.addr + kQueueSlots * 16u + pos * 4u), "r"(meta0) : "memory");
   }
   xq.count += __popc(m);
   __syncwarp();
@@ -885,19 +887,22 @@ HB_DEV void queue_drain(ExitQueue& xq, ExitQueue2& q2, bool all, const TracePara
     uint32_t wl_i = 0u;
     if (lane < n) {
       const float4 e = lds128(xq.addr + (first + lane) * 16u);
-      const uint2 m = lds64(xq.addr + kQueueSlots * 16u + (first + lane) * 8u);
-      const uint32_t slot = m.x & 0x7FFFFFFFu;
+      uint32_t m0;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m0) : "r"(xq.addr + kQueueSlots * 16u + (first + lane) * 4u));
+      const uint32_t slot = m0 & 0x7FFFFFFFu;
+      uint32_t bits = 0u;  // wavelength index 0, shape 0: all a single-wavelength, non-general session needs
+      if (GENERAL || tp.wl_cnt != 1u) bits = __float_as_uint(tp.P[slot].w);
 #if HB_EXIT_STAGES == 2
       if constexpr (!MULTI) {
         uint64_t mask;
         w = e.w;
-        wl_i = bits_wl(m.y);
-        keep = emit_world<GENERAL, MULTI>(tp, slot, m.y, tp.Q[slot], e.x, e.y, e.z, e.w, m.x >> 31, tb, tally, wx, wy, wz, mask) &&
+        wl_i = bits_wl(bits);
+        keep = emit_world<GENERAL, MULTI>(tp, slot, bits, tp.Q[slot], e.x, e.y, e.z, e.w, m0 >> 31, tb, tally, wx, wy, wz, mask) &&
                !project_culls(tp.proj, wx, wy, wz);
       } else
 #endif
       {
-        emit_exit<GENERAL, MULTI>(tp, slot, m.y, tp.Q[slot], e.x, e.y, e.z, e.w, m.x >> 31, tb, tally);
+        emit_exit<GENERAL, MULTI>(tp, slot, bits, tp.Q[slot], e.x, e.y, e.z, e.w, m0 >> 31, tb, tally);
       }
     }
     xq.count = first;
@@ -1093,8 +1098,8 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_BOUNCE_MINB_GENERAL : HB_BOU
 #if HB_PREFETCH_Q
       if (has0 || has1) prefetch_l1(tp.Q + i);  // the emission (some iterations later, another lane) reads the orientation
 #endif
-      queue_push(xq, has0, e0.x, e0.y, e0.z, e0.w, i, bits);
-      queue_push(xq, has1, e1.x, e1.y, e1.z, e1.w, i | 0x80000000u, bits);
+      queue_push(xq, has0, e0.x, e0.y, e0.z, e0.w, i);
+      queue_push(xq, has1, e1.x, e1.y, e1.z, e1.w, i | 0x80000000u);
       stage ^= 1u;
       i = i_next;
       warp_first += stride;
@@ -1445,8 +1450,8 @@ __global__ void __launch_bounds__(256, 4) genbounce_kernel(const GenParams gp, c
         gp.P[slot] = p4;
         gp.D[slot] = d4;
       }
-      queue_push(xq, has0, e0.x, e0.y, e0.z, e0.w, slot, bits);
-      queue_push(xq, has1, e1.x, e1.y, e1.z, e1.w, slot | 0x80000000u, bits);
+      queue_push(xq, has0, e0.x, e0.y, e0.z, e0.w, slot);
+      queue_push(xq, has1, e1.x, e1.y, e1.z, e1.w, slot | 0x80000000u);
       k += stride;
       warp_first += stride;
     }

@@ -734,3 +734,58 @@ def test_two_rank_reduce_equals_single_rank():
     assert res["reduce_image_ok"] and res["reduce_landed_rel"] < 1e-5 and res["reduce_sum_rel"] < 1e-5, res
     assert res["peer_zero"] and res["allreduce_refuses_second_call"] and res["allreduce_landed_rel"] < 1e-5, res
     assert res["layer1_orientations_differ"], res
+
+
+def test_reference_simulator_run_drives_the_engine():
+    """The reference's own driver, unmodified -- Simulator::Run -> CreateBackend -> SimulateOneWavelengthWithBackend ->
+    third-clock DrainDeviceXyz (simulator.cpp:959-1117,1409-1694) -- on this engine: oracle/_ref/libhalo_refb200.so is
+    the reference core compiled with oracle/shim ahead of its include path, so the backend its CreateBackend
+    instantiates IS adapter/b200_trace_backend.hpp. The frames it drains pass the reference's cross-backend battery
+    (4x4 block-mean Pearson >= 0.95, total Y and landed weight within 5 %) against CpuTraceBackend on the same scene,
+    at the reference's CUDA dispatch size (262144 rays per SimBatch) with two wavelengths."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import harness as H
+    so = os.path.join(H.ROOT, "oracle", "_ref", "libhalo_refb200.so")
+    if not os.path.exists(so) or not H.have_ref():
+        pytest.skip("oracle/_ref/libhalo_refb200.so not built (needs /root/reference at build time)")
+    code = f"""
+import ctypes as C, json, sys
+sys.path.insert(0, {H.ROOT!r}); sys.path.insert(0, {os.path.join(H.ROOT, 'tests')!r})
+import numpy as np
+import harness as H
+from ice_halo_sim_b200 import scenes
+case = scenes.CASES["column_config2"]
+desc, rd = case["scene"](), case["render"]()
+rd.img_w, rd.img_h = 480, 270
+wls = [550.0, 610.0]
+n = 4 * 262144
+lib = C.CDLL({so!r})
+vp = C.c_void_p
+lib.ref_backend_bench.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, vp, vp, vp]
+wl = np.array(wls, np.float32); ww = np.ones(len(wl), np.float32)
+img = np.zeros((270, 480, 3), np.float32)
+landed, rate, sec, used = C.c_double(), C.c_double(), C.c_double(), C.c_uint32()
+lib.ref_backend_bench(C.byref(desc), C.byref(rd), wl.ctypes.data, ww.ctypes.data, len(wl), n, 262144, 42,
+                      img.ctypes.data, C.byref(landed), C.byref(rate), C.byref(sec), C.byref(used))
+cpu = np.zeros_like(img); cpu_landed = 0.0
+for w in wls:   # CpuTraceBackend (mt19937 sampling), same scene, fewer rays
+    one = np.zeros_like(img); l = C.c_float(); ec = C.c_uint64(); ws = C.c_double()
+    H.ref().ref_cpu_backend_run(C.byref(desc), C.byref(rd), w, 1.0, 7, 300000, 4096, one.ctypes.data, C.byref(l),
+                                C.byref(ec), C.byref(ws))
+    cpu += one; cpu_landed += l.value
+scale = n / 300000.0
+a = img[:268, :, 1].reshape(67, 4, 120, 4).mean(axis=(1, 3)).ravel()
+b = cpu[:268, :, 1].reshape(67, 4, 120, 4).mean(axis=(1, 3)).ravel()
+print(json.dumps(dict(used=int(used.value), pearson=float(np.corrcoef(a, b)[0, 1]),
+                      y_ratio=float(img[..., 1].sum() / (cpu[..., 1].sum() * scale)),
+                      landed_ratio=float(landed.value / (cpu_landed * scale)), mrays=rate.value / 1e6)))
+"""
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    lines = [x for x in p.stdout.splitlines() if x.startswith("{")]
+    assert p.returncode == 0 and lines, (p.stdout[-500:], p.stderr[-1500:])
+    res = json.loads(lines[-1])
+    assert res["used"] == 1, res                      # the TraceBackend route ran, not the legacy CPU fallback
+    assert res["pearson"] >= 0.95 and abs(res["y_ratio"] - 1) <= 0.05 and abs(res["landed_ratio"] - 1) <= 0.05, res
