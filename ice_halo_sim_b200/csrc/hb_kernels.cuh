@@ -1211,7 +1211,6 @@ __host__ __device__ inline bool derive_shape_tables(const HbCrystalTables& t, ui
   return p4;
 }
 
-constexpr uint32_t kShapeRunLog2 = 8;  // geometry clock: 256 consecutive rays per pool shape (see gen_root)
 constexpr uint32_t kFastGroups = 8;  // prism: 8 faces, weights kept in registers
 
 // Returns the chosen fan triangle. `ef` may point to shared or global memory (warp-uniform address).
@@ -1316,16 +1315,21 @@ HB_DEV void stage_gen_shared(const GenParams& gp, GenShared* gs) {
 
 // Root ray k of a launch (InitRay_*, simulator.cpp:133-339 with the counter-based streams of pcg_shared.h): wavelength
 // draw / continuation gather, orientation, sun-cone direction, shape pick, entry point. Returns the ray state.
+constexpr uint32_t kNoSource = 0xFFFFFFFFu;
 template <bool TRANSIT>
-HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float4& p_out, float4& d_out, float4& q_out) {
+HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float4& p_out, float4& d_out, float4& q_out,
+                     uint32_t src_known = kNoSource) {
   const uint32_t lo = gp.idx_lo + k;
   const uint32_t hi = gp.idx_hi + (lo < gp.idx_lo ? 1u : 0u);
   const uint32_t s0 = seed_with_high(gp.seed, hi);
   uint32_t wl_i = 0u;
   float wx, wy, wz, weight;
   if (TRANSIT) {
-    uint32_t src = gp.cont_first + k;
-    if (gp.shuffle) src = feistel(src, gp.cont_n, gp.shuffle_seed);
+    uint32_t src = src_known;
+    if (src == kNoSource) {
+      src = gp.cont_first + k;
+      if (gp.shuffle) src = feistel(src, gp.cont_n, gp.shuffle_seed);
+    }
     const float4 c = gp.cont_dw[src];
     wx = c.x;
     wy = c.y;
@@ -1356,17 +1360,14 @@ HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float
   }
   float dx, dy, dz;
   rot_apply_t(r.m, wx, wy, wz, dx, dy, dz);
-  // Geometry clock: one shape of the pool serves a run of kShapeRunRays = 256 consecutive ray indices (the reference's
-  // CPU path samples a crystal per kSmallBatchRayNum = 32 rays, simulator.hpp:144-151; its GPU backends pick per
-  // ray), and consecutive runs walk through the pool in order -- the pool is an i.i.d. sample, so a sequential walk
-  // is as random as a drawn one. A warp therefore reads ONE shape's tables in every kernel of the hit loop (uniform
-  // addresses: broadcast loads) and a CTA pass (256 consecutive rays) at most two, so pools too large for shared
-  // memory stay L1-resident per SM whatever the pool size. A pure function of the global ray index: tiles and
-  // sessions may split the range anywhere.
+  // Geometry clock: one shape of the pool serves a block of 32 consecutive ray indices, as on the reference's
+  // CPU path (kSmallBatchRayNum, simulator.hpp:144-151). A warp therefore reads ONE shape's tables in every
+  // kernel of the hit loop (uniform addresses: broadcast loads) instead of 32 different ones. The block's shape is
+  // drawn (measured against a sequential walk through the pool in runs of 32 or 256 rays: the drawn assignment is
+  // 3 % faster on 256-shape pools -- tables of neighbouring CTAs then do not collide in the same L2 lines).
   uint32_t sh = 0u;
   if (gp.shape_cnt > 1u) {
-    const uint64_t run = ((static_cast<uint64_t>(hi) << 32) | lo) >> kShapeRunLog2;
-    sh = static_cast<uint32_t>(run % gp.shape_cnt);
+    sh = min(static_cast<uint32_t>(draw(s0 ^ kNonceShape, lo >> 5, 0u) * static_cast<float>(gp.shape_cnt)), gp.shape_cnt - 1u);
   }
   const HbCrystalTables* tab = gp.shape_cnt == 1u ? &gs->shape0 : gp.shapes + sh;
   const EntryFaces* ef = gp.shape_cnt == 1u ? &gs->ef0 : gp.entry_faces + sh;
@@ -1389,7 +1390,8 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
   GenShared* gs = reinterpret_cast<GenShared*>(smem_raw);
   stage_gen_shared(gp, gs);
   __syncthreads();
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gp.count; k += gridDim.x * blockDim.x) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gp.count; k += stride) {
     float4 p4, d4, q;
     gen_root<TRANSIT>(gp, gs, k, p4, d4, q);
     const uint32_t slot = gp.slot0 + k;

@@ -711,7 +711,8 @@ int orc_gen_roots(const HbScene* scene, uint32_t layer, uint32_t pop_i, uint32_t
     ApplyRotT(m, dw, dl);
     uint32_t sh = 0;
     if (pop.shape_cnt > 1) {
-      sh = static_cast<uint32_t>((g >> 8) % pop.shape_cnt);  // geometry clock: runs of 256 rays walk through the pool
+      sh = static_cast<uint32_t>(Draw(s0 ^ kNonceShape, lo >> 5, 0)  /* geometry clock: 32 rays per shape */ * static_cast<float>(pop.shape_cnt));
+      if (sh >= pop.shape_cnt) sh = pop.shape_cnt - 1;
     }
     const HbCrystalTables& t = pop.shapes[sh];
     float p[3] = { 0, 0, 0 };
@@ -752,7 +753,8 @@ int orc_transit(const HbScene* scene, uint32_t layer, uint32_t pop_i, uint32_t s
     ApplyRotT(m, d_world3 + i * 3, dl);
     uint32_t sh = 0;
     if (pop.shape_cnt > 1) {
-      sh = static_cast<uint32_t>((g >> 8) % pop.shape_cnt);  // geometry clock: runs of 256 rays walk through the pool
+      sh = static_cast<uint32_t>(Draw(s0 ^ kNonceShape, lo >> 5, 0)  /* geometry clock: 32 rays per shape */ * static_cast<float>(pop.shape_cnt));
+      if (sh >= pop.shape_cnt) sh = pop.shape_cnt - 1;
     }
     const HbCrystalTables& t = pop.shapes[sh];
     float p[3] = { 0, 0, 0 };
