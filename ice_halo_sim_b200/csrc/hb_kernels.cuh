@@ -827,7 +827,6 @@ HB_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];"
 struct ExitQueue {
   uint32_t addr;    // shared-space address of this warp's queue
   uint32_t count;   // warp-uniform
-  uint32_t lt;      // lanes below this one
 };
 
 // All 32 lanes call this together. `meta0` = tile slot | role << 31.
@@ -835,7 +834,7 @@ HB_DEV void queue_push(ExitQueue& xq, bool has, float x, float y, float z, float
   const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
   if (m == 0u) return;
   if (has) {
-    const uint32_t pos = xq.count + __popc(m & xq.lt);
+    const uint32_t pos = xq.count + __popc(m & ((1u << (threadIdx.x & 31u)) - 1u));
     sts128(xq.addr + pos * 16u, x, y, z, w);
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(xq.addr + kQueueSlots * 16u + pos * 4u), "r"(meta0) : "memory");
   }
@@ -913,7 +912,7 @@ HB_DEV void queue_drain(ExitQueue& xq, ExitQueue2& q2, bool all, const TracePara
       const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
       if (km != 0u) {
         if (keep) {
-          const uint32_t pos = q2.count + __popc(km & xq.lt);
+          const uint32_t pos = q2.count + __popc(km & ((1u << lane) - 1u));
           sts128(q2.addr + pos * 16u, wx, wy, wz, w);
           asm volatile("st.shared.u32 [%0], %1;" ::"r"(q2.addr + kQueue2Slots * 16u + pos * 4u), "r"(wl_i) : "memory");
         }
@@ -1056,7 +1055,7 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_BOUNCE_MINB_GENERAL : HB_BOU
   const uint32_t total = tp.n_main + *tp.fork_snapshot;
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
-  ExitQueue xq{ smem_base + stage_off + kStage2Bytes + (threadIdx.x >> 5) * kQueueWarpBytes, 0u, (1u << (threadIdx.x & 31u)) - 1u };
+  ExitQueue xq{ smem_base + stage_off + kStage2Bytes + (threadIdx.x >> 5) * kQueueWarpBytes, 0u };
   ExitQueue2 q2{ smem_base + stage_off + kStage2Bytes + kQueueBytes + (threadIdx.x >> 5) * kQueue2WarpBytes, 0u };
   const uint32_t stage0 = smem_base + stage_off + threadIdx.x * 16u;
   uint32_t stage = 0u;
@@ -1081,18 +1080,19 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_BOUNCE_MINB_GENERAL : HB_BOU
       cp_async_commit();
       cp_async_wait<1>();
       bool has0 = false, has1 = false;
-      // the staged words are read unconditionally (the slot is this thread's own shared memory either way): a lane
-      // without a ray sees stale data and is masked by `i < total`; e0 / e1 only matter where has0 / has1 is set
-      const float4 d4 = lds128(cur), p4 = lds128(cur + 4096u);
-      float4 e0 = d4, e1 = d4;
-      const uint32_t bits = __float_as_uint(p4.w);
-      if (i < total && d4.w >= 0.0f && bits_face(bits) != kFaceInvalid) {  // else: no ray / terminated ray
-        float4 d_out, p_out;
-        bool moved;
-        bounce_ray<GENERAL, LAST, SMEM, P4>(tp, tb, i, p4, d4, has0, e0, has1, e1, d_out, p_out, moved);
-        if (!LAST) {
-          tp.D[i] = d_out;
-          if (moved) tp.P[i] = p_out;
+      float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+      uint32_t bits = 0u;
+      if (i < total) {
+        const float4 d4 = lds128(cur), p4 = lds128(cur + 4096u);
+        bits = __float_as_uint(p4.w);
+        if (d4.w >= 0.0f && bits_face(bits) != kFaceInvalid) {  // else: terminated ray
+          float4 d_out, p_out;
+          bool moved;
+          bounce_ray<GENERAL, LAST, SMEM, P4>(tp, tb, i, p4, d4, has0, e0, has1, e1, d_out, p_out, moved);
+          if (!LAST) {
+            tp.D[i] = d_out;
+            if (moved) tp.P[i] = p_out;
+          }
         }
       }
 #if HB_PREFETCH_Q
@@ -1424,7 +1424,7 @@ __global__ void __launch_bounds__(256, 4) genbounce_kernel(const GenParams gp, c
   const Tables<SMEM> tb = stage_tables<SMEM>(tp.lt, smem_raw + q_off + kQueueBytes + kQueue2Bytes, GENERAL);
   if (!SMEM) __syncthreads();
   const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
-  ExitQueue xq{ smem_base + q_off + (threadIdx.x >> 5) * kQueueWarpBytes, 0u, (1u << (threadIdx.x & 31u)) - 1u };
+  ExitQueue xq{ smem_base + q_off + (threadIdx.x >> 5) * kQueueWarpBytes, 0u };
   ExitQueue2 q2{ smem_base + q_off + kQueueBytes + (threadIdx.x >> 5) * kQueue2WarpBytes, 0u };
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
