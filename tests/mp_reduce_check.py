@@ -88,6 +88,31 @@ def main():
     both = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(both, mine)
     out["layer1_orientations_differ"] = bool((both[0] - both[1]).abs().max().item() > 1e-3)
+    # driver.render_config owns the communicator and the frame-end reduce: rank 0 gets the frames, the others nothing
+    from ice_halo_sim_b200 import load_config, render_config
+    cfg_json = {
+        "crystal": [{"id": 1, "type": "prism", "shape": {"height": 1.3},
+                     "axis": {"zenith": {"type": "gauss", "mean": 90.0, "std": 0.3},
+                              "azimuth": {"type": "uniform", "mean": 0.0, "std": 360.0},
+                              "roll": {"type": "uniform", "mean": 0.0, "std": 360.0}}}],
+        "filter": [],
+        "render": [{"id": 4, "lens": {"type": "fisheye_equal_area", "fov": 120.0}, "resolution": [480, 270],
+                    "view": {"azimuth": 0.0, "elevation": 30.0, "roll": 0.0}, "visible": "upper"}],
+        "scene": {"id": 1, "light_source": {"type": "sun", "altitude": 20.0, "azimuth": 0.0, "diameter": 0.5,
+                                            "spectrum": [{"wavelength": 550.0, "weight": 1.0}]},
+                  "ray_num": 1 << 20, "max_hits": 7,
+                  "scattering": [{"prob": 0.0, "entries": [{"crystal": 1, "proportion": 1.0}]}]},
+    }
+    cfg = load_config(cfg_json)
+    be2 = B.B200TraceBackend(local)      # a backend WITHOUT a communicator: render_config must create it
+    frames = render_config(cfg, be2, seed=5, rank=rank, world=world)
+    one = render_config(cfg, be2, seed=5, rank=0, world=1) if rank == 0 else None
+    if rank == 0:
+        out["driver_frames_on_root"] = sorted(frames) == [4]
+        out["driver_landed_rel"] = abs(frames[4].landed_weight - one[4].landed_weight) / one[4].landed_weight
+    else:
+        out["driver_no_frames_on_peer"] = frames == {}
+    be2.close()
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:
