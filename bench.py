@@ -557,10 +557,13 @@ def main():
                         "config-2 scene, same GPU, child process; reference_cuda = the reference's CudaTraceBackend "
                         "(cuda_trace_backend.cu, -arch=sm_100a) at its default 262144-ray dispatch; b200_adapter = the "
                         "same driver on this engine through adapter/b200_trace_backend.hpp (oracle/shim), at the "
-                        "reference's dispatch and at 16 Mi-ray dispatches (the reference's LUMICE_DISPATCH_RAY_NUM knob)",
-                "reference_cuda": reference_driver_run("libhalo_refcuda.so", 64 * 262144, 262144),
-                "b200_adapter_dispatch_262144": reference_driver_run("libhalo_refb200.so", 64 * 262144, 262144),
-                "b200_adapter_dispatch_16Mi": reference_driver_run("libhalo_refb200.so", 3 * SESSION_RAYS, SESSION_RAYS)}
+                        "reference's dispatch and at 16 Mi-ray dispatches (the reference's LUMICE_DISPATCH_RAY_NUM knob); "
+                        "every run creates its backend inside the timed Simulator::Run, as the reference does; the reference "
+                        "CUDA backend keeps the wavelength pool of its first session (450 nm) for the whole run, hence its "
+                        "different image_sum_per_root",
+                "reference_cuda": reference_driver_run("libhalo_refcuda.so", 256 * 262144, 262144),
+                "b200_adapter_dispatch_262144": reference_driver_run("libhalo_refb200.so", 256 * 262144, 262144),
+                "b200_adapter_dispatch_16Mi": reference_driver_run("libhalo_refb200.so", 8 * SESSION_RAYS, SESSION_RAYS)}
         line = {
             "metric": "Mrays/sec (9λ×50M single-scatter)", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,

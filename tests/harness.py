@@ -189,11 +189,18 @@ def exit_keys(recs, roots):
 
 
 def sort_exits(recs, roots):
-    order = sorted(range(len(recs)), key=lambda i: (int(roots[i]), int(recs[i]["path_len"]),
-                                                     bytes(recs[i]["path"][: recs[i]["path_len"]]),
-                                                     float(recs[i]["weight"])))
-    idx = np.array(order, dtype=np.int64)
-    return recs[idx], np.asarray(roots)[idx]
+    """Canonical order of an exit list: (root, path length, path bytes, weight). Vectorised (np.lexsort): the
+    tile-scale parity tests sort millions of records."""
+    roots = np.asarray(roots)
+    if len(recs) == 0:
+        return recs, roots
+    plen = recs["path_len"]
+    width = max(1, int(plen.max()))
+    path = recs["path"][:, :width].copy()
+    path[np.arange(width)[None, :] >= plen[:, None]] = 0      # only the record's own path bytes take part
+    keys = [recs["weight"].astype(np.float64)] + [path[:, k] for k in range(width - 1, -1, -1)] + [plen, roots]
+    idx = np.lexsort(keys)                                      # last key is the primary one
+    return recs[idx], roots[idx]
 
 
 def adversarial_roots(rng, t, n, n_idx):

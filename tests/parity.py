@@ -197,7 +197,7 @@ def run_case(case, n_rays=20000, seed=42, device=0, backend=None, geometry_seed=
             out["mask_bits_seen"] = out.get("mask_bits_seen", 0) | int(np.bitwise_or.reduce(o_ex["component_mask"])) \
                 if len(o_ex) else out.get("mask_bits_seen", 0)
             # continuation masks travel with the (shuffled) pool: compare as multisets
-            out["cont_masks_oracle"] = sorted(int(x) for x in o_cont[3])
+            out["cont_masks_oracle"] = np.sort(o_cont[3])
             r["continuations_gpu"] = handle.continuation_count
             r["continuations_oracle"] = len(o_cont[1])
             r["roots"] = len(roots["w"])
