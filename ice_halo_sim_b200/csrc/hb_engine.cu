@@ -1696,7 +1696,9 @@ int hb_merge_from_peer(HbEngine* dst, HbEngine* src) {
   const uint64_t src_lanes = src->classes.class_cnt != 0 ? src->lanes_floats : 0;
   if (!dst->have_render || !src->have_render || dst->arena_pix != src->arena_pix || dst_lanes != src_lanes)
     return fail(dst, HB_ERR_STATE, "merge_from_peer: the two engines do not hold the same renders");
-  if (dst->in_session || src->in_session) return fail(dst, HB_ERR_STATE, "merge_from_peer inside a session");
+  // Legal wherever hb_readback_xyz is, i.e. also inside a session: the reference driver drains on its third clock from
+  // within SimulateOneWavelengthWithBackend, before EndSession (simulator.cpp:1610-1640). The merge is ordered on the
+  // engines' streams after everything traced so far.
   if (dst->device != src->device) {
     int can = 0;
     cudaDeviceCanAccessPeer(&can, dst->device, src->device);

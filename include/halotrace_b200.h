@@ -344,7 +344,8 @@ int hb_reduce_image(HbEngine* h, int root);
 /* Several engines in ONE process (one host thread driving R devices behind the seam): add `src`'s
  * accumulators (all renders + colour lanes) into `dst`'s and zero `src`'s. Different devices: the kernel runs on
  * dst's device and reads src's fp64 master through peer access (NVLink P2P loads); asynchronous, ordered by events
- * on the two engines' streams. Both engines must hold the same renders; call between sessions. */
+ * on the two engines' streams. Both engines must hold the same renders; legal wherever hb_readback_xyz is
+ * (between sessions or inside one, after the layers traced so far). */
 int hb_merge_from_peer(HbEngine* dst, HbEngine* src);
 
 /* ---------------------------------------------------------------------------
