@@ -1207,7 +1207,11 @@ __host__ __device__ inline bool derive_shape_tables(const HbCrystalTables& t, ui
     axis_cnt++;
     if (partner == 63u) all_paired = false;
   }
-  const bool p4 = all_paired && axis_cnt == 4u;
+  // P4 = full hexagonal prism in MakeCrystal's canonical frame: four paired axes, axis 0 = (0, 0, 1), axis 1 = (1, 0, 0),
+  // axes 2 and 3 in the xy-plane -- exactly (dot_axis_p4 relies on the zeros and ones being exact).
+  const bool canonical = axis_cnt == 4u && axes[0].x == 0.0f && axes[0].y == 0.0f && axes[0].z == 1.0f &&
+                         axes[2].x == 1.0f && axes[2].y == 0.0f && axes[2].z == 0.0f && axes[4].z == 0.0f && axes[6].z == 0.0f;
+  const bool p4 = all_paired && axis_cnt == 4u && canonical;
   *meta = t.face_cnt | (pop << 8) | (axis_cnt << 16) | (p4 ? kMetaP4 : 0u);
   build_entry_faces(t, ef);
   return p4;
