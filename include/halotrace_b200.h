@@ -321,7 +321,18 @@ int hb_export_roots(HbEngine* h, uint64_t cap, float* d3, float* p3, float* w, u
  * layer 0); same order as hb_export_roots. Empty when the scene has no colour classes. */
 int hb_export_root_masks(HbEngine* h, uint64_t cap, uint64_t* masks, uint64_t* count);
 
-/* Tuning + measurement. */
+/* Tuning + measurement. Keys (value):
+ *   tile_rays (1024 .. 2^30)   rays per device tile, default 2^24
+ *   fold_rays (>= 1024)        root rays between folds of the fp32 working image into the fp64 master, default 2^21
+ *   fused_bounce (0 | 1)       1 (default): one bounce kernel per interaction; 0: split optics + intersect kernels
+ *   fused_gen (0 | 1)          1: root generation fused with the entry interaction; default 0 (measured slower)
+ *   filter_hit_bound (0 | 1)   1 (default): end a layer's hit loop at the longest path its filters can admit
+ *   prism_fast_path (0 | 1)    1 (default): unrolled canonical-prism forms; 0: generic paired-axis loop everywhere
+ *   pixel_cache (0 | 1)        1 (default): per-CTA shared-memory pixel cache in front of the image reduction
+ *   profile (0 | 1)            CUDA events around every launch (HbCounters *_ms)
+ *   blocks_per_sm (1 .. 32)    override the occupancy-sized persistent grids (experiments)
+ *   gen_base / stream_base     restart the monotone stream counters (tests: reproducible replays)
+ *   fork_cap, cont_cap         cap the fork-ray slots / continuation pool (0 = automatic; tests force overflows) */
 int hb_set_option(HbEngine* h, const char* key, int64_t value);
 int hb_get_counters(HbEngine* h, HbCounters* out);
 int hb_synchronize(HbEngine* h);
