@@ -82,6 +82,7 @@ class B200TraceBackend : public TraceBackend {
   bool IsCompatible(const RenderConfig&) const override { return true; }  // all 11 lens types
 
   void BeginSession(const SessionSpec& spec) override {
+    ThrowDeferred();
     try {
       raypath_color_ = spec.raypath_color;
       if (spec.scene != scene_ || raypath_color_ != color_uploaded_) {
@@ -135,6 +136,7 @@ class B200TraceBackend : public TraceBackend {
   }
 
   LayerHandlePtr TraceLayer(const RootRaySource& roots) override {
+    ThrowDeferred();
     auto handle = std::make_unique<B200LayerHandle>();
     const bool last = layer_idx_ + 1 == layer_cnt_;
     if (layer_idx_ < layer_axis_stochastic_.size() && layer_axis_stochastic_[layer_idx_]) {
@@ -190,6 +192,7 @@ class B200TraceBackend : public TraceBackend {
   size_t ReadbackExitRays(std::vector<ExitRayRecord>& out) override { return DrainExits(out); }
 
   void ReadbackXyzAccum(XyzImageData& xyz, float& landed_weight) override {
+    ThrowDeferred();
     MergeDevices();
     landed_weight = 0.0f;  // the seam's contract is "copies the running scalar out" (trace_backend.hpp), the C ABI adds
     Check(hb_readback_xyz(h_, xyz.data, &landed_weight), "ReadbackXyzAccum");
@@ -210,17 +213,15 @@ class B200TraceBackend : public TraceBackend {
     lane_data.resize(static_cast<size_t>(n) * pix);
   }
 
+  // Never throws: the reference driver ends sessions from a noexcept scope guard (simulator.cpp:1509-1515). A device
+  // overflow reported here is kept and thrown by the next BeginSession / TraceLayer / ReadbackXyzAccum instead.
   void EndSession() override {
-    int first_bad = HB_OK;
-    HbEngine* bad = nullptr;
     for (HbEngine* e : hs_) {  // close every device's session even when one reports an error
       const int rc = hb_end_session(e);
-      if (rc != HB_OK && first_bad == HB_OK) {
-        first_bad = rc;
-        bad = e;
+      if (rc != HB_OK && deferred_error_.empty()) {
+        deferred_error_ = std::string("B200TraceBackend::EndSession: ") + hb_last_error(e);
       }
     }
-    Check(first_bad, "EndSession", bad);
   }
 
   size_t GetLastBatchStochasticCrystalSampleCount() const override { return stochastic_shapes_last_upload_; }
@@ -230,6 +231,14 @@ class B200TraceBackend : public TraceBackend {
   size_t GetLastBatchStochasticOrientationSampleCount() const override { return orientation_draws_; }
 
  private:
+  void ThrowDeferred() {
+    if (!deferred_error_.empty()) {
+      std::string msg;
+      msg.swap(deferred_error_);
+      throw std::runtime_error(msg);
+    }
+  }
+
   // Device 0 gathers the other devices' accumulators (asynchronous; ordered by events on the engines' streams).
   void MergeDevices() {
     for (size_t r = 1; r < hs_.size(); r++) {
@@ -579,6 +588,7 @@ class B200TraceBackend : public TraceBackend {
 
  private:
 
+  std::string deferred_error_;         // an error EndSession could not throw (see EndSession)
   HbEngine* h_ = nullptr;              // device 0 of hs_: the one that is read back
   std::vector<HbEngine*> hs_;          // one engine per device
   std::vector<size_t> share_;          // root rays of the current session per device

@@ -610,8 +610,8 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
           tp.hit = 0;
           launch_genbounce(launch_ctx(h), false, general, in_smem, p4_mode, gb_smem, gp, tp);
         } else {
-          // persistent grid of exactly the co-resident CTAs (no partially filled second wave)
-          gen_kernel<false><<<resident_grid(launch_ctx(h), gen_kernel<false>, sizeof(GenShared), gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
+          // 8 CTAs per SM (1.6 waves at 5 co-resident CTAs): measured faster than an exactly co-resident grid (0.584 vs 0.605 ms)
+          gen_kernel<false><<<grid_for(h, gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
         }
       } else {
         const int src = h->cont_cur ^ 1;
@@ -629,7 +629,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
           tp.hit = 0;
           launch_genbounce(launch_ctx(h), true, general, in_smem, p4_mode, gb_smem, gp, tp);
         } else {
-          gen_kernel<true><<<resident_grid(launch_ctx(h), gen_kernel<true>, sizeof(GenShared), gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
+          gen_kernel<true><<<grid_for(h, gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
         }
       }
       end_event(h, ev);

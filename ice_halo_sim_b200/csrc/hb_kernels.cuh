@@ -1390,11 +1390,8 @@ HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float
   q_out = q;
 }
 
-#ifndef HB_GEN_MINB
-#define HB_GEN_MINB 5
-#endif
 template <bool TRANSIT>
-__global__ void __launch_bounds__(256, HB_GEN_MINB) gen_kernel(const GenParams gp) {
+__global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GenShared* gs = reinterpret_cast<GenShared*>(smem_raw);
   stage_gen_shared(gp, gs);
