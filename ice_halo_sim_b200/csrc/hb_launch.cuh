@@ -46,12 +46,17 @@ void launch_bounce_p1(const LaunchCtx& c, int key, size_t smem, const TraceParam
 void launch_bounce_p2(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
 void launch_bounce_multi(const LaunchCtx& c, int key, size_t smem, const TraceParams& tp);
 
-// Persistent grid-stride launch: exactly as many CTAs as are co-resident (occupancy x SM count), so there is
-// no partially filled second wave.
+// Grid-stride launch of kGridWaves x the co-resident CTAs (occupancy x SM count). A grid of exactly the resident
+// CTAs leaves SMs idle while the slowest CTAs finish (exit-heavy ranges, the far die's L2 latency); three waves of
+// smaller CTAs let the hardware scheduler even that out at a per-CTA prologue (table staging, pixel-cache init and
+// flush) that stays below 1 % of a CTA's work. Measured on config 2 (CTAs per SM for the 4-resident bounce kernels):
+// 4: 5.41, 8: 5.54, 12: 5.58, 16: 5.58, 24: 5.54, 32: 5.50, 64: 5.20 G rays/s.
+constexpr int kGridWaves = 3;
 template <typename K>
 uint32_t resident_grid(const LaunchCtx& c, K kernel, size_t smem, uint64_t n) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
+  per_sm *= kGridWaves;
   if (c.blocks_per_sm_override > 0) per_sm = c.blocks_per_sm_override;
   const uint64_t blocks = (n + 255) / 256;
   const uint64_t cap = static_cast<uint64_t>(c.sm_count) * per_sm;
