@@ -333,6 +333,12 @@ class B200TraceBackend:
     def Synchronize(self):
         self._check(self._lib.hb_synchronize(self._h))
 
+    def SelftestArith(self, mode: int, n: int, seed: int = 1):
+        """hb_selftest_arith: (mismatches, a_bits, b_bits, result_bits) of the unchecked exact division / sqrt."""
+        out = (C.c_uint64 * 4)()
+        self._check(self._lib.hb_selftest_arith(self._h, int(mode), int(n), int(seed), out))
+        return tuple(int(v) for v in out)
+
     def Counters(self) -> A.HbCounters:
         c = A.HbCounters()
         self._check(self._lib.hb_get_counters(self._h, C.byref(c)))

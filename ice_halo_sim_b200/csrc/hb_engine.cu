@@ -1585,6 +1585,21 @@ int hb_synchronize(HbEngine* h) {
   return HB_OK;
 }
 
+int hb_selftest_arith(HbEngine* h, uint32_t mode, uint64_t n, uint32_t seed, uint64_t* out4) {
+  if (h == nullptr || out4 == nullptr || mode > 2u) return HB_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  unsigned long long* bad = nullptr;
+  HB_CUDA(h, cudaMalloc(&bad, 4 * sizeof(unsigned long long)));
+  cudaMemsetAsync(bad, 0, 4 * sizeof(unsigned long long), h->stream);
+  hb::selftest_arith_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(n, seed, mode, bad);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out4, bad, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(bad);
+  HB_CUDA(h, e);
+  return HB_OK;
+}
+
 int hb_image_device_ptr(HbEngine* h, void** ptr, uint64_t* float_count) {
   if (h == nullptr || ptr == nullptr || float_count == nullptr) return HB_ERR_INVALID_ARG;
   if (!h->have_render) return fail(h, HB_ERR_STATE, "no render set");

@@ -1689,6 +1689,46 @@ __global__ void __launch_bounds__(256) merge_peer_kernel(double4* master, const 
   }
 }
 
+// Self-test of the unchecked exact division / square root (dvd_nr, sqrt_nr, hb_device.cuh) against the IEEE
+// intrinsics over counter-based random operands. mode 0: a / b with |a|, |b| in [2^-40, 2^40], either sign of a,
+// b > 0, one numerator in 64 an exact +-0 (bitwise comparison, so the signed zeros count); mode 1: the same with
+// either sign of b and non-zero a; mode 2: sqrt(x), x in [2^-60, 2^60]. bad[0] counts mismatches, bad[1..3] keep
+// the operand bits and the unchecked result of the last one.
+__global__ void __launch_bounds__(256) selftest_arith_kernel(uint64_t n, uint32_t seed, uint32_t mode, unsigned long long* bad) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const uint32_t lo = static_cast<uint32_t>(k), hi = static_cast<uint32_t>(k >> 32);
+    const uint32_t s0 = seed_with_high(seed, hi);
+    const uint32_t h0 = pcg_hash(s0 ^ pcg_hash(lo * 3u)), h1 = pcg_hash(s0 ^ pcg_hash(lo * 3u + 1u)),
+                   h2 = pcg_hash(s0 ^ pcg_hash(lo * 3u + 2u));
+    // mantissa from one hash, exponent (and signs) from another
+    const uint32_t ea = 127u - 40u + (h2 & 0xFFFFu) % 81u, eb = 127u - 40u + (h2 >> 16) % 81u;
+    uint32_t abits = (h0 & 0x807FFFFFu) | (ea << 23);
+    uint32_t bbits = (h1 & 0x007FFFFFu) | (eb << 23);
+    bool ok;
+    uint32_t got;
+    if (mode == 2u) {
+      const uint32_t ex = 127u - 60u + (h2 & 0xFFFFu) % 121u;
+      const float x = __uint_as_float((h0 & 0x007FFFFFu) | (ex << 23));
+      abits = __float_as_uint(x);
+      got = __float_as_uint(sqrt_nr(x));
+      ok = got == __float_as_uint(__fsqrt_rn(x));
+    } else {
+      if (mode == 0u && (h1 >> 26) == 0u) abits &= 0x80000000u;  // +-0 numerator
+      if (mode == 1u) bbits |= h1 & 0x80000000u;
+      const float a = __uint_as_float(abits), b = __uint_as_float(bbits);
+      got = __float_as_uint(dvd_nr(a, b));
+      ok = got == __float_as_uint(__fdiv_rn(a, b));
+    }
+    if (!ok) {
+      atomicAdd(bad, 1ull);
+      bad[1] = abits;
+      bad[2] = bbits;
+      bad[3] = got;
+    }
+  }
+}
+
 // Export helper: quaternion -> rot9 with the device's own arithmetic (parity harness).
 __global__ void quat_to_rot_kernel(const float4* Q, float* rot9, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

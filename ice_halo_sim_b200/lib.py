@@ -42,6 +42,7 @@ PROTOTYPES = {
     "hb_pyramid_slope": (C.c_double, [C.c_float]),
     "hb_get_counters": (C.c_int, [_vp, _vp]),
     "hb_synchronize": (C.c_int, [_vp]),
+    "hb_selftest_arith": (C.c_int, [_vp, C.c_uint32, C.c_uint64, C.c_uint32, _vp]),
     "hb_image_device_ptr": (C.c_int, [_vp, _vp, _vp]),
     "hb_stream": (_vp, [_vp]),
     "hb_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),

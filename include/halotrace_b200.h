@@ -336,6 +336,11 @@ int hb_export_root_masks(HbEngine* h, uint64_t cap, uint64_t* masks, uint64_t* c
 int hb_set_option(HbEngine* h, const char* key, int64_t value);
 int hb_get_counters(HbEngine* h, HbCounters* out);
 int hb_synchronize(HbEngine* h);
+/* Device self-test of the engine's unchecked exact division / square root (csrc/hb_device.cuh: dvd_nr, sqrt_nr)
+ * against the IEEE intrinsics on n counter-based random operand pairs. mode 0: a / b, b > 0, numerators incl. +-0;
+ * mode 1: either sign of b; mode 2: sqrt. out4[0] = number of bitwise mismatches (must be 0), out4[1..3] = operand
+ * bits and result of the last mismatch. */
+int hb_selftest_arith(HbEngine* h, uint32_t mode, uint64_t n, uint32_t seed, uint64_t* out4);
 /* Device pointer of the DOUBLE master accumulator (x,y,z,landed per pixel; all renders back to back; the
  * fp32 working image is folded into it first) for collectives driven from outside (torch.distributed);
  * valid until hb_set_render(s) / hb_destroy. */

@@ -35,6 +35,15 @@ def test_case_bit_exact(backend, name, pipeline):
         assert all(x > 0 for x in res["lane_sums"][:4]) and res["lane_sums"][4] == 0.0, res["lane_sums"]
 
 
+def test_unchecked_division_is_ieee(backend):
+    """dvd_nr / sqrt_nr (csrc/hb_device.cuh: the IEEE fast paths without the range check and its branch) equal
+    __fdiv_rn / __fsqrt_rn bit for bit on 2^32 random operand pairs per mode: positive divisors with signed-zero
+    numerators mixed in, divisors of either sign, square roots."""
+    for mode in (0, 1, 2):
+        bad, a, b, got = backend.SelftestArith(mode, 1 << 32, seed=20260 + mode)
+        assert bad == 0, (mode, bad, hex(a), hex(b), hex(got))
+
+
 def test_seed_and_tile_invariance(backend):
     """Counter-based RNG: the same seed gives the same exits whatever the tile size; another seed differs."""
     a = parity.run_case(parity.CASES["column_config2"], n_rays=20000, seed=7, backend=backend, tile_rays=4096)
