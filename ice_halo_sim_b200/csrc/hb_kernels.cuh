@@ -166,15 +166,26 @@ struct Tally {
 // direct-mapped table of kCacheSlots pixels in shared memory (first come, first claimed): contributions to a
 // cached pixel are summed in shared memory and reduced into the global image once, when the CTA retires.
 // Everything else goes straight to the L2 with one red.global.add.v4.f32.
+//   * The slot is a TILE hash of the pixel coordinates (low bits of x and of y): the hot pixels of a halo image are
+//     spatially clustered (sun disk, parhelia), and a 16 x 8 tile maps a 7 x 7 cluster without a single collision
+//     where a multiplicative hash of the linear index loses ~4 of 35 to the birthday problem.
+//   * Every slot has kCacheWays value cells, chosen by the lane: the lanes of a warp that hit the same hot pixel in
+//     the same instruction serialise in the compare-and-swap loop (ncu: 3.7 rounds of ATOMS.CAS.128 per 32 projected
+//     exits with one cell); cells per lane class cut the rounds by the number of ways.
 #ifndef HB_CACHE_SLOTS_LOG2
-#define HB_CACHE_SLOTS_LOG2 8
+#define HB_CACHE_SLOTS_LOG2 7
+#endif
+#ifndef HB_CACHE_WAYS_LOG2
+#define HB_CACHE_WAYS_LOG2 2
 #endif
 #ifndef HB_EXIT_STAGES
 #define HB_EXIT_STAGES 2   // 2: exits are projected from a second, visibility-culled queue (see queue_drain)
 #endif
 constexpr uint32_t kCacheSlots = 1u << HB_CACHE_SLOTS_LOG2;
+constexpr uint32_t kCacheWays = 1u << HB_CACHE_WAYS_LOG2;
+constexpr uint32_t kCacheXBits = (HB_CACHE_SLOTS_LOG2 + 1) / 2, kCacheYBits = HB_CACHE_SLOTS_LOG2 - kCacheXBits;
 constexpr uint32_t kCacheEmpty = 0xFFFFFFFFu;
-constexpr size_t kCacheBytes = kCacheSlots * (sizeof(uint32_t) + 4 * sizeof(float));
+constexpr size_t kCacheBytes = kCacheSlots * (2 * sizeof(uint32_t) + kCacheWays * 4 * sizeof(float));  // keys, candidates, cells
 
 // (x, y, z, w) += into one 16-byte shared-memory slot with a single 128-bit compare-and-swap loop
 // (ATOMS.CAS.128). Shared memory has no native fp32 add: four scalar atomicAdd calls are four CAS loops.
@@ -209,16 +220,30 @@ HB_DEV void smem_add_f4(uint32_t addr, float x, float y, float z, float w) {
       : "memory");
 }
 
-HB_DEV void accumulate_pixel(const TraceParams& tp, const Tally& tally, uint32_t pix, float x, float y, float z, float lw) {
+// `px`, `py`: the pixel's coordinates inside its render (tile hash); `pix`: its index in the image arena.
+// Claiming is by SECOND SIGHTING: a pixel that finds its slot unowned leaves its index in the slot's candidate word
+// (plain store: a lost race only delays a claim) and claims the slot (compare-and-swap from empty, so an owner is
+// never replaced) only when it meets its own candidate again. A hot pixel -- most of its slot's traffic -- owns the
+// slot after two or three exits; a cold one would need two consecutive sightings with no other pixel of the slot in
+// between, so cold pixels practically never lock a hot one out (first come, first claimed lost 17-29 % of the hot
+// pixels' traffic per CTA that way, which then went to the L2 one by one and into a large fp32 accumulator).
+HB_DEV void accumulate_pixel(const TraceParams& tp, const Tally& tally, uint32_t pix, uint32_t px, uint32_t py, float x, float y,
+                             float z, float lw) {
   if (tally.cache_keys != nullptr) {
-    const uint32_t slot = (pix * 2654435761u) >> (32 - HB_CACHE_SLOTS_LOG2);  // multiplicative hash, top bits
+    const uint32_t slot = (px & ((1u << kCacheXBits) - 1u)) | ((py & ((1u << kCacheYBits) - 1u)) << kCacheXBits);
     uint32_t k = tally.cache_keys[slot];
     if (k == kCacheEmpty) {
-      k = atomicCAS(&tally.cache_keys[slot], kCacheEmpty, pix);
-      if (k == kCacheEmpty) k = pix;
+      uint32_t* cand = tally.cache_keys + kCacheSlots;
+      if (cand[slot] == pix) {
+        k = atomicCAS(&tally.cache_keys[slot], kCacheEmpty, pix);
+        if (k == kCacheEmpty) k = pix;
+      } else {
+        cand[slot] = pix;
+      }
     }
     if (k == pix) {
-      smem_add_f4(static_cast<uint32_t>(__cvta_generic_to_shared(tally.cache_vals + slot * 4u)), x, y, z, lw);
+      const uint32_t cell = slot * kCacheWays + (threadIdx.x & (kCacheWays - 1u));
+      smem_add_f4(static_cast<uint32_t>(__cvta_generic_to_shared(tally.cache_vals + cell * 4u)), x, y, z, lw);
       return;
     }
   }
@@ -227,24 +252,19 @@ HB_DEV void accumulate_pixel(const TraceParams& tp, const Tally& tally, uint32_t
 
 HB_DEV void cache_init(Tally& tally, unsigned char* smem) {
   tally.cache_keys = reinterpret_cast<uint32_t*>(smem);
-  tally.cache_vals = reinterpret_cast<float*>(smem + kCacheSlots * sizeof(uint32_t));
-  for (uint32_t i = threadIdx.x; i < kCacheSlots; i += blockDim.x) {
-    tally.cache_keys[i] = kCacheEmpty;
-    tally.cache_vals[4u * i + 0] = 0.0f;
-    tally.cache_vals[4u * i + 1] = 0.0f;
-    tally.cache_vals[4u * i + 2] = 0.0f;
-    tally.cache_vals[4u * i + 3] = 0.0f;
-  }
+  tally.cache_vals = reinterpret_cast<float*>(smem + 2u * kCacheSlots * sizeof(uint32_t));
+  for (uint32_t i = threadIdx.x; i < 2u * kCacheSlots; i += blockDim.x) tally.cache_keys[i] = kCacheEmpty;  // keys + candidates
+  float4* v = reinterpret_cast<float4*>(tally.cache_vals);
+  for (uint32_t i = threadIdx.x; i < kCacheSlots * kCacheWays; i += blockDim.x) v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 HB_DEV void cache_flush(const TraceParams& tp, const Tally& tally) {
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < kCacheSlots; i += blockDim.x) {
-    const uint32_t k = tally.cache_keys[i];
-    if (k != kCacheEmpty) {
-      const float* v = tally.cache_vals + 4u * i;
-      red_add_f4(tp.image + k, v[0], v[1], v[2], v[3]);
-    }
+  const float4* v = reinterpret_cast<const float4*>(tally.cache_vals);
+  for (uint32_t i = threadIdx.x; i < kCacheSlots * kCacheWays; i += blockDim.x) {
+    const uint32_t k = tally.cache_keys[i >> HB_CACHE_WAYS_LOG2];
+    const float4 c = v[i];
+    if (k != kCacheEmpty && (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f || c.w != 0.0f)) red_add_f4(tp.image + k, c.x, c.y, c.z, c.w);
   }
 }
 
@@ -395,7 +415,8 @@ HB_DEV void emit_project(const TraceParams& tp, uint32_t wl_i, float wx, float w
       const int px = h.px[k], py = h.py[k];
       if (px >= 0 && px < tp.proj.img_w && py >= 0 && py < tp.proj.img_h) {
         const uint32_t pix = static_cast<uint32_t>(py) * static_cast<uint32_t>(tp.proj.img_w) + static_cast<uint32_t>(px);
-        accumulate_pixel(tp, tally, pix, mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w), h.bump[k] ? w : 0.0f);
+        accumulate_pixel(tp, tally, pix, static_cast<uint32_t>(px), static_cast<uint32_t>(py), mul(we.cmf_x, w), mul(we.cmf_y, w),
+                         mul(we.cmf_z, w), h.bump[k] ? w : 0.0f);
         if constexpr (MULTI) {
           // FanColorClassLanes (cuda_trace_backend.cu:538-556): Y into every satisfied class, overlap-ring hits too
           if (tp.color_on && mask != 0ull) {
@@ -423,7 +444,8 @@ HB_DEV void emit_project(const TraceParams& tp, uint32_t wl_i, float wx, float w
           const int px = hr.px[k], py = hr.py[k];
           if (px >= 0 && px < pr.img_w && py >= 0 && py < pr.img_h) {
             accumulate_pixel(tp, tally, off + static_cast<uint32_t>(py) * static_cast<uint32_t>(pr.img_w) + static_cast<uint32_t>(px),
-                             mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w), hr.bump[k] ? w : 0.0f);
+                             static_cast<uint32_t>(px), static_cast<uint32_t>(py), mul(we.cmf_x, w), mul(we.cmf_y, w), mul(we.cmf_z, w),
+                             hr.bump[k] ? w : 0.0f);
           }
         }
       }
@@ -1132,6 +1154,7 @@ struct GenShared;
 // same face id and normal.
 struct EntryFaces {
   float4 na[HB_MAX_FACES];     // group normal, group area
+  float4 pick[HB_MAX_FACES];   // cum[first], cum[first + 1], cum[first + 2] (+inf beyond the group), bits: first | cnt << 8
   float cum[HB_MAX_SUBTRIS];   // per triangle: cumulative area fraction inside its group
   uint8_t first[HB_MAX_FACES];
   uint8_t cnt[HB_MAX_FACES];
@@ -1143,6 +1166,11 @@ static_assert(sizeof(EntryFaces) % 16 == 0, "EntryFaces is copied as uint4 words
 // Face groups of one shape's entry fan table: runs of consecutive triangles that share the face id and the
 // normal; per triangle the cumulative area fraction inside its run. Host (upload_layer) and device
 // (derive_shapes_kernel) run this same code.
+__host__ __device__ inline float bits_to_float_hd(int v) {
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+}
 __host__ __device__ inline void build_entry_faces(const HbCrystalTables& t, EntryFaces* out) {
   EntryFaces& ef = *out;
   memset(&ef, 0, sizeof(ef));
@@ -1166,6 +1194,15 @@ __host__ __device__ inline void build_entry_faces(const HbCrystalTables& t, Entr
     ef.na[g] = make_float4(t.tri_n[i][0], t.tri_n[i][1], t.tri_n[i][2], area);
     ef.first[g] = static_cast<uint8_t>(i);
     ef.cnt[g] = static_cast<uint8_t>(j - i);
+    {
+      // the same thresholds once more, packed for one 16-byte load (groups of up to 4 triangles: every face of a
+      // hexagonal prism or pyramid); r >= +inf never holds, so missing thresholds count nothing
+      const uint32_t pbits = i | ((j - i) << 8);
+      float pb;
+      memcpy(&pb, &pbits, 4);
+      const float inf = bits_to_float_hd(0x7f800000);
+      ef.pick[g] = make_float4(j - i > 1u ? ef.cum[i] : inf, j - i > 2u ? ef.cum[i + 1u] : inf, j - i > 3u ? ef.cum[i + 2u] : inf, pb);
+    }
     g++;
     i = j;
   }
@@ -1220,6 +1257,10 @@ __host__ __device__ inline bool derive_shape_tables(const HbCrystalTables& t, ui
 constexpr uint32_t kFastGroups = 8;  // prism: 8 faces, weights kept in registers
 
 // Returns the chosen fan triangle. `ef` may point to shared or global memory (warp-uniform address).
+// Level 1 walks the cumulative weights c[g] = c[g-1] + w[g] exactly as a sequential categorical would (first g with
+// c[g] > target; the residual is target - c[g-1]); because c is non-decreasing "first g with c[g] > target" is the
+// NUMBER of g with c[g] <= target, which needs no found-flag chain: per group one compare and three predicated
+// moves. Level 2 counts the cumulative area fractions below the residual ratio from one packed 16-byte load.
 HB_DEV uint32_t pick_entry_triangle(Stream& s, const EntryFaces* ef, float dx, float dy, float dz) {
   const uint32_t ng = ef->group_cnt;
   const float u_cat = s.next();
@@ -1227,7 +1268,7 @@ HB_DEV uint32_t pick_entry_triangle(Stream& s, const EntryFaces* ef, float dx, f
   uint32_t sel = ng - 1u;
   float resid = 0.0f, w_sel = 0.0f, total = 0.0f;
   if (ng <= kFastGroups) {
-    float w[kFastGroups];
+    float w[kFastGroups], c[kFastGroups];
 #pragma unroll
     for (uint32_t g = 0; g < kFastGroups; g++) {
       w[g] = 0.0f;
@@ -1236,23 +1277,22 @@ HB_DEV uint32_t pick_entry_triangle(Stream& s, const EntryFaces* ef, float dx, f
         w[g] = fmaxf(-(dx * na.x + dy * na.y + dz * na.z) * na.w, 0.0f);
         total += w[g];
       }
+      c[g] = total;
     }
     if (!(total > 0.0f)) return 0u;
     const float target = u_cat * total;
-    float cum = 0.0f;
-    bool found = false;
+    uint32_t below = 0u;
+    float lo = 0.0f;
 #pragma unroll
-    for (uint32_t g = 0; g < kFastGroups; g++) {
-      if (g < ng) {
-        const float c1 = cum + w[g];
-        const bool hit = !found && c1 > target;
-        sel = hit ? g : sel;
-        resid = hit ? target - cum : resid;
-        w_sel = hit ? w[g] : w_sel;
-        found = found || hit;
-        cum = c1;
-      }
+    for (int g = static_cast<int>(kFastGroups) - 1; g >= 0; g--) {  // descending: the last write of w_sel is the first c[g] > target
+      const bool le = c[g] <= target;
+      w_sel = le ? w_sel : w[g];
+      lo = le ? fmaxf(lo, c[g]) : lo;
+      below += le ? 1u : 0u;
     }
+    sel = min(below, ng - 1u);   // groups past ng repeat the total: they only count when nothing was found
+    resid = below < ng ? target - lo : 0.0f;
+    w_sel = below < ng ? w_sel : 0.0f;
   } else {
     for (uint32_t g = 0; g < ng; g++) {
       const float4 na = ef->na[g];
@@ -1274,10 +1314,13 @@ HB_DEV uint32_t pick_entry_triangle(Stream& s, const EntryFaces* ef, float dx, f
       cum = c1;
     }
   }
-  const float r = w_sel > 0.0f ? resid / w_sel : 0.0f;
-  const uint32_t t0 = ef->first[sel], c = ef->cnt[sel];
+  const float r = w_sel > 0.0f ? dvd_nr(resid, w_sel) : 0.0f;  // normal-range quotient: == IEEE division
+  const float4 pk = ef->pick[sel];
+  const uint32_t pbits = __float_as_uint(pk.w);
+  const uint32_t t0 = pbits & 255u, cnt = pbits >> 8;
+  if (cnt <= 4u) return t0 + (r >= pk.x ? 1u : 0u) + (r >= pk.y ? 1u : 0u) + (r >= pk.z ? 1u : 0u);
   uint32_t tri = t0;
-  for (uint32_t j = 0; j + 1u < c; j++) {
+  for (uint32_t j = 0; j + 1u < cnt; j++) {
     if (r >= ef->cum[t0 + j]) tri = t0 + j + 1u;
   }
   return tri;
@@ -1355,7 +1398,8 @@ HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float
     // sample_sph_cap (pcg_shared.h:514-529) with the per-launch trigonometry hoisted to the host
     const float u = s.next();
     const float x = u + (1.0f - u) * gp.sun_c_cap;
-    const float rr = sqrtf(fmaxf(1.0f - x * x, 0.0f));
+    const float rr2 = 1.0f - x * x;
+    const float rr = rr2 > 0.0f ? sqrt_nr(rr2) : 0.0f;  // == sqrtf(fmaxf(rr2, 0)): rr2 is 0 or at least an ulp of 1
     float sp, cp;
     sincosf(s.next() * 2.0f * kPiF, &sp, &cp);
     const float y = cp * rr, z = sp * rr;
