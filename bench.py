@@ -72,6 +72,10 @@ WORKLOADS = {
                     what="BASELINE configs[4]: bench_config_stoch.json prism h=1 d_i~gauss(1,0.15) full-sphere axis, "
                          "max_hits 8, rectangular 2048x1024 full sky; 256-shape pool redrawn on the device every session, "
                          "one shape per 32 consecutive rays; 9 x 1 G rays over 8 GPUs"),
+    # not a BASELINE config: the generic (non-prism) slab kernels on a 20-face pyramid, for the kernel notes in DESIGN.md
+    "pyramid": dict(case="pyramid", rays_per_wl=RAYS_PER_WL, gpus=1, session=SESSION_RAYS,
+                    what="parity case 'pyramid': 20-face hexagonal pyramid (10 paired axes, generic slab kernels), "
+                         "max_hits 8, dual_fisheye_equal_area 1024x512 full sky"),
 }
 
 

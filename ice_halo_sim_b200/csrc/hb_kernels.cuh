@@ -864,6 +864,27 @@ HB_DEV void queue_push(ExitQueue& xq, bool has, float x, float y, float z, float
   __syncwarp();
 }
 
+// Both children of one interaction in one go (role 0 entries first, then role 1: the order two queue_push calls
+// would leave): two ballots, one early-out, one __syncwarp.
+HB_DEV void queue_push2(ExitQueue& xq, bool has0, float4 e0, bool has1, float4 e1, uint32_t slot) {
+  const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, has0), m1 = __ballot_sync(0xFFFFFFFFu, has1);
+  if ((m0 | m1) == 0u) return;
+  const uint32_t below = (1u << (threadIdx.x & 31u)) - 1u;
+  const uint32_t n0 = __popc(m0);
+  if (has0) {
+    const uint32_t pos = xq.count + __popc(m0 & below);
+    sts128(xq.addr + pos * 16u, e0.x, e0.y, e0.z, e0.w);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(xq.addr + kQueueSlots * 16u + pos * 4u), "r"(slot) : "memory");
+  }
+  if (has1) {
+    const uint32_t pos = xq.count + n0 + __popc(m1 & below);
+    sts128(xq.addr + pos * 16u, e1.x, e1.y, e1.z, e1.w);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(xq.addr + kQueueSlots * 16u + pos * 4u), "r"(slot | 0x80000000u) : "memory");
+  }
+  xq.count += n0 + __popc(m1);
+  __syncwarp();
+}
+
 // Emit queued exits, 32 at a time (`all`: whatever is left, with the lanes that still have an entry), in two
 // converged stages:
 //   stage 1  orientation matrix, world rotation, filter / gate / record (emit_world), then the exact visibility
@@ -1008,12 +1029,12 @@ HB_DEV void bounce_ray(const TraceParams& tp, const Tables<SMEM>& tb, uint32_t i
       nf = bounce_axes_p4(axes, face, pl, p4.x, p4.y, p4.z, ox, oy, oz, ix, iy, iz, far_exits, nx, ny, nz);
     }
   } else {
-    far_exits = far_child_surely_exits(axes, axis_cnt, face, pl, p4.x, p4.y, p4.z, ox, oy, oz);
     if (LAST) {
+      far_exits = far_child_surely_exits(axes, axis_cnt, face, pl, p4.x, p4.y, p4.z, ox, oy, oz);
       near_done = iw < 0.0f || near_child_surely_hits(axes, axis_cnt, p4.x, p4.y, p4.z, ix, iy, iz);
       if (!near_done) nf = slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
     } else {
-      nf = slab_exit<false>(axes, axis_cnt, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
+      nf = bounce_axes(axes, axis_cnt, face, pl, p4.x, p4.y, p4.z, ox, oy, oz, ix, iy, iz, far_exits, nx, ny, nz);
     }
   }
   // far-side child: leaves (the common case), or stays inside within ~1e-7 of an edge (fork ray)
@@ -1122,8 +1143,7 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_BOUNCE_MINB_GENERAL : HB_BOU
 #if HB_PREFETCH_Q
       if (has0 || has1) prefetch_l1(tp.Q + i);  // the emission (some iterations later, another lane) reads the orientation
 #endif
-      queue_push(xq, has0, e0.x, e0.y, e0.z, e0.w, i);
-      queue_push(xq, has1, e1.x, e1.y, e1.z, e1.w, i | 0x80000000u);
+      queue_push2(xq, has0, e0, has1, e1, i);
       stage ^= 1u;
       i = i_next;
       warp_first += stride;
