@@ -174,7 +174,6 @@ struct HbEngine {
   DevBuf<float> lanes;                 // [class_cnt][pixels of render 0] per-class Y lanes
   uint64_t lanes_floats = 0;
   DevBuf<uint64_t> mask_tile;          // [cap] carried component mask per ray slot (layers >= 1)
-  DevBuf<uint64_t> cont_mask[2];       // component masks of the continuation pools
   DevBuf<uint8_t> rgb_stage;           // 8-bit snapshot staging
   DevBuf<float4> image;
   DevBuf<double4> master;
@@ -218,9 +217,7 @@ struct HbEngine {
   DevBuf<uint32_t> counters;    // [0] fork_count [1] fork_snapshot [2] cont_count [3] exit_count [4] error [5] done_count
   DevBuf<unsigned long long> stat_cnt;
   DevBuf<double> stat_sum;
-  DevBuf<float4> cont_dw[2];
-  DevBuf<uint32_t> cont_meta[2];
-  DevBuf<uint32_t> cont_root[2];
+  DevBuf<ContRec> cont[2];      // continuation pools (appended by one layer, gathered by the next)
   int cont_cur = 0;             // pool being appended by the current layer
   DevBuf<HbExitRecord> exits_dev;
   DevBuf<uint32_t> exit_root_dev;
@@ -525,7 +522,6 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.extra_cnt = static_cast<uint32_t>(h->renders.size()) - 1u;
   tp.color_on = color_on ? 1u : 0u;
   tp.M = (color_on && li > 0) ? h->mask_tile.p : nullptr;
-  tp.cont_mask = (color_on && (flags & kFlagGate)) ? h->cont_mask[h->cont_cur].p : nullptr;
   tp.lane = h->lanes.p;
   tp.lane_stride = h->renders.empty() ? 0u : static_cast<uint32_t>(h->renders[0].img_w) * h->renders[0].img_h;
   tp.classes = h->classes;
@@ -536,11 +532,9 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.gate_seed = h->spec.seed ^ kNonceGate;
   tp.gate_base_lo = static_cast<uint32_t>(h->gate_base);
   tp.gate_base_hi = static_cast<uint32_t>(h->gate_base >> 32);
-  tp.cont_dw = h->cont_dw[h->cont_cur].p;
-  tp.cont_meta = h->cont_meta[h->cont_cur].p;
-  tp.cont_root = h->spec.record_exits ? h->cont_root[h->cont_cur].p : nullptr;
+  tp.cont = h->cont[h->cont_cur].p;
   tp.cont_count = h->counters.p + 2;
-  tp.cont_cap = static_cast<uint32_t>(h->cont_dw[h->cont_cur].n);
+  tp.cont_cap = static_cast<uint32_t>(h->cont[h->cont_cur].n);
   if (h->cont_cap_override) tp.cont_cap = static_cast<uint32_t>(std::min<uint64_t>(tp.cont_cap, h->cont_cap_override));
   tp.exits = h->exits_dev.p;
   tp.exit_root = h->exit_root_dev.p;
@@ -615,12 +609,8 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
         }
       } else {
         const int src = h->cont_cur ^ 1;
-        gp.cont_dw = h->cont_dw[src].p;
-        gp.cont_meta = h->cont_meta[src].p;
-        if (color_on) {
-          gp.cont_mask = h->cont_mask[src].p;
-          gp.M = h->mask_tile.p;
-        }
+        gp.cont = h->cont[src].p;
+        if (color_on) gp.M = h->mask_tile.p;
         gp.cont_n = static_cast<uint32_t>(layer_total);
         gp.cont_first = static_cast<uint32_t>(b);
         gp.shuffle = h->cont_shuffle ? 1u : 0u;
@@ -811,8 +801,6 @@ void hb_destroy(HbEngine* h) {
   h->extra_dev.release();
   h->lanes.release();
   h->mask_tile.release();
-  h->cont_mask[0].release();
-  h->cont_mask[1].release();
   h->rgb_stage.release();
   h->xyz_stage.release();
   h->landed_dev.release();
@@ -832,9 +820,7 @@ void hb_destroy(HbEngine* h) {
   h->stat_cnt.release();
   h->stat_sum.release();
   for (int i = 0; i < 2; i++) {
-    h->cont_dw[i].release();
-    h->cont_meta[i].release();
-    h->cont_root[i].release();
+    h->cont[i].release();
   }
   h->exits_dev.release();
   h->exit_root_dev.release();
@@ -1107,10 +1093,7 @@ int hb_trace_layer(HbEngine* h, uint64_t n_roots, HbLayerStats* stats) {
   if (flags & kFlagGate) {
     uint64_t ccap = std::min<uint64_t>(n * (h->max_hits + 1) + 4096, 0xFFFFFFF0ull);
     if (h->cont_cap_override) ccap = std::min<uint64_t>(ccap, h->cont_cap_override);
-    HB_CUDA(h, h->cont_dw[h->cont_cur].ensure(ccap));
-    HB_CUDA(h, h->cont_meta[h->cont_cur].ensure(ccap));
-    if (h->classes.class_cnt != 0) HB_CUDA(h, h->cont_mask[h->cont_cur].ensure(ccap));
-    if (h->spec.record_exits) HB_CUDA(h, h->cont_root[h->cont_cur].ensure(ccap));
+    HB_CUDA(h, h->cont[h->cont_cur].ensure(ccap));
   }
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -72,6 +72,17 @@ HB_DEV WlDev load_wl(const WlDev& wl0, const WlDev* wl2, uint32_t wl_cnt, uint32
   return WlDev{ a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
 }
 
+// Continuation record (multi-scatter): everything that carries over to the next layer in ONE 32-byte sector, so the
+// Feistel-permuted gather of the transit generator costs one random sector per continuation (it was two -- direction
+// + weight and the meta word in separate arrays -- and three with raypath colour).
+struct __align__(16) ContRec {
+  float4 dw;                    // world direction, weight
+  uint32_t meta;                // wavelength index | population << 8
+  uint32_t root;                // layer-root index of the parent
+  uint64_t mask;                // raypath-colour component mask
+};
+static_assert(sizeof(ContRec) == 32, "one sector");
+
 struct TraceParams {
   float4* P;
   float4* D;
@@ -96,7 +107,6 @@ struct TraceParams {
   // raypath colour (kernels instantiated with MULTI only)
   uint32_t color_on;            // scene has colour classes
   uint64_t* M;                  // [cap + fork_cap] component mask carried in from earlier layers (nullptr on layer 0)
-  uint64_t* cont_mask;          // continuation records: component mask
   float* lane;                  // [class_cnt][lane_stride] per-class Y lanes of render 0
   uint32_t lane_stride;
   HbColorClasses classes;
@@ -104,9 +114,7 @@ struct TraceParams {
   float prob;
   uint32_t gate_seed;           // session seed ^ gate nonce
   uint32_t gate_base_lo, gate_base_hi;  // global gate index of layer-root 0
-  float4* cont_dw;              // continuation records: world dir + weight
-  uint32_t* cont_meta;          // wl index | population << 8
-  uint32_t* cont_root;          // layer-root index of the parent (record mode)
+  ContRec* cont;                // continuation pool being appended (one 32-byte record per continuation)
   uint32_t* cont_count;
   uint32_t cont_cap;
   HbExitRecord* exits;
@@ -140,10 +148,8 @@ struct GenParams {
   float sun_c_cap, sun_c_lon, sun_s_lon, sun_c_lat, sun_s_lat;  // per-launch constants of sample_sph_cap
   uint32_t flags;
   // transit only
-  const float4* cont_dw;
-  const uint32_t* cont_meta;
-  const uint64_t* cont_mask;    // component masks of the continuations (raypath colour) or nullptr
-  uint64_t* M;                  // per-slot carried mask of the next layer
+  const ContRec* cont;          // permuted source pool
+  uint64_t* M;                  // per-slot carried mask of the next layer (raypath colour) or nullptr
   uint32_t cont_n;              // size of the permuted continuation pool
   uint32_t cont_first;          // pool position of slot0
   uint32_t shuffle_seed;
@@ -352,12 +358,9 @@ HB_DEV bool emit_world(const TraceParams& tp, uint32_t slot, uint32_t bits, floa
       base = __shfl_sync(active, base, leader);
       const uint32_t dst = base + __popc(active & ((1u << lane) - 1u));
       if (dst < tp.cont_cap) {
-        tp.cont_dw[dst] = make_float4(wx, wy, wz, w);
-        tp.cont_meta[dst] = wl_i | (pop << 8);
-        if (tp.cont_root != nullptr) tp.cont_root[dst] = root;
-        if constexpr (MULTI) {
-          if (tp.cont_mask != nullptr) tp.cont_mask[dst] = mask;
-        }
+        float4* rec = reinterpret_cast<float4*>(tp.cont + dst);
+        rec[0] = make_float4(wx, wy, wz, w);
+        reinterpret_cast<uint4*>(rec)[1] = make_uint4(wl_i | (pop << 8), root, static_cast<uint32_t>(mask), static_cast<uint32_t>(mask >> 32));
       } else {
         *tp.error_flag = 1u;
       }
@@ -1399,13 +1402,15 @@ HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float
       src = gp.cont_first + k;
       if (gp.shuffle) src = feistel(src, gp.cont_n, gp.shuffle_seed);
     }
-    const float4 c = gp.cont_dw[src];
+    const float4* rec = reinterpret_cast<const float4*>(gp.cont + src);
+    const float4 c = __ldg(rec);
+    const uint4 m = __ldg(reinterpret_cast<const uint4*>(rec) + 1);
     wx = c.x;
     wy = c.y;
     wz = c.z;
     weight = c.w;
-    wl_i = gp.cont_meta[src] & 255u;
-    if (gp.cont_mask != nullptr) gp.M[gp.slot0 + k] = gp.cont_mask[src];
+    wl_i = m.x & 255u;
+    if (gp.M != nullptr) gp.M[gp.slot0 + k] = static_cast<uint64_t>(m.z) | (static_cast<uint64_t>(m.w) << 32);
   } else if (gp.wl_cnt > 1u) {
     wl_i = min(static_cast<uint32_t>(draw(s0 ^ kNonceWl, lo, 0u) * static_cast<float>(gp.wl_cnt)), gp.wl_cnt - 1u);
   }
