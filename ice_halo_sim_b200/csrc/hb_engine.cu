@@ -619,7 +619,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
           tp.hit = 0;
           launch_genbounce(launch_ctx(h), true, general, in_smem, p4_mode, gb_smem, gp, tp);
         } else {
-          gen_kernel<true><<<grid_for(h, gp.count), 256, sizeof(GenShared), h->stream>>>(gp);
+          gen_kernel<true><<<grid_for(h, gp.count), 256, kGenSharedBytes + kTransitSrcBytes, h->stream>>>(gp);
         }
       }
       end_event(h, ev);

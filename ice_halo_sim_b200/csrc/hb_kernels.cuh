@@ -1370,6 +1370,7 @@ struct GenShared {
   HbCrystalTables shape0;        // single-shape populations: entry fan table staged on chip
   EntryFaces ef0;                // ... and its face groups
 };
+constexpr uint32_t kGenSharedBytes = (static_cast<uint32_t>(sizeof(GenShared)) + 15u) & ~15u;
 
 HB_DEV void stage_gen_shared(const GenParams& gp, GenShared* gs) {
   if (gp.axis.lat_path == HB_LAT_LUT) {
@@ -1459,13 +1460,88 @@ HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float
   q_out = q;
 }
 
+// Transit generator: the Feistel-permuted sources of kTransitBatch consecutive iterations of a warp are resolved
+// together, as a pool of 32 x kTransitBatch items the lanes draw from. Cycle-walking needs a geometric number of
+// passes per item (3.4 on average when the pool is just above a quarter of the 2^bits domain), so a warp that walks
+// its 32 items in lock step waits for the slowest lane -- ncu: 9 to 14 of 32 lanes active in 41 % of the kernel's
+// instructions. Here a lane whose item has landed below n takes the next unresolved item, and every pass runs with
+// (almost) all lanes; the sources go through shared memory to the lanes that generate the rays.
+constexpr uint32_t kTransitBatch = 4u;
+constexpr uint32_t kTransitSrcBytes = 8u * 32u * kTransitBatch * 4u;   // 8 warps per CTA
+
+HB_DEV void resolve_sources(const GenParams& gp, uint32_t k_warp, uint32_t stride, uint32_t* src_out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const FeistelDomain fd = feistel_domain(gp.cont_n);
+  // item t: iteration t / 32 of the batch, lane t % 32; items past the end of the launch are not issued
+  uint32_t total = 0u;
+#pragma unroll
+  for (uint32_t c = 0; c < kTransitBatch; c++) {
+    const uint32_t first = k_warp + c * stride;
+    total += first < gp.count ? min(32u, gp.count - first) : 0u;   // only the last iteration of a launch is ragged
+  }
+  uint32_t next = 0u;              // warp-uniform: items handed out so far
+  uint32_t item = 0xFFFFFFFFu, cur = 0u, walks = 0u;
+  for (;;) {
+    const bool need = item == 0xFFFFFFFFu;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+    const uint32_t avail = total - next;
+    if (need) {
+      const uint32_t r = __popc(m & ((1u << lane) - 1u));
+      if (r < avail) {
+        item = next + r;
+        cur = gp.cont_first + k_warp + (item >> 5) * stride + (item & 31u);
+        walks = 0u;
+      }
+    }
+    next += min(static_cast<uint32_t>(__popc(m)), avail);
+    const bool active = item != 0xFFFFFFFFu;
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;
+    if (active) {
+      cur = feistel_walk(cur, fd, gp.shuffle_seed);
+      walks++;
+      if (cur < gp.cont_n || walks == kFeistelMaxWalks) {
+        src_out[item] = cur < gp.cont_n ? cur : cur % gp.cont_n;
+        item = 0xFFFFFFFFu;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Five CTAs per SM (48 registers, no spills) for both generators: the transit form settles at 58 registers without
+// the bound, which costs it a fifth of its resident warps.
+#ifndef HB_GEN_MINB
+#define HB_GEN_MINB 5
+#endif
 template <bool TRANSIT>
-__global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
+__global__ void __launch_bounds__(256, HB_GEN_MINB) gen_kernel(const GenParams gp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GenShared* gs = reinterpret_cast<GenShared*>(smem_raw);
   stage_gen_shared(gp, gs);
   __syncthreads();
   const uint32_t stride = gridDim.x * blockDim.x;
+  if (TRANSIT && gp.shuffle && gp.cont_n > 2u) {
+    uint32_t* src_warp = reinterpret_cast<uint32_t*>(smem_raw + kGenSharedBytes) + (threadIdx.x >> 5) * (32u * kTransitBatch);
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t k_warp = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); k_warp < gp.count; k_warp += kTransitBatch * stride) {
+      resolve_sources(gp, k_warp, stride, src_warp);
+#pragma unroll 1
+      for (uint32_t c = 0; c < kTransitBatch; c++) {
+        const uint32_t k = k_warp + c * stride + lane;
+        if (k < gp.count) {
+          float4 p4, d4, q;
+          gen_root<TRANSIT>(gp, gs, k, p4, d4, q, src_warp[c * 32u + lane]);
+          const uint32_t slot = gp.slot0 + k;
+          gp.P[slot] = p4;
+          gp.D[slot] = d4;
+          gp.Q[slot] = q;
+          if ((gp.flags & kFlagPath) && gp.path != nullptr) gp.path[slot] = static_cast<uint8_t>(bits_face(__float_as_uint(p4.w)));
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gp.count; k += stride) {
     float4 p4, d4, q;
     gen_root<TRANSIT>(gp, gs, k, p4, d4, q);
@@ -1485,8 +1561,6 @@ __global__ void __launch_bounds__(256) gen_kernel(const GenParams gp) {
 // same per-warp exit queue as in bounce_kernel.
 // dynamic shared memory: [GenShared] [pixel cache] [exit queues] [crystal tables]
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kGenSharedBytes = (static_cast<uint32_t>(sizeof(GenShared)) + 15u) & ~15u;
-
 template <bool TRANSIT, bool GENERAL, bool SMEM, bool MULTI, int P4 = 0>
 __global__ void __launch_bounds__(256, 4) genbounce_kernel(const GenParams gp, const TraceParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
