@@ -1465,8 +1465,9 @@ HB_DEV void gen_root(const GenParams& gp, const GenShared* gs, uint32_t k, float
 // passes per item (3.4 on average when the pool is just above a quarter of the 2^bits domain), so a warp that walks
 // its 32 items in lock step waits for the slowest lane -- ncu: 9 to 14 of 32 lanes active in 41 % of the kernel's
 // instructions. Here a lane whose item has landed below n takes the next unresolved item, and every pass runs with
-// (almost) all lanes; the sources go through shared memory to the lanes that generate the rays.
-constexpr uint32_t kTransitBatch = 4u;
+// (almost) all lanes (512 items per pool: the tail, where the last items finish their walks, stays near a tenth of
+// the passes); the sources go through shared memory to the lanes that generate the rays.
+constexpr uint32_t kTransitBatch = 16u;
 constexpr uint32_t kTransitSrcBytes = 8u * 32u * kTransitBatch * 4u;   // 8 warps per CTA
 
 HB_DEV void resolve_sources(const GenParams& gp, uint32_t k_warp, uint32_t stride, uint32_t* src_out) {
