@@ -517,6 +517,7 @@ int trace_tile(HbEngine* h, uint32_t li, uint64_t root0, uint32_t n, const std::
   tp.wl0 = h->wl0;
   tp.wl2 = h->wl2_cur;
   tp.image = h->image.p;
+  tp.master = h->master.p;
   tp.proj = h->proj;
   tp.extra = h->extra_dev.p;
   tp.extra_cnt = static_cast<uint32_t>(h->renders.size()) - 1u;

@@ -101,6 +101,7 @@ struct TraceParams {
   WlDev wl0;                    // entry 0 of the derived table: single-wavelength sessions read it from the parameter bank
   const WlDev* wl2;             // derived table (n, 1/n, CMF), one per pool entry
   float4* image;                // image arena: render r occupies [off_r, off_r + W_r*H_r), (X, Y, Z, landed)
+  double4* master;              // fp64 master of the same arena (the pixel cache flushes straight into it)
   HbProjParams proj;            // render 0 (arena offset 0)
   const ExtraRender* extra;     // renders 1..extra_cnt (device)
   uint32_t extra_cnt;
@@ -267,10 +268,26 @@ HB_DEV void cache_init(Tally& tally, unsigned char* smem) {
 HB_DEV void cache_flush(const TraceParams& tp, const Tally& tally) {
   __syncthreads();
   const float4* v = reinterpret_cast<const float4*>(tally.cache_vals);
-  for (uint32_t i = threadIdx.x; i < kCacheSlots * kCacheWays; i += blockDim.x) {
-    const uint32_t k = tally.cache_keys[i >> HB_CACHE_WAYS_LOG2];
-    const float4 c = v[i];
-    if (k != kCacheEmpty && (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f || c.w != 0.0f)) red_add_f4(tp.image + k, c.x, c.y, c.z, c.w);
+  for (uint32_t i = threadIdx.x; i < kCacheSlots; i += blockDim.x) {
+    const uint32_t k = tally.cache_keys[i];
+    if (k == kCacheEmpty) continue;
+    double x = 0.0, y = 0.0, z = 0.0, w = 0.0;
+#pragma unroll
+    for (uint32_t c = 0; c < kCacheWays; c++) {
+      const float4 cell = v[i * kCacheWays + c];
+      x += static_cast<double>(cell.x);
+      y += static_cast<double>(cell.y);
+      z += static_cast<double>(cell.z);
+      w += static_cast<double>(cell.w);
+    }
+    // A CTA's partial sum of a hot pixel goes to the fp64 master, not to the fp32 working image: the working
+    // accumulator of such a pixel then only ever holds the few contributions that arrived before the claim, stays
+    // small, and does not swallow the ~1e-5-weight exits of long ray paths (a 1e4 fp32 pixel drops addends < 5e-4).
+    double* m = reinterpret_cast<double*>(tp.master + k);
+    atomicAdd(m + 0, x);
+    atomicAdd(m + 1, y);
+    atomicAdd(m + 2, z);
+    atomicAdd(m + 3, w);
   }
 }
 

@@ -19,7 +19,7 @@ be = B.B200TraceBackend(0)
 be.SetScene(B.SceneTables(case["scene"](), 7))
 be.SetRender(case["render"]())
 wl = [B.make_wl_entry(550.0, 1.0)]
-n = 1 << 24
+n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 24)
 
 
 def run(splits, **opts):
@@ -36,15 +36,17 @@ def run(splits, **opts):
     return img.astype(np.float64), float(landed)
 
 
+t8 = max(n >> 3, 4096)
 runs = {
-    "a  one 16Mi tile": run([n], tile_rays=1 << 24, pixel_cache=1),
-    "a2 2Mi tiles": run([n], tile_rays=1 << 21, pixel_cache=1),
+    "a  one tile": run([n], tile_rays=1 << 24, pixel_cache=1),
+    "a2 n/8 tiles": run([n], tile_rays=t8, pixel_cache=1),
     "b  3 sessions": run([n // 2, n // 2 - 12345, 12345], tile_rays=1 << 24, pixel_cache=1),
+    "c  2 halves": run([n // 2, n // 2], tile_rays=1 << 24, pixel_cache=1),
     "a  no cache": run([n], tile_rays=1 << 24, pixel_cache=0),
-    "a2 no cache 2Mi": run([n], tile_rays=1 << 21, pixel_cache=0),
+    "a2 no cache n/8": run([n], tile_rays=t8, pixel_cache=0),
     "a  again": run([n], tile_rays=1 << 24, pixel_cache=1),
 }
-ref_img, ref_l = runs["a2 2Mi tiles"]
+ref_img, ref_l = runs["a2 n/8 tiles"]
 for k, (img, l) in runs.items():
     d = img[..., 1] - ref_img[..., 1]
     hot = np.argsort(ref_img[..., 1].ravel())[-40:]
