@@ -53,7 +53,7 @@ BYTES_GENBOUNCE = 48
 BYTES_GENBOUNCE_EXIT = 16
 EXITS_AT_ENTRY = 1.0
 EXITS_PER_ROOT = 4.7            # config 2, measured (reference CPU: 4.69-4.71)
-TRAFFIC_FILE = "traffic_r2.json"
+TRAFFIC_FILE = "traffic_r2b.json"
 
 # BASELINE.json configs -> scene (ice_halo_sim_b200.scenes), ray budget per wavelength, GPUs the config names,
 # session size. config2 is the headline the bench line is quoted on; the others are reported as sub-records of the
