@@ -850,7 +850,49 @@ constexpr uint32_t kQueueSlots = 96u;                                  // < 32 p
 // during a layer, so the emission re-reads them from P[slot] when it needs them (several wavelengths, GENERAL).
 constexpr uint32_t kQueueWarpBytes = kQueueSlots * 16u + kQueueSlots * 4u;
 constexpr uint32_t kQueueBytes = 8u * kQueueWarpBytes;                 // 8 warps per CTA
-constexpr uint32_t kStage2Bytes = 2u * 2u * 256u * 16u;                // two stages x (D, P) x 256 threads x 16 B
+// HB_BULK_STAGE = 1: the ray stage-in is a per-WARP 1-D bulk copy (cp.async.bulk global -> shared, completion on an
+// mbarrier: SASS UBLKCP + SYNCS) issued by lane 0 -- a warp's 32 rays are 512 contiguous bytes of D and of P --
+// instead of one LDGSTS.128 per thread and array. Per-warp barriers keep the warps of a CTA independent. Measured
+// A/B in profiles/README.md (the kernel is issue-bound: the copy engine saves about four issue slots per iteration).
+#ifndef HB_BULK_STAGE
+#define HB_BULK_STAGE 0
+#endif
+constexpr uint32_t kStage2Bytes = 2u * 2u * 256u * 16u + (HB_BULK_STAGE ? 128u : 0u);  // two stages x (D, P) x 256 threads x 16 B (+ 8 warps x 2 mbarriers)
+
+HB_DEV void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+HB_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+HB_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+HB_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "HB_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra HB_MBAR_DONE;\n"
+      "bra HB_MBAR_WAIT;\n"
+      "HB_MBAR_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// Lane 0 of a warp: copy the D and P entries of the warp's rays [first, first + 32) (clipped to `total`) into stage `s`.
+HB_DEV void bulk_stage_in(const TraceParams& tp, uint32_t stage_base, uint32_t bar0, uint32_t s, uint32_t first, uint32_t total) {
+  if ((threadIdx.x & 31u) == 0u && first < total) {
+    const uint32_t bytes = min(32u, total - first) * 16u;
+    const uint32_t dst = stage_base + s * 8192u + (threadIdx.x >> 5) * 512u, bar = bar0 + s * 8u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warp's earlier LDS of this buffer before the async-proxy write
+    mbar_expect_tx(bar, 2u * bytes);
+    bulk_g2s(dst, tp.D + first, bytes, bar);
+    bulk_g2s(dst + 4096u, tp.P + first, bytes, bar);
+  }
+}
 
 HB_DEV void sts128(uint32_t addr, float x, float y, float z, float w) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
@@ -1042,8 +1084,9 @@ HB_DEV void bounce_ray(const TraceParams& tp, const Tables<SMEM>& tb, uint32_t i
   bool near_done = false;                  // LAST: the near child provably stays inside, nothing to do
   if (shape_p4) {
     if (LAST) {
-      far_exits = far_child_surely_exits_p4(axes, pl, p4.x, p4.y, p4.z, ox, oy, oz);
-      near_done = iw < 0.0f || near_child_surely_hits(axes, 4u, p4.x, p4.y, p4.z, ix, iy, iz);
+      bool near_hits;
+      last_axes_p4(axes, pl, p4.x, p4.y, p4.z, ox, oy, oz, ix, iy, iz, far_exits, near_hits);
+      near_done = iw < 0.0f || near_hits;
       if (!near_done) nf = slab_exit_p4<false>(axes, face, p4.x, p4.y, p4.z, ix, iy, iz, nx, ny, nz);
     } else {
       nf = bounce_axes_p4(axes, face, pl, p4.x, p4.y, p4.z, ox, oy, oz, ix, iy, iz, far_exits, nx, ny, nz);
@@ -1126,24 +1169,44 @@ __global__ void __launch_bounds__(256, GENERAL ? HB_BOUNCE_MINB_GENERAL : HB_BOU
   uint32_t stage = 0u;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t warp_first = i - (threadIdx.x & 31u);  // the loop runs while the WARP has a ray: pushes are warp-wide
+#if HB_BULK_STAGE
+  const uint32_t stage_base = smem_base + stage_off;
+  const uint32_t bar0 = stage_base + 16384u + (threadIdx.x >> 5) * 16u;  // this warp's two mbarriers (one per stage)
+  if ((threadIdx.x & 31u) == 0u) {
+    mbar_init(bar0, 1u);
+    mbar_init(bar0 + 8u, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  bulk_stage_in(tp, stage_base, bar0, 0u, warp_first, total);
+  uint32_t iter = 0u;
+#else
   if (i < total) {
     cp_async16(stage0, tp.D + i);
     cp_async16(stage0 + 4096u, tp.P + i);
   }
   cp_async_commit();
+#endif
   // One emission site: the loop body runs once more after the warp's last ray to flush the queue, so the (large)
   // emission code is instantiated once and nothing of the trace state is live across it.
   for (;;) {
     const bool more = warp_first < total;
     if (more) {
       const uint32_t i_next = i + stride;
-      const uint32_t cur = stage0 + stage * 8192u, nxt = stage0 + (stage ^ 1u) * 8192u;
+      const uint32_t cur = stage0 + stage * 8192u;
+#if HB_BULK_STAGE
+      bulk_stage_in(tp, stage_base, bar0, stage ^ 1u, warp_first + stride, total);
+      mbar_wait(bar0 + stage * 8u, (iter >> 1) & 1u);
+      iter++;
+#else
+      const uint32_t nxt = stage0 + (stage ^ 1u) * 8192u;
       if (i_next < total) {
         cp_async16(nxt, tp.D + i_next);
         cp_async16(nxt + 4096u, tp.P + i_next);
       }
       cp_async_commit();
       cp_async_wait<1>();
+#endif
       bool has0 = false, has1 = false;
       float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
       uint32_t bits = 0u;
