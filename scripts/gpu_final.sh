@@ -12,3 +12,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-fil
   python bench.py --steps 1 --warmup 0 --no-extras --no-cpu-baseline > gpurun_out/${tag}_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"gen_kernel|bounce_kernel" -c 4 -o gpurun_out/${tag}_c2 -f \
   python scripts/profile_step.py 16777216 1 > gpurun_out/${tag}_c2.log 2>&1; tail -1 gpurun_out/${tag}_c2.log
+# grid-size check (CTAs per SM of the trace kernels; default = 3 waves of the co-resident CTAs = 12)
+for b in 8 16; do AB_ARGS="--set blocks_per_sm=$b" bash scripts/ab_bench.sh 5 - | sed "s/^intree/blocks_per_sm=$b/"; done
+for w in config5 pyramid; do AB_ARGS="--workload $w" bash scripts/ab_bench.sh 2 - | sed "s/^intree/$w/"; done
