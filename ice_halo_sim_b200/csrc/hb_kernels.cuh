@@ -163,16 +163,16 @@ struct GenParams {
 struct Tally {
   unsigned long long exits = 0;
   double w_sum = 0.0;
-  uint32_t* cache_keys = nullptr;  // per-CTA pixel cache (see PixelCache below); nullptr = reduce straight to L2
+  uint32_t* cache_keys = nullptr;  // per-CTA pixel cache: [owners | candidates] (below); nullptr = reduce straight to L2
   float* cache_vals = nullptr;
 };
 
 // Per-CTA pixel cache. Halo images are extremely peaked (the undeviated light through parallel faces lands
 // on the ~35 pixels of the sun disk: ~40 % of all exits), and same-address reductions serialise in the L2
 // atomic unit while the fp32 accumulator of such a pixel absorbs small addends. Each CTA therefore keeps a
-// direct-mapped table of kCacheSlots pixels in shared memory (first come, first claimed): contributions to a
-// cached pixel are summed in shared memory and reduced into the global image once, when the CTA retires.
-// Everything else goes straight to the L2 with one red.global.add.v4.f32.
+// direct-mapped table of kCacheSlots pixels in shared memory (claimed on a pixel's second sighting, see
+// accumulate_pixel): contributions to a cached pixel are summed in shared memory and added to the fp64 master once,
+// when the CTA retires (cache_flush). Everything else goes straight to the L2 with one red.global.add.v4.f32.
 //   * The slot is a TILE hash of the pixel coordinates (low bits of x and of y): the hot pixels of a halo image are
 //     spatially clustered (sun disk, parhelia), and a 16 x 8 tile maps a 7 x 7 cluster without a single collision
 //     where a multiplicative hash of the linear index loses ~4 of 35 to the birthday problem.
