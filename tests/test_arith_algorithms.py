@@ -140,3 +140,121 @@ def test_feistel_domain_bits_by_clz_equal_the_counting_loop():
 
     for n in list(range(0, 5000)) + [(1 << k) + d for k in range(2, 32) for d in (-1, 0, 1)] + [0xFFFFFFF0]:
         assert loop(n) == by_clz(n), n
+
+
+def test_entry_face_pick_by_counting_equals_the_sequential_scan():
+    """pick_entry_triangle (csrc/hb_kernels.cuh): 'first group whose cumulative weight exceeds the target' found by
+    counting the cumulative weights <= target (descending pass with predicated moves) gives the group, residual and
+    group weight of the sequential scan -- zero-weight groups, fewer than 8 groups and target == total included."""
+    rng = np.random.default_rng(11)
+    f = np.float32
+
+    def sequential(w, ng, u):
+        total = f(0)
+        for g in range(ng):
+            total = f(total + w[g])
+        target = f(u * total)
+        sel, resid, w_sel, cum = ng - 1, f(0), f(0), f(0)
+        for g in range(ng):
+            c1 = f(cum + w[g])
+            if c1 > target:
+                return g, f(target - cum), w[g]
+            cum = c1
+        return sel, resid, w_sel
+
+    def counting(w, ng, u):
+        c, total = [], f(0)
+        for g in range(8):
+            if g < ng:
+                total = f(total + w[g])
+            c.append(total)
+        target = f(u * total)
+        below, lo, w_sel = 0, f(0), f(0)
+        for g in range(7, -1, -1):
+            le = c[g] <= target
+            w_sel = w_sel if le else (w[g] if g < ng else f(0))
+            lo = max(lo, c[g]) if le else lo
+            below += 1 if le else 0
+        if below < ng:
+            return min(below, ng - 1), f(target - lo), w_sel
+        return ng - 1, f(0), f(0)
+
+    for trial in range(20000):
+        ng = int(rng.integers(1, 9))
+        w = rng.random(8).astype(np.float32) * (rng.random(8) > 0.35)        # ~a third of the groups face away
+        w = np.where(np.arange(8) < ng, w, 0).astype(np.float32)
+        if not w[:ng].sum() > 0:
+            continue
+        u = f(rng.random()) if trial % 50 else f(1.0 - 2.0 ** -24)          # the largest uniform the RNG produces
+        a, b = sequential(w, ng, u), counting(w, ng, u)
+        assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2], (w, ng, u, a, b)
+
+
+def test_warp_pool_feistel_resolution_equals_per_item_walks():
+    """resolve_sources (csrc/hb_kernels.cuh) restated lane by lane: a warp's pool of 32 x batch items, lanes drawing the
+    next unresolved item whenever theirs lands below n, resolves every item exactly once and to the value of the plain
+    per-item cycle walk (feistel(): at most 64 walks, then modulo) -- ragged last iteration and tiny pools included."""
+    M32 = 0xFFFFFFFF
+
+    def pcg_hash(x):
+        x = (x * 747796405 + 2891336453) & M32
+        x = ((((x >> ((x >> 28) + 4)) ^ x) & M32) * 277803737) & M32
+        return ((x >> 22) ^ x) & M32
+
+    def domain(n):
+        b = 0 if n <= 1 else min((n - 1).bit_length(), 30)
+        b += b & 1
+        return b >> 1, (1 << (b >> 1)) - 1
+
+    def walk(cur, hb, hm, seed):
+        L, R = (cur >> hb) & hm, cur & hm
+        for rc in (0x9E3779B9, 0x85EBCA6B, 0xC2B2AE35, 0x27D4EB2F):
+            L, R = R, L ^ (pcg_hash(seed ^ R ^ rc) & hm)
+        return ((L << hb) | R) & M32
+
+    def feistel(i, n, seed):
+        hb, hm = domain(n)
+        cur = i
+        for _ in range(64):
+            cur = walk(cur, hb, hm, seed)
+            if cur < n:
+                return cur
+        return cur % n
+
+    def resolve(k_warp, stride, count, cont_first, n, seed, batch):
+        hb, hm = domain(n)
+        total = sum(min(32, count - (k_warp + c * stride)) for c in range(batch) if k_warp + c * stride < count)
+        out, nxt = {}, 0
+        item, cur, walks = [None] * 32, [0] * 32, [0] * 32
+        while True:
+            need = [lane for lane in range(32) if item[lane] is None]
+            avail = total - nxt
+            for r, lane in enumerate(need):
+                if r < avail:
+                    item[lane] = nxt + r
+                    cur[lane] = cont_first + k_warp + (item[lane] >> 5) * stride + (item[lane] & 31)
+                    walks[lane] = 0
+            nxt += min(len(need), avail)
+            if all(it is None for it in item):
+                return out, total
+            for lane in range(32):
+                if item[lane] is not None:
+                    cur[lane] = walk(cur[lane], hb, hm, seed)
+                    walks[lane] += 1
+                    if cur[lane] < n or walks[lane] == 64:
+                        assert item[lane] not in out
+                        out[item[lane]] = cur[lane] if cur[lane] < n else cur[lane] % n
+                        item[lane] = None
+
+    for (count, n, first, stride, batch) in [(1000, 1000, 0, 256, 4), (777, 5000, 4000, 64, 16), (33, 40, 3, 32, 16),
+                                             (5, 3, 0, 32, 4), (4096, 70000, 1234, 512, 16)]:
+        seed = 0xB17CA3D9 ^ count
+        for k_warp in range(0, min(count, stride), 32):
+            base = k_warp
+            while base < count:
+                out, total = resolve(base, stride, count, first, n, seed, batch)
+                assert len(out) == total
+                for it, src in out.items():
+                    k = base + (it >> 5) * stride + (it & 31)
+                    assert k < count and src == feistel(first + k, n, seed), (count, n, k)
+                base += batch * stride
