@@ -96,6 +96,20 @@ void twin_quick_tests(const float* planes, const float* axes, uint32_t meta, uin
   }
 }
 
+// project_exit (all 11 lens types): up to two pixel hits per direction, -1 where there is none
+void twin_project(const HbProjParams* p, uint64_t n, const float* dir3, int32_t* px2, int32_t* py2, int32_t* cnt,
+                  int32_t* bump2) {
+  for (uint64_t i = 0; i < n; i++) {
+    const PixelHits h = project_exit(*p, dir3[3 * i], dir3[3 * i + 1], dir3[3 * i + 2]);
+    cnt[i] = h.count;
+    for (int k = 0; k < 2; k++) {
+      px2[2 * i + k] = k < h.count ? h.px[k] : -1;
+      py2[2 * i + k] = k < h.count ? h.py[k] : -1;
+      bump2[2 * i + k] = k < h.count ? (h.bump[k] ? 1 : 0) : 0;
+    }
+  }
+}
+
 // dvd_nr / sqrt_nr as compiled here (host reciprocal) against the host's IEEE division / square root
 uint64_t twin_div_mismatches(uint64_t n, const float* a, const float* b) {
   uint64_t bad = 0;

@@ -35,6 +35,7 @@ def twin():
     lib.twin_hit_surface.argtypes = [vp, C.c_float, C.c_float, C.c_uint64] + [vp] * 5
     lib.twin_propagate.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint64] + [vp] * 6
     lib.twin_quick_tests.argtypes = [vp, vp, C.c_uint32, C.c_uint64] + [vp] * 4
+    lib.twin_project.argtypes = [vp, C.c_uint64] + [vp] * 5
     lib.twin_div_mismatches.argtypes = [C.c_uint64, vp, vp]
     lib.twin_div_mismatches.restype = C.c_uint64
     lib.twin_sqrt_mismatches.argtypes = [C.c_uint64, vp]
@@ -140,6 +141,26 @@ def test_one_pass_forms_equal_the_functions_they_fuse(twin, name):
         assert not (quick[:, 1].astype(bool) & (full_to != 0xFFFF)).any()
         assert quick[:, 1].any() and quick[:, 2].any()                # the fast verdicts actually fire
     assert gfe.any()
+
+
+def test_device_projection_source_equals_the_reference_golden_pixels(twin):
+    """project_exit as the kernels compile it, all 11 lens types (12 golden render set-ups of the reference's
+    ProjectExitToPixel, projection_shared.h:196-375): pixel coordinates, hit counts and landed-weight flags."""
+    g = np.load(os.path.join(G, "projection.npz"))
+    dirs = g["dirs"]
+    n = len(dirs)
+    names = sorted({k.split(".")[0] for k in g.files if "." in k})
+    assert len(names) == 12
+    for name in names:
+        pp = A.HbProjParams.from_buffer_copy(g[f"{name}.params"].tobytes())
+        px = np.zeros((n, 2), np.int32)
+        py = np.zeros((n, 2), np.int32)
+        cnt = np.zeros(n, np.int32)
+        bump = np.zeros((n, 2), np.int32)
+        twin.twin_project(C.byref(pp), n, H.ptr(dirs), H.ptr(px), H.ptr(py), H.ptr(cnt), H.ptr(bump))
+        assert np.array_equal(cnt, g[f"{name}.cnt"]), name
+        assert np.array_equal(px, g[f"{name}.px"]) and np.array_equal(py, g[f"{name}.py"]), name
+        assert np.array_equal(bump, g[f"{name}.bump"]), name
 
 
 def test_unchecked_division_as_compiled_for_the_host_is_ieee(twin):
