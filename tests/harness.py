@@ -85,7 +85,7 @@ def sampler_vectors(lib, prefix, axis_samplers):
     [(name, HbAxisSampler)]."""
     out = {}
     n = 4096
-    hash_fn = lib.orc_pcg_hash if prefix == "orc_" else lib.ref_pcg_hash
+    hash_fn = lib.ref_pcg_hash if prefix == "ref_pcg_" else getattr(lib, prefix + "pcg_hash")
     xs = np.concatenate([np.arange(0, 2048, dtype=np.uint64), np.linspace(0, 2 ** 32 - 1, 2048).astype(np.uint64)])
     out["hash"] = np.array([hash_fn(int(x)) for x in xs], np.uint32)
     out["seed_hi"] = np.array([getattr(lib, prefix + "seed_with_high")(0x1234ABCD, h) for h in (0, 1, 2, 77, 2 ** 31)], np.uint32)

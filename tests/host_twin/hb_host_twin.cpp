@@ -110,6 +110,63 @@ void twin_project(const HbProjParams* p, uint64_t n, const float* dir3, int32_t*
   }
 }
 
+// The generator's building blocks, same interface as the oracle's orc_* / the reference pin's ref_* wrappers
+// (tests/harness.py: sampler_vectors), running the device functions of hb_device.cuh.
+uint32_t twin_pcg_hash(uint32_t x) { return pcg_hash(x); }
+uint32_t twin_seed_with_high(uint32_t seed, uint32_t hi) { return seed_with_high(seed, hi); }
+uint32_t twin_feistel(uint32_t i, uint32_t n, uint32_t seed) { return feistel(i, n, seed); }
+void twin_uniforms(uint32_t seed, uint32_t idx, uint32_t slot0, uint32_t n, float* out) {
+  Stream s{ seed, idx, slot0 };
+  for (uint32_t i = 0; i < n; i++) out[i] = s.next();
+}
+void twin_get_dist(uint32_t seed, uint32_t idx0, uint32_t n, uint32_t type, float mean, float stdv, float* out) {
+  for (uint32_t i = 0; i < n; i++) {
+    Stream s{ seed, idx0 + i, 0u };
+    out[i] = get_dist(s, type, mean, stdv);
+  }
+}
+void twin_lat_lon_roll(const HbAxisSampler* a, uint32_t seed, uint32_t idx0, uint32_t n, float* lon_lat_roll3,
+                       uint32_t* slots_used) {
+  // what upload_layer makes of the sampler: the scalar block + [theta | cdf | flip] (hb_engine.cu)
+  const AxisParams ap{ a->lat_path, a->lat_mean, a->lat_std, a->az_type, a->az_mean, a->az_std,
+                       a->roll_type, a->roll_mean, a->roll_std, a->lut_n };
+  static float lut[3 * HB_LUT_NODES];
+  memcpy(lut, a->lut_theta, sizeof(float) * HB_LUT_NODES);
+  memcpy(lut + HB_LUT_NODES, a->lut_cdf, sizeof(float) * HB_LUT_NODES);
+  memcpy(lut + 2 * HB_LUT_NODES, a->lut_flip, sizeof(float) * HB_LUT_NODES);
+  for (uint32_t i = 0; i < n; i++) {
+    Stream s{ seed, idx0 + i, 0u };
+    sample_lon_lat_roll(s, ap, lut, lon_lat_roll3[3 * i], lon_lat_roll3[3 * i + 1], lon_lat_roll3[3 * i + 2]);
+    if (slots_used != nullptr) slots_used[i] = s.slot;
+  }
+}
+void twin_rotation9(uint64_t n, const float* lon_lat_roll3, float* rot9) {
+  for (uint64_t i = 0; i < n; i++) {
+    const Rot r = rot_from_quat(quat_from_angles(lon_lat_roll3[3 * i], lon_lat_roll3[3 * i + 1], lon_lat_roll3[3 * i + 2]));
+    memcpy(rot9 + 9 * i, r.m, sizeof(r.m));
+  }
+}
+void twin_sph_cap(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, float lon, float lat, float half, float* d3) {
+  for (uint32_t i = 0; i < n; i++) {
+    Stream s{ seed, idx0 + i, slot0 };
+    sample_sph_cap(s, lon, lat, half, d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+  }
+}
+void twin_triangle(uint32_t seed, uint32_t idx0, uint32_t slot0, uint32_t n, const float* vtx9, float* p3) {
+  // sample_entry's point-in-triangle step on a one-triangle fan table (weights irrelevant: a single candidate)
+  static HbCrystalTables t;
+  memset(&t, 0, sizeof(t));
+  t.subtri_cnt = 1;
+  memcpy(t.tri_v[0], vtx9, 9 * sizeof(float));
+  t.tri_n[0][2] = 1.0f;
+  t.tri_area[0] = 1.0f;
+  for (uint32_t i = 0; i < n; i++) {
+    Stream s{ seed, idx0 + i, slot0 - 1u };   // sample_entry draws the categorical uniform first
+    uint32_t face;
+    sample_entry(s, &t, 0.0f, 0.0f, -1.0f, p3[3 * i], p3[3 * i + 1], p3[3 * i + 2], face);
+  }
+}
+
 // dvd_nr / sqrt_nr as compiled here (host reciprocal) against the host's IEEE division / square root
 uint64_t twin_div_mismatches(uint64_t n, const float* a, const float* b) {
   uint64_t bad = 0;

@@ -163,6 +163,46 @@ def test_device_projection_source_equals_the_reference_golden_pixels(twin):
         assert np.array_equal(bump, g[f"{name}.bump"]), name
 
 
+def test_device_sampler_source_equals_the_reference_pcg_fixture(twin):
+    """The generator's building blocks as the kernels compile them (pcg_hash, seed_with_high, uniforms, get_dist of
+    all six types, sample_lon_lat_roll on every latitude path incl. the slots it consumes, sample_sph_cap, the
+    point-in-triangle step, feistel) against tests/golden/sampler_pin.npz = outputs of the reference's own lm_pcg::*
+    (core/shared/pcg_shared.h): integers and uniforms exactly, libm-dependent floats to ulp-scale tolerances, the
+    orientation matrix (quaternion here, three axis rotations there) to 1e-6."""
+    g = np.load(os.path.join(G, "sampler_pin.npz"))
+    vp = C.c_void_p
+    twin.twin_pcg_hash.restype = C.c_uint32
+    twin.twin_pcg_hash.argtypes = [C.c_uint32]
+    twin.twin_seed_with_high.restype = C.c_uint32
+    twin.twin_seed_with_high.argtypes = [C.c_uint32, C.c_uint32]
+    twin.twin_feistel.restype = C.c_uint32
+    twin.twin_feistel.argtypes = [C.c_uint32] * 3
+    twin.twin_uniforms.argtypes = [C.c_uint32] * 4 + [vp]
+    twin.twin_get_dist.argtypes = [C.c_uint32] * 4 + [C.c_float, C.c_float, vp]
+    twin.twin_lat_lon_roll.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
+    twin.twin_rotation9.argtypes = [C.c_uint64, vp, vp]
+    twin.twin_sph_cap.argtypes = [C.c_uint32] * 4 + [C.c_float] * 3 + [vp]
+    twin.twin_triangle.argtypes = [C.c_uint32] * 4 + [vp, vp]
+    order = ["full_sphere", "fixed", "gauss_lut", "gauss_legacy", "laplacian", "zigzag", "uniform_band"]
+    axes = sorted(((k[5:], A.HbAxisSampler.from_buffer_copy(g[k].tobytes())) for k in g.files if k.startswith("axis_")),
+                  key=lambda kv: order.index(kv[0]))
+    assert len(axes) == len(order)
+    got = H.sampler_vectors(twin, "twin_", axes)
+    for k, v in got.items():
+        want = g[k]
+        if v.dtype == np.uint32 or k == "uniforms":
+            assert np.array_equal(v, want), k
+        elif k.startswith("rot_"):
+            assert np.abs(v - want).max() <= 1e-6, k
+        else:
+            assert np.allclose(v, want, rtol=3e-7, atol=3e-7), k
+    for k in g.files:
+        if k.startswith("feistel_"):
+            _, n, seed = k.split("_")
+            n, seed = int(n), int(seed)
+            assert np.array_equal(np.array([twin.twin_feistel(i, n, seed) for i in range(n)], np.uint32), g[k]), k
+
+
 def test_unchecked_division_as_compiled_for_the_host_is_ieee(twin):
     rng = np.random.default_rng(5)
     n = 2_000_000
