@@ -409,20 +409,6 @@ HB_DEV bool emit_world(const TraceParams& tp, uint32_t slot, uint32_t bits, floa
   return true;
 }
 
-// Exact "this direction reaches no pixel of render 0" test for the lenses that cull (same expressions as
-// project_exit evaluates first); false = project it. Lets the emission drop invisible exits (about half of them
-// for a one-hemisphere view) before they take a slot of the projection stage.
-HB_DEV bool project_culls(const HbProjParams& p, float wx, float wy, float wz) {
-  const int t = p.proj_type;
-  if (t == HB_LENS_LINEAR || t == HB_LENS_FISHEYE_EQUAL_AREA || t == HB_LENS_FISHEYE_EQUIDISTANT ||
-      t == HB_LENS_FISHEYE_STEREOGRAPHIC || t == HB_LENS_FISHEYE_ORTHOGRAPHIC) {
-    if ((p.visible_range == HB_VISIBLE_UPPER && wz > 0.0f) || (p.visible_range == HB_VISIBLE_LOWER && wz < 0.0f)) return true;
-    return dot3(p.rot[2], p.rot[5], p.rot[8], -wx, -wy, -wz) <= 0.0f;  // cz of rot_apply_t(p.rot, -w)
-  }
-  if (t == HB_LENS_GLOBE) return dot3(p.rot[2], p.rot[5], p.rot[8], -wx, -wy, -wz) >= dvd(-1.0f, 4.0f);
-  return false;
-}
-
 // Emission, second half: projection through every render of the trace + image reduction (+ colour lanes).
 template <bool MULTI>
 HB_DEV void emit_project(const TraceParams& tp, uint32_t wl_i, float wx, float wy, float wz, float w, uint64_t mask,

@@ -110,6 +110,11 @@ void twin_project(const HbProjParams* p, uint64_t n, const float* dir3, int32_t*
   }
 }
 
+// project_culls: the exact early "reaches no pixel of render 0" test of the emission's first stage
+void twin_project_culls(const HbProjParams* p, uint64_t n, const float* dir3, uint8_t* culled) {
+  for (uint64_t i = 0; i < n; i++) culled[i] = project_culls(*p, dir3[3 * i], dir3[3 * i + 1], dir3[3 * i + 2]) ? 1 : 0;
+}
+
 // The generator's building blocks, same interface as the oracle's orc_* / the reference pin's ref_* wrappers
 // (tests/harness.py: sampler_vectors), running the device functions of hb_device.cuh.
 uint32_t twin_pcg_hash(uint32_t x) { return pcg_hash(x); }

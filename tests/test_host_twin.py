@@ -36,6 +36,7 @@ def twin():
     lib.twin_propagate.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint64] + [vp] * 6
     lib.twin_quick_tests.argtypes = [vp, vp, C.c_uint32, C.c_uint64] + [vp] * 4
     lib.twin_project.argtypes = [vp, C.c_uint64] + [vp] * 5
+    lib.twin_project_culls.argtypes = [vp, C.c_uint64, vp, vp]
     lib.twin_div_mismatches.argtypes = [C.c_uint64, vp, vp]
     lib.twin_div_mismatches.restype = C.c_uint64
     lib.twin_sqrt_mismatches.argtypes = [C.c_uint64, vp]
@@ -161,6 +162,12 @@ def test_device_projection_source_equals_the_reference_golden_pixels(twin):
         assert np.array_equal(cnt, g[f"{name}.cnt"]), name
         assert np.array_equal(px, g[f"{name}.px"]) and np.array_equal(py, g[f"{name}.py"]), name
         assert np.array_equal(bump, g[f"{name}.bump"]), name
+        # the emission's early cull never drops a direction the lens would have drawn, and does fire where it applies
+        culled = np.zeros(n, np.uint8)
+        twin.twin_project_culls(C.byref(pp), n, H.ptr(dirs), H.ptr(culled))
+        assert not (culled.astype(bool) & (cnt > 0)).any(), name
+        if pp.proj_type in (0, 1, 2, 3, 8) and (cnt == 0).any():   # the single-hemisphere lenses (halotrace_b200.h: HB_LENS_*)
+            assert culled.any(), name
 
 
 def test_device_sampler_source_equals_the_reference_pcg_fixture(twin):
