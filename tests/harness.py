@@ -80,6 +80,45 @@ def _sampler_prototypes(lib, prefix):
     getattr(lib, prefix + "triangle").argtypes = [u32, u32, u32, u32, _vp, _vp]
 
 
+_twin = None
+
+
+def host_twin():
+    """The product's device arithmetic compiled for the CPU (tests/host_twin/: csrc/hb_device.cuh, hb_tables.h and
+    hb_filter.h under g++ with -DHB_HOST_TWIN); built on first use."""
+    global _twin
+    if _twin is None:
+        here = os.path.join(ROOT, "tests", "host_twin")
+        out = os.path.join(here, "_build", "libhb_host_twin.so")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-frounding-math", "-fPIC", "-shared",
+                               "-DHB_HOST_TWIN=1", "-I" + os.path.join(ROOT, "include"),
+                               "-I" + os.path.join(ROOT, "ice_halo_sim_b200", "csrc"), "-I" + here, "-o", out,
+                               os.path.join(here, "hb_host_twin.cpp")])
+        lib = C.CDLL(out)
+        u32, f32, u64 = C.c_uint32, C.c_float, C.c_uint64
+        lib.twin_derive.argtypes = [_vp] * 5
+        lib.twin_hit_surface.argtypes = [_vp, f32, f32, u64] + [_vp] * 5
+        lib.twin_propagate.argtypes = [_vp, _vp, u32, u32, u64] + [_vp] * 6
+        lib.twin_quick_tests.argtypes = [_vp, _vp, u32, u64] + [_vp] * 4
+        lib.twin_project.argtypes = [_vp, u64] + [_vp] * 5
+        lib.twin_project_culls.argtypes = [_vp, u64, _vp, _vp]
+        lib.twin_filter_check.argtypes = [_vp, _vp, u32, u64] + [_vp] * 4
+        lib.twin_filter_max_len.restype = u32
+        lib.twin_filter_max_len.argtypes = [_vp]
+        lib.twin_div_mismatches.argtypes = [u64, _vp, _vp]
+        lib.twin_div_mismatches.restype = u64
+        lib.twin_sqrt_mismatches.argtypes = [u64, _vp]
+        lib.twin_sqrt_mismatches.restype = u64
+        lib.twin_pcg_hash.restype = u32
+        lib.twin_pcg_hash.argtypes = [u32]
+        lib.twin_feistel.restype = u32
+        lib.twin_feistel.argtypes = [u32] * 3
+        _sampler_prototypes(lib, "twin_")
+        _twin = lib
+    return _twin
+
+
 def sampler_vectors(lib, prefix, axis_samplers):
     """Run every building block of the generator on fixed inputs; returns {name: array}. `axis_samplers`:
     [(name, HbAxisSampler)]."""

@@ -115,6 +115,18 @@ void twin_project_culls(const HbProjParams* p, uint64_t n, const float* dir3, ui
   for (uint64_t i = 0; i < n; i++) culled[i] = project_culls(*p, dir3[3 * i], dir3[3 * i + 1], dir3[3 * i + 2]) ? 1 : 0;
 }
 
+// filter_check (csrc/hb_filter.h, the matcher the emission runs), interface of the oracle's orc_filter_check
+int twin_filter_check(const HbFilterDesc* f, const uint8_t* face_fn, uint32_t crystal_id, uint64_t n, const uint8_t* paths64,
+                      const uint8_t* path_len, const float* dir3, uint8_t* pass) {
+  for (uint64_t i = 0; i < n; i++) {
+    uint8_t fn[64];
+    for (uint32_t k = 0; k < path_len[i]; k++) fn[k] = face_fn[paths64[i * 64 + k]];
+    pass[i] = filter_check(*f, fn, path_len[i], dir3 + 3 * i, crystal_id) ? 1 : 0;
+  }
+  return 0;
+}
+uint32_t twin_filter_max_len(const HbFilterDesc* f) { return filter_max_len(*f); }
+
 // The generator's building blocks, same interface as the oracle's orc_* / the reference pin's ref_* wrappers
 // (tests/harness.py: sampler_vectors), running the device functions of hb_device.cuh.
 uint32_t twin_pcg_hash(uint32_t x) { return pcg_hash(x); }

@@ -5,7 +5,6 @@ kernels equals the stand-alone functions it replaces). No GPU: this is the `-m "
 arithmetic; the GPU suite checks the compiled kernels."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -22,26 +21,7 @@ NAMES = ["prism_h1", "column_h1p3", "pyramid_full", "prism_irregular"]
 
 @pytest.fixture(scope="module")
 def twin():
-    out = os.path.join(HERE, "host_twin", "_build", "libhb_host_twin.so")
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    src = os.path.join(HERE, "host_twin", "hb_host_twin.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-frounding-math", "-fPIC", "-shared",
-                           "-DHB_HOST_TWIN=1", "-I" + os.path.join(ROOT, "include"),
-                           "-I" + os.path.join(ROOT, "ice_halo_sim_b200", "csrc"), "-I" + os.path.join(HERE, "host_twin"),
-                           "-o", out, src])
-    lib = C.CDLL(out)
-    vp = C.c_void_p
-    lib.twin_derive.argtypes = [vp] * 5
-    lib.twin_hit_surface.argtypes = [vp, C.c_float, C.c_float, C.c_uint64] + [vp] * 5
-    lib.twin_propagate.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint64] + [vp] * 6
-    lib.twin_quick_tests.argtypes = [vp, vp, C.c_uint32, C.c_uint64] + [vp] * 4
-    lib.twin_project.argtypes = [vp, C.c_uint64] + [vp] * 5
-    lib.twin_project_culls.argtypes = [vp, C.c_uint64, vp, vp]
-    lib.twin_div_mismatches.argtypes = [C.c_uint64, vp, vp]
-    lib.twin_div_mismatches.restype = C.c_uint64
-    lib.twin_sqrt_mismatches.argtypes = [C.c_uint64, vp]
-    lib.twin_sqrt_mismatches.restype = C.c_uint64
-    return lib
+    return H.host_twin()
 
 
 def derive(twin, t):
@@ -177,19 +157,6 @@ def test_device_sampler_source_equals_the_reference_pcg_fixture(twin):
     (core/shared/pcg_shared.h): integers and uniforms exactly, libm-dependent floats to ulp-scale tolerances, the
     orientation matrix (quaternion here, three axis rotations there) to 1e-6."""
     g = np.load(os.path.join(G, "sampler_pin.npz"))
-    vp = C.c_void_p
-    twin.twin_pcg_hash.restype = C.c_uint32
-    twin.twin_pcg_hash.argtypes = [C.c_uint32]
-    twin.twin_seed_with_high.restype = C.c_uint32
-    twin.twin_seed_with_high.argtypes = [C.c_uint32, C.c_uint32]
-    twin.twin_feistel.restype = C.c_uint32
-    twin.twin_feistel.argtypes = [C.c_uint32] * 3
-    twin.twin_uniforms.argtypes = [C.c_uint32] * 4 + [vp]
-    twin.twin_get_dist.argtypes = [C.c_uint32] * 4 + [C.c_float, C.c_float, vp]
-    twin.twin_lat_lon_roll.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
-    twin.twin_rotation9.argtypes = [C.c_uint64, vp, vp]
-    twin.twin_sph_cap.argtypes = [C.c_uint32] * 4 + [C.c_float] * 3 + [vp]
-    twin.twin_triangle.argtypes = [C.c_uint32] * 4 + [vp, vp]
     order = ["full_sphere", "fixed", "gauss_lut", "gauss_legacy", "laplacian", "zigzag", "uniform_band"]
     axes = sorted(((k[5:], A.HbAxisSampler.from_buffer_copy(g[k].tobytes())) for k in g.files if k.startswith("axis_")),
                   key=lambda kv: order.index(kv[0]))

@@ -225,6 +225,11 @@ def test_filter_check_matches_filter_spec(spec, roll):
     orc.orc_filter_check(C.byref(mine), H.ptr(fn), pop.crystal.id, n, H.ptr(paths), H.ptr(plen), H.ptr(d), H.ptr(pass_o))
     assert np.array_equal(pass_r, pass_o)
     assert 0 < pass_o.sum() < n or spec["kind"] == 4
+    # ... and so does the matcher the kernels run (csrc/hb_filter.h compiled for the CPU, tests/host_twin)
+    pass_t = np.zeros(n, np.uint8)
+    H.host_twin().twin_filter_check(C.byref(mine), H.ptr(fn), pop.crystal.id, n, H.ptr(paths), H.ptr(plen), H.ptr(d),
+                                    H.ptr(pass_t))
+    assert np.array_equal(pass_r, pass_t)
 
 
 def test_orientation_sampler_statistics_match_cpu_sampler():
